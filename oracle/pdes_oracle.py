@@ -1,0 +1,281 @@
+"""CPU oracle for the physics-constrained DenseED training hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package (`pde_surrogate_b200/`, `models/`,
+`utils/`) may import this module; only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` do, and only as the checker or the
+CPU baseline — never as the thing shipped.
+
+It restates, with plain `torch` CPU ops and explicit slicing arithmetic, what the reference
+computes on this path.  Each function cites the reference file:line it follows
+(paths relative to the cics-nd/pde-surrogate root).  The arithmetic of the reference lives in
+PyTorch (un-vendored dependency, requirements.txt:1 `pytorch>=1.0.0`; 2.11.0 here); its
+documented semantics are used: conv2d = cross-correlation, BatchNorm2d normalises with the
+biased batch variance and updates running_var with the unbiased one, nearest upsampling maps
+dst -> floor(dst/2).
+
+Pinning: the reference ships no tests or golden vectors, so the oracle is
+pinned against outputs of the reference itself, imported from /root/reference in the build
+container by tests/golden/make_golden.py; tests/test_oracle.py replays those fixtures.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# ---------------------------------------------------------------------------------------
+# DenseED structure (models/codec.py:211-293)
+# ---------------------------------------------------------------------------------------
+
+
+def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), growth_rate=16,
+                  init_features=48):
+    """Ordered list of stages describing DenseED with the defaults the training script uses
+    (bottleneck=False in dense layers, bottleneck=True transitions, upsample='nearest',
+    drop_rate=0, out_activation=None).
+
+    Each stage is a dict.  kind:
+      'conv'   : plain convolution (In_conv)                         codec.py:242-243
+      'dense'  : BN -> ReLU -> conv3x3(cin->growth) -> cat([x, y])   codec.py:65-69, 73-75
+      'bnconv' : BN -> ReLU -> [nearest x2] -> conv                  codec.py:103-150, 163-188
+    """
+    blocks = list(blocks)
+    if len(blocks) > 1 and len(blocks) % 2 == 0:
+        raise ValueError("length of blocks must be odd")  # codec.py:231-233
+    enc = blocks[: len(blocks) // 2]  # codec.py:234
+    dec = blocks[len(blocks) // 2:]  # codec.py:235
+    pad = 3 if imsize % 2 == 0 else 2  # codec.py:238
+    st = []
+    st.append(dict(kind="conv", name="features.In_conv", cin=in_channels, cout=init_features, k=7,
+                   stride=2, pad=pad, up=False))
+    c = init_features
+    for i, n in enumerate(enc):  # codec.py:247-262
+        for j in range(n):
+            st.append(dict(kind="dense", name=f"features.EncBlock{i + 1}.denselayer{j + 1}",
+                           cin=c + j * growth_rate, cout=growth_rate, k=3, stride=1, pad=1, up=False))
+        c += n * growth_rate
+        t = f"features.TransDown{i + 1}"
+        st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=1,
+                       stride=1, pad=0, up=False))
+        st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 2, k=3,
+                       stride=2, pad=1, up=False))
+        c //= 2
+    for i, n in enumerate(dec):  # codec.py:265-282
+        for j in range(n):
+            st.append(dict(kind="dense", name=f"features.DecBlock{i + 1}.denselayer{j + 1}",
+                           cin=c + j * growth_rate, cout=growth_rate, k=3, stride=1, pad=1, up=False))
+        c += n * growth_rate
+        if i < len(dec) - 1:
+            t = f"features.TransUp{i + 1}"
+            st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=1,
+                           stride=1, pad=0, up=False))
+            st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 2,
+                           k=3, stride=1, pad=1, up=True))
+            c //= 2
+    t = "features.LastTransUp"  # codec.py:163-188
+    st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=3, stride=1,
+                   pad=1, up=False))
+    st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 4, k=3,
+                   stride=1, pad=1, up=True))
+    st.append(dict(kind="bnconv", name=t, bn="norm3", conv="conv3", cin=c // 4, cout=out_channels, k=5,
+                   stride=1, pad=2, up=False))
+    return st
+
+
+def _bn_name(s):
+    return s["name"] + "." + (s["bn"] if s["kind"] == "bnconv" else "norm1")
+
+
+def _conv_name(s):
+    if s["kind"] == "conv":
+        return s["name"]
+    return s["name"] + "." + (s["conv"] if s["kind"] == "bnconv" else "conv1")
+
+
+def state_layout(plan):
+    """(name, shape) of every state_dict entry in the reference's order
+    (BatchNorm: weight, bias, running_mean, running_var, num_batches_tracked; then conv)."""
+    out = []
+    for s in plan:
+        if s["kind"] != "conv":
+            b = _bn_name(s)
+            c = s["cin"]
+            out += [(b + ".weight", (c,)), (b + ".bias", (c,)), (b + ".running_mean", (c,)),
+                    (b + ".running_var", (c,)), (b + ".num_batches_tracked", ())]
+        out.append((_conv_name(s) + ".weight", (s["cout"], s["cin"], s["k"], s["k"])))
+    return out
+
+
+def param_names(plan):
+    return [n for n, _ in state_layout(plan) if not n.endswith(("running_mean", "running_var",
+                                                                "num_batches_tracked"))]
+
+
+def make_state(plan, seed=0, dtype=torch.float32):
+    """Deterministic, well-scaled synthetic weights (numpy legacy MT19937 stream: identical
+    on every machine, so fixtures need not store 740k weights)."""
+    rs = np.random.RandomState(seed)
+    sd = OrderedDict()
+    for name, shape in state_layout(plan):
+        if name.endswith("num_batches_tracked"):
+            sd[name] = torch.zeros((), dtype=torch.int64)
+        elif name.endswith("running_mean"):
+            sd[name] = torch.tensor(0.1 * rs.standard_normal(shape), dtype=dtype)
+        elif name.endswith("running_var"):
+            sd[name] = torch.tensor(rs.uniform(0.5, 1.5, shape), dtype=dtype)
+        elif len(shape) == 4:
+            bound = 1.0 / math.sqrt(shape[1] * shape[2] * shape[3])
+            sd[name] = torch.tensor(rs.uniform(-bound, bound, shape), dtype=dtype)
+        elif name.endswith(".weight"):
+            sd[name] = torch.tensor(rs.uniform(0.5, 1.5, shape), dtype=dtype)
+        else:
+            sd[name] = torch.tensor(rs.uniform(-0.3, 0.3, shape), dtype=dtype)
+    return sd
+
+
+def make_input(B, imsize, seed=0, dtype=torch.float32):
+    """Positive permeability-like field K = exp(0.5 * smooth-ish noise)."""
+    rs = np.random.RandomState(1000 + seed)
+    g = rs.standard_normal((B, 1, imsize, imsize))
+    return torch.tensor(np.exp(0.5 * g), dtype=dtype)
+
+
+def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_running=True):
+    """DenseED.forward (codec.py:295-296) as a flat functional program.
+
+    sd maps reference state_dict keys to tensors (parameters may require grad).  In training
+    mode running_mean / running_var / num_batches_tracked entries of `sd` are updated in place
+    exactly as nn.BatchNorm2d does.
+    """
+    h = x
+    for s in plan:
+        if s["kind"] == "conv":
+            h = F.conv2d(h, sd[_conv_name(s) + ".weight"], None, s["stride"], s["pad"])
+            continue
+        b = _bn_name(s)
+        rm, rv = sd[b + ".running_mean"], sd[b + ".running_var"]
+        if training:
+            # nn.BatchNorm2d training semantics (codec.py:57-66,103,113,135,167,173,184)
+            a = F.batch_norm(h, rm if update_running else None, rv if update_running else None,
+                             sd[b + ".weight"], sd[b + ".bias"], True, momentum, eps)
+            if update_running:
+                sd[b + ".num_batches_tracked"] += 1
+        else:
+            a = F.batch_norm(h, rm, rv, sd[b + ".weight"], sd[b + ".bias"], False, momentum, eps)
+        a = F.relu(a)
+        if s["up"]:
+            a = F.interpolate(a, scale_factor=2.0, mode="nearest")  # codec.py:24-30
+        y = F.conv2d(a, sd[_conv_name(s) + ".weight"], None, s["stride"], s["pad"])
+        h = torch.cat([h, y], 1) if s["kind"] == "dense" else y  # codec.py:73-75
+    return h
+
+
+# ---------------------------------------------------------------------------------------
+# Sobel stencils (utils/image_gradient.py:24-92), filter_size = 3
+# ---------------------------------------------------------------------------------------
+
+
+def _pad_rep(img):
+    return F.pad(img, (1, 1, 1, 1), mode="replicate")  # image_gradient.py:68, 85
+
+
+def sobel_grad_h(img, correct=True):
+    """SobelFilter.grad_h: d/dx.  Cross-correlation with VSOBEL = [[-1,0,1],[-2,0,2],[-1,0,1]]/8
+    (image_gradient.py:28-33, 62-69), times image width (line 69), then right-multiplication by
+    the modifier matrix (lines 43-46, 72-73): column 0 := 4 g0 - g1, column W-1 := 4 g[W-1] - g[W-2]."""
+    W = img.shape[-1]
+    p = _pad_rep(img)
+    g = ((p[..., 0:-2, 2:] - p[..., 0:-2, 0:-2]) + 2.0 * (p[..., 1:-1, 2:] - p[..., 1:-1, 0:-2]) +
+         (p[..., 2:, 2:] - p[..., 2:, 0:-2])) / 8.0 * W
+    if not correct:
+        return g
+    first = 4.0 * g[..., :, 0:1] - g[..., :, 1:2]
+    last = 4.0 * g[..., :, -1:] - g[..., :, -2:-1]
+    return torch.cat([first, g[..., :, 1:-1], last], dim=-1)
+
+
+def sobel_grad_v(img, correct=True):
+    """SobelFilter.grad_v: d/dy with HSOBEL (image_gradient.py:28-31, 77-92); rows 0 and H-1
+    corrected by left-multiplication with modifier^T."""
+    H = img.shape[-2]
+    p = _pad_rep(img)
+    g = ((p[..., 2:, 0:-2] - p[..., 0:-2, 0:-2]) + 2.0 * (p[..., 2:, 1:-1] - p[..., 0:-2, 1:-1]) +
+         (p[..., 2:, 2:] - p[..., 0:-2, 2:])) / 8.0 * H
+    if not correct:
+        return g
+    first = 4.0 * g[..., 0:1, :] - g[..., 1:2, :]
+    last = 4.0 * g[..., -1:, :] - g[..., -2:-1, :]
+    return torch.cat([first, g[..., 1:-1, :], last], dim=-2)
+
+
+# ---------------------------------------------------------------------------------------
+# Darcy mixed-residual loss (models/darcy.py:162-176, 210-224, 226-233)
+# ---------------------------------------------------------------------------------------
+
+
+def constitutive(K, out):
+    """conv_constitutive_constraint (darcy.py:170-176)."""
+    u = out[:, 0:1]
+    r1 = out[:, 1:2] + K * sobel_grad_h(u)
+    r2 = out[:, 2:3] + K * sobel_grad_v(u)
+    return (r1 ** 2 + r2 ** 2).mean()
+
+
+def continuity(out, use_tb=True):
+    """conv_continuity_constraint (darcy.py:217-224)."""
+    r3 = sobel_grad_h(out[:, 1:2]) + sobel_grad_v(out[:, 2:3])
+    if use_tb:
+        return (r3 ** 2).mean()
+    return (r3 ** 2)[:, :, 1:-1, :].mean()
+
+
+def boundary(out):
+    """conv_boundary_condition (darcy.py:227-233) -> (dirichlet, neumann)."""
+    left, right = out[:, 0, :, 0], out[:, 0, :, -1]
+    tb = out[:, 2, [0, -1], :]
+    return ((left - 1.0) ** 2).mean() + (right ** 2).mean(), (tb ** 2).mean()
+
+
+def darcy_losses(K, out, use_tb=True):
+    d, n = boundary(out)
+    return torch.stack([constitutive(K, out), continuity(out, use_tb), d, n])
+
+
+def total_loss(K, out, weight_bound=10.0):
+    """train_codec_mixed_residual.py:228-232."""
+    l4 = darcy_losses(K, out)
+    return (l4[0] + l4[1]) + (l4[2] + l4[3]) * weight_bound, l4
+
+
+def train_step(plan, sd, K, weight_bound=10.0):
+    """One step body of train_codec_mixed_residual.py:226-233 (zero_grad, forward, loss,
+    backward).  Returns output, 4 partial losses, loss, dL/d(output), {param name: grad}."""
+    names = param_names(plan)
+    for n in names:
+        sd[n].requires_grad_(True)
+        sd[n].grad = None
+    out = densenet_forward(plan, sd, K, training=True)
+    out.retain_grad()
+    loss, l4 = total_loss(K, out, weight_bound)
+    loss.backward()
+    grads = OrderedDict((n, sd[n].grad.detach().clone()) for n in names)
+    return out.detach(), l4.detach(), loss.detach(), out.grad.detach().clone(), grads
+
+
+def adam_reference(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8, wd=0.0):
+    """torch.optim.Adam single-tensor update (train_codec_mixed_residual.py:151, 239)."""
+    if wd != 0.0:
+        g = g + wd * p
+    m = b1 * m + (1 - b1) * g
+    v = b2 * v + (1 - b2) * g * g
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    p = p - (lr / bc1) * m / (v.sqrt() / math.sqrt(bc2) + eps)
+    return p, m, v
+
+
+def to_dtype(sd, dtype):
+    return OrderedDict((k, v.clone() if v.dtype == torch.int64 else v.detach().to(dtype).clone())
+                       for k, v in sd.items())

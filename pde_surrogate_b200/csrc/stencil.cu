@@ -1,0 +1,530 @@
+// stencil.cu — Sobel operators and the fused Darcy mixed-residual loss (forward + closed-form
+// backward) for sm_100a.
+//
+// Two implementations of each loss kernel:
+//  * "tile": one CTA streams whole samples (K,u,sigma1,sigma2 planes, contiguous in NCHW)
+//    through a 2-stage TMA bulk-copy (cp.async.bulk, SASS UBLKCP) + mbarrier pipeline into
+//    shared memory, computes on register strips (stencil_core.cuh), and — for the backward —
+//    writes the three gradient planes back with TMA bulk stores.  HBM-bound by construction:
+//    every input byte is read once, every output byte written once.
+//  * "generic": any H, W (e.g. 65x65), straight from global memory; backward by scatter.
+//
+// Reference semantics: utils/image_gradient.py:24-92 (SobelFilter), models/darcy.py:162-176,
+// 210-224, 226-233.
+#include "common.cuh"
+#include "stencil_core.cuh"
+
+namespace pdes {
+namespace {
+
+using namespace stencil;
+
+constexpr int kTileThreads = 256;
+int g_loss_impl = 0;  // 0 auto, 1 generic, 2 tile
+
+struct LossWs {
+  double acc[4];
+  unsigned int counter;
+  unsigned int pad;
+};
+
+// ---------------------------------------------------------------------------------------
+// generic helpers (global memory, one pixel at a time)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float dxc_row(const float* r, int x, int W, bool correct) {
+  if (correct) {
+    if (x == 0) return 4.f * (r[1] - r[0]) - (r[2] - r[0]);
+    if (x == W - 1) return 4.f * (r[W - 1] - r[W - 2]) - (r[W - 1] - r[W - 3]);
+  }
+  const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
+  return r[xp] - r[xm];
+}
+__device__ __forceinline__ float dyc_col(const float* f, int y, int x, int H, int W,
+                                         bool correct) {
+  if (correct) {
+    if (y == 0) return 4.f * (f[W + x] - f[x]) - (f[2 * W + x] - f[x]);
+    if (y == H - 1)
+      return 4.f * (f[(H - 1) * W + x] - f[(H - 2) * W + x]) -
+             (f[(H - 1) * W + x] - f[(H - 3) * W + x]);
+  }
+  const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
+  return f[yp * W + x] - f[ym * W + x];
+}
+__device__ __forceinline__ float sobel_dx(const float* f, int y, int x, int H, int W,
+                                          bool correct) {
+  const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
+  return (float)W * 0.125f *
+         (dxc_row(f + ym * W, x, W, correct) + 2.f * dxc_row(f + y * W, x, W, correct) +
+          dxc_row(f + yp * W, x, W, correct));
+}
+__device__ __forceinline__ float sobel_dy(const float* f, int y, int x, int H, int W,
+                                          bool correct) {
+  const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
+  return (float)H * 0.125f *
+         (dyc_col(f, y, xm, H, W, correct) + 2.f * dyc_col(f, y, x, H, W, correct) +
+          dyc_col(f, y, xp, H, W, correct));
+}
+// transposes by scatter: g[q] += coef * d(Dx f)[y][x]/d f[q]
+__device__ __forceinline__ void scat_dxc_row(float* r, int x, int W, bool correct, float w) {
+  if (correct && x == 0) {
+    atomicAdd(r + 1, 4.f * w);
+    atomicAdd(r + 0, -3.f * w);
+    atomicAdd(r + 2, -w);
+    return;
+  }
+  if (correct && x == W - 1) {
+    atomicAdd(r + W - 1, 3.f * w);
+    atomicAdd(r + W - 2, -4.f * w);
+    atomicAdd(r + W - 3, w);
+    return;
+  }
+  const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
+  atomicAdd(r + xp, w);
+  atomicAdd(r + xm, -w);
+}
+__device__ __forceinline__ void scat_dyc_col(float* f, int y, int x, int H, int W, bool correct,
+                                             float w) {
+  if (correct && y == 0) {
+    atomicAdd(f + W + x, 4.f * w);
+    atomicAdd(f + x, -3.f * w);
+    atomicAdd(f + 2 * W + x, -w);
+    return;
+  }
+  if (correct && y == H - 1) {
+    atomicAdd(f + (H - 1) * W + x, 3.f * w);
+    atomicAdd(f + (H - 2) * W + x, -4.f * w);
+    atomicAdd(f + (H - 3) * W + x, w);
+    return;
+  }
+  const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
+  atomicAdd(f + yp * W + x, w);
+  atomicAdd(f + ym * W + x, -w);
+}
+__device__ __forceinline__ void scat_dx(float* g, int y, int x, int H, int W, bool correct,
+                                        float coef) {
+  const int ym = y > 0 ? y - 1 : 0, yp = y < H - 1 ? y + 1 : H - 1;
+  const float w = coef * (float)W * 0.125f;
+  scat_dxc_row(g + ym * W, x, W, correct, w);
+  scat_dxc_row(g + y * W, x, W, correct, 2.f * w);
+  scat_dxc_row(g + yp * W, x, W, correct, w);
+}
+__device__ __forceinline__ void scat_dy(float* g, int y, int x, int H, int W, bool correct,
+                                        float coef) {
+  const int xm = x > 0 ? x - 1 : 0, xp = x < W - 1 ? x + 1 : W - 1;
+  const float w = coef * (float)H * 0.125f;
+  scat_dyc_col(g, y, xm, H, W, correct, w);
+  scat_dyc_col(g, y, x, H, W, correct, 2.f * w);
+  scat_dyc_col(g, y, xp, H, W, correct, w);
+}
+
+// ---------------------------------------------------------------------------------------
+// stand-alone Sobel (SobelFilter.grad_h / grad_v) — generic
+// ---------------------------------------------------------------------------------------
+__global__ void sobel_apply_kernel(const float* __restrict__ img, float* __restrict__ out,
+                                   int64_t n_img, int H, int W, int dir, int correct) {
+  const int64_t total = n_img * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / (H * W);
+    const int p = (int)(i - n * H * W);
+    const int y = p / W, x = p - y * W;
+    const float* f = img + n * H * W;
+    out[i] = dir == 0 ? sobel_dx(f, y, x, H, W, correct != 0) : sobel_dy(f, y, x, H, W, correct != 0);
+  }
+}
+__global__ void sobel_adjoint_kernel(const float* __restrict__ gin, float* __restrict__ out,
+                                     int64_t n_img, int H, int W, int dir, int correct) {
+  const int64_t total = n_img * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / (H * W);
+    const int p = (int)(i - n * H * W);
+    const int y = p / W, x = p - y * W;
+    float* g = out + n * H * W;
+    if (dir == 0)
+      scat_dx(g, y, x, H, W, correct != 0, gin[i]);
+    else
+      scat_dy(g, y, x, H, W, correct != 0, gin[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// loss reduction epilogue shared by both forward kernels
+// ---------------------------------------------------------------------------------------
+struct LossNorm {
+  double inv_c, inv_d, inv_dir, inv_neu;
+};
+
+__device__ __forceinline__ void loss_block_reduce_and_finish(FwdPartial part, LossWs* ws,
+                                                             float* loss4, LossNorm nrm) {
+  __shared__ double red[4][32];
+  __shared__ unsigned int s_ticket;
+  double v0 = warp_sum((double)part.c), v1 = warp_sum((double)part.d);
+  double v2 = warp_sum((double)part.dir), v3 = warp_sum((double)part.neu);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) {
+    red[0][wid] = v0;
+    red[1][wid] = v1;
+    red[2][wid] = v2;
+    red[3][wid] = v3;
+  }
+  __syncthreads();
+  if (wid == 0) {
+    double a0 = lane < nw ? red[0][lane] : 0.0, a1 = lane < nw ? red[1][lane] : 0.0;
+    double a2 = lane < nw ? red[2][lane] : 0.0, a3 = lane < nw ? red[3][lane] : 0.0;
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    a2 = warp_sum(a2);
+    a3 = warp_sum(a3);
+    if (lane == 0) {
+      atomicAdd(&ws->acc[0], a0 * nrm.inv_c);
+      atomicAdd(&ws->acc[1], a1 * nrm.inv_d);
+      atomicAdd(&ws->acc[2], a2 * nrm.inv_dir);
+      atomicAdd(&ws->acc[3], a3 * nrm.inv_neu);
+      __threadfence();
+      s_ticket = atomicAdd(&ws->counter, 1u);
+    }
+  }
+  __syncthreads();
+  if (s_ticket == gridDim.x - 1 && threadIdx.x == 0) {
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double v = atomicAdd(&ws->acc[i], 0.0);
+      loss4[i] = (float)v;
+    }
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ws->acc[i] = 0.0;
+    ws->counter = 0u;
+    __threadfence();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic forward / backward
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+darcy_fwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ out, int B, int H,
+                         int W, int use_tb, float* loss4, LossWs* ws, LossNorm nrm) {
+  FwdPartial part;
+  part.c = part.d = part.dir = part.neu = 0.f;
+  const int64_t total = (int64_t)B * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / (H * W));
+    const int p = (int)(i - (int64_t)b * H * W);
+    const int y = p / W, x = p - y * W;
+    const float* u = out + (size_t)b * 3 * H * W;
+    const float* s1 = u + H * W;
+    const float* s2 = s1 + H * W;
+    if (K != nullptr) {
+      const float k = K[i];
+      const float r1 = s1[p] + k * sobel_dx(u, y, x, H, W, true);
+      const float r2 = s2[p] + k * sobel_dy(u, y, x, H, W, true);
+      part.c += r1 * r1 + r2 * r2;
+    }
+    if (use_tb || (y >= 1 && y <= H - 2)) {
+      const float r3 = sobel_dx(s1, y, x, H, W, true) + sobel_dy(s2, y, x, H, W, true);
+      part.d += r3 * r3;
+    }
+    if (x == 0) part.dir += (u[p] - 1.f) * (u[p] - 1.f);
+    if (x == W - 1) part.dir += u[p] * u[p];
+    if (y == 0 || y == H - 1) part.neu += s2[p] * s2[p];
+  }
+  loss_block_reduce_and_finish(part, ws, loss4, nrm);
+}
+
+struct BwdCoef {
+  float n_c, n_d, n_dir, n_neu;  // 2/N_c, 2/N_d, 2/(B*H), 2/(2*B*W): multiplied by gw4[] on device
+};
+
+__global__ void __launch_bounds__(256)
+darcy_bwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ out,
+                         const float* __restrict__ gw4, int B, int H, int W, int use_tb,
+                         float* dout, BwdCoef cf) {
+  const float a = K != nullptr ? gw4[0] * cf.n_c : 0.f;
+  const float bb = gw4[1] * cf.n_d;
+  const float cdir = gw4[2] * cf.n_dir, cneu = gw4[3] * cf.n_neu;
+  const int64_t total = (int64_t)B * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / (H * W));
+    const int p = (int)(i - (int64_t)b * H * W);
+    const int y = p / W, x = p - y * W;
+    const float* u = out + (size_t)b * 3 * H * W;
+    const float* s1 = u + H * W;
+    const float* s2 = s1 + H * W;
+    float* gu = dout + (size_t)b * 3 * H * W;
+    float* g1 = gu + H * W;
+    float* g2 = g1 + H * W;
+    if (K != nullptr) {
+      const float k = K[i];
+      const float r1 = s1[p] + k * sobel_dx(u, y, x, H, W, true);
+      const float r2 = s2[p] + k * sobel_dy(u, y, x, H, W, true);
+      atomicAdd(g1 + p, a * r1);
+      atomicAdd(g2 + p, a * r2);
+      scat_dx(gu, y, x, H, W, true, a * k * r1);
+      scat_dy(gu, y, x, H, W, true, a * k * r2);
+    }
+    if (use_tb || (y >= 1 && y <= H - 2)) {
+      const float r3 = sobel_dx(s1, y, x, H, W, true) + sobel_dy(s2, y, x, H, W, true);
+      scat_dx(g1, y, x, H, W, true, bb * r3);
+      scat_dy(g2, y, x, H, W, true, bb * r3);
+    }
+    if (x == 0) atomicAdd(gu + p, cdir * (u[p] - 1.f));
+    if (x == W - 1) atomicAdd(gu + p, cdir * u[p]);
+    if (y == 0 || y == H - 1) atomicAdd(g2 + p, cneu * s2[p]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// tile kernels: whole sample in shared memory, TMA-fed, persistent over samples
+// ---------------------------------------------------------------------------------------
+// smem: [mbar x2 (16 B)] pad to 128 | stage0: K,u,s1,s2 | stage1: K,u,s1,s2 | (bwd) P1,P2,P3,Q1,Q2
+__global__ void __launch_bounds__(kTileThreads, 1)
+darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out, int B, int H,
+                      int W, int use_tb, float* loss4, LossWs* ws, LossNorm nrm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* stage_base = reinterpret_cast<float*>(smem_raw + 128);
+  const int HW = H * W;
+  const uint32_t plane_bytes = (uint32_t)HW * 4u;
+  const bool hasK = (K != nullptr);
+  const uint32_t tx_bytes = plane_bytes * (hasK ? 4u : 3u);
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int b, int s) {
+    float* st = stage_base + (size_t)s * 4 * HW;
+    mbar_arrive_expect_tx(&bars[s], tx_bytes);
+    if (hasK) tma_load_1d(st, K + (size_t)b * HW, plane_bytes, &bars[s]);
+    tma_load_1d(st + HW, out + (size_t)b * 3 * HW, plane_bytes * 3u, &bars[s]);
+  };
+
+  const int first = blockIdx.x;
+  if (threadIdx.x == 0) {
+    if (first < B) issue(first, 0);
+    if (first + (int)gridDim.x < B) issue(first + gridDim.x, 1);
+  }
+  FwdPartial part;
+  part.c = part.d = part.dir = part.neu = 0.f;
+  int it = 0;
+  for (int b = first; b < B; b += gridDim.x, ++it) {
+    const int s = it & 1;
+    mbar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
+    const float* st = stage_base + (size_t)s * 4 * HW;
+    const FwdPartial p = fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W,
+                                   threadIdx.x, kTileThreads, true, use_tb != 0, 0.f, 0.f,
+                                   nullptr, nullptr, nullptr, nullptr, nullptr);
+    part.c += p.c;
+    part.d += p.d;
+    part.dir += p.dir;
+    part.neu += p.neu;
+    __syncthreads();  // everyone finished reading stage s
+    const int nb = b + 2 * (int)gridDim.x;
+    if (threadIdx.x == 0 && nb < B) issue(nb, s);
+  }
+  loss_block_reduce_and_finish(part, ws, loss4, nrm);
+}
+
+__global__ void __launch_bounds__(kTileThreads, 1)
+darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out,
+                      const float* __restrict__ gw4, int B, int H, int W, int use_tb, float* dout,
+                      BwdCoef cf) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* stage_base = reinterpret_cast<float*>(smem_raw + 128);
+  const int HW = H * W;
+  float* scratch = stage_base + (size_t)2 * 4 * HW;  // P1,P2,P3,Q1,Q2
+  const uint32_t plane_bytes = (uint32_t)HW * 4u;
+  const bool hasK = (K != nullptr);
+  const uint32_t tx_bytes = plane_bytes * (hasK ? 4u : 3u);
+  const float a = hasK ? gw4[0] * cf.n_c : 0.f;
+  const float bb = gw4[1] * cf.n_d;
+  const float cdir = gw4[2] * cf.n_dir, cneu = gw4[3] * cf.n_neu;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int b, int s) {
+    float* st = stage_base + (size_t)s * 4 * HW;
+    mbar_arrive_expect_tx(&bars[s], tx_bytes);
+    if (hasK) tma_load_1d(st, K + (size_t)b * HW, plane_bytes, &bars[s]);
+    tma_load_1d(st + HW, out + (size_t)b * 3 * HW, plane_bytes * 3u, &bars[s]);
+  };
+
+  const int first = blockIdx.x;
+  if (threadIdx.x == 0) {
+    if (first < B) issue(first, 0);
+    if (first + (int)gridDim.x < B) issue(first + gridDim.x, 1);
+  }
+  int it = 0;
+  for (int b = first; b < B; b += gridDim.x, ++it) {
+    const int s = it & 1;
+    mbar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
+    float* st = stage_base + (size_t)s * 4 * HW;
+    float* P1 = scratch;
+    float* P2 = scratch + HW;
+    float* P3 = scratch + 2 * HW;
+    float* Q1 = scratch + 3 * HW;
+    float* Q2 = scratch + 4 * HW;
+    (void)fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W, threadIdx.x,
+                    kTileThreads, true, use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
+    __syncthreads();  // residual planes complete; nobody reads neighbours of u/s1/s2 any more
+    // gradient planes overwrite u, s1, s2 in place (own-position reads only)
+    bwd_strip_pass2(P1, P2, P3, Q1, Q2, st + HW, st + 3 * HW, st + HW, st + 2 * HW, st + 3 * HW, H,
+                    W, threadIdx.x, kTileThreads, true, cdir, cneu);
+    fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tma_store_1d(dout + (size_t)b * 3 * HW, st + HW, plane_bytes * 3u);
+      tma_store_commit();
+      const int nb = b + 2 * (int)gridDim.x;
+      if (nb < B) {
+        tma_store_wait_read<0>();  // the store has finished reading stage s
+        issue(nb, s);
+      }
+    }
+  }
+  if (threadIdx.x == 0) tma_store_wait_all<0>();
+}
+
+bool tile_ok(int H, int W, const void* a, const void* b, bool bwd) {
+  if (W % 4 != 0 || H < 3 || W < 4) return false;
+  if (kTileThreads / (W / 4) < 1) return false;
+  if (((uintptr_t)a & 15u) != 0 || ((uintptr_t)b & 15u) != 0) return false;
+  const size_t need = 128 + (size_t)H * W * 4 * (bwd ? 13 : 8);
+  return need <= 227 * 1024;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------
+extern "C" int pdes_sobel_grad(const float* img, float* out, int64_t n_img, int H, int W, int dir,
+                               int correct, int adjoint, void* stream) {
+  PDES_REQUIRE(img && out, PDES_ERR_INVALID, "pdes_sobel_grad: null pointer");
+  PDES_REQUIRE(n_img >= 0 && H >= 3 && W >= 3, PDES_ERR_INVALID,
+               "pdes_sobel_grad: need H,W >= 3 (got %d x %d)", H, W);
+  PDES_REQUIRE(dir == 0 || dir == 1, PDES_ERR_INVALID, "pdes_sobel_grad: dir must be 0 or 1");
+  if (n_img == 0) return PDES_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t total = n_img * H * W;
+  int blocks = (int)((total + 255) / 256);
+  const int cap = sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  if (!adjoint) {
+    sobel_apply_kernel<<<blocks, 256, 0, st>>>(img, out, n_img, H, W, dir, correct);
+  } else {
+    PDES_CUDA(cudaMemsetAsync(out, 0, (size_t)total * sizeof(float), st));
+    sobel_adjoint_kernel<<<blocks, 256, 0, st>>>(img, out, n_img, H, W, dir, correct);
+  }
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+extern "C" size_t pdes_darcy_loss_workspace_bytes(void) { return sizeof(LossWs); }
+
+extern "C" int pdes_darcy_loss_set_impl(int impl) {
+  PDES_REQUIRE(impl >= 0 && impl <= 2, PDES_ERR_INVALID, "pdes_darcy_loss_set_impl: impl in 0..2");
+  g_loss_impl = impl;
+  return PDES_OK;
+}
+
+static int check_loss_args(const float* out, int B, int H, int W, const char* fn) {
+  PDES_REQUIRE(out != nullptr, PDES_ERR_INVALID, "%s: null output field pointer", fn);
+  PDES_REQUIRE(B >= 1 && H >= 3 && W >= 3, PDES_ERR_INVALID, "%s: need B>=1, H,W>=3 (got %d,%d,%d)",
+               fn, B, H, W);
+  return PDES_OK;
+}
+
+extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int H, int W,
+                                   int use_tb, float* loss4, void* ws, void* stream) {
+  int rc = check_loss_args(out, B, H, W, "pdes_darcy_loss_fwd");
+  if (rc) return rc;
+  PDES_REQUIRE(loss4 && ws, PDES_ERR_INVALID, "pdes_darcy_loss_fwd: null loss4/workspace");
+  PDES_REQUIRE(use_tb || H >= 3, PDES_ERR_INVALID, "pdes_darcy_loss_fwd: use_tb=0 needs H>=3");
+  cudaStream_t st = (cudaStream_t)stream;
+  LossNorm nrm;
+  nrm.inv_c = 1.0 / ((double)B * H * W);
+  nrm.inv_d = 1.0 / ((double)B * (use_tb ? H : H - 2) * W);
+  nrm.inv_dir = 1.0 / ((double)B * H);
+  nrm.inv_neu = 1.0 / ((double)B * 2 * W);
+  const bool can_tile = tile_ok(H, W, K ? (const void*)K : (const void*)out, out, false);
+  PDES_REQUIRE(g_loss_impl != 2 || can_tile, PDES_ERR_UNSUPPORTED,
+               "pdes_darcy_loss_fwd: tile kernel forced but %dx%d does not qualify", H, W);
+  if (g_loss_impl != 1 && can_tile) {
+    const size_t smem = 128 + (size_t)H * W * 4 * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    int grid = sm_count();
+    if (grid > B) grid = B;
+    darcy_fwd_tile_kernel<<<grid, kTileThreads, smem, st>>>(K, out, B, H, W, use_tb, loss4,
+                                                           (LossWs*)ws, nrm);
+  } else {
+    const int64_t total = (int64_t)B * H * W;
+    int blocks = (int)((total + 255) / 256);
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    darcy_fwd_generic_kernel<<<blocks, 256, 0, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws,
+                                                     nrm);
+  }
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float* gw4, int B,
+                                   int H, int W, int use_tb, float* dout, void* stream) {
+  int rc = check_loss_args(out, B, H, W, "pdes_darcy_loss_bwd");
+  if (rc) return rc;
+  PDES_REQUIRE(gw4 && dout, PDES_ERR_INVALID, "pdes_darcy_loss_bwd: null gw4/dout");
+  cudaStream_t st = (cudaStream_t)stream;
+  BwdCoef cf;
+  cf.n_c = (float)(2.0 / ((double)B * H * W));
+  cf.n_d = (float)(2.0 / ((double)B * (use_tb ? H : H - 2) * W));
+  cf.n_dir = (float)(2.0 / ((double)B * H));
+  cf.n_neu = (float)(2.0 / ((double)B * 2 * W));
+  const bool can_tile = tile_ok(H, W, K ? (const void*)K : (const void*)out, out, true) &&
+                        (((uintptr_t)dout & 15u) == 0);
+  PDES_REQUIRE(g_loss_impl != 2 || can_tile, PDES_ERR_UNSUPPORTED,
+               "pdes_darcy_loss_bwd: tile kernel forced but %dx%d does not qualify", H, W);
+  if (g_loss_impl != 1 && can_tile) {
+    const size_t smem = 128 + (size_t)H * W * 4 * 13;
+    static bool attr_set = false;
+    if (!attr_set) {
+      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+    int grid = sm_count();
+    if (grid > B) grid = B;
+    darcy_bwd_tile_kernel<<<grid, kTileThreads, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
+  } else {
+    const int64_t total = (int64_t)B * H * W;
+    PDES_CUDA(cudaMemsetAsync(dout, 0, (size_t)total * 3 * sizeof(float), st));
+    int blocks = (int)((total + 255) / 256);
+    const int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    darcy_bwd_generic_kernel<<<blocks, 256, 0, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
+  }
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+}  // namespace pdes

@@ -1,0 +1,166 @@
+"""Generate golden fixtures by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference imports matplotlib at module top (models/codec.py:10-11, models/darcy.py:9-10);
+matplotlib is not installed here, so an empty stub package is put on sys.path for the import.
+Weights / inputs come from oracle.pdes_oracle.make_state / make_input (numpy MT19937 streams,
+machine independent), so fixtures store only inputs' seeds and the reference's OUTPUTS.
+"""
+import os
+import sys
+import tempfile
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("PDES_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    stub = tempfile.mkdtemp(prefix="mplstub_")
+    os.makedirs(os.path.join(stub, "matplotlib"))
+    open(os.path.join(stub, "matplotlib", "__init__.py"), "w").close()
+    with open(os.path.join(stub, "matplotlib", "pyplot.py"), "w") as f:
+        f.write("def switch_backend(*a, **k):\n    return None\n")
+    sys.path.insert(0, stub)
+    sys.path.insert(0, REF)
+    for m in [k for k in sys.modules if k.split(".")[0] in ("models", "utils")]:
+        del sys.modules[m]
+    from models.codec import DenseED
+    from models import darcy
+    from utils.image_gradient import SobelFilter
+    sys.path.remove(REF)
+    return DenseED, darcy, SobelFilter
+
+
+def main():
+    torch.set_num_threads(1)  # bit-stable fixtures
+    sys.path.insert(0, ROOT)
+    from oracle import pdes_oracle as orc
+
+    DenseED, darcy, SobelFilter = import_reference()
+
+    def ref_step(cfg, B, seed, dtype):
+        plan = orc.densenet_plan(**cfg)
+        sd = orc.to_dtype(orc.make_state(plan, seed), dtype)
+        K = orc.make_input(B, cfg["imsize"], seed).to(dtype)
+        model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
+                        growth_rate=cfg["growth_rate"], init_features=cfg["init_features"])
+        model = model.to(dtype)
+        missing = model.load_state_dict(sd, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        assert [k for k in model.state_dict().keys()] == list(sd.keys()), "state_dict key order"
+        sob = SobelFilter(cfg["imsize"], correct=True, device="cpu")
+        if dtype == torch.float64:
+            for a in ("HSOBEL_WEIGHTS_3x3", "VSOBEL_WEIGHTS_3x3", "modifier"):
+                setattr(sob, a, getattr(sob, a).double())
+        # eval-mode forward first (running stats as given)
+        model.eval()
+        with torch.no_grad():
+            out_eval = model(K).clone()
+        # one training step body: train_codec_mixed_residual.py:226-233
+        model.train()
+        model.zero_grad()
+        out = model(K)
+        out.retain_grad()
+        l_c = darcy.conv_constitutive_constraint(K, out, sob)
+        l_d = darcy.conv_continuity_constraint(out, sob)
+        l_dir, l_neu = darcy.conv_boundary_condition(out)
+        loss = (l_c + l_d) + (l_dir + l_neu) * 10.0
+        loss.backward()
+        l_d_notb = darcy.conv_continuity_constraint(out.detach(), sob, use_tb=False)
+        grads = OrderedDict((n, p.grad.detach().clone()) for n, p in model.named_parameters())
+        running = OrderedDict((n, b.detach().clone()) for n, b in model.named_buffers())
+        return dict(K=K, out=out.detach(), out_eval=out_eval, l4=torch.stack([l_c, l_d, l_dir, l_neu]).detach(),
+                    loss=loss.detach(), dout=out.grad.detach().clone(), grads=grads, running=running,
+                    l_d_notb=l_d_notb.detach(), names=[n for n, _ in model.named_parameters()],
+                    model_size=model.model_size)
+
+    def save_case(fname, cfg, B, seed, full_grads):
+        r32 = ref_step(cfg, B, seed, torch.float32)
+        r64 = ref_step(cfg, B, seed, torch.float64)
+        d = dict(cfg_in_channels=cfg["in_channels"], cfg_out_channels=cfg["out_channels"],
+                 cfg_imsize=cfg["imsize"], cfg_blocks=np.array(cfg["blocks"]),
+                 cfg_growth_rate=cfg["growth_rate"], cfg_init_features=cfg["init_features"], B=B,
+                 seed=seed, model_size=np.array(r32["model_size"]),
+                 out=r32["out"].numpy(), out_eval=r32["out_eval"].numpy(), l4=r32["l4"].numpy(),
+                 loss=r32["loss"].numpy(), dout=r32["dout"].numpy(), l_d_notb=r32["l_d_notb"].numpy(),
+                 out64=r64["out"].numpy().astype(np.float64), l4_64=r64["l4"].numpy(),
+                 loss64=r64["loss"].numpy(), dout64=r64["dout"].numpy(),
+                 out_eval64=r64["out_eval"].numpy())
+        names = r32["names"]
+        d["param_names"] = np.array(names)
+        d["grad_norm32"] = np.array([float(r32["grads"][n].double().norm()) for n in names])
+        d["grad_norm64"] = np.array([float(r64["grads"][n].norm()) for n in names])
+        # fp32-vs-fp64 error of the reference itself = the gradient noise floor
+        d["grad_err32"] = np.array([float((r32["grads"][n].double() - r64["grads"][n]).norm())
+                                    for n in names])
+        if full_grads:
+            d["grads32"] = np.concatenate([r32["grads"][n].numpy().ravel() for n in names])
+            d["grads64"] = np.concatenate([r64["grads"][n].numpy().ravel() for n in names])
+        else:
+            d["grads64_head"] = np.concatenate([r64["grads"][n].numpy().ravel()[:16] for n in names])
+            d["grads64_head_len"] = np.array([min(16, r64["grads"][n].numel()) for n in names])
+        bn_names = [n for n in r32["running"] if n.endswith(("running_mean", "running_var"))]
+        d["running_names"] = np.array(bn_names)
+        d["running64"] = np.concatenate([r64["running"][n].numpy().ravel() for n in bn_names])
+        nbt = [int(v) for n, v in r32["running"].items() if n.endswith("num_batches_tracked")]
+        d["num_batches_tracked"] = np.array(nbt)
+        np.savez_compressed(os.path.join(HERE, fname), **d)
+        print(fname, "loss", float(r32["loss"]), "l4", r32["l4"].tolist(), "model_size", r32["model_size"])
+
+    small = dict(in_channels=1, out_channels=3, imsize=16, blocks=[1, 2, 1], growth_rate=4,
+                 init_features=8)
+    save_case("densenet_small16.npz", small, B=3, seed=3, full_grads=True)
+    small5 = dict(in_channels=1, out_channels=3, imsize=16, blocks=[2, 1, 2, 1, 2], growth_rate=8,
+                  init_features=16)
+    save_case("densenet_fiveblk16.npz", small5, B=2, seed=5, full_grads=True)
+    full = dict(in_channels=1, out_channels=3, blocks=[6, 8, 6], growth_rate=16, init_features=48)
+    save_case("densenet_full32.npz", dict(full, imsize=32), B=2, seed=7, full_grads=False)
+    save_case("densenet_full64.npz", dict(full, imsize=64), B=2, seed=11, full_grads=False)
+
+    # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----
+    rs = np.random.RandomState(42)
+    d = {}
+    for tag, (n, H) in dict(a=(2, 16), b=(1, 65), c=(1, 32)).items():
+        img = torch.tensor(rs.standard_normal((n, 1, H, H)), dtype=torch.float64, requires_grad=True)
+        for correct in (True, False):
+            sob = SobelFilter(H, correct=correct, device="cpu")
+            for a in ("HSOBEL_WEIGHTS_3x3", "VSOBEL_WEIGHTS_3x3", "modifier"):
+                setattr(sob, a, getattr(sob, a).double())
+            gh, gv = sob.grad_h(img), sob.grad_v(img)
+            w = torch.tensor(rs.standard_normal(gh.shape))
+            ah, = torch.autograd.grad((gh * w).sum(), img, retain_graph=True)
+            av, = torch.autograd.grad((gv * w).sum(), img)
+            c = int(correct)
+            d[f"{tag}{c}_gh"], d[f"{tag}{c}_gv"] = gh.detach().numpy(), gv.detach().numpy()
+            d[f"{tag}{c}_w"], d[f"{tag}{c}_ah"], d[f"{tag}{c}_av"] = w.numpy(), ah.numpy(), av.numpy()
+        d[f"{tag}_img"] = img.detach().numpy()
+    for tag, (B, H) in dict(p=(3, 16), q=(1, 65), r=(2, 64)).items():
+        K = torch.tensor(np.exp(0.5 * rs.standard_normal((B, 1, H, H))))
+        out = torch.tensor(rs.standard_normal((B, 3, H, H)), requires_grad=True)
+        sob = SobelFilter(H, correct=True, device="cpu")
+        for a in ("HSOBEL_WEIGHTS_3x3", "VSOBEL_WEIGHTS_3x3", "modifier"):
+            setattr(sob, a, getattr(sob, a).double())
+        for tb in (1, 0):
+            l_c = darcy.conv_constitutive_constraint(K, out, sob)
+            l_d = darcy.conv_continuity_constraint(out, sob, use_tb=bool(tb))
+            l_dir, l_neu = darcy.conv_boundary_condition(out)
+            gw = torch.tensor([0.7, 1.3, 10.0, 4.0], dtype=torch.float64)
+            tot = gw[0] * l_c + gw[1] * l_d + gw[2] * l_dir + gw[3] * l_neu
+            g, = torch.autograd.grad(tot, out)
+            d[f"{tag}{tb}_l4"] = torch.stack([l_c, l_d, l_dir, l_neu]).detach().numpy()
+            d[f"{tag}{tb}_dout"] = g.numpy()
+        d[f"{tag}_K"], d[f"{tag}_out"], d[f"{tag}_gw"] = K.numpy(), out.detach().numpy(), gw.numpy()
+    np.savez_compressed(os.path.join(HERE, "sobel_darcy.npz"), **d)
+    print("sobel_darcy.npz written")
+
+
+if __name__ == "__main__":
+    main()

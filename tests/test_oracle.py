@@ -1,0 +1,107 @@
+"""Pins the CPU oracle (oracle/pdes_oracle.py) against fixtures produced by the unmodified
+reference (tests/golden/make_golden.py).  Runs without a GPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdes_oracle as orc
+
+CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64"]
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def _cfg(g):
+    return dict(in_channels=int(g["cfg_in_channels"]), out_channels=int(g["cfg_out_channels"]),
+                imsize=int(g["cfg_imsize"]), blocks=[int(b) for b in g["cfg_blocks"]],
+                growth_rate=int(g["cfg_growth_rate"]), init_features=int(g["cfg_init_features"]))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_structure_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    plan = orc.densenet_plan(**_cfg(g))
+    assert orc.param_names(plan) == [str(s) for s in g["param_names"]]
+    n_params = sum(int(np.prod(s)) for n, s in orc.state_layout(plan)
+                   if n in set(orc.param_names(plan)))
+    n_conv = sum(1 for n in orc.param_names(plan) if "conv" in n)
+    assert (n_params, n_conv) == tuple(int(v) for v in g["model_size"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_step_fp64_matches_reference(golden_dir, name):
+    torch.set_num_threads(4)
+    g = _load(golden_dir, name)
+    cfg = _cfg(g)
+    plan = orc.densenet_plan(**cfg)
+    sd = orc.to_dtype(orc.make_state(plan, int(g["seed"])), torch.float64)
+    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"])).double()
+    sd_eval = orc.to_dtype(sd, torch.float64)
+    with torch.no_grad():
+        out_eval = orc.densenet_forward(plan, sd_eval, K, training=False)
+    assert rel(out_eval.numpy(), g["out_eval64"]) < 1e-12
+    out, l4, loss, dout, grads = orc.train_step(plan, sd, K)
+    assert rel(out.numpy(), g["out64"]) < 1e-11
+    assert rel(l4.numpy(), g["l4_64"]) < 1e-11
+    assert abs(float(loss) - float(g["loss64"])) / float(g["loss64"]) < 1e-11
+    assert rel(dout.numpy(), g["dout64"]) < 1e-10
+    names = [str(s) for s in g["param_names"]]
+    norms = np.array([float(grads[n].norm()) for n in names])
+    assert np.allclose(norms, g["grad_norm64"], rtol=1e-8, atol=1e-300)
+    if "grads64" in g.files:
+        flat = np.concatenate([grads[n].numpy().ravel() for n in names])
+        assert rel(flat, g["grads64"]) < 1e-9
+    else:
+        head = np.concatenate([grads[n].numpy().ravel()[:16] for n in names])
+        assert rel(head, g["grads64_head"]) < 1e-8
+    run = np.concatenate([sd[str(n)].detach().numpy().ravel() for n in g["running_names"]])
+    assert rel(run, g["running64"]) < 1e-12
+    nbt = [int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")]
+    assert nbt == [int(v) for v in g["num_batches_tracked"]]
+
+
+@pytest.mark.parametrize("name", CASES[:3])
+def test_train_step_fp32_within_noise_floor(golden_dir, name):
+    torch.set_num_threads(1)
+    g = _load(golden_dir, name)
+    cfg = _cfg(g)
+    plan = orc.densenet_plan(**cfg)
+    sd = orc.make_state(plan, int(g["seed"]))
+    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]))
+    out, l4, loss, dout, grads = orc.train_step(plan, sd, K)
+    assert rel(out.numpy(), g["out"]) < 2e-5
+    assert rel(l4.numpy(), g["l4"]) < 1e-5
+    assert rel(dout.numpy(), g["dout"]) < 2e-5
+
+
+def test_sobel_and_losses_match_reference(golden_dir):
+    g = _load(golden_dir, "sobel_darcy")
+    for tag in "abc":
+        img = torch.tensor(g[f"{tag}_img"], requires_grad=True)
+        for c in (1, 0):
+            gh, gv = orc.sobel_grad_h(img, bool(c)), orc.sobel_grad_v(img, bool(c))
+            assert rel(gh.detach().numpy(), g[f"{tag}{c}_gh"]) < 1e-13
+            assert rel(gv.detach().numpy(), g[f"{tag}{c}_gv"]) < 1e-13
+            w = torch.tensor(g[f"{tag}{c}_w"])
+            ah, = torch.autograd.grad((gh * w).sum(), img, retain_graph=True)
+            av, = torch.autograd.grad((gv * w).sum(), img)
+            assert rel(ah.numpy(), g[f"{tag}{c}_ah"]) < 1e-13
+            assert rel(av.numpy(), g[f"{tag}{c}_av"]) < 1e-13
+    for tag in "pqr":
+        K = torch.tensor(g[f"{tag}_K"])
+        out = torch.tensor(g[f"{tag}_out"], requires_grad=True)
+        gw = torch.tensor(g[f"{tag}_gw"])
+        for tb in (1, 0):
+            l4 = orc.darcy_losses(K, out, use_tb=bool(tb))
+            assert rel(l4.detach().numpy(), g[f"{tag}{tb}_l4"]) < 1e-13
+            d, = torch.autograd.grad((gw * l4).sum(), out)
+            assert rel(d.numpy(), g[f"{tag}{tb}_dout"]) < 1e-12
