@@ -1,0 +1,378 @@
+"""DenseED on the sm_100a executor.
+
+Host-side mirror of models/codec.py:210-318 of the reference: same constructor signature,
+same state_dict keys / shapes / order, same default initialisation stream, `model_size`,
+`reset_parameters`, train()/eval() semantics of nn.BatchNorm2d — but the module tree only HOLDS
+parameters.  All arithmetic (28 convolutions, 27 BatchNorm+ReLU, 2 nearest upsamplings, the
+dense-block concatenations and the whole backward) runs in libpdes_b200.so
+(csrc/net.cu, csrc/conv_*.cu) through the C-ABI in include/pdes_b200.h.
+
+Storage: all parameters are views into ONE flat fp32 buffer (and their .grad into one flat
+gradient buffer) so that the kernels see stable pointers, wgrad writes straight into the bucket
+that data-parallel training all-reduces, and a fused Adam can walk one array.
+"""
+import math
+from collections import OrderedDict
+from ctypes import byref, c_int32, c_int64, c_void_p, create_string_buffer
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def module_size(module):
+    """(n_params, n_conv_layers) — reference models/codec.py:14-21."""
+    n_params, n_conv = 0, 0
+    for name, p in module.named_parameters():
+        n_conv += int("conv" in name)
+        n_params += p.numel()
+    return n_params, n_conv
+
+
+class _Group(nn.Module):
+    """Name-only container (a dense block / transition of the reference tree)."""
+
+    def extra_repr(self):
+        return getattr(self, "_pdes_repr", "")
+
+
+class _ConvParams(nn.Module):
+    """Holds `weight` (Cout, Cin, K, K); bias-free like every conv of DenseED."""
+
+    def __init__(self, cout, cin, k, desc=""):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(cout, cin, k, k))
+        self._pdes_repr = desc
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        # identical to nn.Conv2d.reset_parameters with bias=False (same RNG consumption)
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+
+    def extra_repr(self):
+        return self._pdes_repr
+
+
+class _BNParams(nn.Module):
+    """Holds the parameters / buffers of an nn.BatchNorm2d (eps 1e-5, momentum 0.1)."""
+
+    def __init__(self, c):
+        super().__init__()
+        self.num_features = c
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def reset_parameters(self):
+        with torch.no_grad():
+            self.running_mean.zero_()
+            self.running_var.fill_(1)
+            self.num_batches_tracked.zero_()
+            self.weight.fill_(1)
+            self.bias.zero_()
+
+    def extra_repr(self):
+        return "%d, eps=1e-05, momentum=0.1 (fused into the consuming conv)" % self.num_features
+
+
+class _NetHandle(object):
+    """Owns a pdes_net_t* (host-side object of the C library)."""
+
+    def __init__(self, cfg, max_batch):
+        L = _lib.lib()
+        c = _lib.DensenetConfig()
+        c.in_channels, c.out_channels, c.imsize = cfg["in_channels"], cfg["out_channels"], cfg["imsize"]
+        c.n_blocks = len(cfg["blocks"])
+        for i, b in enumerate(cfg["blocks"]):
+            c.blocks[i] = int(b)
+        c.growth_rate, c.init_features, c.max_batch = cfg["growth_rate"], cfg["init_features"], max_batch
+        h = c_void_p()
+        _lib.check(L.pdes_densenet_create(byref(c), byref(h)), "pdes_densenet_create")
+        self.h, self.max_batch = h, max_batch
+
+    def __del__(self):
+        try:
+            if self.h:
+                _lib.lib().pdes_densenet_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def params(self):
+        L, out = _lib.lib(), []
+        for i in range(L.pdes_densenet_num_params(self.h)):
+            name = create_string_buffer(256)
+            off, nd, kind = c_int64(), c_int32(), c_int32()
+            shape = (c_int64 * 4)()
+            _lib.check(L.pdes_densenet_param_info(self.h, i, name, 256, byref(off), byref(nd), shape,
+                                                  byref(kind)), "pdes_densenet_param_info")
+            out.append((name.value.decode(), off.value, tuple(shape[:nd.value]), kind.value))
+        return out, L.pdes_densenet_param_floats(self.h)
+
+    def bns(self):
+        L, out = _lib.lib(), []
+        for i in range(L.pdes_densenet_num_bn(self.h)):
+            name = create_string_buffer(256)
+            mo, vo, ch = c_int64(), c_int64(), c_int32()
+            _lib.check(L.pdes_densenet_bn_info(self.h, i, name, 256, byref(mo), byref(vo), byref(ch)),
+                       "pdes_densenet_bn_info")
+            out.append((name.value.decode(), mo.value, vo.value, ch.value))
+        return out, L.pdes_densenet_running_floats(self.h)
+
+
+class CudaExecutor(object):
+    """Binds the module's flat buffers to a pdes_net_t and runs forward/backward on the current
+    CUDA stream.  (Tests substitute this class to exercise the host logic without a GPU.)"""
+
+    def __init__(self, module):
+        self.m = module
+        self.handle = None
+        self.ws = None
+        self.bound = None
+
+    def _ensure(self, x):
+        m = self.m
+        if not x.is_cuda:
+            raise RuntimeError("pde_surrogate_b200.DenseED: CUDA tensors only (input is on %s); there is no "
+                               "CPU fallback in this backend" % x.device)
+        if x.dtype != torch.float32 or m._flat.dtype != torch.float32:
+            raise TypeError("pde_surrogate_b200.DenseED: float32 only (input %s, parameters %s)"
+                            % (x.dtype, m._flat.dtype))
+        if m._flat.device != x.device:
+            raise RuntimeError("DenseED parameters are on %s but the input is on %s" % (m._flat.device, x.device))
+        c = m._cfg
+        if x.dim() != 4 or tuple(x.shape[1:]) != (c["in_channels"], c["imsize"], c["imsize"]):
+            raise ValueError("DenseED expects input (B, %d, %d, %d), got %s"
+                             % (c["in_channels"], c["imsize"], c["imsize"], tuple(x.shape)))
+        B = x.shape[0]
+        if self.handle is None or B > self.handle.max_batch:
+            self.handle = _NetHandle(c, max(B, 1))
+            self.ws, self.bound = None, None
+        key = (m._flat.data_ptr(), m._flat_grad.data_ptr(), m._flat_running.data_ptr(), str(x.device))
+        if self.bound != key:
+            L = _lib.lib()
+            with torch.cuda.device(x.device):
+                nbytes = int(L.pdes_densenet_workspace_bytes(self.handle.h))
+                if self.ws is None or self.ws.numel() < nbytes or self.ws.device != x.device:
+                    self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=x.device)
+                _lib.check(L.pdes_densenet_bind(self.handle.h, _lib.ptr(m._flat), _lib.ptr(m._flat_grad),
+                                                _lib.ptr(m._flat_running), _lib.ptr(self.ws), nbytes),
+                           "pdes_densenet_bind")
+            self.bound = key
+
+    def forward(self, x, training):
+        self._ensure(x)
+        x = x.contiguous()
+        c = self.m._cfg
+        out = torch.empty(x.shape[0], c["out_channels"], c["imsize"], c["imsize"], dtype=torch.float32,
+                          device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().pdes_densenet_forward(self.handle.h, _lib.ptr(x), _lib.ptr(out), x.shape[0],
+                                                  int(bool(training)), _lib.stream_ptr())
+        _lib.check(rc, "pdes_densenet_forward")
+        return out
+
+    def backward(self, dout):
+        dout = dout.contiguous()
+        with torch.cuda.device(dout.device):
+            rc = _lib.lib().pdes_densenet_backward(self.handle.h, _lib.ptr(dout), _lib.stream_ptr())
+        _lib.check(rc, "pdes_densenet_backward")
+
+    def flops(self, B, training):
+        if self.handle is None:
+            self.handle = _NetHandle(self.m._cfg, max(B, 1))
+            self.ws, self.bound = None, None
+        return float(_lib.lib().pdes_densenet_flops(self.handle.h, B, int(training)))
+
+
+_executor_factory = CudaExecutor
+
+
+class _DenseEDTrainFn(torch.autograd.Function):
+    """Training-mode forward with the executor's own backward.  Parameter gradients are
+    accumulated by the kernels directly into the module's flat gradient buffer (of which every
+    p.grad is a view), so the function returns no tensors for them."""
+
+    @staticmethod
+    def forward(ctx, x, anchor, module):
+        ctx.module = module
+        return module._ex.forward(x, True)
+
+    @staticmethod
+    def backward(ctx, dout):
+        m = ctx.module
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError("pde_surrogate_b200.DenseED: gradient w.r.t. the network input is "
+                                      "not implemented (the training path never needs it)")
+        m._prepare_grads()
+        m._ex.backward(dout)
+        return None, None, None
+
+
+class _EvalGuardFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, out, anchor):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, g):
+        raise NotImplementedError("pde_surrogate_b200.DenseED: backward through eval-mode BatchNorm is not "
+                                  "implemented; call model.train() or use torch.no_grad()")
+
+
+class DenseED(nn.Module):
+    """Dense convolutional encoder-decoder (reference models/codec.py:210-318).
+
+    Args as in the reference.  Options the training script never uses raise a clear error
+    instead of silently differing: drop_rate > 0, bottleneck dense layers, upsample other than
+    'nearest', out_activation.
+    """
+
+    def __init__(self, in_channels, out_channels, imsize, blocks, growth_rate=16, init_features=48,
+                 drop_rate=0, bn_size=8, bottleneck=False, out_activation=None, upsample='nearest'):
+        super(DenseED, self).__init__()
+        blocks = [int(b) for b in blocks]
+        if len(blocks) > 1 and len(blocks) % 2 == 0:
+            raise ValueError('length of blocks must be an odd number, but got {}'.format(len(blocks)))
+        unsupported = []
+        if drop_rate and drop_rate > 0:
+            unsupported.append("drop_rate=%r" % drop_rate)
+        if bottleneck:
+            unsupported.append("bottleneck=True")
+        if upsample != 'nearest':
+            unsupported.append("upsample=%r" % (upsample,))
+        if out_activation is not None:
+            unsupported.append("out_activation=%r" % (out_activation,))
+        if unsupported:
+            raise NotImplementedError("pde_surrogate_b200.DenseED does not implement: " + ", ".join(unsupported))
+        self._cfg = dict(in_channels=int(in_channels), out_channels=int(out_channels), imsize=int(imsize),
+                         blocks=blocks, growth_rate=int(growth_rate), init_features=int(init_features))
+        layout = _NetHandle(self._cfg, 1)
+        self._param_table, self._n_flat = layout.params()
+        self._bn_table, self._n_running = layout.bns()
+        del layout
+        # module tree with the reference's names; creation order == reference order so that the
+        # default initialisation consumes the torch RNG identically
+        self.features = _Group()
+        leaves = OrderedDict()
+        for name, _off, shape, kind in self._param_table:
+            path = name.split(".")[:-1]
+            key = ".".join(path)
+            if key in leaves:
+                continue
+            parent = self
+            for part in path[:-1]:
+                if part not in parent._modules:
+                    parent.add_module(part, _Group())
+                parent = parent._modules[part]
+            if kind == 0:
+                leaf = _ConvParams(shape[0], shape[1], shape[2])
+            else:
+                leaf = _BNParams(shape[0])
+            parent.add_module(path[-1], leaf)
+            leaves[key] = leaf
+        self._flat = self._flat_grad = self._flat_running = self._flat_nbt = None
+        self._ex = _executor_factory(self)
+        self._flatten()
+        print('# params {}, # conv layers {}'.format(*self.model_size))
+
+    # ------------------------------------------------------------------ flat storage
+    def _named_param_list(self):
+        d = dict(self.named_parameters())
+        return [(d[name], off, shape) for name, off, shape, _k in self._param_table]
+
+    def _flatten(self):
+        plist = self._named_param_list()
+        ref = plist[0][0]
+        flat = torch.zeros(self._n_flat, dtype=ref.dtype, device=ref.device)
+        gflat = torch.zeros(self._n_flat, dtype=ref.dtype, device=ref.device)
+        self._params, self._grad_views = [], []
+        with torch.no_grad():
+            for p, off, shape in plist:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = flat[off:off + n].view(shape)
+                gv = gflat[off:off + n].view(shape)
+                if p.grad is not None:
+                    gv.copy_(p.grad)
+                    p.grad = gv
+                self._params.append(p)
+                self._grad_views.append(gv)
+            mods = dict(self.named_modules())
+            run = torch.zeros(self._n_running, dtype=ref.dtype, device=ref.device)
+            nbt = torch.zeros(len(self._bn_table), dtype=torch.long, device=ref.device)
+            for i, (name, mo, vo, ch) in enumerate(self._bn_table):
+                bn = mods[name]
+                run[mo:mo + ch].copy_(bn.running_mean)
+                run[vo:vo + ch].copy_(bn.running_var)
+                nbt[i] = bn.num_batches_tracked.to(nbt.device)
+                bn._buffers["running_mean"] = run[mo:mo + ch]
+                bn._buffers["running_var"] = run[vo:vo + ch]
+                bn._buffers["num_batches_tracked"] = nbt[i]
+        self._flat, self._flat_grad, self._flat_running, self._flat_nbt = flat, gflat, run, nbt
+
+    def _apply(self, fn, recurse=True):
+        r = super(DenseED, self)._apply(fn, recurse)
+        if self._flat is not None:
+            self._flatten()
+        return r
+
+    def _prepare_grads(self):
+        """Make every p.grad the matching view of the flat gradient buffer before the kernels
+        accumulate into it (p.grad is None after zero_grad(set_to_none=True))."""
+        params, views = self._params, self._grad_views
+        n_none = 0
+        for p in params:
+            if p.grad is None:
+                n_none += 1
+        if n_none == len(params):
+            self._flat_grad.zero_()
+            for p, v in zip(params, views):
+                p.grad = v
+            return
+        for p, v in zip(params, views):
+            g = p.grad
+            if g is None:
+                v.zero_()
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+                p.grad = v
+
+    # ------------------------------------------------------------------ nn.Module surface
+    def forward(self, x):
+        anchor = self._params[0]
+        grad_on = torch.is_grad_enabled() and anchor.requires_grad
+        if self.training:
+            if grad_on:
+                out = _DenseEDTrainFn.apply(x, anchor, self)
+            else:
+                out = self._ex.forward(x, True)
+            self._flat_nbt.add_(1)
+            return out
+        out = self._ex.forward(x, False)
+        if grad_on:
+            out = _EvalGuardFn.apply(out, anchor)
+        return out
+
+    @property
+    def model_size(self):
+        return module_size(self)
+
+    def reset_parameters(self, verbose=False):
+        for module in self.modules():
+            if isinstance(module, (_ConvParams, _BNParams)):
+                module.reset_parameters()
+                if verbose:
+                    print("Reset parameters in {}".format(module))
+
+    def flat_parameters(self):
+        """(params, grads) flat fp32 buffers; every parameter / .grad is a view into them."""
+        return self._flat, self._flat_grad
+
+    def flops(self, batch, training=True):
+        """Useful 2*MAC FLOPs of one forward (or forward+backward) at this batch size."""
+        return self._ex.flops(batch, training)

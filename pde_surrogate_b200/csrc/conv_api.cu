@@ -1,0 +1,176 @@
+// conv_api.cu — single-convolution C-ABI entry points (unit-test surface over the same kernels
+// the DenseED executor launches).  These three calls are the only ones in the library that
+// allocate: a stream-ordered scratch buffer for the packed weights.
+#include <string.h>
+#include "conv.cuh"
+
+using namespace pdes;
+
+namespace {
+int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+int check_desc(const pdes_conv_desc* d, const char* fn) {
+  PDES_REQUIRE(d != nullptr, PDES_ERR_INVALID, "%s: null descriptor", fn);
+  PDES_REQUIRE(d->B >= 1 && d->Hin >= 1 && d->Win >= 1 && d->Cin >= 1 && d->Cout >= 1, PDES_ERR_INVALID,
+               "%s: non-positive shape", fn);
+  PDES_REQUIRE(d->KH == d->KW, PDES_ERR_UNSUPPORTED, "%s: only square kernels", fn);
+  PDES_REQUIRE(d->ld_in >= d->Cin && d->ld_out >= d->c_off_out + d->Cout, PDES_ERR_INVALID,
+               "%s: pixel strides too small", fn);
+  const int Hv = d->upsample ? 2 * d->Hin : d->Hin, Wv = d->upsample ? 2 * d->Win : d->Win;
+  PDES_REQUIRE(d->Hout == (Hv + 2 * d->pad - d->KH) / d->stride + 1 &&
+                   d->Wout == (Wv + 2 * d->pad - d->KW) / d->stride + 1,
+               PDES_ERR_INVALID, "%s: Hout/Wout inconsistent with the convolution geometry", fn);
+  return PDES_OK;
+}
+
+struct Packed {
+  float* buf = nullptr;
+  float* wf = nullptr;
+  float* wb = nullptr;
+  PackDesc* tab = nullptr;
+  int CinP, CoP, CoutPb, CiPb;
+};
+
+int pack(const pdes_conv_desc* d, const float* w, cudaStream_t st, Packed& pk) {
+  const int taps = d->KH * d->KW;
+  pk.CinP = rup(d->Cin, 4);
+  pk.CoP = rup(d->Cout, 16);
+  pk.CoutPb = rup(d->Cout, 4);
+  pk.CiPb = rup(d->Cin, 16);
+  const size_t nf = (size_t)taps * pk.CinP * pk.CoP, nb = (size_t)taps * pk.CoutPb * pk.CiPb;
+  PDES_CUDA(cudaMallocAsync((void**)&pk.buf, (nf + nb) * sizeof(float) + 256, st));
+  pk.wf = pk.buf;
+  pk.wb = pk.buf + nf;
+  pk.tab = reinterpret_cast<PackDesc*>(pk.buf + nf + nb);
+  PackDesc h;
+  h.w = w;
+  h.wf = pk.wf;
+  h.wb = pk.wb;
+  h.Cout = d->Cout;
+  h.Cin = d->Cin;
+  h.KS = d->KH;
+  h.CinP = pk.CinP;
+  h.CoP = pk.CoP;
+  h.CoutPb = pk.CoutPb;
+  h.CiPb = pk.CiPb;
+  PDES_CUDA(cudaMemcpyAsync(pk.tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  PDES_CUDA(cudaStreamSynchronize(st));  // h is a stack variable
+  return launch_pack_weights(pk.tab, 1, (int)(nf + nb), st);
+}
+}  // namespace
+
+extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const float* w,
+                               const float* scale, const float* shift, float* y, double* ch_sum,
+                               double* ch_sumsq, int impl, void* stream) {
+  int rc = check_desc(d, "pdes_conv2d_fwd");
+  if (rc) return rc;
+  PDES_REQUIRE(x && w && y, PDES_ERR_INVALID, "pdes_conv2d_fwd: null pointer");
+  PDES_REQUIRE(!d->bn_relu || (scale && shift), PDES_ERR_INVALID, "pdes_conv2d_fwd: bn_relu needs scale/shift");
+  PDES_REQUIRE(impl == 0 || impl == 1, PDES_ERR_UNSUPPORTED, "pdes_conv2d_fwd: impl %d not available", impl);
+  cudaStream_t st = (cudaStream_t)stream;
+  Packed pk;
+  rc = pack(d, w, st, pk);
+  if (rc) return rc;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x;
+  a.ldx = d->ld_in;
+  a.Cin = d->Cin;
+  a.Hs = d->Hin;
+  a.Ws = d->Win;
+  a.B = d->B;
+  a.in_mode = d->upsample ? IN_UPSAMPLE : IN_DIRECT;
+  a.pro = d->bn_relu;
+  a.bn.scale = scale;
+  a.bn.shift = shift;
+  a.w = pk.wf;
+  a.CinP = pk.CinP;
+  a.CoP = pk.CoP;
+  a.Cout = d->Cout;
+  a.KS = d->KH;
+  a.pad = d->pad;
+  a.stride = d->stride;
+  a.Ho = d->Hout;
+  a.Wo = d->Wout;
+  a.epi = d->out_nchw ? EPI_NCHW : EPI_NHWC;
+  a.y = y;
+  a.ldy = d->ld_out;
+  a.coff = d->c_off_out;
+  a.o_sum = ch_sum;
+  a.o_sumsq = ch_sumsq;
+  rc = launch_conv_simt(a, st);
+  cudaFreeAsync(pk.buf, st);
+  return rc;
+}
+
+extern "C" int pdes_conv2d_dgrad(const pdes_conv_desc* d, const float* dy, const float* w, float* da,
+                                 int impl, void* stream) {
+  int rc = check_desc(d, "pdes_conv2d_dgrad");
+  if (rc) return rc;
+  PDES_REQUIRE(dy && w && da, PDES_ERR_INVALID, "pdes_conv2d_dgrad: null pointer");
+  PDES_REQUIRE(impl == 0 || impl == 1, PDES_ERR_UNSUPPORTED, "pdes_conv2d_dgrad: impl %d not available", impl);
+  PDES_REQUIRE(!d->out_nchw, PDES_ERR_UNSUPPORTED, "pdes_conv2d_dgrad: NHWC dy only");
+  cudaStream_t st = (cudaStream_t)stream;
+  Packed pk;
+  rc = pack(d, w, st, pk);
+  if (rc) return rc;
+  ConvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = dy + d->c_off_out;
+  a.ldx = d->ld_out;
+  a.Cin = d->Cout;
+  a.Hs = d->Hout;
+  a.Ws = d->Wout;
+  a.B = d->B;
+  a.in_mode = d->stride == 2 ? IN_ZEROINS : IN_DIRECT;
+  a.w = pk.wb;
+  a.CinP = pk.CoutPb;
+  a.CoP = pk.CiPb;
+  a.Cout = d->Cin;
+  a.KS = d->KH;
+  a.pad = d->KH - 1 - d->pad;
+  a.stride = 1;
+  a.Ho = d->upsample ? 2 * d->Hin : d->Hin;
+  a.Wo = d->upsample ? 2 * d->Win : d->Win;
+  a.epi = EPI_NHWC;
+  a.pool = d->upsample;
+  a.y = da;
+  a.ldy = d->Cin;
+  a.coff = 0;
+  rc = launch_conv_simt(a, st);
+  cudaFreeAsync(pk.buf, st);
+  return rc;
+}
+
+extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const float* scale,
+                                 const float* shift, const float* dy, float* dw, int impl,
+                                 void* stream) {
+  int rc = check_desc(d, "pdes_conv2d_wgrad");
+  if (rc) return rc;
+  PDES_REQUIRE(x && dy && dw, PDES_ERR_INVALID, "pdes_conv2d_wgrad: null pointer");
+  PDES_REQUIRE(!d->bn_relu || (scale && shift), PDES_ERR_INVALID, "pdes_conv2d_wgrad: bn_relu needs scale/shift");
+  PDES_REQUIRE(impl == 0 || impl == 1, PDES_ERR_UNSUPPORTED, "pdes_conv2d_wgrad: impl %d not available", impl);
+  WgradArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x;
+  a.ldx = d->ld_in;
+  a.Cin = d->Cin;
+  a.Hs = d->Hin;
+  a.Ws = d->Win;
+  a.B = d->B;
+  a.in_mode = d->upsample ? IN_UPSAMPLE : IN_DIRECT;
+  a.pro = d->bn_relu;
+  a.bn.scale = scale;
+  a.bn.shift = shift;
+  a.dy = d->out_nchw ? dy : dy + d->c_off_out;
+  a.lddy = d->ld_out;
+  a.dy_nchw = d->out_nchw;
+  a.Cout = d->Cout;
+  a.KS = d->KH;
+  a.pad = d->pad;
+  a.stride = d->stride;
+  a.Ho = d->Hout;
+  a.Wo = d->Wout;
+  a.dw = dw;
+  return launch_wgrad_simt(a, (cudaStream_t)stream);
+}

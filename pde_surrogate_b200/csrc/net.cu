@@ -1,0 +1,629 @@
+// net.cu — DenseED executor: builds the layer list of the reference's DenseED
+// (models/codec.py:211-293), owns the workspace layout, and runs forward / backward as a fixed
+// sequence of kernel launches on the caller's stream.  Also the single-convolution C-ABI entry
+// points used by the unit tests.
+//
+// Design (B200-first, not a translation of nn.Sequential):
+//  * activations are NHWC; every dense block lives in ONE preallocated buffer and each layer
+//    writes its growth_rate-channel slice (no torch.cat copies, codec.py:73-75);
+//  * BatchNorm+ReLU never materialise: the producing conv's epilogue accumulates per-channel
+//    sum / sum-of-squares (fp64 atomics) once, every consumer folds its own gamma/beta into the
+//    load of its operand;
+//  * nearest x2 upsampling (codec.py:24-30) is an addressing mode of the consumer conv;
+//  * backward: the dgrad epilogue applies ReLU mask + BatchNorm backward and accumulates
+//    scale*dZ into the block's gradient buffer; the per-channel mean corrections of all
+//    consumers are applied lazily, once, to the 16-channel slice a producer reads as its dY
+//    (fix_dy), so no dZ tensor is ever written.
+#include <string>
+#include <vector>
+#include <string.h>
+#include "conv.cuh"
+
+namespace pdes {
+
+struct Buf {
+  int H, W, C, ld;
+  size_t act, grad;  // float offsets into the workspace
+  size_t stat;       // double offset: sum[C], sumsq[C]
+};
+
+struct Layer {
+  int kind;  // 0 plain conv (In_conv), 1 dense layer, 2 BN-ReLU-conv of a transition / last decoding
+  std::string conv_name, bn_name;
+  int in_buf, out_buf, coff;
+  int Cin, Cout, KS, stride, pad, up;
+  int Hs, Ws, Ho, Wo;
+  int64_t w_off, g_off, b_off, rm_off, rv_off;
+  size_t wf, wb;  // float offsets of the packed weights
+  size_t bsum;    // double offset
+  int CinP, CoP, CoutPb, CiPb;
+  bool last_consumer;
+};
+
+struct ParamInfo {
+  std::string name;
+  int64_t offset;
+  int ndim;
+  int64_t shape[4];
+  int kind;
+};
+
+}  // namespace pdes
+
+using namespace pdes;
+
+struct pdes_net {
+  pdes_densenet_config cfg;
+  std::vector<Buf> bufs;
+  std::vector<Layer> layers;
+  std::vector<ParamInfo> params;
+  int64_t param_floats = 0, running_floats = 0;
+  size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
+  size_t xin = 0;  // float offset: NCHW copy of the last training input (needed by In_conv's wgrad)
+  int n_bn = 0, maxC = 0, max_pack = 0;
+  // bound
+  float* p = nullptr;
+  float* g = nullptr;
+  float* run = nullptr;
+  unsigned char* ws = nullptr;
+  int last_B = 0;
+  bool fwd_train_done = false;
+  int launches = 0;
+  int conv_impl = 0;
+};
+
+namespace {
+
+int64_t pad4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+int add_buf(pdes_net* n, int H, int W, int C) {
+  Buf b;
+  b.H = H;
+  b.W = W;
+  b.C = C;
+  b.ld = rup(C, 4);
+  b.act = b.grad = b.stat = 0;
+  n->bufs.push_back(b);
+  return (int)n->bufs.size() - 1;
+}
+
+int conv_out(int in, int k, int s, int p) { return (in + 2 * p - k) / s + 1; }
+
+void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::string& bn_name,
+               int in_buf, int out_buf, int coff, int Cin, int Cout, int KS, int stride, int pad,
+               int up, int Hs, int Ws) {
+  Layer L;
+  L.kind = kind;
+  L.conv_name = conv_name;
+  L.bn_name = bn_name;
+  L.in_buf = in_buf;
+  L.out_buf = out_buf;
+  L.coff = coff;
+  L.Cin = Cin;
+  L.Cout = Cout;
+  L.KS = KS;
+  L.stride = stride;
+  L.pad = pad;
+  L.up = up;
+  L.Hs = Hs;
+  L.Ws = Ws;
+  const int Hv = up ? 2 * Hs : Hs, Wv = up ? 2 * Ws : Ws;
+  L.Ho = conv_out(Hv, KS, stride, pad);
+  L.Wo = conv_out(Wv, KS, stride, pad);
+  L.w_off = L.g_off = L.b_off = L.rm_off = L.rv_off = -1;
+  L.wf = L.wb = L.bsum = 0;
+  L.CinP = rup(Cin, 4);
+  L.CoP = rup(Cout, 16);
+  L.CoutPb = rup(Cout, 4);
+  L.CiPb = rup(Cin, 16);
+  L.last_consumer = false;
+  n->layers.push_back(L);
+}
+
+// Mirrors DenseED.__init__ (models/codec.py:230-290) for the configuration the training script
+// uses: dense layers without bottleneck, bottleneck transitions, nearest upsampling.
+int build(pdes_net* n) {
+  const pdes_densenet_config& c = n->cfg;
+  PDES_REQUIRE(c.n_blocks >= 1 && c.n_blocks <= 15 && (c.n_blocks == 1 || c.n_blocks % 2 == 1),
+               PDES_ERR_INVALID, "length of blocks must be an odd number, but got %d", c.n_blocks);
+  PDES_REQUIRE(c.in_channels >= 1 && c.out_channels >= 1 && c.imsize >= 8 && c.growth_rate >= 1 &&
+                   c.init_features >= 1 && c.max_batch >= 1,
+               PDES_ERR_INVALID, "pdes_densenet_create: invalid configuration");
+  for (int i = 0; i < c.n_blocks; ++i)
+    PDES_REQUIRE(c.blocks[i] >= 1 && c.blocks[i] < kMaxConsumers - 1, PDES_ERR_UNSUPPORTED,
+                 "dense block of %d layers (supported: 1..%d)", c.blocks[i], kMaxConsumers - 2);
+  const int n_enc = c.n_blocks / 2;
+  const int pad0 = (c.imsize % 2 == 0) ? 3 : 2;  // codec.py:238
+  int H = conv_out(c.imsize, 7, 2, pad0);
+  int C = c.init_features;
+  // every dense block (or single-consumer tensor) is one buffer
+  auto block_channels = [&](int C0, int nl) { return C0 + nl * c.growth_rate; };
+  int cur = add_buf(n, H, H, block_channels(C, c.blocks[0]));
+  if (n_enc == 0 && c.n_blocks == 1) { /* single decoding block */ }
+  add_layer(n, 0, "features.In_conv", "", -1, cur, 0, c.in_channels, C, 7, 2, pad0, 0, c.imsize,
+            c.imsize);
+  char nm[128];
+  for (int bi = 0; bi < c.n_blocks; ++bi) {
+    const bool enc = bi < n_enc;
+    const int idx = enc ? bi + 1 : bi - n_enc + 1;
+    for (int j = 0; j < c.blocks[bi]; ++j) {
+      snprintf(nm, sizeof(nm), "features.%sBlock%d.denselayer%d", enc ? "Enc" : "Dec", idx, j + 1);
+      add_layer(n, 1, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, cur,
+                C + j * c.growth_rate, C + j * c.growth_rate, c.growth_rate, 3, 1, 1, 0, H, H);
+    }
+    C += c.blocks[bi] * c.growth_rate;
+    const bool last = (bi == c.n_blocks - 1);
+    if (!last) {
+      snprintf(nm, sizeof(nm), "features.Trans%s%d", enc ? "Down" : "Up", idx);
+      const int mid = add_buf(n, H, H, C / 2);
+      add_layer(n, 2, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, mid, 0, C, C / 2, 1,
+                1, 0, 0, H, H);
+      const int Hn = enc ? conv_out(H, 3, 2, 1) : 2 * H;
+      const int nxt = add_buf(n, Hn, Hn, block_channels(C / 2, c.blocks[bi + 1]));
+      add_layer(n, 2, std::string(nm) + ".conv2", std::string(nm) + ".norm2", mid, nxt, 0, C / 2, C / 2,
+                3, enc ? 2 : 1, 1, enc ? 0 : 1, H, H);
+      C /= 2;
+      H = Hn;
+      cur = nxt;
+    } else {
+      const std::string t = "features.LastTransUp";
+      const int b1 = add_buf(n, H, H, C / 2);
+      add_layer(n, 2, t + ".conv1", t + ".norm1", cur, b1, 0, C, C / 2, 3, 1, 1, 0, H, H);
+      const int b2 = add_buf(n, 2 * H, 2 * H, C / 4);
+      add_layer(n, 2, t + ".conv2", t + ".norm2", b1, b2, 0, C / 2, C / 4, 3, 1, 1, 1, H, H);
+      add_layer(n, 2, t + ".conv3", t + ".norm3", b2, -1, 0, C / 4, c.out_channels, 5, 1, 2, 0, 2 * H,
+                2 * H);
+      PDES_REQUIRE(2 * H == c.imsize, PDES_ERR_UNSUPPORTED,
+                   "imsize %d does not map back to itself through the encoder-decoder (got %d)",
+                   c.imsize, 2 * H);
+    }
+  }
+  // last consumer of every buffer (first dgrad to run in reverse order stores, the rest accumulate)
+  for (size_t b = 0; b < n->bufs.size(); ++b) {
+    int lastL = -1;
+    for (size_t l = 0; l < n->layers.size(); ++l)
+      if (n->layers[l].in_buf == (int)b) lastL = (int)l;
+    if (lastL >= 0) n->layers[lastL].last_consumer = true;
+  }
+  // parameters in named_parameters() order: per module norm.weight, norm.bias, conv.weight
+  int64_t off = 0, roff = 0;
+  for (auto& L : n->layers) {
+    if (L.kind != 0) {
+      ParamInfo pw, pb;
+      pw.name = L.bn_name + ".weight";
+      pw.offset = off;
+      pw.ndim = 1;
+      pw.shape[0] = L.Cin;
+      pw.shape[1] = pw.shape[2] = pw.shape[3] = 1;
+      pw.kind = 1;
+      L.g_off = off;
+      off += pad4(L.Cin);
+      pb = pw;
+      pb.name = L.bn_name + ".bias";
+      pb.offset = off;
+      pb.kind = 2;
+      L.b_off = off;
+      off += pad4(L.Cin);
+      n->params.push_back(pw);
+      n->params.push_back(pb);
+      L.rm_off = roff;
+      roff += pad4(L.Cin);
+      L.rv_off = roff;
+      roff += pad4(L.Cin);
+      n->n_bn++;
+      if (L.Cin > n->maxC) n->maxC = L.Cin;
+    }
+    ParamInfo pc;
+    pc.name = L.conv_name + ".weight";
+    pc.offset = off;
+    pc.ndim = 4;
+    pc.shape[0] = L.Cout;
+    pc.shape[1] = L.Cin;
+    pc.shape[2] = pc.shape[3] = L.KS;
+    pc.kind = 0;
+    L.w_off = off;
+    off += pad4((int64_t)L.Cout * L.Cin * L.KS * L.KS);
+    n->params.push_back(pc);
+  }
+  n->param_floats = off;
+  n->running_floats = roff;
+  // workspace: floats (activations, gradients, packed weights) | doubles | tables
+  const int B = c.max_batch;
+  size_t f = 0;
+  for (auto& b : n->bufs) {
+    const size_t sz = (size_t)B * b.H * b.W * b.ld;
+    b.act = f;
+    f += pad4((int64_t)sz);
+    b.grad = f;
+    f += pad4((int64_t)sz);
+  }
+  for (auto& L : n->layers) {
+    const size_t taps = (size_t)L.KS * L.KS;
+    L.wf = f;
+    f += taps * L.CinP * L.CoP;
+    L.wb = f;
+    f += taps * L.CoutPb * L.CiPb;
+    const int pk = (int)(taps * L.CinP * L.CoP + taps * L.CoutPb * L.CiPb);
+    if (pk > n->max_pack) n->max_pack = pk;
+  }
+  n->xin = f;
+  f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
+  n->ws_floats = f;
+  size_t d = 0;
+  for (auto& b : n->bufs) {
+    b.stat = d;
+    d += 2 * (size_t)b.C;
+  }
+  for (auto& L : n->layers) {
+    L.bsum = d;
+    d += 2 * (size_t)L.Cin;
+  }
+  n->ws_doubles = d;
+  n->off_doubles = (n->ws_floats * sizeof(float) + 255) & ~(size_t)255;
+  n->off_tables = (n->off_doubles + n->ws_doubles * sizeof(double) + 255) & ~(size_t)255;
+  n->ws_bytes = n->off_tables + sizeof(PackDesc) * n->layers.size() +
+                sizeof(BnLayerDesc) * (size_t)n->n_bn + 256;
+  return PDES_OK;
+}
+
+inline float* wsf(const pdes_net* n, size_t off) { return reinterpret_cast<float*>(n->ws) + off; }
+inline double* wsd(const pdes_net* n, size_t off) {
+  return reinterpret_cast<double*>(n->ws + n->off_doubles) + off;
+}
+inline PackDesc* pack_table(const pdes_net* n) { return reinterpret_cast<PackDesc*>(n->ws + n->off_tables); }
+inline BnLayerDesc* bn_table(const pdes_net* n) {
+  return reinterpret_cast<BnLayerDesc*>(n->ws + n->off_tables + sizeof(PackDesc) * n->layers.size());
+}
+
+BnSrc bn_src(const pdes_net* n, const Layer& L, int B, bool training) {
+  BnSrc s;
+  memset(&s, 0, sizeof(s));
+  const Buf& ib = n->bufs[L.in_buf];
+  s.gamma = n->p + L.g_off;
+  s.beta = n->p + L.b_off;
+  s.eps = 1e-5f;
+  if (training) {
+    s.sum = wsd(n, ib.stat);
+    s.sumsq = wsd(n, ib.stat) + ib.C;
+    s.inv_count = 1.0 / ((double)B * ib.H * ib.W);
+  } else {
+    s.use_running = 1;
+    s.run_mean = n->run + L.rm_off;
+    s.run_var = n->run + L.rv_off;
+  }
+  return s;
+}
+
+}  // namespace
+
+extern "C" int pdes_densenet_create(const pdes_densenet_config* cfg, pdes_net_t** out) {
+  PDES_REQUIRE(cfg && out, PDES_ERR_INVALID, "pdes_densenet_create: null argument");
+  pdes_net* n = new pdes_net();
+  n->cfg = *cfg;
+  const int rc = build(n);
+  if (rc != PDES_OK) {
+    delete n;
+    return rc;
+  }
+  *out = n;
+  return PDES_OK;
+}
+
+extern "C" void pdes_densenet_destroy(pdes_net_t* net) { delete net; }
+
+extern "C" int pdes_densenet_num_params(const pdes_net_t* n) { return n ? (int)n->params.size() : 0; }
+extern "C" int64_t pdes_densenet_param_floats(const pdes_net_t* n) { return n ? n->param_floats : 0; }
+extern "C" int pdes_densenet_param_info(const pdes_net_t* n, int idx, char* name, size_t cap,
+                                        int64_t* offset, int32_t* ndim, int64_t shape[4],
+                                        int32_t* kind) {
+  PDES_REQUIRE(n && idx >= 0 && idx < (int)n->params.size(), PDES_ERR_INVALID,
+               "pdes_densenet_param_info: index %d out of range", idx);
+  const ParamInfo& p = n->params[idx];
+  if (name && cap) {
+    strncpy(name, p.name.c_str(), cap - 1);
+    name[cap - 1] = 0;
+  }
+  if (offset) *offset = p.offset;
+  if (ndim) *ndim = p.ndim;
+  if (shape)
+    for (int i = 0; i < 4; ++i) shape[i] = p.shape[i];
+  if (kind) *kind = p.kind;
+  return PDES_OK;
+}
+extern "C" int pdes_densenet_num_bn(const pdes_net_t* n) { return n ? n->n_bn : 0; }
+extern "C" int64_t pdes_densenet_running_floats(const pdes_net_t* n) { return n ? n->running_floats : 0; }
+extern "C" int pdes_densenet_bn_info(const pdes_net_t* n, int idx, char* name, size_t cap,
+                                     int64_t* mean_offset, int64_t* var_offset, int32_t* channels) {
+  PDES_REQUIRE(n && idx >= 0 && idx < n->n_bn, PDES_ERR_INVALID,
+               "pdes_densenet_bn_info: index %d out of range", idx);
+  int k = -1;
+  for (const auto& L : n->layers) {
+    if (L.kind == 0) continue;
+    if (++k == idx) {
+      if (name && cap) {
+        strncpy(name, L.bn_name.c_str(), cap - 1);
+        name[cap - 1] = 0;
+      }
+      if (mean_offset) *mean_offset = L.rm_off;
+      if (var_offset) *var_offset = L.rv_off;
+      if (channels) *channels = L.Cin;
+      return PDES_OK;
+    }
+  }
+  return PDES_ERR_INVALID;
+}
+
+extern "C" size_t pdes_densenet_workspace_bytes(const pdes_net_t* n) { return n ? n->ws_bytes : 0; }
+
+extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, float* running,
+                                  void* workspace, size_t workspace_bytes) {
+  PDES_REQUIRE(n && params && running && workspace, PDES_ERR_INVALID, "pdes_densenet_bind: null pointer");
+  PDES_REQUIRE(workspace_bytes >= n->ws_bytes, PDES_ERR_INVALID,
+               "pdes_densenet_bind: workspace %zu < %zu bytes", workspace_bytes, n->ws_bytes);
+  PDES_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)running | (uintptr_t)workspace) & 15u) == 0,
+               PDES_ERR_INVALID, "pdes_densenet_bind: buffers must be 16-byte aligned");
+  n->p = params;
+  n->g = grads;
+  n->run = running;
+  n->ws = (unsigned char*)workspace;
+  n->fwd_train_done = false;
+  std::vector<PackDesc> pt(n->layers.size());
+  std::vector<BnLayerDesc> bt;
+  for (size_t i = 0; i < n->layers.size(); ++i) {
+    const Layer& L = n->layers[i];
+    PackDesc& d = pt[i];
+    d.w = n->p + L.w_off;
+    d.wf = wsf(n, L.wf);
+    d.wb = L.in_buf >= 0 ? wsf(n, L.wb) : nullptr;
+    d.Cout = L.Cout;
+    d.Cin = L.Cin;
+    d.KS = L.KS;
+    d.CinP = L.CinP;
+    d.CoP = L.CoP;
+    d.CoutPb = L.CoutPb;
+    d.CiPb = L.CiPb;
+    if (L.kind != 0) {
+      const Buf& ib = n->bufs[L.in_buf];
+      BnLayerDesc b;
+      b.sum = wsd(n, ib.stat);
+      b.sumsq = wsd(n, ib.stat) + ib.C;
+      b.bsum = wsd(n, L.bsum);
+      b.run_mean = n->run + L.rm_off;
+      b.run_var = n->run + L.rv_off;
+      b.dgamma = n->g ? n->g + L.g_off : nullptr;
+      b.dbeta = n->g ? n->g + L.b_off : nullptr;
+      b.count = (double)ib.H * ib.W;  // per sample; multiplied by B on the device
+      b.C = L.Cin;
+      bt.push_back(b);
+    }
+  }
+  PDES_CUDA(cudaMemcpy(pack_table(n), pt.data(), sizeof(PackDesc) * pt.size(), cudaMemcpyHostToDevice));
+  if (!bt.empty())
+    PDES_CUDA(cudaMemcpy(bn_table(n), bt.data(), sizeof(BnLayerDesc) * bt.size(), cudaMemcpyHostToDevice));
+  return PDES_OK;
+}
+
+extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
+  PDES_REQUIRE(n && impl >= 0 && impl <= 1, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..1");
+  n->conv_impl = impl;
+  return PDES_OK;
+}
+
+extern "C" int pdes_densenet_last_launches(const pdes_net_t* n) { return n ? n->launches : 0; }
+
+extern "C" double pdes_densenet_flops(const pdes_net_t* n, int B, int training) {
+  if (!n) return 0.0;
+  double f = 0.0;
+  for (const auto& L : n->layers) {
+    const double one = 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B;
+    f += one;
+    if (training) f += one + (L.in_buf >= 0 ? one : 0.0);
+  }
+  return f;
+}
+
+extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, int B, int training,
+                                     void* stream) {
+  PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_forward: bind() first");
+  PDES_REQUIRE(x && out, PDES_ERR_INVALID, "pdes_densenet_forward: null pointer");
+  PDES_REQUIRE(B >= 1 && B <= n->cfg.max_batch, PDES_ERR_INVALID,
+               "pdes_densenet_forward: batch %d outside 1..%d", B, n->cfg.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  n->launches = 0;
+  const bool tr = training != 0;
+  if (tr) {
+    PDES_CUDA(cudaMemsetAsync(wsd(n, 0), 0, n->ws_doubles * sizeof(double), st));
+    n->launches++;
+  }
+  int rc = launch_pack_weights(pack_table(n), (int)n->layers.size(), n->max_pack, st);
+  if (rc) return rc;
+  n->launches++;
+  if (tr) {
+    PDES_CUDA(cudaMemcpyAsync(wsf(n, n->xin), x,
+                              sizeof(float) * (size_t)B * n->cfg.in_channels * n->cfg.imsize * n->cfg.imsize,
+                              cudaMemcpyDeviceToDevice, st));
+    n->launches++;
+  }
+  for (const auto& L : n->layers) {
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    if (L.in_buf < 0) {
+      a.x = tr ? wsf(n, n->xin) : x;
+      a.in_nchw = 1;
+      a.Cin = L.Cin;
+      a.Hs = L.Hs;
+      a.Ws = L.Ws;
+    } else {
+      const Buf& ib = n->bufs[L.in_buf];
+      a.x = wsf(n, ib.act);
+      a.ldx = ib.ld;
+      a.Cin = L.Cin;
+      a.Hs = ib.H;
+      a.Ws = ib.W;
+      a.pro = 1;
+      a.bn = bn_src(n, L, B, tr);
+    }
+    a.B = B;
+    a.in_mode = L.up ? IN_UPSAMPLE : IN_DIRECT;
+    a.w = wsf(n, L.wf);
+    a.CinP = L.CinP;
+    a.CoP = L.CoP;
+    a.Cout = L.Cout;
+    a.KS = L.KS;
+    a.pad = L.pad;
+    a.stride = L.stride;
+    a.Ho = L.Ho;
+    a.Wo = L.Wo;
+    if (L.out_buf < 0) {
+      a.epi = EPI_NCHW;
+      a.y = out;
+    } else {
+      const Buf& ob = n->bufs[L.out_buf];
+      a.epi = EPI_NHWC;
+      a.y = wsf(n, ob.act);
+      a.ldy = ob.ld;
+      a.coff = L.coff;
+      if (tr) {
+        a.o_sum = wsd(n, ob.stat) + L.coff;
+        a.o_sumsq = wsd(n, ob.stat) + ob.C + L.coff;
+      }
+    }
+    rc = launch_conv_simt(a, st);
+    if (rc) return rc;
+    n->launches++;
+  }
+  if (tr) {
+    rc = launch_bn_running_update(bn_table(n), n->n_bn, n->maxC, 0.1f, B, st);
+    if (rc) return rc;
+    n->launches++;
+    n->last_B = B;
+    n->fwd_train_done = true;
+  }
+  return PDES_OK;
+}
+
+extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* stream) {
+  PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_backward: bind() first");
+  PDES_REQUIRE(n->fwd_train_done, PDES_ERR_STATE,
+               "pdes_densenet_backward: needs a preceding training-mode forward");
+  PDES_REQUIRE(n->g != nullptr, PDES_ERR_STATE, "pdes_densenet_backward: no gradient buffer bound");
+  PDES_REQUIRE(dout != nullptr, PDES_ERR_INVALID, "pdes_densenet_backward: null dout");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = n->last_B;
+  n->launches = 0;
+  int rc;
+  for (int li = (int)n->layers.size() - 1; li >= 0; --li) {
+    const Layer& L = n->layers[li];
+    const float* dy;
+    int lddy = 0, dy_nchw = 0;
+    if (L.out_buf < 0) {
+      dy = dout;
+      dy_nchw = 1;
+    } else {
+      const Buf& ob = n->bufs[L.out_buf];
+      FixDyArgs f;
+      memset(&f, 0, sizeof(f));
+      f.G = wsf(n, ob.grad) + L.coff;
+      f.X = wsf(n, ob.act) + L.coff;
+      f.ldG = f.ldX = ob.ld;
+      f.C = L.Cout;
+      f.npix = (int64_t)B * ob.H * ob.W;
+      f.sum = wsd(n, ob.stat) + L.coff;
+      f.sumsq = wsd(n, ob.stat) + ob.C + L.coff;
+      f.inv_count = 1.0 / ((double)B * ob.H * ob.W);
+      f.eps = 1e-5f;
+      for (const auto& M : n->layers) {
+        if (M.in_buf != L.out_buf || M.Cin <= L.coff) continue;
+        PDES_REQUIRE(f.n_cons < kMaxConsumers, PDES_ERR_UNSUPPORTED, "too many consumers of one tensor");
+        f.cons_gamma[f.n_cons] = n->p + M.g_off + L.coff;
+        f.cons_bsum[f.n_cons] = wsd(n, M.bsum) + L.coff;
+        f.cons_C[f.n_cons] = M.Cin;
+        f.n_cons++;
+      }
+      rc = launch_fix_dy(f, st);
+      if (rc) return rc;
+      n->launches++;
+      dy = f.G;
+      lddy = ob.ld;
+    }
+    // ---- wgrad ---------------------------------------------------------------------
+    {
+      WgradArgs w;
+      memset(&w, 0, sizeof(w));
+      w.B = B;
+      w.in_mode = L.up ? IN_UPSAMPLE : IN_DIRECT;
+      w.Cin = L.Cin;
+      if (L.in_buf >= 0) {
+        const Buf& ib = n->bufs[L.in_buf];
+        w.x = wsf(n, ib.act);
+        w.ldx = ib.ld;
+        w.Hs = ib.H;
+        w.Ws = ib.W;
+        w.pro = 1;
+        w.bn = bn_src(n, L, B, true);
+      }
+      w.dy = dy;
+      w.lddy = lddy;
+      w.dy_nchw = dy_nchw;
+      w.Cout = L.Cout;
+      w.KS = L.KS;
+      w.pad = L.pad;
+      w.stride = L.stride;
+      w.Ho = L.Ho;
+      w.Wo = L.Wo;
+      w.dw = n->g + L.w_off;
+      if (L.in_buf < 0) {
+        w.x = wsf(n, n->xin);  // NCHW copy made by the training forward
+        w.in_nchw = 1;
+        w.Hs = L.Hs;
+        w.Ws = L.Ws;
+      }
+      rc = launch_wgrad_simt(w, st);
+      if (rc) return rc;
+      n->launches++;
+    }
+    // ---- dgrad (not needed for the first conv: the input does not require grad) ------
+    if (L.in_buf >= 0) {
+      const Buf& ib = n->bufs[L.in_buf];
+      ConvArgs a;
+      memset(&a, 0, sizeof(a));
+      a.x = dy;
+      a.ldx = lddy;
+      a.in_nchw = dy_nchw;
+      a.Cin = L.Cout;
+      a.Hs = L.Ho;
+      a.Ws = L.Wo;
+      a.B = B;
+      a.in_mode = L.stride == 2 ? IN_ZEROINS : IN_DIRECT;
+      a.w = wsf(n, L.wb);
+      a.CinP = L.CoutPb;
+      a.CoP = L.CiPb;
+      a.Cout = L.Cin;
+      a.KS = L.KS;
+      a.pad = L.KS - 1 - L.pad;
+      a.stride = 1;
+      a.Ho = L.up ? 2 * ib.H : ib.H;
+      a.Wo = L.up ? 2 * ib.W : ib.W;
+      a.epi = EPI_BNBWD;
+      a.pool = L.up;
+      a.fx = wsf(n, ib.act);
+      a.ldfx = ib.ld;
+      a.Hf = ib.H;
+      a.Wf = ib.W;
+      a.fbn = bn_src(n, L, B, true);
+      a.G = wsf(n, ib.grad);
+      a.ldG = ib.ld;
+      a.g_accum = L.last_consumer ? 0 : 1;
+      a.bsum = wsd(n, L.bsum);
+      rc = launch_conv_simt(a, st);
+      if (rc) return rc;
+      n->launches++;
+    }
+  }
+  rc = launch_bn_param_grad(bn_table(n), n->n_bn, n->maxC, st);
+  if (rc) return rc;
+  n->launches++;
+  n->fwd_train_done = false;
+  return PDES_OK;
+}

@@ -1,0 +1,96 @@
+"""Single-convolution kernels (forward with fused BN+ReLU / upsampling / stats, dgrad, wgrad)
+against torch fp64 CPU convolutions of the same op."""
+from ctypes import byref
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, H, Cin, Cout, K, stride, pad, up, bn
+    (2, 16, 1, 48, 7, 2, 3, 0, 0),     # In_conv
+    (2, 16, 48, 16, 3, 1, 1, 0, 1),    # dense layer
+    (1, 8, 184, 16, 3, 1, 1, 0, 1),
+    (2, 16, 144, 72, 1, 1, 0, 0, 1),   # transition 1x1
+    (2, 16, 72, 72, 3, 2, 1, 0, 1),    # stride-2 transition
+    (2, 8, 100, 100, 3, 1, 1, 1, 1),   # nearest-up + conv
+    (1, 16, 98, 49, 3, 1, 1, 1, 1),
+    (2, 16, 49, 3, 5, 1, 2, 0, 1),     # last conv
+    (1, 13, 20, 16, 3, 1, 1, 0, 1),    # ragged spatial size
+    (1, 11, 12, 8, 3, 2, 1, 0, 1),
+]
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def _desc(B, H, Cin, Cout, K, s, p, up, bn, ld_in, ld_out, coff, nchw=0):
+    from pde_surrogate_b200 import _lib
+    d = _lib.ConvDesc()
+    Hv = 2 * H if up else H
+    Ho = (Hv + 2 * p - K) // s + 1
+    d.B, d.Hin, d.Win, d.Cin, d.ld_in = B, H, H, Cin, ld_in
+    d.Hout, d.Wout, d.Cout, d.ld_out, d.c_off_out = Ho, Ho, Cout, ld_out, coff
+    d.KH, d.KW, d.stride, d.pad, d.upsample, d.bn_relu, d.out_nchw = K, K, s, p, up, bn, nchw
+    return d, Ho
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_fwd_dgrad_wgrad(case):
+    from pde_surrogate_b200 import _lib
+    L = _lib.lib()
+    B, H, Cin, Cout, K, s, p, up, bn = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    ld_in = (Cin + 3) // 4 * 4 + 4
+    coff = 8
+    ld_out = coff + (Cout + 3) // 4 * 4
+    x = torch.randn(B, H, H, ld_in, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
+    scale = torch.rand(Cin, generator=g) + 0.5
+    shift = torch.randn(Cin, generator=g) * 0.3
+    d, Ho = _desc(B, H, Cin, Cout, K, s, p, up, bn, ld_in, ld_out, coff)
+    # fp64 reference
+    xr = x[..., :Cin].permute(0, 3, 1, 2).double().requires_grad_(True)
+    a = xr
+    if bn:
+        a = F.relu(a * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1))
+    a.retain_grad()
+    au = F.interpolate(a, scale_factor=2.0, mode="nearest") if up else a
+    wr = w.double().requires_grad_(True)
+    yr = F.conv2d(au, wr, None, s, p)
+    dy = torch.randn(yr.shape, generator=g, dtype=torch.float64)
+    yr.backward(dy)
+    st = _lib.stream_ptr()
+    xd, wd, sd, hd = x.cuda(), w.cuda(), scale.cuda(), shift.cuda()
+    y = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
+    csum = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    csq = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    _lib.check(L.pdes_conv2d_fwd(byref(d), _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(sd) if bn else None,
+                                 _lib.ptr(hd) if bn else None, _lib.ptr(y), _lib.ptr(csum), _lib.ptr(csq), 0, st))
+    ynhwc = yr.detach().permute(0, 2, 3, 1)
+    assert rel(y[..., coff:coff + Cout], ynhwc) < 2e-6
+    assert float(y[..., :coff].abs().max()) == 0.0 and float(y[..., coff + Cout:].abs().max()) == 0.0
+    assert rel(csum, ynhwc.sum((0, 1, 2))) < 1e-5 or float(ynhwc.sum((0, 1, 2)).norm()) < 1e-3
+    assert rel(csq, (ynhwc ** 2).sum((0, 1, 2))) < 1e-5
+    # planar output variant
+    d2, _ = _desc(B, H, Cin, Cout, K, s, p, up, bn, ld_in, ld_out, coff, nchw=1)
+    y2 = torch.zeros(B, Cout, Ho, Ho, device="cuda")
+    _lib.check(L.pdes_conv2d_fwd(byref(d2), _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(sd) if bn else None,
+                                 _lib.ptr(hd) if bn else None, _lib.ptr(y2), None, None, 0, st))
+    assert rel(y2, yr.detach()) < 2e-6
+    # dgrad (w.r.t. the BN+ReLU'd operand, summed over the upsampling footprint)
+    dyd = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
+    dyd[..., coff:coff + Cout] = dy.permute(0, 2, 3, 1).float().cuda()
+    da = torch.full((B, H, H, Cin), 7.0, device="cuda")
+    _lib.check(L.pdes_conv2d_dgrad(byref(d), _lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(da), 0, st))
+    assert rel(da, a.grad.permute(0, 2, 3, 1)) < 3e-6
+    # wgrad (accumulates)
+    dw = torch.ones(Cout, Cin, K, K, device="cuda")
+    _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), _lib.ptr(sd) if bn else None,
+                                   _lib.ptr(hd) if bn else None, _lib.ptr(dyd), _lib.ptr(dw), 0, st))
+    assert rel(dw - 1.0, wr.grad) < 1e-5

@@ -1,0 +1,164 @@
+"""DenseED executor parity: training/eval forward, losses, dL/d(output), parameter gradients,
+running statistics — against the reference-generated fixtures and the fp64 oracle.
+
+Bars: fields and the four partial losses within 1e-4 relative of the
+reference; gradients within 3x the reference's own fp32-vs-fp64 error (noise-floor criterion),
+measured against the fp64 reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdes_oracle as orc
+
+pytestmark = pytest.mark.gpu
+CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64"]
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def _cfg(g):
+    return dict(in_channels=int(g["cfg_in_channels"]), out_channels=int(g["cfg_out_channels"]),
+                imsize=int(g["cfg_imsize"]), blocks=[int(b) for b in g["cfg_blocks"]],
+                growth_rate=int(g["cfg_growth_rate"]), init_features=int(g["cfg_init_features"]))
+
+
+def _model(g):
+    from models.codec import DenseED
+    cfg = _cfg(g)
+    plan = orc.densenet_plan(**cfg)
+    sd = orc.make_state(plan, int(g["seed"]))
+    model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
+                    growth_rate=cfg["growth_rate"], init_features=cfg["init_features"])
+    assert list(model.state_dict().keys()) == list(sd.keys())
+    model.load_state_dict(sd)
+    model = model.to("cuda")
+    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"])).to("cuda")
+    return model, K, cfg
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_step_matches_reference(golden_dir, name):
+    from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
+    from utils.image_gradient import SobelFilter
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model, K, cfg = _model(g)
+    assert tuple(model.model_size) == tuple(int(v) for v in g["model_size"])
+    sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
+    # eval forward with the given running statistics
+    model.eval()
+    with torch.no_grad():
+        out_eval = model(K)
+    assert rel(out_eval.cpu().numpy(), g["out_eval64"]) < 1e-4
+    # the step body of train_codec_mixed_residual.py:226-233
+    model.train()
+    model.zero_grad()
+    out = model(K)
+    out.retain_grad()
+    l_c = conv_constitutive_constraint(K, out, sob)
+    l_d = conv_continuity_constraint(out, sob)
+    l_dir, l_neu = conv_boundary_condition(out)
+    loss = (l_c + l_d) + (l_dir + l_neu) * 10.0
+    loss.backward()
+    torch.cuda.synchronize()
+    assert rel(out.detach().cpu().numpy(), g["out64"]) < 1e-4
+    l4 = torch.stack([l_c, l_d, l_dir, l_neu]).detach().cpu().numpy()
+    assert np.all(np.abs(l4 - g["l4_64"]) <= 1e-4 * np.abs(g["l4_64"])), (l4, g["l4_64"])
+    assert abs(float(loss) - float(g["loss64"])) <= 1e-4 * float(g["loss64"])
+    assert rel(out.grad.cpu().numpy(), g["dout64"]) < 1e-4
+    # parameter gradients vs the fp64 reference, noise-floor relative
+    names = [str(s) for s in g["param_names"]]
+    params = dict(model.named_parameters())
+    assert list(params.keys()) == names
+    tot_err, tot_floor, tot_norm = 0.0, 0.0, 0.0
+    pos = 0
+    for i, n in enumerate(names):
+        gr = params[n].grad.detach().double().cpu().numpy().ravel()
+        if "grads64" in g.files:
+            ref = g["grads64"][pos:pos + gr.size]
+            pos += gr.size
+            err = np.linalg.norm(gr - ref)
+        else:
+            k = int(g["grads64_head_len"][i])
+            ref = g["grads64_head"][pos:pos + k]
+            pos += k
+            err = np.linalg.norm(gr[:k] - ref) * np.sqrt(gr.size / k)
+            assert abs(np.linalg.norm(gr) - g["grad_norm64"][i]) <= 3 * g["grad_err32"][i] + 1e-3 * g["grad_norm64"][i]
+        tot_err += err ** 2
+        tot_floor += float(g["grad_err32"][i]) ** 2
+        tot_norm += float(g["grad_norm64"][i]) ** 2
+    agg = np.sqrt(tot_err / tot_norm)
+    floor = np.sqrt(tot_floor / tot_norm)
+    assert agg <= max(3 * floor, 1e-5), "aggregate grad rel-L2 %.3e vs reference fp32 floor %.3e" % (agg, floor)
+    # running statistics and step counters
+    sd = model.state_dict()
+    run = np.concatenate([sd[str(n)].double().cpu().numpy().ravel() for n in g["running_names"]])
+    assert rel(run, g["running64"]) < 1e-5
+    nbt = [int(v) for k, v in sd.items() if k.endswith("num_batches_tracked")]
+    assert nbt == [int(v) for v in g["num_batches_tracked"]]
+
+
+def test_grad_accumulation_and_zero_grad(golden_dir):
+    from models.darcy import conv_boundary_condition
+    g = np.load(os.path.join(golden_dir, "densenet_small16.npz"))
+    model, K, cfg = _model(g)
+    model.train()
+
+    def run():
+        out = model(K)
+        d, n = conv_boundary_condition(out)
+        (d + n).backward()
+
+    model.zero_grad()
+    run()
+    g1 = model.flat_parameters()[1].clone()
+    run()  # no zero_grad: accumulates (BN running stats moved, batch stats identical)
+    g2 = model.flat_parameters()[1].clone()
+    assert rel(g2.cpu().numpy(), 2 * g1.cpu().numpy()) < 1e-4
+    model.zero_grad()
+    assert all(p.grad is None for p in model.parameters())
+    run()
+    assert rel(model.flat_parameters()[1].cpu().numpy(), g1.cpu().numpy()) < 1e-4
+
+
+def test_adam_step_matches_torch(golden_dir):
+    """The unmodified script's torch.optim.Adam works on the flat-view parameters, and the fused
+    flat Adam kernel reproduces it."""
+    from pde_surrogate_b200 import _lib
+    g = np.load(os.path.join(golden_dir, "densenet_small16.npz"))
+    model, K, cfg = _model(g)
+    from models.darcy import conv_boundary_condition
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    flat, gflat = model.flat_parameters()
+    p0 = flat.clone()
+    m = torch.zeros_like(flat)
+    v = torch.zeros_like(flat)
+    mine = flat.clone()
+    for step in (1, 2, 3):
+        model.zero_grad()
+        d, n = conv_boundary_condition(model(K))
+        (d + n).backward()
+        _lib.check(_lib.lib().pdes_adam_step(_lib.ptr(mine), _lib.ptr(gflat), _lib.ptr(m), _lib.ptr(v),
+                                             mine.numel(), 1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, step,
+                                             _lib.stream_ptr()))
+        opt.step()
+        assert rel(flat.cpu().numpy() - p0.cpu().numpy(), mine.cpu().numpy() - p0.cpu().numpy()) < 1e-5
+
+
+def test_errors_are_loud():
+    from models.codec import DenseED
+    with pytest.raises(ValueError):
+        DenseED(1, 3, 64, [6, 8])
+    with pytest.raises(NotImplementedError):
+        DenseED(1, 3, 64, [6, 8, 6], drop_rate=0.1)
+    m = DenseED(1, 3, 16, [1, 1, 1], growth_rate=4, init_features=8)
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 16, 16))  # CPU: no fallback
+    m = m.cuda()
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 1, 32, 32, device="cuda"))
