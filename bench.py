@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Benchmark of the physics-constrained DenseED training step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A step = one optimisation step on one batch of 32 synthetic GRF-KLE512 64x64 fields per GPU:
+H2D copy (e2e only) -> zero_grad -> DenseED forward -> fused Darcy loss -> backward ->
+[NCCL all-reduce of the flat gradient bucket] -> Adam -> loss read-back (e2e only).
+Prints ONE JSON line on rank 0.  Timing: CUDA events on the launching stream, barrier +
+synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "training-samples/sec GRF-KLE512 64x64 codec mixed-residual"
+IMSIZE, BATCH, NTRAIN = 64, 32, 4096
+WORKLOAD = "DenseED[6,8,6] codec mixed-residual, GRF KLE512 64x64, ntrain=4096, batch 32/GPU, fp32"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ntrain", type=int, default=NTRAIN)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=6, help="bounded CPU-baseline sample (steps of 32)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"],
+                    bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(smax) if smax else None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+def cpu_baseline(steps, threads=None):
+    """Oracle port (same PyTorch CPU kernels as the reference) on the host cores, bounded sample."""
+    import torch
+    from oracle.cpu_train import CpuTrainer
+    tr = CpuTrainer(IMSIZE, threads=threads)
+    g = torch.Generator().manual_seed(1)
+    batches = [torch.exp(0.5 * torch.randn(BATCH, 1, IMSIZE, IMSIZE, generator=g)) for _ in range(steps)]
+    sps, dt = tr.timed(batches, warmup=1)
+    return dict(value=round(sps, 2), unit="samples/s", cores=tr.threads, kind="port",
+                sample="%d steps of batch %d at 64x64 after 1 warm-up (%.1f s), oracle/cpu_train.py on "
+                       "torch %s CPU kernels" % (steps, BATCH, dt, torch.__version__))
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    pure Python/PyTorch and absent from the GPU box).  Rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    from oracle.cpu_train import CpuTrainer
+    tr = CpuTrainer(IMSIZE)
+    g = torch.Generator().manual_seed(1)
+    n = max(1, min(args.steps, 40))
+    batches = [torch.exp(0.5 * torch.randn(BATCH, 1, IMSIZE, IMSIZE, generator=g)) for _ in range(min(n, 8))]
+    for i in range(max(1, min(args.warmup, 3))):
+        tr.step(batches[i % len(batches)])
+    t0 = time.perf_counter()
+    for i in range(n):
+        tr.step(batches[i % len(batches)])
+    dt = time.perf_counter() - t0
+    sps = n * BATCH / dt
+    line = dict(metric=METRIC, value=round(sps, 2), unit="samples/s", n_gpus=args.gpus, steps=n,
+                warmup=args.warmup, ms_per_step=round(1e3 * dt / n, 3), higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD + " (CPU, one process, all host threads)"),
+                cpu_baseline=dict(value=round(sps, 2), unit="samples/s", cores=tr.threads, kind="port",
+                                  sample="%d timed steps of batch %d (bounded from --steps %d)" % (n, BATCH, args.steps)),
+                e2e=dict(value=round(sps, 2), unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        dist.init_process_group("nccl", device_id=dev)
+    from models.codec import DenseED
+    from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
+    from pde_surrogate_b200 import _lib, data
+    from pde_surrogate_b200.engine import TrainStep
+    from utils.image_gradient import SobelFilter
+    from utils.practices import OneCycleScheduler, adjust_learning_rate
+
+    pk = peaks()
+    # ---- data: synthetic GRF KLE512 64x64, rank-sharded ------------------------------------
+    n_local = args.ntrain // world
+    host = data.grf_kle(n_local, IMSIZE, 512, 0.1, seed=1 + rank, device=dev).pin_memory()
+    dset = host.to(dev)
+    n_batches = n_local // BATCH
+
+    def make_model():
+        torch.manual_seed(1)
+        return DenseED(1, 3, IMSIZE, [6, 8, 6]).to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sched = OneCycleScheduler(lr_max=1e-3, div_factor=2.0, pct_start=0.3)
+    total_steps = 300 * n_batches
+
+    # ---- value: inputs resident in HBM, whole step on the device ---------------------------
+    model = make_model()
+    pg = dist.group.WORLD if world > 1 else None
+    ts = TrainStep(model, weight_bound=10.0, lr=1e-3, process_group=pg, world_size=world)
+    if world > 1:
+        ts.broadcast_parameters()
+    last = {}
+
+    def dev_step(i):
+        K = dset[(i % n_batches) * BATCH:(i % n_batches + 1) * BATCH]
+        last["loss"] = ts.step(K, lr=sched.step((i + 1) / total_steps))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(dev_step, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    launches = ts.kernel_launches * args.steps
+    final_loss = float(last["loss"].item())
+
+    # ---- roofline of the conv path (dominant): useful FLOPs of fwd+bwd / device time ---------
+    L = _lib.lib()
+    ex = model._ex
+    flops_step = model.flops(BATCH, True)
+    Kb = dset[:BATCH]
+    dummy = torch.randn(BATCH, 3, IMSIZE, IMSIZE, device=dev) * 1e-3
+
+    def conv_only(i):
+        ex.forward(Kb, True)
+        ex.backward(dummy)
+
+    ms_conv = timed(conv_only, max(5, args.steps // 4), 3)
+    conv_ms_step = ms_conv / max(5, args.steps // 4)
+    ach_tf = flops_step / (conv_ms_step * 1e-3) / 1e12
+    roofline = dict(bound="tensor", kernel="DenseED conv path (fwd+dgrad+wgrad, %d launches)" % 0,
+                    achieved=round(ach_tf, 3), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                    frac=round(ach_tf / pk["bf16_tflops_sustained"], 5), traffic=None,
+                    note="useful fp32 FLOPs (2*MAC, %.1f GFLOP/step) / CUDA-event time of the executor's "
+                         "forward+backward; peak = %s dense bf16 (sustained) — fp32-accurate convs can "
+                         "reach at most 1/2 (TF32) .. 1/6 (3xTF32) of it" % (flops_step / 1e9, pk["src"]))
+
+    # ---- roofline of the fused stencil kernel on a cold, larger-than-L2 batch ----------------
+    nb = 8192
+    Kbig = dset[:min(nb, dset.shape[0])].repeat((nb + dset.shape[0] - 1) // dset.shape[0], 1, 1, 1)[:nb].contiguous()
+    obig = torch.randn(nb, 3, IMSIZE, IMSIZE, device=dev)
+    dbig = torch.empty_like(obig)
+    l4 = torch.zeros(4, device=dev)
+    gw = torch.tensor([1., 1., 10., 10.], device=dev)
+    from pde_surrogate_b200 import darcy as _d
+    ws = _d._workspace(dev)
+    st = _lib.stream_ptr()
+
+    def sten_f(i):
+        _lib.check(L.pdes_darcy_loss_fwd(_lib.ptr(Kbig), _lib.ptr(obig), nb, IMSIZE, IMSIZE, 1, _lib.ptr(l4),
+                                         _lib.ptr(ws), st))
+
+    def sten_b(i):
+        _lib.check(L.pdes_darcy_loss_bwd(_lib.ptr(Kbig), _lib.ptr(obig), _lib.ptr(gw), nb, IMSIZE, IMSIZE, 1,
+                                         _lib.ptr(dbig), st))
+
+    msf = timed(sten_f, 10, 3) / 10
+    msb = timed(sten_b, 10, 3) / 10
+    gbs_f = nb * 65536 / (msf * 1e-3) / 1e9
+    gbs_b = nb * 114688 / (msb * 1e-3) / 1e9
+    roofline_stencil = dict(bound="hbm", kernel="darcy_fwd_tile_kernel / darcy_bwd_tile_kernel",
+                            achieved=round(gbs_b, 1), peak=pk["hbm_gbs"], unit="GB/s",
+                            frac=round(gbs_b / pk["hbm_gbs"], 4), traffic=None,
+                            fwd_achieved=round(gbs_f, 1), fwd_frac=round(gbs_f / pk["hbm_gbs"], 4),
+                            note="cold %d-sample batch (%.1f GB, > L2); algorithmic bytes 65536 (fwd) / "
+                                 "114688 (bwd) per sample; peak = %s copy bandwidth" % (nb, nb * 114688 / 1e9, pk["src"]))
+    del Kbig, obig, dbig
+
+    # ---- e2e: the unmodified script's loop body through the reference-facing modules ---------
+    model2 = make_model()
+    opt = torch.optim.Adam(model2.parameters(), lr=1e-3, weight_decay=0.0)
+    sob = SobelFilter(IMSIZE, correct=True, device=dev)
+    if world > 1:
+        flat2, gflat2 = model2.flat_parameters()
+        dist.broadcast(flat2, 0)
+
+    def e2e_step(i):
+        inp = host[(i % n_batches) * BATCH:(i % n_batches + 1) * BATCH].to(dev, non_blocking=True)
+        model2.zero_grad()
+        out = model2(inp)
+        loss_pde = conv_constitutive_constraint(inp, out, sob) + conv_continuity_constraint(out, sob)
+        l_dir, l_neu = conv_boundary_condition(out)
+        loss = loss_pde + (l_dir + l_neu) * 10.0
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(gflat2)
+            gflat2.div_(world)
+        adjust_learning_rate(opt, sched.step((i + 1) / total_steps))
+        opt.step()
+        last["e2e_loss"] = loss.item()
+
+    ms_e = timed(e2e_step, args.steps, max(args.warmup, 3))
+    e2e_val = world * BATCH * args.steps / (ms_e * 1e-3)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.cpu_steps)
+
+    if rank == 0:
+        line = dict(metric=METRIC, value=round(value, 1), unit="samples/s", n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 4), higher_is_better=True,
+                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=WORKLOAD, global_batch=BATCH * world,
+                                parallelism="dp%d" % world if world > 1 else "single",
+                                l2="each step streams ~210 MB of activations+gradients (> 126 MB L2) and a "
+                                   "different batch of the HBM-resident dataset; no explicit flush",
+                                grf="exp covariance, l=0.1, 512 KLE modes, seed 1"),
+                    e2e=dict(value=round(e2e_val, 1), unit="samples/s", h2d_bytes_per_step=BATCH * IMSIZE * IMSIZE * 4,
+                             d2h_bytes_per_step=4, ms_per_step=round(ms_e / args.steps, 4),
+                             api="models.codec.DenseED + models.darcy.conv_* + torch.optim.Adam, loss.item() per step"),
+                    gpu_launches=launches, launches_per_step=ts.kernel_launches, clocks=clocks,
+                    roofline=roofline, roofline_stencil=roofline_stencil, cpu_baseline=cpu,
+                    final_loss=round(final_loss, 5), conv_path_ms_per_step=round(conv_ms_step, 4),
+                    useful_gflop_per_step=round(flops_step / 1e9, 2))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,7 @@ __device__ __forceinline__ void stage_halo(const A& a, float* a_s, const float* 
           if (c + i < a.Cin) v[i] = a.x[(((size_t)b * a.Cin + c + i) * a.Hs + sy) * a.Ws + sx];
       } else {
         const float* p = a.x + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
-        if (c + 3 < a.Cin && ((a.ldx & 3) == 0)) {
+        if (c + 3 < a.Cin && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
           const float4 q = *reinterpret_cast<const float4*>(p);
           v[0] = q.x;
           v[1] = q.y;
@@ -538,11 +538,11 @@ int launch_conv_t(const ConvArgs& a, cudaStream_t st) {
   const size_t smem = conv_smem_bytes(a.Cin, KS, a.stride, TN);
   PDES_REQUIRE(smem <= 227 * 1024, PDES_ERR_UNSUPPORTED,
                "conv_simt: tile needs %zu bytes of shared memory", smem);
-  static bool attr = false;
-  if (!attr) {
+  static size_t attr = 0;
+  if (smem > attr) {
     PDES_CUDA(cudaFuncSetAttribute(conv_simt_kernel<TN, KS>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
   }
   const int tiles = ((a.Wo + kTile - 1) / kTile) * ((a.Ho + kTile - 1) / kTile) * a.B;
   dim3 grid(tiles, (a.Cout + TN - 1) / TN);
@@ -556,11 +556,11 @@ int launch_wgrad_t(const WgradArgs& a, cudaStream_t st) {
   const size_t smem = wgrad_smem_bytes(a.Cin, KS, a.stride, TN);
   PDES_REQUIRE(smem <= 227 * 1024, PDES_ERR_UNSUPPORTED,
                "wgrad_simt: tile needs %zu bytes of shared memory", smem);
-  static bool attr = false;
-  if (!attr) {
+  static size_t attr = 0;
+  if (smem > attr) {
     PDES_CUDA(cudaFuncSetAttribute(wgrad_simt_kernel<TN, KS, TR>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
   }
   const int CinP4 = (a.Cin + 3) & ~3;
   const int KC = CinP4 < 16 ? CinP4 : 16;

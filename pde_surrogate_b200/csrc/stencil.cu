@@ -405,7 +405,7 @@ bool tile_ok(int H, int W, const void* a, const void* b, bool bwd) {
   if (kTileThreads / (W / 4) < 1) return false;
   if (((uintptr_t)a & 15u) != 0 || ((uintptr_t)b & 15u) != 0) return false;
   const size_t need = 128 + (size_t)H * W * 4 * (bwd ? 13 : 8);
-  return need <= 227 * 1024;
+  return need + 2048 <= 227 * 1024;
 }
 
 }  // namespace
@@ -467,11 +467,11 @@ extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int 
                "pdes_darcy_loss_fwd: tile kernel forced but %dx%d does not qualify", H, W);
   if (g_loss_impl != 1 && can_tile) {
     const size_t smem = 128 + (size_t)H * W * 4 * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
       PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
     }
     int grid = sm_count();
     if (grid > B) grid = B;
@@ -506,11 +506,11 @@ extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float
                "pdes_darcy_loss_bwd: tile kernel forced but %dx%d does not qualify", H, W);
   if (g_loss_impl != 1 && can_tile) {
     const size_t smem = 128 + (size_t)H * W * 4 * 13;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
       PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set = true;
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_smem = smem;
     }
     int grid = sm_count();
     if (grid > B) grid = B;

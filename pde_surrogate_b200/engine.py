@@ -1,0 +1,64 @@
+"""Whole training step on device-resident data (the loop body of
+train_codec_mixed_residual.py:224-240 without the host round trips): zero the flat gradient
+bucket, DenseED forward, fused Darcy loss forward+backward, DenseED backward (wgrad writes into
+the flat bucket), optional NCCL all-reduce of the bucket over NVLink, fused flat Adam.
+One process per GPU; data parallel = shard the minibatch, average gradients.
+"""
+import torch
+
+from . import _lib
+from . import darcy as _darcy
+
+
+class TrainStep(object):
+    def __init__(self, model, weight_bound=10.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+                 process_group=None, world_size=1):
+        self.model = model
+        self.flat, self.gflat = model.flat_parameters()
+        if not self.flat.is_cuda:
+            raise RuntimeError("TrainStep needs the model on a CUDA device")
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.gw = torch.tensor([1.0, 1.0, weight_bound, weight_bound], device=self.flat.device)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.pg, self.world = process_group, world_size
+        self.steps = 0
+        self.kernel_launches = 0
+        self.l4 = torch.zeros(4, device=self.flat.device)
+        model.train()
+        for p, v in zip(model._params, model._grad_views):
+            p.grad = v
+
+    def broadcast_parameters(self):
+        """Rank 0's parameters and BatchNorm buffers to every rank (start of DDP training)."""
+        import torch.distributed as dist
+        dist.broadcast(self.flat, 0, group=self.pg)
+        dist.broadcast(self.model._flat_running, 0, group=self.pg)
+
+    def step(self, K, lr=None):
+        """One optimisation step on the (B,1,H,W) device batch K; returns the 0-d device loss."""
+        L = _lib.lib()
+        ex = self.model._ex
+        st = _lib.stream_ptr()
+        B, _, H, W = K.shape
+        self.gflat.zero_()
+        out = ex.forward(K, True)
+        n = L.pdes_densenet_last_launches(ex.handle.h)
+        _lib.check(L.pdes_darcy_loss_fwd(_lib.ptr(K), _lib.ptr(out), B, H, W, 1, _lib.ptr(self.l4),
+                                         _lib.ptr(_darcy._workspace(K.device)), st), "pdes_darcy_loss_fwd")
+        dout = torch.empty_like(out)
+        _lib.check(L.pdes_darcy_loss_bwd(_lib.ptr(K), _lib.ptr(out), _lib.ptr(self.gw), B, H, W, 1,
+                                         _lib.ptr(dout), st), "pdes_darcy_loss_bwd")
+        ex.backward(dout)
+        n += L.pdes_densenet_last_launches(ex.handle.h) + 2
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.gflat, group=self.pg)
+        self.steps += 1
+        _lib.check(L.pdes_adam_step(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m),
+                                    _lib.ptr(self.v), self.flat.numel(), float(self.lr if lr is None else lr),
+                                    self.betas[0], self.betas[1], self.eps, self.wd, 1.0 / self.world,
+                                    self.steps, st), "pdes_adam_step")
+        self.model._flat_nbt.add_(1)
+        self.kernel_launches = n + 1
+        return torch.dot(self.l4, self.gw)

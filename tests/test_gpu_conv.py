@@ -48,7 +48,7 @@ def test_conv_fwd_dgrad_wgrad(case):
     g = torch.Generator().manual_seed(hash(case) % 1000)
     ld_in = (Cin + 3) // 4 * 4 + 4
     coff = 8
-    ld_out = coff + (Cout + 3) // 4 * 4
+    ld_out = coff + (Cout + 3) // 4 * 4 + 4
     x = torch.randn(B, H, H, ld_in, generator=g)
     w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
     scale = torch.rand(Cin, generator=g) + 0.5
