@@ -72,7 +72,8 @@ int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int H, int W, i
 int pdes_darcy_loss_bwd(const float* K, const float* out, const float* gw4, int B, int H,
                         int W, int use_tb, float* dout, void* stream);
 /* Selects the implementation of the two calls above: 0 = auto, 1 = force the generic
- * (any H,W) kernels, 2 = force the whole-image-in-shared-memory TMA kernels. Test hook. */
+ * (any H,W) kernels, 2 / 3 = force the whole-image-in-shared-memory TMA kernels with 256 / 512
+ * threads per CTA. Test hook. */
 int pdes_darcy_loss_set_impl(int impl);
 
 /* ------------------------------------------------------------------------------------

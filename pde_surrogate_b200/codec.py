@@ -12,6 +12,7 @@ gradient buffer) so that the kernels see stable pointers, wgrad writes straight 
 that data-parallel training all-reduces, and a fused Adam can walk one array.
 """
 import math
+import os
 from collections import OrderedDict
 from ctypes import byref, c_int32, c_int64, c_void_p, create_string_buffer
 
@@ -132,6 +133,7 @@ class CudaExecutor(object):
         self.handle = None
         self.ws = None
         self.bound = None
+        self.applied_impl = None
 
     def _ensure(self, x):
         m = self.m
@@ -151,6 +153,11 @@ class CudaExecutor(object):
         if self.handle is None or B > self.handle.max_batch:
             self.handle = _NetHandle(c, max(B, 1))
             self.ws, self.bound = None, None
+            self.applied_impl = None
+        if self.applied_impl != m.conv_impl:
+            _lib.check(_lib.lib().pdes_densenet_set_conv_impl(self.handle.h, int(m.conv_impl)),
+                       "pdes_densenet_set_conv_impl")
+            self.applied_impl = m.conv_impl
         key = (m._flat.data_ptr(), m._flat_grad.data_ptr(), m._flat_running.data_ptr(), str(x.device))
         if self.bound != key:
             L = _lib.lib()
@@ -275,6 +282,9 @@ class DenseED(nn.Module):
             parent.add_module(path[-1], leaf)
             leaves[key] = leaf
         self._flat = self._flat_grad = self._flat_running = self._flat_nbt = None
+        # convolution implementation: 0 = tcgen05 3xTF32 where supported (default), 1 = SIMT fp32
+        # everywhere, 2 = tcgen05 single-pass TF32 (fails the 1e-4 parity bar; benchmarking only)
+        self.conv_impl = int(os.environ.get("PDES_CONV_IMPL", "0"))
         self._ex = _executor_factory(self)
         self._flatten()
         print('# params {}, # conv layers {}'.format(*self.model_size))

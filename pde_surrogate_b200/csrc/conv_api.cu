@@ -3,6 +3,7 @@
 // allocate: a stream-ordered scratch buffer for the packed weights.
 #include <string.h>
 #include "conv.cuh"
+#include "conv_tc.cuh"
 
 using namespace pdes;
 
@@ -57,6 +58,46 @@ int pack(const pdes_conv_desc* d, const float* w, cudaStream_t st, Packed& pk) {
   PDES_CUDA(cudaStreamSynchronize(st));  // h is a stack variable
   return launch_pack_weights(pk.tab, 1, (int)(nf + nb), st);
 }
+// tcgen05 path for the unit-test entry points: pack filter tiles into scratch, then launch.
+int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int transpose, cudaStream_t st) {
+  const int Cin_k = transpose ? d->Cout : d->Cin;
+  const int N = rup(transpose ? d->Cin : d->Cout, 16);
+  PDES_REQUIRE(tc_supported(d->KH, d->stride, Cin_k, N), PDES_ERR_UNSUPPORTED,
+               "tensor-core path does not support this convolution (K=%d stride=%d N=%d)", d->KH,
+               d->stride, N);
+  TcPlan p;
+  tc_plan(d->KH, Cin_k, N, &p);
+  float* buf = nullptr;
+  PDES_CUDA(cudaMallocAsync((void**)&buf, p.pack_floats * sizeof(float) + 256, st));
+  TcPackDesc h;
+  h.w = w;
+  h.dst = buf;
+  h.Cout = d->Cout;
+  h.Cin = d->Cin;
+  h.KS = d->KH;
+  h.N = N;
+  h.KC = p.KC;
+  h.nchunks = p.nchunks;
+  h.transpose = transpose;
+  TcPackDesc* tab = reinterpret_cast<TcPackDesc*>(buf + p.pack_floats);
+  PDES_CUDA(cudaMemcpyAsync(tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  PDES_CUDA(cudaStreamSynchronize(st));
+  int rc = launch_pack_tc(tab, 1, p.pack_floats, st);
+  if (rc == PDES_OK) {
+    TcConvArgs t;
+    t.c = a;
+    t.wtc = buf;
+    t.N = N;
+    t.KC = p.KC;
+    t.NB = p.NB;
+    t.nchunks = p.nchunks;
+    t.S = p.S;
+    t.prec = 0;
+    rc = launch_conv_tc(t, st);
+  }
+  cudaFreeAsync(buf, st);
+  return rc;
+}
 }  // namespace
 
 extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const float* w,
@@ -66,7 +107,7 @@ extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const fl
   if (rc) return rc;
   PDES_REQUIRE(x && w && y, PDES_ERR_INVALID, "pdes_conv2d_fwd: null pointer");
   PDES_REQUIRE(!d->bn_relu || (scale && shift), PDES_ERR_INVALID, "pdes_conv2d_fwd: bn_relu needs scale/shift");
-  PDES_REQUIRE(impl == 0 || impl == 1, PDES_ERR_UNSUPPORTED, "pdes_conv2d_fwd: impl %d not available", impl);
+  PDES_REQUIRE(impl >= 0 && impl <= 2, PDES_ERR_UNSUPPORTED, "pdes_conv2d_fwd: impl %d not available", impl);
   cudaStream_t st = (cudaStream_t)stream;
   Packed pk;
   rc = pack(d, w, st, pk);
@@ -98,7 +139,10 @@ extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const fl
   a.coff = d->c_off_out;
   a.o_sum = ch_sum;
   a.o_sumsq = ch_sumsq;
-  rc = launch_conv_simt(a, st);
+  if (impl == 2)
+    rc = run_tc(a, d, w, 0, st);
+  else
+    rc = launch_conv_simt(a, st);
   cudaFreeAsync(pk.buf, st);
   return rc;
 }
@@ -108,7 +152,7 @@ extern "C" int pdes_conv2d_dgrad(const pdes_conv_desc* d, const float* dy, const
   int rc = check_desc(d, "pdes_conv2d_dgrad");
   if (rc) return rc;
   PDES_REQUIRE(dy && w && da, PDES_ERR_INVALID, "pdes_conv2d_dgrad: null pointer");
-  PDES_REQUIRE(impl == 0 || impl == 1, PDES_ERR_UNSUPPORTED, "pdes_conv2d_dgrad: impl %d not available", impl);
+  PDES_REQUIRE(impl >= 0 && impl <= 2, PDES_ERR_UNSUPPORTED, "pdes_conv2d_dgrad: impl %d not available", impl);
   PDES_REQUIRE(!d->out_nchw, PDES_ERR_UNSUPPORTED, "pdes_conv2d_dgrad: NHWC dy only");
   cudaStream_t st = (cudaStream_t)stream;
   Packed pk;
@@ -137,7 +181,10 @@ extern "C" int pdes_conv2d_dgrad(const pdes_conv_desc* d, const float* dy, const
   a.y = da;
   a.ldy = d->Cin;
   a.coff = 0;
-  rc = launch_conv_simt(a, st);
+  if (impl == 2)
+    rc = run_tc(a, d, w, 1, st);
+  else
+    rc = launch_conv_simt(a, st);
   cudaFreeAsync(pk.buf, st);
   return rc;
 }

@@ -18,6 +18,7 @@
 #include <vector>
 #include <string.h>
 #include "conv.cuh"
+#include "conv_tc.cuh"
 
 namespace pdes {
 
@@ -38,6 +39,11 @@ struct Layer {
   size_t bsum;    // double offset
   int CinP, CoP, CoutPb, CiPb;
   bool last_consumer;
+  // tcgen05 path
+  bool tc_fwd, tc_bwd;
+  TcPlan pf, pb;     // tiling of the forward / dgrad GEMM
+  int Nf, Nb;        // padded GEMM-N (Cout / Cin rounded up to 16)
+  size_t wtf, wtb;   // float offsets of the packed filter tiles
 };
 
 struct ParamInfo {
@@ -61,6 +67,10 @@ struct pdes_net {
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
   size_t xin = 0;  // float offset: NCHW copy of the last training input (needed by In_conv's wgrad)
   int n_bn = 0, maxC = 0, max_pack = 0;
+  int n_tc = 0;
+  size_t max_tc_pack = 0;
+  int prec = 0;
+  int tc_mask = 3;  // bit 0: forward on tcgen05, bit 1: dgrad on tcgen05
   // bound
   float* p = nullptr;
   float* g = nullptr;
@@ -118,6 +128,12 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.CoutPb = rup(Cout, 4);
   L.CiPb = rup(Cin, 16);
   L.last_consumer = false;
+  L.tc_fwd = L.tc_bwd = false;
+  L.Nf = rup(Cout, 16);
+  L.Nb = rup(Cin, 16);
+  L.wtf = L.wtb = 0;
+  memset(&L.pf, 0, sizeof(L.pf));
+  memset(&L.pb, 0, sizeof(L.pb));
   n->layers.push_back(L);
 }
 
@@ -247,6 +263,28 @@ int build(pdes_net* n) {
     const int pk = (int)(taps * L.CinP * L.CoP + taps * L.CoutPb * L.CiPb);
     if (pk > n->max_pack) n->max_pack = pk;
   }
+  for (auto& L : n->layers) {
+    if (L.kind == 0 || L.out_buf < 0 || L.in_buf < 0) continue;
+    const Buf& ib = n->bufs[L.in_buf];
+    const Buf& ob = n->bufs[L.out_buf];
+    const bool aligned = (ib.ld % 4 == 0) && (ob.ld % 4 == 0) && (L.coff % 4 == 0);
+    if (aligned && tc_supported(L.KS, L.stride, L.Cin, L.Nf)) {
+      L.tc_fwd = true;
+      tc_plan(L.KS, L.Cin, L.Nf, &L.pf);
+      L.wtf = f;
+      f += L.pf.pack_floats;
+      n->n_tc++;
+      if (L.pf.pack_floats > n->max_tc_pack) n->max_tc_pack = L.pf.pack_floats;
+    }
+    if (aligned && tc_supported(L.KS, L.stride, L.Cout, L.Nb)) {
+      L.tc_bwd = true;
+      tc_plan(L.KS, L.Cout, L.Nb, &L.pb);
+      L.wtb = f;
+      f += L.pb.pack_floats;
+      n->n_tc++;
+      if (L.pb.pack_floats > n->max_tc_pack) n->max_tc_pack = L.pb.pack_floats;
+    }
+  }
   n->xin = f;
   f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
   n->ws_floats = f;
@@ -263,7 +301,7 @@ int build(pdes_net* n) {
   n->off_doubles = (n->ws_floats * sizeof(float) + 255) & ~(size_t)255;
   n->off_tables = (n->off_doubles + n->ws_doubles * sizeof(double) + 255) & ~(size_t)255;
   n->ws_bytes = n->off_tables + sizeof(PackDesc) * n->layers.size() +
-                sizeof(BnLayerDesc) * (size_t)n->n_bn + 256;
+                sizeof(BnLayerDesc) * (size_t)n->n_bn + sizeof(TcPackDesc) * (size_t)n->n_tc + 256;
   return PDES_OK;
 }
 
@@ -274,6 +312,11 @@ inline double* wsd(const pdes_net* n, size_t off) {
 inline PackDesc* pack_table(const pdes_net* n) { return reinterpret_cast<PackDesc*>(n->ws + n->off_tables); }
 inline BnLayerDesc* bn_table(const pdes_net* n) {
   return reinterpret_cast<BnLayerDesc*>(n->ws + n->off_tables + sizeof(PackDesc) * n->layers.size());
+}
+
+inline TcPackDesc* tc_table(const pdes_net* n) {
+  return reinterpret_cast<TcPackDesc*>(n->ws + n->off_tables + sizeof(PackDesc) * n->layers.size() +
+                                       sizeof(BnLayerDesc) * (size_t)n->n_bn);
 }
 
 BnSrc bn_src(const pdes_net* n, const Layer& L, int B, bool training) {
@@ -398,6 +441,25 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       bt.push_back(b);
     }
   }
+  std::vector<TcPackDesc> tt;
+  for (const auto& L : n->layers) {
+    for (int dir = 0; dir < 2; ++dir) {
+      if (!(dir == 0 ? L.tc_fwd : L.tc_bwd)) continue;
+      TcPackDesc d;
+      d.w = n->p + L.w_off;
+      d.dst = wsf(n, dir == 0 ? L.wtf : L.wtb);
+      d.Cout = L.Cout;
+      d.Cin = L.Cin;
+      d.KS = L.KS;
+      d.N = dir == 0 ? L.Nf : L.Nb;
+      d.KC = dir == 0 ? L.pf.KC : L.pb.KC;
+      d.nchunks = dir == 0 ? L.pf.nchunks : L.pb.nchunks;
+      d.transpose = dir;
+      tt.push_back(d);
+    }
+  }
+  if (!tt.empty())
+    PDES_CUDA(cudaMemcpy(tc_table(n), tt.data(), sizeof(TcPackDesc) * tt.size(), cudaMemcpyHostToDevice));
   PDES_CUDA(cudaMemcpy(pack_table(n), pt.data(), sizeof(PackDesc) * pt.size(), cudaMemcpyHostToDevice));
   if (!bt.empty())
     PDES_CUDA(cudaMemcpy(bn_table(n), bt.data(), sizeof(BnLayerDesc) * bt.size(), cudaMemcpyHostToDevice));
@@ -405,8 +467,12 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
 }
 
 extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
-  PDES_REQUIRE(n && impl >= 0 && impl <= 1, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..1");
-  n->conv_impl = impl;
+  // 0 = tcgen05 (3xTF32) where supported, 1 = SIMT fp32 everywhere, 2 = tcgen05 single-pass TF32
+  // 3 / 4 = tcgen05 for the forward only / the dgrad only (diagnostics)
+  PDES_REQUIRE(n && impl >= 0 && impl <= 4, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..4");
+  n->conv_impl = impl == 1 ? 1 : 0;
+  n->prec = impl == 2 ? 1 : 0;
+  n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : 3);
   return PDES_OK;
 }
 
@@ -439,6 +505,11 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   int rc = launch_pack_weights(pack_table(n), (int)n->layers.size(), n->max_pack, st);
   if (rc) return rc;
   n->launches++;
+  if (n->conv_impl == 0 && n->n_tc > 0) {
+    rc = launch_pack_tc(tc_table(n), n->n_tc, n->max_tc_pack, st);
+    if (rc) return rc;
+    n->launches++;
+  }
   if (tr) {
     PDES_CUDA(cudaMemcpyAsync(wsf(n, n->xin), x,
                               sizeof(float) * (size_t)B * n->cfg.in_channels * n->cfg.imsize * n->cfg.imsize,
@@ -489,7 +560,20 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
         a.o_sumsq = wsd(n, ob.stat) + ob.C + L.coff;
       }
     }
-    rc = launch_conv_simt(a, st);
+    if (n->conv_impl == 0 && L.tc_fwd && (n->tc_mask & 1)) {
+      TcConvArgs t;
+      t.c = a;
+      t.wtc = wsf(n, L.wtf);
+      t.N = L.Nf;
+      t.KC = L.pf.KC;
+      t.NB = L.pf.NB;
+      t.nchunks = L.pf.nchunks;
+      t.S = L.pf.S;
+      t.prec = n->prec;
+      rc = launch_conv_tc(t, st);
+    } else {
+      rc = launch_conv_simt(a, st);
+    }
     if (rc) return rc;
     n->launches++;
   }
@@ -616,7 +700,20 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
       a.ldG = ib.ld;
       a.g_accum = L.last_consumer ? 0 : 1;
       a.bsum = wsd(n, L.bsum);
-      rc = launch_conv_simt(a, st);
+      if (n->conv_impl == 0 && L.tc_bwd && (n->tc_mask & 2)) {
+        TcConvArgs t;
+        t.c = a;
+        t.wtc = wsf(n, L.wtb);
+        t.N = L.Nb;
+        t.KC = L.pb.KC;
+        t.NB = L.pb.NB;
+        t.nchunks = L.pb.nchunks;
+        t.S = L.pb.S;
+        t.prec = n->prec;
+        rc = launch_conv_tc(t, st);
+      } else {
+        rc = launch_conv_simt(a, st);
+      }
       if (rc) return rc;
       n->launches++;
     }

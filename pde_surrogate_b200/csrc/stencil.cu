@@ -20,7 +20,7 @@ namespace {
 using namespace stencil;
 
 constexpr int kTileThreads = 256;
-int g_loss_impl = 0;  // 0 auto, 1 generic, 2 tile
+int g_loss_impl = 0;  // 0 auto, 1 generic, 2 tile (256 threads), 3 tile (512 threads)
 
 struct LossWs {
   double acc[4];
@@ -283,7 +283,8 @@ darcy_bwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ 
 // tile kernels: whole sample in shared memory, TMA-fed, persistent over samples
 // ---------------------------------------------------------------------------------------
 // smem: [mbar x2 (16 B)] pad to 128 | stage0: K,u,s1,s2 | stage1: K,u,s1,s2 | (bwd) P1,P2,P3,Q1,Q2
-__global__ void __launch_bounds__(kTileThreads, 1)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out, int B, int H,
                       int W, int use_tb, float* loss4, LossWs* ws, LossNorm nrm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -321,7 +322,7 @@ darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
     mbar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
     const float* st = stage_base + (size_t)s * 4 * HW;
     const FwdPartial p = fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W,
-                                   threadIdx.x, kTileThreads, true, use_tb != 0, 0.f, 0.f,
+                                   threadIdx.x, NT, true, use_tb != 0, 0.f, 0.f,
                                    nullptr, nullptr, nullptr, nullptr, nullptr);
     part.c += p.c;
     part.d += p.d;
@@ -334,7 +335,8 @@ darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
   loss_block_reduce_and_finish(part, ws, loss4, nrm);
 }
 
-__global__ void __launch_bounds__(kTileThreads, 1)
+template <int NT>
+__global__ void __launch_bounds__(NT, 1)
 darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out,
                       const float* __restrict__ gw4, int B, int H, int W, int use_tb, float* dout,
                       BwdCoef cf) {
@@ -380,11 +382,11 @@ darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
     float* Q1 = scratch + 3 * HW;
     float* Q2 = scratch + 4 * HW;
     (void)fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W, threadIdx.x,
-                    kTileThreads, true, use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
+                    NT, true, use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
     __syncthreads();  // residual planes complete; nobody reads neighbours of u/s1/s2 any more
     // gradient planes overwrite u, s1, s2 in place (own-position reads only)
     bwd_strip_pass2(P1, P2, P3, Q1, Q2, st + HW, st + 3 * HW, st + HW, st + 2 * HW, st + 3 * HW, H,
-                    W, threadIdx.x, kTileThreads, true, cdir, cneu);
+                    W, threadIdx.x, NT, true, cdir, cneu);
     fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -402,7 +404,7 @@ darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
 
 bool tile_ok(int H, int W, const void* a, const void* b, bool bwd) {
   if (W % 4 != 0 || H < 3 || W < 4) return false;
-  if (kTileThreads / (W / 4) < 1) return false;
+  if (W / 4 > 256) return false;
   if (((uintptr_t)a & 15u) != 0 || ((uintptr_t)b & 15u) != 0) return false;
   const size_t need = 128 + (size_t)H * W * 4 * (bwd ? 13 : 8);
   return need + 2048 <= 227 * 1024;
@@ -438,7 +440,7 @@ extern "C" int pdes_sobel_grad(const float* img, float* out, int64_t n_img, int 
 extern "C" size_t pdes_darcy_loss_workspace_bytes(void) { return sizeof(LossWs); }
 
 extern "C" int pdes_darcy_loss_set_impl(int impl) {
-  PDES_REQUIRE(impl >= 0 && impl <= 2, PDES_ERR_INVALID, "pdes_darcy_loss_set_impl: impl in 0..2");
+  PDES_REQUIRE(impl >= 0 && impl <= 3, PDES_ERR_INVALID, "pdes_darcy_loss_set_impl: impl in 0..3");
   g_loss_impl = impl;
   return PDES_OK;
 }
@@ -463,20 +465,25 @@ extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int 
   nrm.inv_dir = 1.0 / ((double)B * H);
   nrm.inv_neu = 1.0 / ((double)B * 2 * W);
   const bool can_tile = tile_ok(H, W, K ? (const void*)K : (const void*)out, out, false);
-  PDES_REQUIRE(g_loss_impl != 2 || can_tile, PDES_ERR_UNSUPPORTED,
+  PDES_REQUIRE(g_loss_impl < 2 || can_tile, PDES_ERR_UNSUPPORTED,
                "pdes_darcy_loss_fwd: tile kernel forced but %dx%d does not qualify", H, W);
   if (g_loss_impl != 1 && can_tile) {
     const size_t smem = 128 + (size_t)H * W * 4 * 8;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel,
+      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel<256>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel<512>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
     int grid = sm_count();
     if (grid > B) grid = B;
-    darcy_fwd_tile_kernel<<<grid, kTileThreads, smem, st>>>(K, out, B, H, W, use_tb, loss4,
-                                                           (LossWs*)ws, nrm);
+    const bool big = g_loss_impl == 3 || (g_loss_impl == 0 && H * W >= 2048);
+    if (big)
+      darcy_fwd_tile_kernel<512><<<grid, 512, smem, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm);
+    else
+      darcy_fwd_tile_kernel<256><<<grid, 256, smem, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm);
   } else {
     const int64_t total = (int64_t)B * H * W;
     int blocks = (int)((total + 255) / 256);
@@ -502,19 +509,25 @@ extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float
   cf.n_neu = (float)(2.0 / ((double)B * 2 * W));
   const bool can_tile = tile_ok(H, W, K ? (const void*)K : (const void*)out, out, true) &&
                         (((uintptr_t)dout & 15u) == 0);
-  PDES_REQUIRE(g_loss_impl != 2 || can_tile, PDES_ERR_UNSUPPORTED,
+  PDES_REQUIRE(g_loss_impl < 2 || can_tile, PDES_ERR_UNSUPPORTED,
                "pdes_darcy_loss_bwd: tile kernel forced but %dx%d does not qualify", H, W);
   if (g_loss_impl != 1 && can_tile) {
     const size_t smem = 128 + (size_t)H * W * 4 * 13;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel,
+      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel<256>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel<512>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_smem = smem;
     }
     int grid = sm_count();
     if (grid > B) grid = B;
-    darcy_bwd_tile_kernel<<<grid, kTileThreads, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
+    const bool big = g_loss_impl == 3 || (g_loss_impl == 0 && H * W >= 2048);
+    if (big)
+      darcy_bwd_tile_kernel<512><<<grid, 512, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
+    else
+      darcy_bwd_tile_kernel<256><<<grid, 256, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
   } else {
     const int64_t total = (int64_t)B * H * W;
     PDES_CUDA(cudaMemsetAsync(dout, 0, (size_t)total * 3 * sizeof(float), st));

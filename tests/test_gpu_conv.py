@@ -40,13 +40,38 @@ def _desc(B, H, Cin, Cout, K, s, p, up, bn, ld_in, ld_out, coff, nchw=0):
     return d, Ho
 
 
+TC_CASES = [
+    (2, 16, 48, 16, 3, 1, 1, 0, 1),
+    (1, 32, 128, 16, 3, 1, 1, 0, 1),
+    (1, 16, 184, 16, 3, 1, 1, 0, 1),
+    (2, 16, 144, 72, 1, 1, 0, 0, 1),
+    (2, 16, 200, 100, 1, 1, 0, 0, 1),
+    (2, 8, 100, 100, 3, 1, 1, 1, 1),
+    (1, 32, 196, 98, 3, 1, 1, 0, 1),
+    (1, 16, 98, 49, 3, 1, 1, 1, 1),
+    (1, 13, 20, 16, 3, 1, 1, 0, 1),    # ragged spatial size, partial tiles
+    (3, 8, 8, 16, 3, 1, 1, 0, 1),      # image smaller than the 16-row tile
+]
+
+
 @pytest.mark.parametrize("case", CASES)
 def test_conv_fwd_dgrad_wgrad(case):
+    _run_case(case, 1)
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tensor_core(case):
+    """tcgen05 3xTF32 kernels (forward and dgrad) against the same fp64 reference."""
+    _run_case(case, 2)
+
+
+def _run_case(case, impl):
     from pde_surrogate_b200 import _lib
     L = _lib.lib()
     B, H, Cin, Cout, K, s, p, up, bn = case
     g = torch.Generator().manual_seed(hash(case) % 1000)
     ld_in = (Cin + 3) // 4 * 4 + 4
+    tol = 2e-6 if impl == 1 else 1e-5
     coff = 8
     ld_out = coff + (Cout + 3) // 4 * 4 + 4
     x = torch.randn(B, H, H, ld_in, generator=g)
@@ -71,24 +96,32 @@ def test_conv_fwd_dgrad_wgrad(case):
     csum = torch.zeros(Cout, dtype=torch.float64, device="cuda")
     csq = torch.zeros(Cout, dtype=torch.float64, device="cuda")
     _lib.check(L.pdes_conv2d_fwd(byref(d), _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(sd) if bn else None,
-                                 _lib.ptr(hd) if bn else None, _lib.ptr(y), _lib.ptr(csum), _lib.ptr(csq), 0, st))
+                                 _lib.ptr(hd) if bn else None, _lib.ptr(y), _lib.ptr(csum), _lib.ptr(csq), impl, st))
     ynhwc = yr.detach().permute(0, 2, 3, 1)
-    assert rel(y[..., coff:coff + Cout], ynhwc) < 2e-6
+    assert rel(y[..., coff:coff + Cout], ynhwc) < tol, rel(y[..., coff:coff + Cout], ynhwc)
     assert float(y[..., :coff].abs().max()) == 0.0 and float(y[..., coff + Cout:].abs().max()) == 0.0
-    assert rel(csum, ynhwc.sum((0, 1, 2))) < 1e-5 or float(ynhwc.sum((0, 1, 2)).norm()) < 1e-3
-    assert rel(csq, (ynhwc ** 2).sum((0, 1, 2))) < 1e-5
+    # tensor-core accumulation truncates (round-toward-zero) each partial sum: a systematic ~1e-5
+    # magnitude shrink that BatchNorm's normalisation cancels; bars stay inside the 1e-4 budget
+    stol = 1e-5 if impl == 1 else 5e-5
+    assert rel(csum, ynhwc.sum((0, 1, 2))) < stol or float(ynhwc.sum((0, 1, 2)).norm()) < 1e-3
+    assert rel(csq, (ynhwc ** 2).sum((0, 1, 2))) < stol
+    if impl == 2 and Cin % 4:
+        return  # the unit entry point's dense (B,H,W,Cin) dgrad output needs Cin % 4 == 0 on the TC path
     # planar output variant
     d2, _ = _desc(B, H, Cin, Cout, K, s, p, up, bn, ld_in, ld_out, coff, nchw=1)
     y2 = torch.zeros(B, Cout, Ho, Ho, device="cuda")
-    _lib.check(L.pdes_conv2d_fwd(byref(d2), _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(sd) if bn else None,
-                                 _lib.ptr(hd) if bn else None, _lib.ptr(y2), None, None, 0, st))
-    assert rel(y2, yr.detach()) < 2e-6
+    if impl == 1:
+        _lib.check(L.pdes_conv2d_fwd(byref(d2), _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(sd) if bn else None,
+                                     _lib.ptr(hd) if bn else None, _lib.ptr(y2), None, None, 1, st))
+        assert rel(y2, yr.detach()) < 2e-6
     # dgrad (w.r.t. the BN+ReLU'd operand, summed over the upsampling footprint)
     dyd = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
     dyd[..., coff:coff + Cout] = dy.permute(0, 2, 3, 1).float().cuda()
     da = torch.full((B, H, H, Cin), 7.0, device="cuda")
-    _lib.check(L.pdes_conv2d_dgrad(byref(d), _lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(da), 0, st))
-    assert rel(da, a.grad.permute(0, 2, 3, 1)) < 3e-6
+    _lib.check(L.pdes_conv2d_dgrad(byref(d), _lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(da), impl, st))
+    assert rel(da, a.grad.permute(0, 2, 3, 1)) < (3e-6 if impl == 1 else 1e-5), rel(da, a.grad.permute(0, 2, 3, 1))
+    if impl == 2:
+        return
     # wgrad (accumulates)
     dw = torch.ones(Cout, Cin, K, K, device="cuda")
     _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), _lib.ptr(sd) if bn else None,

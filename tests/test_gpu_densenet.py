@@ -41,12 +41,14 @@ def _model(g):
     return model, K, cfg
 
 
+@pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("name", CASES)
-def test_train_step_matches_reference(golden_dir, name):
+def test_train_step_matches_reference(golden_dir, name, impl):
     from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
     from utils.image_gradient import SobelFilter
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     model, K, cfg = _model(g)
+    model.conv_impl = impl  # 0: tcgen05 3xTF32 where supported, 1: SIMT fp32 everywhere
     assert tuple(model.model_size) == tuple(int(v) for v in g["model_size"])
     sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
     # eval forward with the given running statistics
