@@ -196,7 +196,7 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   if (rc) return rc;
   PDES_REQUIRE(x && dy && dw, PDES_ERR_INVALID, "pdes_conv2d_wgrad: null pointer");
   PDES_REQUIRE(!d->bn_relu || (scale && shift), PDES_ERR_INVALID, "pdes_conv2d_wgrad: bn_relu needs scale/shift");
-  PDES_REQUIRE(impl == 0 || impl == 1, PDES_ERR_UNSUPPORTED, "pdes_conv2d_wgrad: impl %d not available", impl);
+  PDES_REQUIRE(impl >= 0 && impl <= 2, PDES_ERR_UNSUPPORTED, "pdes_conv2d_wgrad: impl %d not available", impl);
   WgradArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x;
@@ -219,5 +219,34 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   a.Ho = d->Hout;
   a.Wo = d->Wout;
   a.dw = dw;
-  return launch_wgrad_simt(a, (cudaStream_t)stream);
+  if (impl != 2) return launch_wgrad_simt(a, (cudaStream_t)stream);
+  // tcgen05 path: zeroed staging buffer, kernel, fold into OIHW
+  cudaStream_t st = (cudaStream_t)stream;
+  PDES_REQUIRE(wgrad_tc_supported(d->KH, d->stride) && !d->out_nchw, PDES_ERR_UNSUPPORTED,
+               "tensor-core wgrad does not support this convolution");
+  TcWgradArgs tw;
+  tw.w = a;
+  wgrad_tc_dims(d->Cin, d->Cout, &tw.ci_pad, &tw.co_pad);
+  const size_t nf = (size_t)d->KH * d->KW * tw.ci_pad * tw.co_pad;
+  float* buf = nullptr;
+  PDES_CUDA(cudaMallocAsync((void**)&buf, nf * sizeof(float) + 256, st));
+  PDES_CUDA(cudaMemsetAsync(buf, 0, nf * sizeof(float), st));
+  tw.dwp = buf;
+  rc = launch_wgrad_tc(tw, st);
+  if (rc == PDES_OK) {
+    TcWgradUnpack u;
+    u.dw = dw;
+    u.dwp = buf;
+    u.Cout = d->Cout;
+    u.Cin = d->Cin;
+    u.KS = d->KH;
+    u.ci_pad = tw.ci_pad;
+    u.co_pad = tw.co_pad;
+    TcWgradUnpack* tab = reinterpret_cast<TcWgradUnpack*>(buf + nf);
+    PDES_CUDA(cudaMemcpyAsync(tab, &u, sizeof(u), cudaMemcpyHostToDevice, st));
+    PDES_CUDA(cudaStreamSynchronize(st));
+    rc = launch_wgrad_unpack(tab, 1, d->Cout * d->Cin * d->KH * d->KW, st);
+  }
+  cudaFreeAsync(buf, st);
+  return rc;
 }

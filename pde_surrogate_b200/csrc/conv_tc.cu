@@ -19,109 +19,15 @@
 // ReLU-mask + BatchNorm backward).
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "tc_common.cuh"
 
 namespace pdes {
 namespace {
 
+using namespace tc;
+
 constexpr int kTcThreads = 192;
 constexpr int kTH = 16, kTW = 8;  // pixel tile (rows x cols) = 128 GEMM rows
-
-// ---- tcgen05 / TMEM PTX wrappers -----------------------------------------------------------
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                   smem_u32(smem_dst)),
-               "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish() {
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// UMMA shared-memory descriptor, SWIZZLE_NONE, K-major canonical layout
-//   ((8,m),(4,2)) : ((16 B, SBO), (4 B, LBO))   [tf32: 4 elements per 16-byte core-matrix row]
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
-  return d;
-}
-// instruction descriptor: D fp32, A/B tf32, both K-major, M x N
-__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  lo = v - hi;
-}
-
-__device__ __forceinline__ void bn_consts_tc(const BnSrc& s, int c, float& scale, float& shift,
-                                             float& mean, float& invstd) {
-  if (s.scale != nullptr) {
-    scale = s.scale[c];
-    shift = s.shift[c];
-    mean = 0.f;
-    invstd = 1.f;
-    return;
-  }
-  double m, var;
-  if (s.use_running) {
-    m = (double)s.run_mean[c];
-    var = (double)s.run_var[c];
-  } else {
-    m = s.sum[c] * s.inv_count;
-    var = s.sumsq[c] * s.inv_count - m * m;
-    if (var < 0.0) var = 0.0;
-  }
-  const double is = 1.0 / sqrt(var + (double)s.eps);
-  invstd = (float)is;
-  mean = (float)m;
-  scale = s.gamma[c] * invstd;
-  shift = s.beta[c] - mean * scale;
-}
 
 // ---------------------------------------------------------------------------------------
 // main kernel
@@ -288,33 +194,51 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(TcConvArgs t) {
       mbar_wait(&a_empty[sa], (uint32_t)(((ch >> 1) & 1) ^ 1));
       unsigned char* As = A_s + (size_t)sa * a_stage_bytes;
       const int c0 = ch * KC;
-      for (int i = tt; i < HP * kq; i += 128) {
-        const int q = i % kq, hp = i / kq;
-        const int hy = hp / HWp, hx = hp - hy * HWp;
-        const int vy = iy0 + hy, vx = ix0 + hx;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (vy >= 0 && vy < Hv && vx >= 0 && vx < Wv) {
-          const int sy = a.in_mode == IN_DIRECT ? vy : (vy >> 1);
-          const int sx = a.in_mode == IN_DIRECT ? vx : (vx >> 1);
-          const int c = c0 + 4 * q;
-          const float* p = a.x + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
-          if (c + 3 < a.Cin) {
-            const float4 f = *reinterpret_cast<const float4*>(p);
-            v[0] = f.x;
-            v[1] = f.y;
-            v[2] = f.z;
-            v[3] = f.w;
-          } else {
+      // all global loads of the chunk are issued before any is consumed (memory-level
+      // parallelism: one L2/HBM latency per chunk instead of one per item)
+      constexpr int MAXI = (HP * 8 + 127) / 128;
+      float4 raw[MAXI];
+      int meta[MAXI];  // (hp << 8) | (q << 1) | in-image ; -1 = no item
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (c + k < a.Cin) v[k] = p[k];
-          }
-          if (a.pro) {
+      for (int j = 0; j < MAXI; ++j) {
+        const int i = tt + j * 128;
+        raw[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        meta[j] = -1;
+        if (i < HP * kq) {
+          const int q = i % kq, hp = i / kq;
+          const int hy = hp / HWp, hx = hp - hy * HWp;
+          const int vy = iy0 + hy, vx = ix0 + hx;
+          const bool in = vy >= 0 && vy < Hv && vx >= 0 && vx < Wv;
+          meta[j] = (hp << 8) | (q << 1) | (in ? 1 : 0);
+          if (in) {
+            const int sy = a.in_mode == IN_DIRECT ? vy : (vy >> 1);
+            const int sx = a.in_mode == IN_DIRECT ? vx : (vx >> 1);
+            const int c = c0 + 4 * q;
+            const float* p = a.x + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
+            if (c + 3 < a.Cin) {
+              raw[j] = __ldg(reinterpret_cast<const float4*>(p));
+            } else {
+              float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int cc = c + k;
-              v[k] = cc < a.Cin ? fmaxf(0.f, fmaf(v[k], sc_s[cc], sh_s[cc])) : 0.f;
+              for (int k = 0; k < 4; ++k)
+                if (c + k < a.Cin) v[k] = p[k];
+              raw[j] = make_float4(v[0], v[1], v[2], v[3]);
             }
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < MAXI; ++j) {
+        if (meta[j] < 0) continue;
+        const int hp = meta[j] >> 8, q = (meta[j] >> 1) & 127;
+        float v[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+        if (a.pro) {
+          const int c = c0 + 4 * q;
+          const bool in = meta[j] & 1;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int cc = c + k;
+            v[k] = (in && cc < a.Cin) ? fmaxf(0.f, fmaf(v[k], sc_s[cc], sh_s[cc])) : 0.f;
           }
         }
         float hi[4], lo[4];

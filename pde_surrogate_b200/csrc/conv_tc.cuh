@@ -26,6 +26,24 @@ struct TcPackDesc {
   int Cout, Cin, KS, N, KC, nchunks, transpose;
 };
 
+struct TcWgradArgs {
+  WgradArgs w;       // geometry / prologue (dw unused)
+  float* dwp;        // staging gradient [tap][ci_pad][co_pad], accumulated with vector reductions
+  int ci_pad, co_pad;
+  int dbg;           // debug switches (env PDES_WG_DBG), 0 in production
+};
+
+struct TcWgradUnpack {
+  float* dw;         // OIHW gradient (+=)
+  float* dwp;        // staging buffer (read, then cleared)
+  int Cout, Cin, KS, ci_pad, co_pad;
+};
+
+bool wgrad_tc_supported(int KS, int stride);
+void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad);
+int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st);
+int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_elems, cudaStream_t st);
+
 // tiling for a convolution whose GEMM-K operand has Cin_k channels and GEMM-N is N
 void tc_plan(int KS, int Cin_k, int N, TcPlan* p);
 bool tc_supported(int KS, int stride, int Cin_k, int N);

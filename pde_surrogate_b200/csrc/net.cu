@@ -44,6 +44,9 @@ struct Layer {
   TcPlan pf, pb;     // tiling of the forward / dgrad GEMM
   int Nf, Nb;        // padded GEMM-N (Cout / Cin rounded up to 16)
   size_t wtf, wtb;   // float offsets of the packed filter tiles
+  bool tc_wg;        // weight gradient on tcgen05
+  int ci_pad, co_pad;
+  size_t dwp;        // float offset of the [tap][ci_pad][co_pad] staging gradient
 };
 
 struct ParamInfo {
@@ -67,10 +70,12 @@ struct pdes_net {
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
   size_t xin = 0;  // float offset: NCHW copy of the last training input (needed by In_conv's wgrad)
   int n_bn = 0, maxC = 0, max_pack = 0;
-  int n_tc = 0;
+  int n_tc = 0, n_wg = 0;
   size_t max_tc_pack = 0;
+  int max_wg_elems = 0;
   int prec = 0;
-  int tc_mask = 3;  // bit 0: forward on tcgen05, bit 1: dgrad on tcgen05
+  int n_wg_bound = 0;
+  int tc_mask = 7;  // bit 0: forward, bit 1: dgrad, bit 2: wgrad on tcgen05
   // bound
   float* p = nullptr;
   float* g = nullptr;
@@ -132,6 +137,9 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.Nf = rup(Cout, 16);
   L.Nb = rup(Cin, 16);
   L.wtf = L.wtb = 0;
+  L.tc_wg = false;
+  L.ci_pad = L.co_pad = 0;
+  L.dwp = 0;
   memset(&L.pf, 0, sizeof(L.pf));
   memset(&L.pb, 0, sizeof(L.pb));
   n->layers.push_back(L);
@@ -276,6 +284,14 @@ int build(pdes_net* n) {
       n->n_tc++;
       if (L.pf.pack_floats > n->max_tc_pack) n->max_tc_pack = L.pf.pack_floats;
     }
+    if (aligned && wgrad_tc_supported(L.KS, L.stride)) {
+      L.tc_wg = true;
+      wgrad_tc_dims(L.Cin, L.Cout, &L.ci_pad, &L.co_pad);
+      L.dwp = f;
+      f += (size_t)L.KS * L.KS * L.ci_pad * L.co_pad;
+      n->n_wg++;
+      if (L.Cout * L.Cin * L.KS * L.KS > n->max_wg_elems) n->max_wg_elems = L.Cout * L.Cin * L.KS * L.KS;
+    }
     if (aligned && tc_supported(L.KS, L.stride, L.Cout, L.Nb)) {
       L.tc_bwd = true;
       tc_plan(L.KS, L.Cout, L.Nb, &L.pb);
@@ -301,7 +317,8 @@ int build(pdes_net* n) {
   n->off_doubles = (n->ws_floats * sizeof(float) + 255) & ~(size_t)255;
   n->off_tables = (n->off_doubles + n->ws_doubles * sizeof(double) + 255) & ~(size_t)255;
   n->ws_bytes = n->off_tables + sizeof(PackDesc) * n->layers.size() +
-                sizeof(BnLayerDesc) * (size_t)n->n_bn + sizeof(TcPackDesc) * (size_t)n->n_tc + 256;
+                sizeof(BnLayerDesc) * (size_t)n->n_bn + sizeof(TcPackDesc) * (size_t)n->n_tc +
+                sizeof(TcWgradUnpack) * (size_t)n->n_wg + 256;
   return PDES_OK;
 }
 
@@ -317,6 +334,11 @@ inline BnLayerDesc* bn_table(const pdes_net* n) {
 inline TcPackDesc* tc_table(const pdes_net* n) {
   return reinterpret_cast<TcPackDesc*>(n->ws + n->off_tables + sizeof(PackDesc) * n->layers.size() +
                                        sizeof(BnLayerDesc) * (size_t)n->n_bn);
+}
+
+inline TcWgradUnpack* wg_table(const pdes_net* n) {
+  return reinterpret_cast<TcWgradUnpack*>(reinterpret_cast<unsigned char*>(tc_table(n)) +
+                                          sizeof(TcPackDesc) * (size_t)n->n_tc);
 }
 
 BnSrc bn_src(const pdes_net* n, const Layer& L, int B, bool training) {
@@ -460,6 +482,22 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
   }
   if (!tt.empty())
     PDES_CUDA(cudaMemcpy(tc_table(n), tt.data(), sizeof(TcPackDesc) * tt.size(), cudaMemcpyHostToDevice));
+  std::vector<TcWgradUnpack> wt;
+  for (const auto& L : n->layers) {
+    if (!L.tc_wg || !n->g) continue;
+    TcWgradUnpack u;
+    u.dw = n->g + L.w_off;
+    u.dwp = wsf(n, L.dwp);
+    u.Cout = L.Cout;
+    u.Cin = L.Cin;
+    u.KS = L.KS;
+    u.ci_pad = L.ci_pad;
+    u.co_pad = L.co_pad;
+    wt.push_back(u);
+  }
+  n->n_wg_bound = (int)wt.size();
+  if (!wt.empty())
+    PDES_CUDA(cudaMemcpy(wg_table(n), wt.data(), sizeof(TcWgradUnpack) * wt.size(), cudaMemcpyHostToDevice));
   PDES_CUDA(cudaMemcpy(pack_table(n), pt.data(), sizeof(PackDesc) * pt.size(), cudaMemcpyHostToDevice));
   if (!bt.empty())
     PDES_CUDA(cudaMemcpy(bn_table(n), bt.data(), sizeof(BnLayerDesc) * bt.size(), cudaMemcpyHostToDevice));
@@ -468,11 +506,11 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
 
 extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
   // 0 = tcgen05 (3xTF32) where supported, 1 = SIMT fp32 everywhere, 2 = tcgen05 single-pass TF32
-  // 3 / 4 = tcgen05 for the forward only / the dgrad only (diagnostics)
-  PDES_REQUIRE(n && impl >= 0 && impl <= 4, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..4");
+  // 3 / 4 / 5 = tcgen05 for the forward only / the dgrad only / the wgrad only (diagnostics)
+  PDES_REQUIRE(n && impl >= 0 && impl <= 5, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..5");
   n->conv_impl = impl == 1 ? 1 : 0;
   n->prec = impl == 2 ? 1 : 0;
-  n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : 3);
+  n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : (impl == 5 ? 4 : 7));
   return PDES_OK;
 }
 
@@ -597,6 +635,7 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
   const int B = n->last_B;
   n->launches = 0;
   int rc;
+  bool used_wg = false;
   for (int li = (int)n->layers.size() - 1; li >= 0; --li) {
     const Layer& L = n->layers[li];
     const float* dy;
@@ -663,7 +702,17 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         w.Hs = L.Hs;
         w.Ws = L.Ws;
       }
-      rc = launch_wgrad_simt(w, st);
+      if (n->conv_impl == 0 && L.tc_wg && (n->tc_mask & 4)) {
+        TcWgradArgs tw;
+        tw.w = w;
+        tw.dwp = wsf(n, L.dwp);
+        tw.ci_pad = L.ci_pad;
+        tw.co_pad = L.co_pad;
+        rc = launch_wgrad_tc(tw, st);
+        used_wg = true;
+      } else {
+        rc = launch_wgrad_simt(w, st);
+      }
       if (rc) return rc;
       n->launches++;
     }
@@ -717,6 +766,11 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
       if (rc) return rc;
       n->launches++;
     }
+  }
+  if (used_wg) {
+    rc = launch_wgrad_unpack(wg_table(n), n->n_wg_bound, n->max_wg_elems, st);
+    if (rc) return rc;
+    n->launches++;
   }
   rc = launch_bn_param_grad(bn_table(n), n->n_bn, n->maxC, st);
   if (rc) return rc;

@@ -120,10 +120,8 @@ def _run_case(case, impl):
     da = torch.full((B, H, H, Cin), 7.0, device="cuda")
     _lib.check(L.pdes_conv2d_dgrad(byref(d), _lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(da), impl, st))
     assert rel(da, a.grad.permute(0, 2, 3, 1)) < (3e-6 if impl == 1 else 1e-5), rel(da, a.grad.permute(0, 2, 3, 1))
-    if impl == 2:
-        return
     # wgrad (accumulates)
     dw = torch.ones(Cout, Cin, K, K, device="cuda")
     _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), _lib.ptr(sd) if bn else None,
-                                   _lib.ptr(hd) if bn else None, _lib.ptr(dyd), _lib.ptr(dw), 0, st))
-    assert rel(dw - 1.0, wr.grad) < 1e-5
+                                   _lib.ptr(hd) if bn else None, _lib.ptr(dyd), _lib.ptr(dw), impl, st))
+    assert rel(dw - 1.0, wr.grad) < 1e-5, rel(dw - 1.0, wr.grad)
