@@ -92,6 +92,7 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
     t.NB = p.NB;
     t.nchunks = p.nchunks;
     t.S = p.S;
+    t.TPB = p.TPB;
     t.prec = 0;
     rc = launch_conv_tc(t, st);
   }
@@ -225,13 +226,56 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   PDES_REQUIRE(wgrad_tc_supported(d->KH, d->stride) && !d->out_nchw, PDES_ERR_UNSUPPORTED,
                "tensor-core wgrad does not support this convolution");
   TcWgradArgs tw;
-  tw.w = a;
+  memset(&tw, 0, sizeof(tw));
   wgrad_tc_dims(d->Cin, d->Cout, &tw.ci_pad, &tw.co_pad);
   const size_t nf = (size_t)d->KH * d->KW * tw.ci_pad * tw.co_pad;
+  const int Hv = d->upsample ? 2 * d->Hin : d->Hin, Wv = d->upsample ? 2 * d->Win : d->Win;
+  const size_t bytesA = act_planes_bytes(d->B, Hv, Wv, d->Cin), bytesB = act_planes_bytes(d->B, d->Hout, d->Wout, d->Cout);
+  const size_t offA = (nf * sizeof(float) + 512 + 255) & ~(size_t)255, offB = (offA + bytesA + 255) & ~(size_t)255;
   float* buf = nullptr;
-  PDES_CUDA(cudaMallocAsync((void**)&buf, nf * sizeof(float) + 256, st));
+  PDES_CUDA(cudaMallocAsync((void**)&buf, offB + bytesB + 256, st));
   PDES_CUDA(cudaMemsetAsync(buf, 0, nf * sizeof(float), st));
+  __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(buf) + offA);
+  __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(buf) + offB);
+  ActSplitArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.x = a.x;
+  sa.ldx = a.ldx;
+  sa.C = d->Cin;
+  sa.Hs = d->Hin;
+  sa.Ws = d->Win;
+  sa.B = d->B;
+  sa.up = d->upsample;
+  sa.pro = a.pro;
+  sa.bn = a.bn;
+  sa.out = pa;
+  sa.Cp = (d->Cin + 7) & ~7;
+  rc = launch_act_split(sa, st);
+  if (rc) return rc;
+  ActSplitArgs sb;
+  memset(&sb, 0, sizeof(sb));
+  sb.x = a.dy;
+  sb.ldx = a.lddy;
+  sb.C = d->Cout;
+  sb.Hs = d->Hout;
+  sb.Ws = d->Wout;
+  sb.B = d->B;
+  sb.out = pb;
+  sb.Cp = (d->Cout + 7) & ~7;
+  rc = launch_act_split(sb, st);
+  if (rc) return rc;
+  tw.planesA = pa;
+  tw.planesB = pb;
   tw.dwp = buf;
+  tw.B = d->B;
+  tw.Hv = Hv;
+  tw.Wv = Wv;
+  tw.Ho = d->Hout;
+  tw.Wo = d->Wout;
+  tw.Cin = d->Cin;
+  tw.Cout = d->Cout;
+  tw.KS = d->KH;
+  tw.pad = d->pad;
   rc = launch_wgrad_tc(tw, st);
   if (rc == PDES_OK) {
     TcWgradUnpack u;

@@ -57,7 +57,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(TcConvArgs t) {
   float* red_s = ep_s + 4 * N;                         // 4*N*2
   const size_t hdr = (256 + sizeof(float) * ((size_t)2 * CinP4 + 12 * (size_t)N) + 127) & ~(size_t)127;
   const uint32_t a_stage_bytes = 2u * HPpad * KC * 4u;  // hi + lo
-  const uint32_t b_stage_bytes = 2u * N * KC * 4u;      // hi + lo
+  const int TPB = t.TPB;                                 // filter taps per TMA stage
+  const uint32_t b_tap_bytes = 2u * N * KC * 4u;        // hi + lo of one tap
+  const uint32_t b_stage_bytes = (uint32_t)TPB * b_tap_bytes;
   unsigned char* A_s = smem + hdr;
   unsigned char* B_s = A_s + 2 * (size_t)a_stage_bytes;
 
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(TcConvArgs t) {
   const int oy0 = ty * kTH, ox0 = tx * kTW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = t.nchunks;
-  const int nsteps = nchunks * T;
+  const int nsteps = nchunks * (T / TPB);               // TMA stages over the whole K loop
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(t.S * 2 * N)) tmem_cols <<= 1;
 
@@ -152,24 +154,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(TcConvArgs t) {
         const uint32_t d_x = d_hh + (uint32_t)N;
         mbar_wait(&a_full[sa], (uint32_t)((ch >> 1) & 1));
         const uint32_t a_base = smem_u32(A_s + (size_t)sa * a_stage_bytes);
-        for (int tap = 0; tap < T; ++tap, ++step) {
+        const uint64_t a_desc0 = make_desc(a_base, lbo_a, sbo_a);
+        for (int tap = 0; tap < T; ++tap) {
           const int sb = step % NB;
-          mbar_wait(&b_full[sb], (uint32_t)((step / NB) & 1));
-          tc_fence_after();
-          const uint32_t b_base = smem_u32(B_s + (size_t)sb * b_stage_bytes);
-          const uint32_t a_tap = a_base + (uint32_t)((tap / KS) * HWp + (tap % KS)) * 16u;
+          const int tin = tap % TPB;
+          if (tin == 0) {
+            mbar_wait(&b_full[sb], (uint32_t)((step / NB) & 1));
+            tc_fence_after();
+          }
+          const uint32_t b_base = smem_u32(B_s + (size_t)sb * b_stage_bytes) + (uint32_t)tin * b_tap_bytes;
+          const uint64_t b_desc0 = make_desc(b_base, lbo_b, sbo_b);
+          const uint64_t a_tap = a_desc0 + (uint64_t)((uint32_t)((tap / KS) * HWp + (tap % KS)));  // +16 B units
           for (int ks = 0; ks < KC / 8; ++ks) {
             const uint32_t acc = (used >> set) & 1u;
-            const uint64_t ahi = make_desc(a_tap + 2u * ks * lbo_a, lbo_a, sbo_a);
-            const uint64_t bhi = make_desc(b_base + 2u * ks * lbo_b, lbo_b, sbo_b);
+            const uint64_t ahi = a_tap + (uint64_t)((2u * ks * lbo_a) >> 4);
+            const uint64_t bhi = b_desc0 + (uint64_t)((2u * ks * lbo_b) >> 4);
             if (t.prec != 0) {
               umma_tf32(d_hh, ahi, bhi, idesc_n, acc);
             } else {
-              const uint64_t alo = make_desc(a_tap + a_lo_off + 2u * ks * lbo_a, lbo_a, sbo_a);
+              const uint64_t alo = ahi + (uint64_t)(a_lo_off >> 4);
               if (fused) {
                 umma_tf32(d_hh, ahi, bhi, idesc_2n, acc);  // [hh | x] += Ahi * [Bhi | Blo]
               } else {
-                const uint64_t blo = make_desc(b_base + b_lo_off + 2u * ks * lbo_b, lbo_b, sbo_b);
+                const uint64_t blo = bhi + (uint64_t)(b_lo_off >> 4);
                 umma_tf32(d_hh, ahi, bhi, idesc_n, acc);
                 umma_tf32(d_x, ahi, blo, idesc_n, acc);
               }
@@ -177,7 +184,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(TcConvArgs t) {
             }
             used |= 1u << set;
           }
-          umma_commit(&b_empty[sb]);
+          if (tin == TPB - 1) {
+            umma_commit(&b_empty[sb]);
+            ++step;
+          }
         }
         umma_commit(&a_empty[sa]);
       }
@@ -444,13 +454,13 @@ __global__ void __launch_bounds__(256) pack_tc_kernel(const TcPackDesc* tab) {
   }
 }
 
-size_t tc_smem_bytes(int KS, int Cin, int N, int KC, int NB) {
+size_t tc_smem_bytes(int KS, int Cin, int N, int KC, int NB, int TPB) {
   const int HWp = kTW + KS - 1;
   const int HP = (kTH + KS - 1) * HWp;
   const int HPpad = HP | 1;
   const int CinP4 = (Cin + 3) & ~3;
   const size_t hdr = (256 + sizeof(float) * ((size_t)2 * CinP4 + 12 * (size_t)N) + 127) & ~(size_t)127;
-  return hdr + 2 * (size_t)(2 * HPpad * KC * 4) + (size_t)NB * (2 * (size_t)N * KC * 4);
+  return hdr + 2 * (size_t)(2 * HPpad * KC * 4) + (size_t)NB * TPB * (2 * (size_t)N * KC * 4);
 }
 
 }  // namespace
@@ -462,10 +472,21 @@ void tc_plan(int KS, int Cin_k, int N, TcPlan* p) {
   if (Cin_k <= 8) KC = 8;
   p->KC = KC;
   p->nchunks = (Cin_k + KC - 1) / KC;
-  int NB = 4;
-  while (NB > 2 && tc_smem_bytes(KS, Cin_k, N, KC, NB) > 220 * 1024) --NB;
+  // filter taps per TMA stage: few large bulk copies instead of many latency-bound small ones
+  const int T = KS * KS;
+  int TPB = 1, NB = 4;
+  const size_t tap_bytes = 2 * (size_t)N * KC * 4;
+  if (T * tap_bytes <= 40 * 1024) {
+    TPB = T;
+    NB = 2;
+  } else if (T % 3 == 0 && 3 * tap_bytes <= 50 * 1024) {
+    TPB = 3;
+    NB = 2;
+  }
+  while (NB > 2 && tc_smem_bytes(KS, Cin_k, N, KC, NB, TPB) > 220 * 1024) --NB;
   p->NB = NB;
-  p->smem = tc_smem_bytes(KS, Cin_k, N, KC, NB);
+  p->TPB = TPB;
+  p->smem = tc_smem_bytes(KS, Cin_k, N, KC, NB, TPB);
   int S = 512 / (2 * N);
   if (S < 1) S = 1;
   if (S > p->nchunks) S = p->nchunks;
@@ -495,7 +516,7 @@ int launch_conv_tc(const TcConvArgs& t, cudaStream_t st) {
   if (a.epi == EPI_BNBWD)
     PDES_REQUIRE(((a.ldfx | a.ldG) & 3) == 0, PDES_ERR_INVALID, "conv_tc: gradient buffers misaligned");
   PDES_REQUIRE(!a.pool || ((a.Ho | a.Wo) & 1) == 0, PDES_ERR_INVALID, "conv_tc: pool needs even size");
-  const size_t smem = tc_smem_bytes(a.KS, a.Cin, t.N, t.KC, t.NB);
+  const size_t smem = tc_smem_bytes(a.KS, a.Cin, t.N, t.KC, t.NB, t.TPB);
   PDES_REQUIRE(smem <= 227 * 1024, PDES_ERR_UNSUPPORTED, "conv_tc: needs %zu bytes of shared memory", smem);
   const int tiles = ((a.Wo + kTW - 1) / kTW) * ((a.Ho + kTH - 1) / kTH) * a.B;
   if (a.KS == 3) {

@@ -1,5 +1,6 @@
 // conv_tc.cuh — interface of the tcgen05 convolution kernels.
 #pragma once
+#include <cuda_bf16.h>
 #include "conv.cuh"
 
 namespace pdes {
@@ -10,13 +11,14 @@ struct TcConvArgs {
   int N;             // GEMM N = output channels padded to a multiple of 16 (<= 256)
   int KC;            // input channels per pipeline chunk (8, 16 or 32)
   int NB;            // filter-tile ring depth
+  int TPB;           // filter taps per ring stage (one TMA bulk copy)
   int nchunks;
   int S;             // accumulator sets in TMEM (K range spread over S accumulators)
   int prec;          // 0 = 3xTF32 (fp32 parity), 1 = single-pass TF32
 };
 
 struct TcPlan {
-  int KC, nchunks, NB, S;
+  int KC, nchunks, NB, S, TPB;
   size_t smem, pack_floats;
 };
 
@@ -26,11 +28,23 @@ struct TcPackDesc {
   int Cout, Cin, KS, N, KC, nchunks, transpose;
 };
 
+// elementwise pre-pass of the tensor-core wgrad: three bf16 piece planes of the operand
+struct ActSplitArgs {
+  const float* x;        // NHWC, ldx floats per pixel (channel offset already applied)
+  int ldx, C, Hs, Ws, B;
+  int up;                // 1: write the nearest x2 upsampled image
+  int pro;               // 1: a = max(0, x*scale+shift) first
+  BnSrc bn;
+  __nv_bfloat16* out;    // [3][B][Hv][Wv][Cp]
+  int Cp;                // C rounded up to 8
+};
+
 struct TcWgradArgs {
-  WgradArgs w;       // geometry / prologue (dw unused)
-  float* dwp;        // staging gradient [tap][ci_pad][co_pad], accumulated with vector reductions
+  const __nv_bfloat16* planesA;  // [3][B][Hv][Wv][CpA]  activation pieces (after BN+ReLU / upsampling)
+  const __nv_bfloat16* planesB;  // [3][B][Ho][Wo][CpB]  dY pieces
+  float* dwp;                    // staging gradient [tap][ci_pad][co_pad] (vector reductions)
+  int B, Hv, Wv, Ho, Wo, Cin, Cout, KS, pad;
   int ci_pad, co_pad;
-  int dbg;           // debug switches (env PDES_WG_DBG), 0 in production
 };
 
 struct TcWgradUnpack {
@@ -42,6 +56,8 @@ struct TcWgradUnpack {
 bool wgrad_tc_supported(int KS, int stride);
 void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad);
 int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st);
+int launch_act_split(const ActSplitArgs& a, cudaStream_t st);
+size_t act_planes_bytes(int B, int H, int W, int C);
 int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_elems, cudaStream_t st);
 
 // tiling for a convolution whose GEMM-K operand has Cin_k channels and GEMM-N is N

@@ -68,7 +68,8 @@ struct pdes_net {
   std::vector<ParamInfo> params;
   int64_t param_floats = 0, running_floats = 0;
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
-  size_t xin = 0;  // float offset: NCHW copy of the last training input (needed by In_conv's wgrad)
+  size_t xin = 0;
+  size_t planesA = 0, planesB = 0;  // float offsets of the bf16 operand-piece scratch planes (wgrad)  // float offset: NCHW copy of the last training input (needed by In_conv's wgrad)
   int n_bn = 0, maxC = 0, max_pack = 0;
   int n_tc = 0, n_wg = 0;
   size_t max_tc_pack = 0;
@@ -300,6 +301,21 @@ int build(pdes_net* n) {
       n->n_tc++;
       if (L.pb.pack_floats > n->max_tc_pack) n->max_tc_pack = L.pb.pack_floats;
     }
+  }
+  {
+    size_t maxA = 0, maxB = 0;
+    for (const auto& L : n->layers) {
+      if (!L.tc_wg) continue;
+      const Buf& ib = n->bufs[L.in_buf];
+      const int Hv = L.up ? 2 * ib.H : ib.H, Wv = L.up ? 2 * ib.W : ib.W;
+      const size_t a = act_planes_bytes(B, Hv, Wv, L.Cin), bb = act_planes_bytes(B, L.Ho, L.Wo, L.Cout);
+      if (a > maxA) maxA = a;
+      if (bb > maxB) maxB = bb;
+    }
+    n->planesA = f;
+    f += pad4((int64_t)((maxA + 3) / 4)) + 64;
+    n->planesB = f;
+    f += pad4((int64_t)((maxB + 3) / 4)) + 64;
   }
   n->xin = f;
   f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
@@ -607,6 +623,7 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
       t.NB = L.pf.NB;
       t.nchunks = L.pf.nchunks;
       t.S = L.pf.S;
+      t.TPB = L.pf.TPB;
       t.prec = n->prec;
       rc = launch_conv_tc(t, st);
     } else {
@@ -703,9 +720,51 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         w.Ws = L.Ws;
       }
       if (n->conv_impl == 0 && L.tc_wg && (n->tc_mask & 4)) {
+        const Buf& ib = n->bufs[L.in_buf];
+        __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(wsf(n, n->planesA));
+        __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(wsf(n, n->planesB));
+        ActSplitArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.x = w.x;
+        sa.ldx = w.ldx;
+        sa.C = L.Cin;
+        sa.Hs = ib.H;
+        sa.Ws = ib.W;
+        sa.B = B;
+        sa.up = L.up;
+        sa.pro = 1;
+        sa.bn = w.bn;
+        sa.out = pa;
+        sa.Cp = (L.Cin + 7) & ~7;
+        rc = launch_act_split(sa, st);
+        if (rc) return rc;
+        ActSplitArgs sb;
+        memset(&sb, 0, sizeof(sb));
+        sb.x = dy;
+        sb.ldx = lddy;
+        sb.C = L.Cout;
+        sb.Hs = L.Ho;
+        sb.Ws = L.Wo;
+        sb.B = B;
+        sb.out = pb;
+        sb.Cp = (L.Cout + 7) & ~7;
+        rc = launch_act_split(sb, st);
+        if (rc) return rc;
+        n->launches += 2;
         TcWgradArgs tw;
-        tw.w = w;
+        memset(&tw, 0, sizeof(tw));
+        tw.planesA = pa;
+        tw.planesB = pb;
         tw.dwp = wsf(n, L.dwp);
+        tw.B = B;
+        tw.Hv = L.up ? 2 * ib.H : ib.H;
+        tw.Wv = L.up ? 2 * ib.W : ib.W;
+        tw.Ho = L.Ho;
+        tw.Wo = L.Wo;
+        tw.Cin = L.Cin;
+        tw.Cout = L.Cout;
+        tw.KS = L.KS;
+        tw.pad = L.pad;
         tw.ci_pad = L.ci_pad;
         tw.co_pad = L.co_pad;
         rc = launch_wgrad_tc(tw, st);
@@ -758,6 +817,7 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         t.NB = L.pb.NB;
         t.nchunks = L.pb.nchunks;
         t.S = L.pb.S;
+        t.TPB = L.pb.TPB;
         t.prec = n->prec;
         rc = launch_conv_tc(t, st);
       } else {
