@@ -58,20 +58,42 @@ int pack(const pdes_conv_desc* d, const float* w, cudaStream_t st, Packed& pk) {
   PDES_CUDA(cudaStreamSynchronize(st));  // h is a stack variable
   return launch_pack_weights(pk.tab, 1, (int)(nf + nb), st);
 }
-// tcgen05 path for the unit-test entry points: pack filter tiles into scratch, then launch.
+// tcgen05 path for the unit-test entry points: split the GEMM-K operand into bf16 piece planes,
+// pack the filter pieces into scratch, then launch the TMA-fed kernel.
 int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int transpose, cudaStream_t st) {
   const int Cin_k = transpose ? d->Cout : d->Cin;
   const int N = rup(transpose ? d->Cin : d->Cout, 16);
-  PDES_REQUIRE(tc_supported(d->KH, d->stride, Cin_k, N), PDES_ERR_UNSUPPORTED,
+  PDES_REQUIRE(tc2_supported(d->KH, d->stride, Cin_k, N), PDES_ERR_UNSUPPORTED,
                "tensor-core path does not support this convolution (K=%d stride=%d N=%d)", d->KH,
                d->stride, N);
-  TcPlan p;
-  tc_plan(d->KH, Cin_k, N, &p);
-  float* buf = nullptr;
-  PDES_CUDA(cudaMallocAsync((void**)&buf, p.pack_floats * sizeof(float) + 256, st));
-  TcPackDesc h;
+  Tc2Plan p;
+  tc2_plan(d->KH, Cin_k, N, &p);
+  // operand planes
+  ActSplitArgs sa;
+  memset(&sa, 0, sizeof(sa));
+  sa.x = a.x;
+  sa.ldx = a.ldx;
+  sa.C = Cin_k;
+  sa.Hs = a.Hs;
+  sa.Ws = a.Ws;
+  sa.B = a.B;
+  sa.up = a.in_mode == IN_UPSAMPLE ? 1 : 0;
+  sa.pro = a.pro;
+  sa.bn = a.bn;
+  sa.Cp = (Cin_k + 7) & ~7;
+  const int Hv = sa.up ? 2 * a.Hs : a.Hs, Wv = sa.up ? 2 * a.Ws : a.Ws;
+  const size_t plane_bytes = act_planes_bytes(a.B, Hv, Wv, Cin_k);
+  const size_t pack_bytes = (p.pack_elems * 2 + 255) & ~(size_t)255;
+  unsigned char* buf = nullptr;
+  PDES_CUDA(cudaMallocAsync((void**)&buf, pack_bytes + ((plane_bytes + 255) & ~(size_t)255) + 512, st));
+  __nv_bfloat16* wpk = reinterpret_cast<__nv_bfloat16*>(buf);
+  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(buf + pack_bytes);
+  Tc2PackDesc* tab = reinterpret_cast<Tc2PackDesc*>(buf + pack_bytes + ((plane_bytes + 255) & ~(size_t)255));
+  sa.out = planes;
+  int rc = launch_act_split(sa, st);
+  Tc2PackDesc h;
   h.w = w;
-  h.dst = buf;
+  h.dst = wpk;
   h.Cout = d->Cout;
   h.Cin = d->Cin;
   h.KS = d->KH;
@@ -79,22 +101,26 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
   h.KC = p.KC;
   h.nchunks = p.nchunks;
   h.transpose = transpose;
-  TcPackDesc* tab = reinterpret_cast<TcPackDesc*>(buf + p.pack_floats);
-  PDES_CUDA(cudaMemcpyAsync(tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  PDES_CUDA(cudaStreamSynchronize(st));
-  int rc = launch_pack_tc(tab, 1, p.pack_floats, st);
   if (rc == PDES_OK) {
-    TcConvArgs t;
+    PDES_CUDA(cudaMemcpyAsync(tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    PDES_CUDA(cudaStreamSynchronize(st));
+    rc = launch_pack_tc2(tab, 1, p.pack_elems, st);
+  }
+  if (rc == PDES_OK) {
+    Tc2Args t;
+    memset(&t, 0, sizeof(t));
     t.c = a;
-    t.wtc = buf;
+    t.wpk = wpk;
     t.N = N;
     t.KC = p.KC;
-    t.NB = p.NB;
     t.nchunks = p.nchunks;
+    t.ngroups = p.ngroups;
     t.S = p.S;
+    t.TS = p.TS;
+    t.AST = p.AST;
+    t.NB = p.NB;
     t.TPB = p.TPB;
-    t.prec = 0;
-    rc = launch_conv_tc(t, st);
+    rc = launch_conv_tc2(t, planes, Hv, Wv, Cin_k, st);
   }
   cudaFreeAsync(buf, st);
   return rc;

@@ -60,6 +60,27 @@ int launch_act_split(const ActSplitArgs& a, cudaStream_t st);
 size_t act_planes_bytes(int B, int H, int W, int C);
 int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_elems, cudaStream_t st);
 
+// ---- TMA-fed bf16x3 convolution (conv_tc2.cu) -----------------------------------------------
+struct Tc2Plan {
+  int KC, nchunks, ngroups, S, TS, AST, NB, TPB;
+  size_t smem, pack_elems;  // pack_elems: bf16 elements of the packed filter
+};
+struct Tc2Args {
+  ConvArgs c;                  // geometry (B, Ho, Wo, KS, pad, Cout) and epilogue; x/w/prologue unused
+  const __nv_bfloat16* wpk;    // [chunk][tap][k-octet][piece][N][8]
+  int N, KC, nchunks, ngroups, S, TS, AST, NB, TPB;
+};
+struct Tc2PackDesc {
+  const float* w;  // OIHW
+  __nv_bfloat16* dst;
+  int Cout, Cin, KS, N, KC, nchunks, transpose;
+};
+void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p);
+bool tc2_supported(int KS, int stride, int Cin_k, int N);
+// planes: [3][B][Hv][Wv][round8(Cin_k)] bf16 pieces of the GEMM-K operand (act_split_kernel)
+int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int Wv, int Cin_k, cudaStream_t st);
+int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st);
+
 // tiling for a convolution whose GEMM-K operand has Cin_k channels and GEMM-N is N
 void tc_plan(int KS, int Cin_k, int N, TcPlan* p);
 bool tc_supported(int KS, int stride, int Cin_k, int N);

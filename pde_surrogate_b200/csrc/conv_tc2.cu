@@ -1,0 +1,664 @@
+// conv_tc2.cu — TMA-fed, persistent, warp-specialised tcgen05 implicit-GEMM convolution
+// (forward and dgrad) on exact three-way bf16 operand splits.
+//
+// Operands never pass through registers: the activation side (BN+ReLU'd, optionally nearest-
+// upsampled input — or the corrected dY slice for dgrad) is pre-split once per layer into three
+// bf16 planes by act_split_kernel; 5-D TMA boxes (cp.async.bulk.tensor, zero fill outside the
+// image = convolution padding) drop a (TH+2)x(TW+2) halo tile of one channel chunk into shared
+// memory as [channel octet][halo pixel][16 B] — the canonical no-swizzle K-major UMMA layout —
+// and the KSxKS filter taps are shifted descriptors into that one tile (im2col-free).  Filter
+// tiles are pre-packed per (chunk, tap) in their shared-memory image and arrive by 1-D bulk TMA.
+//
+// fp32 parity: x = b1 + b2 + b3 exactly (8+8+8 mantissa bits); the six products of weight >= 2^-16
+//   a1*[w1|w2|w3], a2*[w1|w2], a3*[w1]
+// are issued as (up to) three tcgen05.mma.kind::f16 instructions whose N-concatenated filter
+// operand sends each product class to its own TMEM column group (G0 = a1w1, G1 = a1w2+a2w1,
+// G2 = a1w3+a2w2+a3w1): tensor-core accumulation truncates, so big and small terms never share
+// an accumulator, the K range is spread over S accumulator sets, and the epilogue adds everything
+// with round-to-nearest fp32.
+//
+// Warp roles (384 threads, persistent over pixel tiles): warp 0 = TMA producer of activation
+// tiles, warp 1 = TMA producer of filter tiles, warp 2 = TMEM allocator + MMA issuer (one lane),
+// warps 4-11 = epilogue (two warps per TMEM lane quarter).  With two TMEM accumulator stages the
+// epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "conv.cuh"
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+namespace pdes {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 384;
+constexpr int kTH = 16, kTW = 8;
+constexpr int kEpiWarp0 = 4, kEpiWarps = 8;
+
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {  // D fp32, A/B bf16, K-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+      "%5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bf16_split3(float x, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
+  const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(b1);
+  const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b2);
+  p0 = (uint32_t)__bfloat16_as_ushort(b1);
+  p1 = (uint32_t)__bfloat16_as_ushort(b2);
+  p2 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r2));
+}
+__device__ __forceinline__ void bn_consts2(const BnSrc& s, int c, float& scale, float& shift, float& mean,
+                                           float& invstd) {
+  if (s.scale != nullptr) {
+    scale = s.scale[c];
+    shift = s.shift[c];
+    mean = 0.f;
+    invstd = 1.f;
+    return;
+  }
+  double m, var;
+  if (s.use_running) {
+    m = (double)s.run_mean[c];
+    var = (double)s.run_var[c];
+  } else {
+    m = s.sum[c] * s.inv_count;
+    var = s.sumsq[c] * s.inv_count - m * m;
+    if (var < 0.0) var = 0.0;
+  }
+  invstd = (float)(1.0 / sqrt(var + (double)s.eps));
+  mean = (float)m;
+  scale = s.gamma[c] * invstd;
+  shift = s.beta[c] - mean * scale;
+}
+
+// column sums over the 32 lanes of a warp for 16 values per lane, by recursive halving:
+// 8+4+2+1+1 = 16 shuffles.  On return lane l holds in `out` the sum of column col_of_lane(l).
+__device__ __forceinline__ float colsum16(const float v[16], int lane) {
+  float a[8];
+  const bool up16 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = up16 ? v[i] : v[i + 8];
+    const float keep = up16 ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float b[4];
+  const bool up8 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = up8 ? a[i] : a[i + 4];
+    const float keep = up8 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float c[2];
+  const bool up4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = up4 ? b[i] : b[i + 2];
+    const float keep = up4 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const bool up2 = lane & 2;
+  const float send = up2 ? c[0] : c[1];
+  const float keep = up2 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+// column index held by `lane` after colsum16
+__device__ __forceinline__ int colsum16_col(int lane) {
+  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+
+// instruction list of one k16 step per MODE: (a piece, first filter piece, #pieces, first group)
+//  MODE 0: 3N <= 256            a1x[w1|w2|w3]->G0..2, a2x[w1|w2]->G1..2, a3xw1->G2
+//  MODE 1: 2N <= 256 < 3N       a1x[w1|w2]->G0..1, a1xw3->G2, a2x[w1|w2]->G1..2, a3xw1->G2
+//  MODE 2: 3 groups, N > 128    six single-piece instructions
+//  MODE 3: 2 groups (3N > 512)  six single-piece instructions, all cross terms in G1
+// nibble-packed tables (entry i = bits [4i, 4i+4)) so that they fold to constants in device code
+template <int MODE> struct Ops;
+template <> struct Ops<0> {
+  static constexpr int n = 3;
+  static constexpr uint32_t A = 0x210u, Bp = 0x0u, NP = 0x123u, G = 0x210u;
+};
+template <> struct Ops<1> {
+  static constexpr int n = 4;
+  static constexpr uint32_t A = 0x2100u, Bp = 0x20u, NP = 0x1212u, G = 0x2120u;
+};
+template <> struct Ops<2> {
+  static constexpr int n = 6;
+  static constexpr uint32_t A = 0x211000u, Bp = 0x10210u, NP = 0x111111u, G = 0x221210u;
+};
+template <> struct Ops<3> {
+  static constexpr int n = 6;
+  static constexpr uint32_t A = 0x211000u, Bp = 0x10210u, NP = 0x111111u, G = 0x111110u;
+};
+#define OPF(tab, i) ((int)(((tab) >> (4 * (i))) & 0xFu))
+
+template <int KS, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
+  constexpr int T = KS * KS;
+  constexpr int HWp = kTW + KS - 1;
+  constexpr int HH = kTH + KS - 1;
+  constexpr int HP = HH * HWp;
+  const ConvArgs& a = t.c;
+  const int N = t.N, KC = t.KC, NB = t.NB, TPB = t.TPB, AST = t.AST;
+  const int koct = KC >> 3;
+  const uint32_t a_piece_bytes = (uint32_t)koct * HP * 16u;
+  const uint32_t a_stage_bytes = 3u * a_piece_bytes;
+  const uint32_t b_tap_bytes = (uint32_t)koct * 3u * (uint32_t)N * 16u;
+  const uint32_t b_stage_bytes = (uint32_t)TPB * b_tap_bytes;
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* a_full = bars;        // [4]
+  uint64_t* a_empty = bars + 4;   // [4]
+  uint64_t* b_full = bars + 8;    // [8]
+  uint64_t* b_empty = bars + 16;  // [8]
+  uint64_t* acc_full = bars + 24; // [2]
+  uint64_t* acc_empty = bars + 26;// [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  float* ep_s = reinterpret_cast<float*>(smem + 256);   // 4*N : scale, shift, mean, invstd
+  float* red_s = ep_s + 4 * N;                          // kEpiWarps * N * 2
+  const size_t hdr = (256 + sizeof(float) * (size_t)(4 + 2 * kEpiWarps) * N + 127) & ~(size_t)127;
+  unsigned char* A_s = smem + hdr;
+  unsigned char* B_s = A_s + (size_t)AST * a_stage_bytes;
+
+  const int tiles_x = (a.Wo + kTW - 1) / kTW, tiles_y = (a.Ho + kTH - 1) / kTH;
+  const int n_tiles = tiles_x * tiles_y * a.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = t.nchunks;
+  const int bstages_per_chunk = T / TPB;
+  const int TS = t.TS;
+  const uint32_t ts_cols = (uint32_t)(t.S * t.ngroups * N);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < ts_cols * (uint32_t)TS) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AST; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < NB; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kEpiWarps);
+    }
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  if (warp >= kEpiWarp0) {
+    const int tt = threadIdx.x - kEpiWarp0 * 32;
+    for (int n = tt; n < N; n += kEpiWarps * 32) {
+      float s = 0.f, h = 0.f, m = 0.f, is = 0.f;
+      if (a.epi == EPI_BNBWD && n < a.Cout) bn_consts2(a.fbn, n, s, h, m, is);
+      ep_s[n] = s;
+      ep_s[N + n] = h;
+      ep_s[2 * N + n] = m;
+      ep_s[3 * N + n] = is;
+    }
+    for (int i = tt; i < kEpiWarps * N * 2; i += kEpiWarps * 32) red_s[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: activation halo tiles (three bf16 pieces per chunk) =====
+    if (lane == 0) {
+      int q = 0;  // global chunk counter
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int rem = tile;
+        const int tx = rem % tiles_x;
+        rem /= tiles_x;
+        const int ty = rem % tiles_y;
+        const int b = rem / tiles_y;
+        const int ix0 = tx * kTW - a.pad, iy0 = ty * kTH - a.pad;
+        for (int ch = 0; ch < nchunks; ++ch, ++q) {
+          const int s = q % AST;
+          mbar_wait(&a_empty[s], (uint32_t)(((q / AST) & 1) ^ 1));
+          unsigned char* st = A_s + (size_t)s * a_stage_bytes;
+          mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
+#pragma unroll
+          for (int p = 0; p < 3; ++p)
+            tma_load_5d(st + (size_t)p * a_piece_bytes, &tmA, 0, ix0, iy0, ch * koct, p * a.B + b, &a_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== TMA producer: filter tiles =====
+    if (lane == 0) {
+      int q = 0;  // global filter-stage counter
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int st = 0; st < nchunks * bstages_per_chunk; ++st, ++q) {
+          const int s = q % NB;
+          mbar_wait(&b_empty[s], (uint32_t)(((q / NB) & 1) ^ 1));
+          mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
+          tma_load_1d(B_s + (size_t)s * b_stage_bytes,
+                      reinterpret_cast<const unsigned char*>(t.wpk) + (size_t)st * b_stage_bytes, b_stage_bytes,
+                      &b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      using OP = Ops<MODE>;
+      uint32_t idesc[OP::n];
+#pragma unroll
+      for (int i = 0; i < OP::n; ++i) idesc[i] = make_idesc_bf16(128, OPF(OP::NP, i) * N);
+      const uint32_t lbo_a = HP * 16u, sbo_a = HWp * 16u;            // K-major: LBO = next channel octet
+      const uint32_t lbo_b = 3u * (uint32_t)N * 16u, sbo_b = 128u;   // [koct][piece][n][16 B]
+      int qa = 0, qb = 0, tile_it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+        const int ts = tile_it % TS;
+        mbar_wait(&acc_empty[ts], (uint32_t)(((tile_it / TS) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)ts * ts_cols;
+        uint32_t used = 0;  // bit (set*3+group)
+        for (int ch = 0; ch < nchunks; ++ch, ++qa) {
+          const int sa = qa % AST;
+          const int set = ch % t.S;
+          mbar_wait(&a_full[sa], (uint32_t)((qa / AST) & 1));
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(A_s + (size_t)sa * a_stage_bytes);
+          uint64_t adesc[3];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) adesc[p] = make_desc(a_base + (uint32_t)p * a_piece_bytes, lbo_a, sbo_a);
+          for (int tap = 0; tap < T; ++tap) {
+            const int sb = qb % NB;
+            const int tin = tap % TPB;
+            if (tin == 0) {
+              mbar_wait(&b_full[sb], (uint32_t)((qb / NB) & 1));
+              tc_fence_after();
+            }
+            const uint64_t bdesc0 =
+                make_desc(smem_u32(B_s + (size_t)sb * b_stage_bytes) + (uint32_t)tin * b_tap_bytes, lbo_b, sbo_b);
+            const uint64_t tapoff = (uint64_t)((tap / KS) * HWp + (tap % KS));
+            for (int k16 = 0; k16 < KC / 16; ++k16) {
+              const uint64_t ka = tapoff + (uint64_t)((2u * k16 * lbo_a) >> 4);
+              const uint64_t kb = (uint64_t)((2u * k16 * lbo_b) >> 4);
+#pragma unroll
+              for (int i = 0; i < OP::n; ++i) {
+                // accumulate iff every group this instruction writes already holds data
+                const uint32_t bits = ((1u << OPF(OP::NP, i)) - 1u) << (set * 3 + OPF(OP::G, i));
+                const uint32_t acc = (used & bits) == bits ? 1u : 0u;
+                umma_bf16(d_base + (uint32_t)((set * t.ngroups + OPF(OP::G, i)) * N), adesc[OPF(OP::A, i)] + ka,
+                          bdesc0 + kb + (uint64_t)(OPF(OP::Bp, i) * N), idesc[i], acc);
+                used |= bits;
+              }
+            }
+            if (tin == TPB - 1) {
+              umma_commit(&b_empty[sb]);
+              ++qb;
+            }
+          }
+          umma_commit(&a_empty[sa]);
+        }
+        umma_commit(&acc_full[ts]);
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ===== epilogue =====
+    const int ew = warp - kEpiWarp0;       // 0..7
+    const int quarter = warp & 3;          // TMEM lane quarter of this warp
+    const int half = ew >> 2;              // which half of the 16-column chunks
+    const int row = quarter * 32 + lane;   // GEMM row = tile pixel
+    const int py_t = row >> 3, px_t = row & 7;
+    const bool want_red = (a.epi == EPI_NHWC && a.o_sum != nullptr) || a.epi == EPI_BNBWD;
+    const int my_col = colsum16_col(lane);
+    const int nsets = nchunks < t.S ? nchunks : t.S;
+    int tile_it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+      const int ts = tile_it % TS;
+      int rem = tile;
+      const int tx = rem % tiles_x;
+      rem /= tiles_x;
+      const int ty = rem % tiles_y;
+      const int b = rem / tiles_y;
+      int oy = ty * kTH + py_t, ox = tx * kTW + px_t;
+      bool valid = oy < a.Ho && ox < a.Wo;
+      int Hd = a.Ho, Wd = a.Wo;
+      if (a.pool) {
+        valid = valid && ((py_t | px_t) & 1) == 0;
+        oy >>= 1;
+        ox >>= 1;
+        Hd >>= 1;
+        Wd >>= 1;
+      }
+      const size_t pix = ((size_t)b * Hd + oy) * Wd + ox;
+      mbar_wait(&acc_full[ts], (uint32_t)((tile_it / TS) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ts * ts_cols;
+      for (int n0 = half * 16; n0 < N; n0 += 32) {
+        // operands of the BatchNorm-backward epilogue do not depend on the accumulator: fetch first
+        float xv[16], gv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xv[i] = gv[i] = 0.f;
+        if (a.epi == EPI_BNBWD && valid) {
+          const float* xs = a.fx + pix * a.ldfx + n0;
+          const float* gp = a.G + pix * a.ldG + n0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            if (n0 + i + 3 < a.Cout) {
+              const float4 f = __ldg(reinterpret_cast<const float4*>(xs + i));
+              xv[i] = f.x; xv[i + 1] = f.y; xv[i + 2] = f.z; xv[i + 3] = f.w;
+              if (a.g_accum) {
+                const float4 g4 = *reinterpret_cast<const float4*>(gp + i);
+                gv[i] = g4.x; gv[i + 1] = g4.y; gv[i + 2] = g4.z; gv[i + 3] = g4.w;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (n0 + i + k < a.Cout) {
+                  xv[i + k] = xs[i + k];
+                  if (a.g_accum) gv[i + k] = gp[i + k];
+                }
+            }
+          }
+        }
+        // accumulator: small groups first, then the big one, over all sets
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        for (int g = t.ngroups - 1; g >= 0; --g) {
+          for (int sset = 0; sset < nsets; ++sset) {
+            float w1[16];
+            tmem_ld16(taddr + (uint32_t)((sset * t.ngroups + g) * N + n0), w1);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w1[i];
+          }
+        }
+        if (a.pool) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float s = v[i] + __shfl_xor_sync(0xffffffffu, v[i], 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 8);
+            v[i] = s;
+          }
+        }
+        float s1[16], s2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) s1[i] = s2[i] = 0.f;
+        if (valid) {
+          if (a.epi == EPI_NHWC) {
+            float* dst = a.y + pix * a.ldy + a.coff + n0;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (n0 + i + 3 < a.Cout) {
+                *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (n0 + i + k < a.Cout) dst[i + k] = v[i + k];
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const bool in = n0 + i < a.Cout;
+              s1[i] = in ? v[i] : 0.f;
+              s2[i] = in ? v[i] * v[i] : 0.f;
+            }
+          } else {  // EPI_BNBWD
+            float* gp = a.G + pix * a.ldG + n0;
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int nl = n0 + i;
+              const float z = fmaf(xv[i], ep_s[nl], ep_s[N + nl]);
+              const float dz = (nl < a.Cout && z > 0.f) ? v[i] : 0.f;
+              const float xh = (xv[i] - ep_s[2 * N + nl]) * ep_s[3 * N + nl];
+              s1[i] = dz;
+              s2[i] = dz * xh;
+              o[i] = gv[i] + ep_s[nl] * dz;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (n0 + i + 3 < a.Cout) {
+                *reinterpret_cast<float4*>(gp + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+              } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  if (n0 + i + k < a.Cout) gp[i + k] = o[i + k];
+              }
+            }
+          }
+        }
+        if (want_red) {
+          const float u = colsum16(s1, lane), w = colsum16(s2, lane);
+          if ((lane & 1) == 0) {  // lanes l and l^1 hold the same column
+            float* r = red_s + ((size_t)ew * N + n0 + my_col) * 2;
+            r[0] += u;
+            r[1] += w;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ts]);
+    }
+    if (want_red) {
+      named_bar_sync(1, kEpiWarps * 32);
+      for (int n = threadIdx.x - kEpiWarp0 * 32; n < a.Cout; n += kEpiWarps * 32) {
+        double u = 0.0, w = 0.0;
+#pragma unroll
+        for (int q = 0; q < kEpiWarps; ++q) {
+          u += (double)red_s[((size_t)q * N + n) * 2 + 0];
+          w += (double)red_s[((size_t)q * N + n) * 2 + 1];
+        }
+        if (a.epi == EPI_NHWC) {
+          atomicAdd(a.o_sum + n, u);
+          atomicAdd(a.o_sumsq + n, w);
+        } else {
+          atomicAdd(a.bsum + n, u);
+          atomicAdd(a.bsum + a.Cout + n, w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// filter packing: OIHW fp32 -> [chunk][tap][k-octet][piece][n][8] bf16 pieces
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
+  const Tc2PackDesc d = tab[blockIdx.y];
+  const int T = d.KS * d.KS;
+  const int koct = d.KC >> 3;
+  const size_t per_tap = (size_t)koct * d.N * 8;  // elements of ONE piece of one (chunk, tap)
+  const size_t total = (size_t)d.nchunks * T * per_tap;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t step = i / per_tap;
+    size_t r = i - step * per_tap;
+    const int ko = (int)(r / ((size_t)d.N * 8));
+    r -= (size_t)ko * d.N * 8;
+    const int n = (int)(r >> 3), k8 = (int)(r & 7);
+    const int chunk = (int)(step / T), tap = (int)(step % T);
+    const int k = chunk * d.KC + ko * 8 + k8;
+    float v = 0.f;
+    if (!d.transpose) {
+      if (n < d.Cout && k < d.Cin) v = d.w[((size_t)n * d.Cin + k) * T + tap];
+    } else {
+      if (n < d.Cin && k < d.Cout) v = d.w[((size_t)k * d.Cin + n) * T + (T - 1 - tap)];
+    }
+    uint32_t p[3];
+    bf16_split3(v, p[0], p[1], p[2]);
+    __nv_bfloat16* base = d.dst + step * per_tap * 3 + (size_t)ko * 3 * d.N * 8 + (size_t)n * 8 + k8;
+#pragma unroll
+    for (int pc = 0; pc < 3; ++pc) base[(size_t)pc * d.N * 8] = __ushort_as_bfloat16((unsigned short)p[pc]);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode2() {
+  static EncodeFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeFn>(p);
+  return fn;
+}
+
+size_t tc2_smem(int KS, int N, int KC, int AST, int NB, int TPB) {
+  const int HP = (kTH + KS - 1) * (kTW + KS - 1);
+  const size_t hdr = (256 + sizeof(float) * (size_t)(4 + 2 * kEpiWarps) * N + 127) & ~(size_t)127;
+  return hdr + (size_t)AST * 3 * (KC / 8) * HP * 16 + (size_t)NB * TPB * (KC / 8) * 3 * N * 16;
+}
+
+}  // namespace
+
+void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p) {
+  const int T = KS * KS;
+  int KC = Cin_k >= 32 ? 32 : 16;
+  p->KC = KC;
+  p->nchunks = (Cin_k + KC - 1) / KC;
+  p->ngroups = (3 * N <= 512) ? 3 : 2;
+  int S = 256 / (p->ngroups * N), TS = 2;
+  if (S < 1) {
+    S = 512 / (p->ngroups * N);
+    TS = 1;
+  }
+  if (S > p->nchunks) S = p->nchunks;
+  if (S > 4) S = 4;
+  if (S < 1) S = 1;
+  p->S = S;
+  p->TS = TS;
+  const size_t tap_bytes = (size_t)(KC / 8) * 3 * N * 16;
+  int TPB = 1, NB = 4;
+  if (T * tap_bytes <= 32 * 1024) {
+    TPB = T;
+    NB = 3;
+  } else if (T % 3 == 0 && 3 * tap_bytes <= 36 * 1024) {
+    TPB = 3;
+    NB = 3;
+  }
+  int AST = 3;
+  while (tc2_smem(KS, N, KC, AST, NB, TPB) > 224 * 1024 && (NB > 2 || AST > 2)) {
+    if (NB > 2) --NB;
+    else --AST;
+  }
+  p->AST = AST;
+  p->NB = NB;
+  p->TPB = TPB;
+  p->smem = tc2_smem(KS, N, KC, AST, NB, TPB);
+  p->pack_elems = (size_t)p->nchunks * T * (KC / 8) * 3 * N * 8;
+}
+
+bool tc2_supported(int KS, int stride, int Cin_k, int N) {
+  if (!(KS == 1 || KS == 3) || stride != 1) return false;
+  if (N < 16 || N > 256 || (N & 15)) return false;
+  Tc2Plan p;
+  tc2_plan(KS, Cin_k, N, &p);
+  return p.smem <= 225 * 1024 && (uint32_t)(p.S * p.ngroups * N * p.TS) <= 512u;
+}
+
+int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int Wv, int Cin_k,
+                    cudaStream_t st) {
+  const ConvArgs& a = t.c;
+  PDES_REQUIRE(a.KS == 1 || a.KS == 3, PDES_ERR_UNSUPPORTED, "conv_tc2: kernel size %d", a.KS);
+  PDES_REQUIRE(a.epi != EPI_NCHW, PDES_ERR_UNSUPPORTED, "conv_tc2: NHWC epilogues only");
+  if (a.epi == EPI_NHWC)
+    PDES_REQUIRE(((a.ldy | a.coff) & 3) == 0 && ((uintptr_t)a.y & 15u) == 0, PDES_ERR_INVALID,
+                 "conv_tc2: output slice must be 16-byte aligned");
+  if (a.epi == EPI_BNBWD)
+    PDES_REQUIRE(((a.ldfx | a.ldG) & 3) == 0, PDES_ERR_INVALID, "conv_tc2: gradient buffers misaligned");
+  PDES_REQUIRE(!a.pool || ((a.Ho | a.Wo) & 1) == 0, PDES_ERR_INVALID, "conv_tc2: pool needs even size");
+  EncodeFn enc = get_encode2();
+  PDES_REQUIRE(enc != nullptr, PDES_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const int Cp = (Cin_k + 7) & ~7;
+  CUtensorMap tm;
+  {
+    const cuuint64_t gdim[5] = {8, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)(Cp / 8), (cuuint64_t)3 * a.B};
+    const cuuint64_t gstr[4] = {(cuuint64_t)Cp * 2, (cuuint64_t)Wv * Cp * 2, 16, (cuuint64_t)Hv * Wv * Cp * 2};
+    const cuuint32_t box[5] = {8, (cuuint32_t)(kTW + a.KS - 1), (cuuint32_t)(kTH + a.KS - 1),
+                               (cuuint32_t)(t.KC / 8), 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(planes), gdim,
+                           gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  }
+  const size_t smem = tc2_smem(a.KS, t.N, t.KC, t.AST, t.NB, t.TPB);
+  PDES_REQUIRE(smem <= 227 * 1024, PDES_ERR_UNSUPPORTED, "conv_tc2: needs %zu bytes of shared memory", smem);
+  const int tiles = ((a.Wo + kTW - 1) / kTW) * ((a.Ho + kTH - 1) / kTH) * a.B;
+  int grid = sm_count();
+  if (grid > tiles) grid = tiles;
+  const int mode = t.ngroups == 2 ? 3 : (3 * t.N <= 256 ? 0 : (2 * t.N <= 256 ? 1 : 2));
+#define PDES_TC2_LAUNCH(KSV, MODEV)                                                                          \
+  {                                                                                                          \
+    static size_t attr = 0;                                                                                  \
+    if (smem > attr) {                                                                                       \
+      PDES_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<KSV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                     (int)smem));                                                            \
+      attr = smem;                                                                                           \
+    }                                                                                                        \
+    conv_tc2_kernel<KSV, MODEV><<<grid, kThreads, smem, st>>>(tm, t);                                        \
+  }
+  if (a.KS == 3) {
+    if (mode == 0) PDES_TC2_LAUNCH(3, 0)
+    else if (mode == 1) PDES_TC2_LAUNCH(3, 1)
+    else if (mode == 2) PDES_TC2_LAUNCH(3, 2)
+    else PDES_TC2_LAUNCH(3, 3)
+  } else {
+    if (mode == 0) PDES_TC2_LAUNCH(1, 0)
+    else if (mode == 1) PDES_TC2_LAUNCH(1, 1)
+    else if (mode == 2) PDES_TC2_LAUNCH(1, 2)
+    else PDES_TC2_LAUNCH(1, 3)
+  }
+#undef PDES_TC2_LAUNCH
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st) {
+  if (n == 0) return PDES_OK;
+  int bx = (int)((max_elems / 3 + 255) / 256);
+  if (bx > 128) bx = 128;
+  if (bx < 1) bx = 1;
+  pack_tc2_kernel<<<dim3(bx, n), 256, 0, st>>>(dev_table);
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+}  // namespace pdes

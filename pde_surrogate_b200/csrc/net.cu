@@ -44,6 +44,10 @@ struct Layer {
   TcPlan pf, pb;     // tiling of the forward / dgrad GEMM
   int Nf, Nb;        // padded GEMM-N (Cout / Cin rounded up to 16)
   size_t wtf, wtb;   // float offsets of the packed filter tiles
+  bool tc2_fwd, tc2_bwd;  // TMA-fed bf16x3 tcgen05 path (conv_tc2.cu)
+  Tc2Plan p2f, p2b;
+  size_t w2f, w2b;   // float offsets of the packed bf16 filter pieces
+  size_t planes;     // float offset of this layer's activation piece planes [3][B][Hv][Wv][Cp] bf16
   bool tc_wg;        // weight gradient on tcgen05
   int ci_pad, co_pad;
   size_t dwp;        // float offset of the [tap][ci_pad][co_pad] staging gradient
@@ -69,9 +73,10 @@ struct pdes_net {
   int64_t param_floats = 0, running_floats = 0;
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
   size_t xin = 0;
-  size_t planesA = 0, planesB = 0;  // float offsets of the bf16 operand-piece scratch planes (wgrad)  // float offset: NCHW copy of the last training input (needed by In_conv's wgrad)
+  size_t planesB = 0;  // float offset of the bf16 dY-piece scratch planes (wgrad + dgrad)  // float offset: NCHW copy of the last training input (needed by In_conv's wgrad)
   int n_bn = 0, maxC = 0, max_pack = 0;
-  int n_tc = 0, n_wg = 0;
+  int n_tc = 0, n_wg = 0, n_tc2 = 0;
+  size_t max_tc2_pack = 0;
   size_t max_tc_pack = 0;
   int max_wg_elems = 0;
   int prec = 0;
@@ -138,6 +143,10 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.Nf = rup(Cout, 16);
   L.Nb = rup(Cin, 16);
   L.wtf = L.wtb = 0;
+  L.tc2_fwd = L.tc2_bwd = false;
+  L.w2f = L.w2b = L.planes = 0;
+  memset(&L.p2f, 0, sizeof(L.p2f));
+  memset(&L.p2b, 0, sizeof(L.p2b));
   L.tc_wg = false;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
@@ -277,13 +286,21 @@ int build(pdes_net* n) {
     const Buf& ib = n->bufs[L.in_buf];
     const Buf& ob = n->bufs[L.out_buf];
     const bool aligned = (ib.ld % 4 == 0) && (ob.ld % 4 == 0) && (L.coff % 4 == 0);
-    if (aligned && tc_supported(L.KS, L.stride, L.Cin, L.Nf)) {
-      L.tc_fwd = true;
-      tc_plan(L.KS, L.Cin, L.Nf, &L.pf);
-      L.wtf = f;
-      f += L.pf.pack_floats;
-      n->n_tc++;
-      if (L.pf.pack_floats > n->max_tc_pack) n->max_tc_pack = L.pf.pack_floats;
+    if (aligned && tc2_supported(L.KS, L.stride, L.Cin, L.Nf)) {
+      L.tc2_fwd = true;
+      tc2_plan(L.KS, L.Cin, L.Nf, &L.p2f);
+      L.w2f = f;
+      f += pad4((int64_t)((L.p2f.pack_elems + 1) / 2));
+      n->n_tc2++;
+      if (L.p2f.pack_elems > n->max_tc2_pack) n->max_tc2_pack = L.p2f.pack_elems;
+    }
+    if (aligned && tc2_supported(L.KS, L.stride, L.Cout, L.Nb)) {
+      L.tc2_bwd = true;
+      tc2_plan(L.KS, L.Cout, L.Nb, &L.p2b);
+      L.w2b = f;
+      f += pad4((int64_t)((L.p2b.pack_elems + 1) / 2));
+      n->n_tc2++;
+      if (L.p2b.pack_elems > n->max_tc2_pack) n->max_tc2_pack = L.p2b.pack_elems;
     }
     if (aligned && wgrad_tc_supported(L.KS, L.stride)) {
       L.tc_wg = true;
@@ -293,27 +310,20 @@ int build(pdes_net* n) {
       n->n_wg++;
       if (L.Cout * L.Cin * L.KS * L.KS > n->max_wg_elems) n->max_wg_elems = L.Cout * L.Cin * L.KS * L.KS;
     }
-    if (aligned && tc_supported(L.KS, L.stride, L.Cout, L.Nb)) {
-      L.tc_bwd = true;
-      tc_plan(L.KS, L.Cout, L.Nb, &L.pb);
-      L.wtb = f;
-      f += L.pb.pack_floats;
-      n->n_tc++;
-      if (L.pb.pack_floats > n->max_tc_pack) n->max_tc_pack = L.pb.pack_floats;
-    }
   }
   {
-    size_t maxA = 0, maxB = 0;
-    for (const auto& L : n->layers) {
-      if (!L.tc_wg) continue;
+    size_t maxB = 0;
+    for (auto& L : n->layers) {
+      if (!(L.tc_wg || L.tc2_fwd || L.tc2_bwd)) continue;
       const Buf& ib = n->bufs[L.in_buf];
       const int Hv = L.up ? 2 * ib.H : ib.H, Wv = L.up ? 2 * ib.W : ib.W;
-      const size_t a = act_planes_bytes(B, Hv, Wv, L.Cin), bb = act_planes_bytes(B, L.Ho, L.Wo, L.Cout);
-      if (a > maxA) maxA = a;
+      if (L.tc_wg || L.tc2_fwd) {
+        L.planes = f;
+        f += pad4((int64_t)((act_planes_bytes(B, Hv, Wv, L.Cin) + 3) / 4)) + 64;
+      }
+      const size_t bb = act_planes_bytes(B, L.Ho, L.Wo, L.Cout);
       if (bb > maxB) maxB = bb;
     }
-    n->planesA = f;
-    f += pad4((int64_t)((maxA + 3) / 4)) + 64;
     n->planesB = f;
     f += pad4((int64_t)((maxB + 3) / 4)) + 64;
   }
@@ -334,7 +344,7 @@ int build(pdes_net* n) {
   n->off_tables = (n->off_doubles + n->ws_doubles * sizeof(double) + 255) & ~(size_t)255;
   n->ws_bytes = n->off_tables + sizeof(PackDesc) * n->layers.size() +
                 sizeof(BnLayerDesc) * (size_t)n->n_bn + sizeof(TcPackDesc) * (size_t)n->n_tc +
-                sizeof(TcWgradUnpack) * (size_t)n->n_wg + 256;
+                sizeof(TcWgradUnpack) * (size_t)n->n_wg + sizeof(Tc2PackDesc) * (size_t)n->n_tc2 + 256;
   return PDES_OK;
 }
 
@@ -355,6 +365,11 @@ inline TcPackDesc* tc_table(const pdes_net* n) {
 inline TcWgradUnpack* wg_table(const pdes_net* n) {
   return reinterpret_cast<TcWgradUnpack*>(reinterpret_cast<unsigned char*>(tc_table(n)) +
                                           sizeof(TcPackDesc) * (size_t)n->n_tc);
+}
+
+inline Tc2PackDesc* tc2_table(const pdes_net* n) {
+  return reinterpret_cast<Tc2PackDesc*>(reinterpret_cast<unsigned char*>(wg_table(n)) +
+                                        sizeof(TcWgradUnpack) * (size_t)n->n_wg);
 }
 
 BnSrc bn_src(const pdes_net* n, const Layer& L, int B, bool training) {
@@ -498,6 +513,25 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
   }
   if (!tt.empty())
     PDES_CUDA(cudaMemcpy(tc_table(n), tt.data(), sizeof(TcPackDesc) * tt.size(), cudaMemcpyHostToDevice));
+  std::vector<Tc2PackDesc> t2;
+  for (const auto& L : n->layers) {
+    for (int dir = 0; dir < 2; ++dir) {
+      if (!(dir == 0 ? L.tc2_fwd : L.tc2_bwd)) continue;
+      Tc2PackDesc d;
+      d.w = n->p + L.w_off;
+      d.dst = reinterpret_cast<__nv_bfloat16*>(wsf(n, dir == 0 ? L.w2f : L.w2b));
+      d.Cout = L.Cout;
+      d.Cin = L.Cin;
+      d.KS = L.KS;
+      d.N = dir == 0 ? L.Nf : L.Nb;
+      d.KC = dir == 0 ? L.p2f.KC : L.p2b.KC;
+      d.nchunks = dir == 0 ? L.p2f.nchunks : L.p2b.nchunks;
+      d.transpose = dir;
+      t2.push_back(d);
+    }
+  }
+  if (!t2.empty())
+    PDES_CUDA(cudaMemcpy(tc2_table(n), t2.data(), sizeof(Tc2PackDesc) * t2.size(), cudaMemcpyHostToDevice));
   std::vector<TcWgradUnpack> wt;
   for (const auto& L : n->layers) {
     if (!L.tc_wg || !n->g) continue;
@@ -559,8 +593,8 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   int rc = launch_pack_weights(pack_table(n), (int)n->layers.size(), n->max_pack, st);
   if (rc) return rc;
   n->launches++;
-  if (n->conv_impl == 0 && n->n_tc > 0) {
-    rc = launch_pack_tc(tc_table(n), n->n_tc, n->max_tc_pack, st);
+  if (n->conv_impl == 0 && n->n_tc2 > 0) {
+    rc = launch_pack_tc2(tc2_table(n), n->n_tc2, n->max_tc2_pack, st);
     if (rc) return rc;
     n->launches++;
   }
@@ -614,18 +648,45 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
         a.o_sumsq = wsd(n, ob.stat) + ob.C + L.coff;
       }
     }
-    if (n->conv_impl == 0 && L.tc_fwd && (n->tc_mask & 1)) {
-      TcConvArgs t;
+    const bool want_planes = n->conv_impl == 0 && (L.tc2_fwd || (tr && L.tc_wg));
+    if (want_planes) {
+      // bf16 pieces of relu(bn(x)) (nearest-upsampled if needed): read by the forward conv and,
+      // in training, again by the weight-gradient kernel
+      const Buf& ib = n->bufs[L.in_buf];
+      ActSplitArgs sa;
+      memset(&sa, 0, sizeof(sa));
+      sa.x = a.x;
+      sa.ldx = a.ldx;
+      sa.C = L.Cin;
+      sa.Hs = ib.H;
+      sa.Ws = ib.W;
+      sa.B = B;
+      sa.up = L.up;
+      sa.pro = 1;
+      sa.bn = a.bn;
+      sa.out = reinterpret_cast<__nv_bfloat16*>(wsf(n, L.planes));
+      sa.Cp = (L.Cin + 7) & ~7;
+      rc = launch_act_split(sa, st);
+      if (rc) return rc;
+      n->launches++;
+    }
+    if (n->conv_impl == 0 && L.tc2_fwd && (n->tc_mask & 1)) {
+      const Buf& ib = n->bufs[L.in_buf];
+      Tc2Args t;
+      memset(&t, 0, sizeof(t));
       t.c = a;
-      t.wtc = wsf(n, L.wtf);
+      t.wpk = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.w2f));
       t.N = L.Nf;
-      t.KC = L.pf.KC;
-      t.NB = L.pf.NB;
-      t.nchunks = L.pf.nchunks;
-      t.S = L.pf.S;
-      t.TPB = L.pf.TPB;
-      t.prec = n->prec;
-      rc = launch_conv_tc(t, st);
+      t.KC = L.p2f.KC;
+      t.nchunks = L.p2f.nchunks;
+      t.ngroups = L.p2f.ngroups;
+      t.S = L.p2f.S;
+      t.TS = L.p2f.TS;
+      t.AST = L.p2f.AST;
+      t.NB = L.p2f.NB;
+      t.TPB = L.p2f.TPB;
+      rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planes)),
+                           L.up ? 2 * ib.H : ib.H, L.up ? 2 * ib.W : ib.W, L.Cin, st);
     } else {
       rc = launch_conv_simt(a, st);
     }
@@ -719,25 +780,10 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         w.Hs = L.Hs;
         w.Ws = L.Ws;
       }
-      if (n->conv_impl == 0 && L.tc_wg && (n->tc_mask & 4)) {
-        const Buf& ib = n->bufs[L.in_buf];
-        __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(wsf(n, n->planesA));
-        __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(wsf(n, n->planesB));
-        ActSplitArgs sa;
-        memset(&sa, 0, sizeof(sa));
-        sa.x = w.x;
-        sa.ldx = w.ldx;
-        sa.C = L.Cin;
-        sa.Hs = ib.H;
-        sa.Ws = ib.W;
-        sa.B = B;
-        sa.up = L.up;
-        sa.pro = 1;
-        sa.bn = w.bn;
-        sa.out = pa;
-        sa.Cp = (L.Cin + 7) & ~7;
-        rc = launch_act_split(sa, st);
-        if (rc) return rc;
+      const bool use_wg = n->conv_impl == 0 && L.tc_wg && (n->tc_mask & 4);
+      const bool use_dg = n->conv_impl == 0 && L.tc2_bwd && (n->tc_mask & 2) && L.in_buf >= 0;
+      if (use_wg || use_dg) {
+        // bf16 pieces of the corrected dY slice: GEMM-K operand of dgrad, GEMM-N operand of wgrad
         ActSplitArgs sb;
         memset(&sb, 0, sizeof(sb));
         sb.x = dy;
@@ -746,15 +792,18 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         sb.Hs = L.Ho;
         sb.Ws = L.Wo;
         sb.B = B;
-        sb.out = pb;
+        sb.out = reinterpret_cast<__nv_bfloat16*>(wsf(n, n->planesB));
         sb.Cp = (L.Cout + 7) & ~7;
         rc = launch_act_split(sb, st);
         if (rc) return rc;
-        n->launches += 2;
+        n->launches++;
+      }
+      if (use_wg) {
+        const Buf& ib = n->bufs[L.in_buf];
         TcWgradArgs tw;
         memset(&tw, 0, sizeof(tw));
-        tw.planesA = pa;
-        tw.planesB = pb;
+        tw.planesA = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planes));
+        tw.planesB = reinterpret_cast<const __nv_bfloat16*>(wsf(n, n->planesB));
         tw.dwp = wsf(n, L.dwp);
         tw.B = B;
         tw.Hv = L.up ? 2 * ib.H : ib.H;
@@ -808,18 +857,22 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
       a.ldG = ib.ld;
       a.g_accum = L.last_consumer ? 0 : 1;
       a.bsum = wsd(n, L.bsum);
-      if (n->conv_impl == 0 && L.tc_bwd && (n->tc_mask & 2)) {
-        TcConvArgs t;
+      if (n->conv_impl == 0 && L.tc2_bwd && (n->tc_mask & 2)) {
+        Tc2Args t;
+        memset(&t, 0, sizeof(t));
         t.c = a;
-        t.wtc = wsf(n, L.wtb);
+        t.wpk = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.w2b));
         t.N = L.Nb;
-        t.KC = L.pb.KC;
-        t.NB = L.pb.NB;
-        t.nchunks = L.pb.nchunks;
-        t.S = L.pb.S;
-        t.TPB = L.pb.TPB;
-        t.prec = n->prec;
-        rc = launch_conv_tc(t, st);
+        t.KC = L.p2b.KC;
+        t.nchunks = L.p2b.nchunks;
+        t.ngroups = L.p2b.ngroups;
+        t.S = L.p2b.S;
+        t.TS = L.p2b.TS;
+        t.AST = L.p2b.AST;
+        t.NB = L.p2b.NB;
+        t.TPB = L.p2b.TPB;
+        rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, n->planesB)), L.Ho, L.Wo,
+                             L.Cout, st);
       } else {
         rc = launch_conv_simt(a, st);
       }
