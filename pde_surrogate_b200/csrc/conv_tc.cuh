@@ -32,7 +32,8 @@ struct TcPackDesc {
 struct ActSplitArgs {
   const float* x;        // NHWC, ldx floats per pixel (channel offset already applied)
   int ldx, C, Hs, Ws, B;
-  int up;                // 1: write the nearest x2 upsampled image
+  int up;                // 1: write the nearest x2 upsampled image; 2: zero-insert x2 (value at even positions)
+  int nchw;              // 1: x is planar (B,C,Hs,Ws)
   int pro;               // 1: a = max(0, x*scale+shift) first
   BnSrc bn;
   __nv_bfloat16* out;    // [3][B][Hv][Wv][Cp]
@@ -69,6 +70,7 @@ struct Tc2Args {
   ConvArgs c;                  // geometry (B, Ho, Wo, KS, pad, Cout) and epilogue; x/w/prologue unused
   const __nv_bfloat16* wpk;    // [chunk][tap][k-octet][piece][N][8]
   int N, KC, nchunks, ngroups, S, TS, AST, NB, TPB;
+  int osub;                    // 1: store only even output positions at (y/2, x/2)  (stride-2 as stride-1)
 };
 struct Tc2PackDesc {
   const float* w;  // OIHW

@@ -348,12 +348,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       int oy = ty * kTH + py_t, ox = tx * kTW + px_t;
       bool valid = oy < a.Ho && ox < a.Wo;
       int Hd = a.Ho, Wd = a.Wo;
-      if (a.pool) {
+      if (a.pool || t.osub) {
+        // pool: 2x2 sum (adjoint of nearest upsampling); osub: keep even positions only (a stride-2
+        // convolution evaluated as a stride-1 convolution and subsampled)
         valid = valid && ((py_t | px_t) & 1) == 0;
         oy >>= 1;
         ox >>= 1;
-        Hd >>= 1;
-        Wd >>= 1;
+        Hd = (Hd + 1) >> 1;
+        Wd = (Wd + 1) >> 1;
       }
       const size_t pix = ((size_t)b * Hd + oy) * Wd + ox;
       mbar_wait(&acc_full[ts], (uint32_t)((tile_it / TS) & 1));
@@ -428,6 +430,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
               s1[i] = in ? v[i] : 0.f;
               s2[i] = in ? v[i] * v[i] : 0.f;
             }
+          } else if (a.epi == EPI_NCHW) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + i < a.Cout) a.y[(((size_t)b * a.Cout + n0 + i) * Hd + oy) * Wd + ox] = v[i];
           } else {  // EPI_BNBWD
             float* gp = a.G + pix * a.ldG + n0;
             float o[16];
@@ -565,14 +571,10 @@ void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p) {
   p->S = S;
   p->TS = TS;
   const size_t tap_bytes = (size_t)(KC / 8) * 3 * N * 16;
-  int TPB = 1, NB = 4;
-  if (T * tap_bytes <= 32 * 1024) {
-    TPB = T;
-    NB = 3;
-  } else if (T % 3 == 0 && 3 * tap_bytes <= 36 * 1024) {
-    TPB = 3;
-    NB = 3;
-  }
+  int TPB = 1;
+  for (int d = 1; d <= T; ++d)
+    if (T % d == 0 && d * tap_bytes <= 32 * 1024) TPB = d;
+  int NB = TPB * tap_bytes >= 16 * 1024 ? 3 : 4;
   int AST = 3;
   while (tc2_smem(KS, N, KC, AST, NB, TPB) > 224 * 1024 && (NB > 2 || AST > 2)) {
     if (NB > 2) --NB;
@@ -586,7 +588,7 @@ void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p) {
 }
 
 bool tc2_supported(int KS, int stride, int Cin_k, int N) {
-  if (!(KS == 1 || KS == 3) || stride != 1) return false;
+  if (!(KS == 1 || KS == 3 || KS == 5 || KS == 7) || stride != 1) return false;
   if (N < 16 || N > 256 || (N & 15)) return false;
   Tc2Plan p;
   tc2_plan(KS, Cin_k, N, &p);
@@ -596,14 +598,14 @@ bool tc2_supported(int KS, int stride, int Cin_k, int N) {
 int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int Wv, int Cin_k,
                     cudaStream_t st) {
   const ConvArgs& a = t.c;
-  PDES_REQUIRE(a.KS == 1 || a.KS == 3, PDES_ERR_UNSUPPORTED, "conv_tc2: kernel size %d", a.KS);
-  PDES_REQUIRE(a.epi != EPI_NCHW, PDES_ERR_UNSUPPORTED, "conv_tc2: NHWC epilogues only");
+  PDES_REQUIRE(a.KS == 1 || a.KS == 3 || a.KS == 5 || a.KS == 7, PDES_ERR_UNSUPPORTED, "conv_tc2: kernel size %d", a.KS);
   if (a.epi == EPI_NHWC)
     PDES_REQUIRE(((a.ldy | a.coff) & 3) == 0 && ((uintptr_t)a.y & 15u) == 0, PDES_ERR_INVALID,
                  "conv_tc2: output slice must be 16-byte aligned");
   if (a.epi == EPI_BNBWD)
     PDES_REQUIRE(((a.ldfx | a.ldG) & 3) == 0, PDES_ERR_INVALID, "conv_tc2: gradient buffers misaligned");
   PDES_REQUIRE(!a.pool || ((a.Ho | a.Wo) & 1) == 0, PDES_ERR_INVALID, "conv_tc2: pool needs even size");
+  PDES_REQUIRE(!(a.pool && t.osub), PDES_ERR_INVALID, "conv_tc2: pool and subsample are exclusive");
   EncodeFn enc = get_encode2();
   PDES_REQUIRE(enc != nullptr, PDES_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const int Cp = (Cin_k + 7) & ~7;
@@ -635,17 +637,18 @@ int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int W
     }                                                                                                        \
     conv_tc2_kernel<KSV, MODEV><<<grid, kThreads, smem, st>>>(tm, t);                                        \
   }
-  if (a.KS == 3) {
-    if (mode == 0) PDES_TC2_LAUNCH(3, 0)
-    else if (mode == 1) PDES_TC2_LAUNCH(3, 1)
-    else if (mode == 2) PDES_TC2_LAUNCH(3, 2)
-    else PDES_TC2_LAUNCH(3, 3)
-  } else {
-    if (mode == 0) PDES_TC2_LAUNCH(1, 0)
-    else if (mode == 1) PDES_TC2_LAUNCH(1, 1)
-    else if (mode == 2) PDES_TC2_LAUNCH(1, 2)
-    else PDES_TC2_LAUNCH(1, 3)
+#define PDES_TC2_MODES(KSV)                        \
+  {                                                \
+    if (mode == 0) PDES_TC2_LAUNCH(KSV, 0)         \
+    else if (mode == 1) PDES_TC2_LAUNCH(KSV, 1)    \
+    else if (mode == 2) PDES_TC2_LAUNCH(KSV, 2)    \
+    else PDES_TC2_LAUNCH(KSV, 3)                   \
   }
+  if (a.KS == 3) PDES_TC2_MODES(3)
+  else if (a.KS == 1) PDES_TC2_MODES(1)
+  else if (a.KS == 5) PDES_TC2_MODES(5)
+  else PDES_TC2_MODES(7)
+#undef PDES_TC2_MODES
 #undef PDES_TC2_LAUNCH
   PDES_LAUNCH_CHECK();
   return PDES_OK;

@@ -282,11 +282,14 @@ int build(pdes_net* n) {
     if (pk > n->max_pack) n->max_pack = pk;
   }
   for (auto& L : n->layers) {
-    if (L.kind == 0 || L.out_buf < 0 || L.in_buf < 0) continue;
-    const Buf& ib = n->bufs[L.in_buf];
-    const Buf& ob = n->bufs[L.out_buf];
-    const bool aligned = (ib.ld % 4 == 0) && (ob.ld % 4 == 0) && (L.coff % 4 == 0);
-    if (aligned && tc2_supported(L.KS, L.stride, L.Cin, L.Nf)) {
+    // Tensor-core eligibility.  Stride-2 convolutions are run as stride-1 convolutions whose
+    // epilogue keeps the even positions (forward) / on a zero-inserted dY (dgrad, wgrad); the first
+    // convolution reads the planar network input, the last one writes the planar output.
+    const bool in_ok = L.in_buf < 0 || (n->bufs[L.in_buf].ld % 4 == 0);
+    const bool out_ok = L.out_buf < 0 || ((n->bufs[L.out_buf].ld % 4 == 0) && (L.coff % 4 == 0));
+    const bool sub_ok = L.stride == 1 || (L.stride == 2 && !L.up);
+    const bool aligned = in_ok && out_ok && sub_ok;
+    if (aligned && tc2_supported(L.KS, 1, L.Cin, L.Nf)) {
       L.tc2_fwd = true;
       tc2_plan(L.KS, L.Cin, L.Nf, &L.p2f);
       L.w2f = f;
@@ -294,7 +297,8 @@ int build(pdes_net* n) {
       n->n_tc2++;
       if (L.p2f.pack_elems > n->max_tc2_pack) n->max_tc2_pack = L.p2f.pack_elems;
     }
-    if (aligned && tc2_supported(L.KS, L.stride, L.Cout, L.Nb)) {
+    if (L.in_buf < 0) continue;  // the first convolution needs no dgrad; its wgrad stays SIMT
+    if (aligned && tc2_supported(L.KS, 1, L.Cout, L.Nb)) {
       L.tc2_bwd = true;
       tc2_plan(L.KS, L.Cout, L.Nb, &L.p2b);
       L.w2b = f;
@@ -302,7 +306,7 @@ int build(pdes_net* n) {
       n->n_tc2++;
       if (L.p2b.pack_elems > n->max_tc2_pack) n->max_tc2_pack = L.p2b.pack_elems;
     }
-    if (aligned && wgrad_tc_supported(L.KS, L.stride)) {
+    if (aligned && wgrad_tc_supported(L.KS, 1)) {
       L.tc_wg = true;
       wgrad_tc_dims(L.Cin, L.Cout, &L.ci_pad, &L.co_pad);
       L.dwp = f;
@@ -315,13 +319,14 @@ int build(pdes_net* n) {
     size_t maxB = 0;
     for (auto& L : n->layers) {
       if (!(L.tc_wg || L.tc2_fwd || L.tc2_bwd)) continue;
-      const Buf& ib = n->bufs[L.in_buf];
-      const int Hv = L.up ? 2 * ib.H : ib.H, Wv = L.up ? 2 * ib.W : ib.W;
+      const int Hs = L.in_buf >= 0 ? n->bufs[L.in_buf].H : L.Hs, Ws = L.in_buf >= 0 ? n->bufs[L.in_buf].W : L.Ws;
+      const int Hv = L.up ? 2 * Hs : Hs, Wv = L.up ? 2 * Ws : Ws;
       if (L.tc_wg || L.tc2_fwd) {
         L.planes = f;
         f += pad4((int64_t)((act_planes_bytes(B, Hv, Wv, L.Cin) + 3) / 4)) + 64;
       }
-      const size_t bb = act_planes_bytes(B, L.Ho, L.Wo, L.Cout);
+      const int zi = L.stride == 2 ? 2 : 1;  // dY planes are zero-inserted for stride-2 layers
+      const size_t bb = act_planes_bytes(B, zi * L.Ho, zi * L.Wo, L.Cout);
       if (bb > maxB) maxB = bb;
     }
     n->planesB = f;
@@ -649,20 +654,21 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
       }
     }
     const bool want_planes = n->conv_impl == 0 && (L.tc2_fwd || (tr && L.tc_wg));
+    const int Hs_l = L.in_buf >= 0 ? n->bufs[L.in_buf].H : L.Hs, Ws_l = L.in_buf >= 0 ? n->bufs[L.in_buf].W : L.Ws;
     if (want_planes) {
       // bf16 pieces of relu(bn(x)) (nearest-upsampled if needed): read by the forward conv and,
       // in training, again by the weight-gradient kernel
-      const Buf& ib = n->bufs[L.in_buf];
       ActSplitArgs sa;
       memset(&sa, 0, sizeof(sa));
       sa.x = a.x;
       sa.ldx = a.ldx;
+      sa.nchw = a.in_nchw;
       sa.C = L.Cin;
-      sa.Hs = ib.H;
-      sa.Ws = ib.W;
+      sa.Hs = Hs_l;
+      sa.Ws = Ws_l;
       sa.B = B;
       sa.up = L.up;
-      sa.pro = 1;
+      sa.pro = a.pro;
       sa.bn = a.bn;
       sa.out = reinterpret_cast<__nv_bfloat16*>(wsf(n, L.planes));
       sa.Cp = (L.Cin + 7) & ~7;
@@ -671,10 +677,16 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
       n->launches++;
     }
     if (n->conv_impl == 0 && L.tc2_fwd && (n->tc_mask & 1)) {
-      const Buf& ib = n->bufs[L.in_buf];
+      const int Hv = L.up ? 2 * Hs_l : Hs_l, Wv = L.up ? 2 * Ws_l : Ws_l;
       Tc2Args t;
       memset(&t, 0, sizeof(t));
       t.c = a;
+      if (L.stride == 2) {  // stride-1 evaluation + subsampled store
+        t.c.stride = 1;
+        t.c.Ho = Hv + 2 * L.pad - L.KS + 1;
+        t.c.Wo = Wv + 2 * L.pad - L.KS + 1;
+        t.osub = 1;
+      }
       t.wpk = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.w2f));
       t.N = L.Nf;
       t.KC = L.p2f.KC;
@@ -685,8 +697,7 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
       t.AST = L.p2f.AST;
       t.NB = L.p2f.NB;
       t.TPB = L.p2f.TPB;
-      rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planes)),
-                           L.up ? 2 * ib.H : ib.H, L.up ? 2 * ib.W : ib.W, L.Cin, st);
+      rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planes)), Hv, Wv, L.Cin, st);
     } else {
       rc = launch_conv_simt(a, st);
     }
@@ -788,10 +799,12 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         memset(&sb, 0, sizeof(sb));
         sb.x = dy;
         sb.ldx = lddy;
+        sb.nchw = dy_nchw;
         sb.C = L.Cout;
         sb.Hs = L.Ho;
         sb.Ws = L.Wo;
         sb.B = B;
+        sb.up = L.stride == 2 ? 2 : 0;  // zero-insert: stride-2 layers run as stride-1 kernels
         sb.out = reinterpret_cast<__nv_bfloat16*>(wsf(n, n->planesB));
         sb.Cp = (L.Cout + 7) & ~7;
         rc = launch_act_split(sb, st);
@@ -808,8 +821,8 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         tw.B = B;
         tw.Hv = L.up ? 2 * ib.H : ib.H;
         tw.Wv = L.up ? 2 * ib.W : ib.W;
-        tw.Ho = L.Ho;
-        tw.Wo = L.Wo;
+        tw.Ho = (L.stride == 2 ? 2 : 1) * L.Ho;
+        tw.Wo = (L.stride == 2 ? 2 : 1) * L.Wo;
         tw.Cin = L.Cin;
         tw.Cout = L.Cout;
         tw.KS = L.KS;
@@ -871,8 +884,10 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         t.AST = L.p2b.AST;
         t.NB = L.p2b.NB;
         t.TPB = L.p2b.TPB;
-        rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, n->planesB)), L.Ho, L.Wo,
-                             L.Cout, st);
+        if (L.stride == 2) t.c.in_mode = IN_DIRECT;  // the zero insertion is in the dY planes
+        const int zi = L.stride == 2 ? 2 : 1;
+        rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, n->planesB)), zi * L.Ho,
+                             zi * L.Wo, L.Cout, st);
       } else {
         rc = launch_conv_simt(a, st);
       }

@@ -135,20 +135,31 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
     const int b = (int)(r / Hv);
     const int sy = a.up ? (vy >> 1) : vy, sx = a.up ? (vx >> 1) : vx;
     const int c = 8 * q;
-    const float* p = a.x + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
+    const bool hole = a.up == 2 && ((vy | vx) & 1);  // zero-insert: odd positions are zero
     float v[8];
-    if (c + 7 < a.C && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
-      const float4 f0 = __ldg(reinterpret_cast<const float4*>(p));
-      const float4 f1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-      v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w;
-      v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
-    } else {
+    if (hole) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = (c + k < a.C) ? p[k] : 0.f;
+      for (int k = 0; k < 8; ++k) v[k] = 0.f;
+    } else if (a.nchw) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        v[k] = (c + k < a.C) ? a.x[(((size_t)b * a.C + c + k) * a.Hs + sy) * a.Ws + sx] : 0.f;
+    } else {
+      const float* p = a.x + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
+      if (c + 7 < a.C && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
+        const float4 f0 = __ldg(reinterpret_cast<const float4*>(p));
+        const float4 f1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+        v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w;
+        v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (c + k < a.C) ? p[k] : 0.f;
+      }
     }
     if (a.pro) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = (c + k < a.C) ? fmaxf(0.f, fmaf(v[k], sc_s[c + k], sh_s[c + k])) : 0.f;
+      for (int k = 0; k < 8; ++k)
+        v[k] = (!hole && c + k < a.C) ? fmaxf(0.f, fmaf(v[k], sc_s[c + k], sh_s[c + k])) : 0.f;
     }
     uint32_t o[3][8];
 #pragma unroll
@@ -178,7 +189,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr uint32_t B_OCT = 128u * 16u;            // one co-octet: 128 pixels x 16 B
   constexpr uint32_t B_PIECE = 2u * B_OCT;          // 16 output channels of one piece
   constexpr uint32_t STAGE = (A_BYTES + 3u * B_PIECE + 127u) & ~127u;
-  const int pass = blockIdx.z;                      // which bf16 piece of `a` this CTA streams
+  constexpr int TG = T <= 9 ? T : 10;               // filter taps per CTA (TMEM holds TG accumulators)
+  const int pass = blockIdx.z % kPasses;            // which bf16 piece of `a` this CTA streams
+  const int tap0 = (blockIdx.z / kPasses) * TG;     // first tap of this CTA's tap group
+  const int ntap = (T - tap0) < TG ? (T - tap0) : TG;
   const int NP = kPasses - pass;                    // dY pieces multiplied: 3, 2, 1
   const int NW = NP * kNC;                          // accumulator columns per tap
 
@@ -196,7 +210,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int n_tiles = tiles_x * tiles_y * t.B;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
-  while (tmem_cols < (uint32_t)(T * NW)) tmem_cols <<= 1;
+  while (tmem_cols < (uint32_t)(TG * NW)) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -260,9 +274,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int r = 0; r < kTH; r += 2) {
           const uint64_t bd = b_desc0 + (uint64_t)(r * 8);  // r * 128 B
 #pragma unroll
-          for (int tap = 0; tap < T; ++tap) {
-            const uint64_t ad = a_desc0 + (uint64_t)((r + tap / KS) * HWp + (tap % KS));
-            umma_bf16(tmem_base + (uint32_t)(tap * NW), ad, bd, idesc, (it | r) != 0 ? 1u : 0u);
+          for (int j = 0; j < TG; ++j) {
+            const int tap = tap0 + j;
+            if (j < ntap) {
+              const uint64_t ad = a_desc0 + (uint64_t)((r + tap / KS) * HWp + (tap % KS));
+              umma_bf16(tmem_base + (uint32_t)(j * NW), ad, bd, idesc, (it | r) != 0 ? 1u : 0u);
+            }
           }
         }
         umma_commit(&empty[s]);
@@ -276,12 +293,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quarter = warp & 3;
     const int ci = c0 + quarter * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int tap = 0; tap < T; ++tap) {
+    for (int j = 0; j < ntap; ++j) {
+      const int tap = tap0 + j;
       float v[16];
-      tmem_ld16(taddr + (uint32_t)(tap * NW + (NP - 1) * kNC), v);  // smallest terms first
+      tmem_ld16(taddr + (uint32_t)(j * NW + (NP - 1) * kNC), v);  // smallest terms first
       for (int piece = NP - 2; piece >= 0; --piece) {
         float x[16];
-        tmem_ld16(taddr + (uint32_t)(tap * NW + piece * kNC), x);
+        tmem_ld16(taddr + (uint32_t)(j * NW + piece * kNC), x);
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += x[i];
       }
@@ -356,7 +374,7 @@ size_t wg_smem() {
 
 }  // namespace
 
-bool wgrad_tc_supported(int KS, int stride) { return (KS == 1 || KS == 3) && stride == 1; }
+bool wgrad_tc_supported(int KS, int stride) { return (KS == 1 || KS == 3 || KS == 5) && stride == 1; }
 
 void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad) {
   *ci_pad = (Cin + kMC - 1) / kMC * kMC;
@@ -383,7 +401,7 @@ int launch_act_split(const ActSplitArgs& a, cudaStream_t st) {
 }
 
 int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
-  PDES_REQUIRE(wgrad_tc_supported(t.KS, 1), PDES_ERR_UNSUPPORTED, "wgrad_tc: 1x1 / 3x3 only");
+  PDES_REQUIRE(wgrad_tc_supported(t.KS, 1), PDES_ERR_UNSUPPORTED, "wgrad_tc: 1x1 / 3x3 / 5x5 only");
   PDES_REQUIRE(t.planesA && t.planesB && t.dwp, PDES_ERR_INVALID, "wgrad_tc: null operand planes");
   const int CpA = (t.Cin + 7) & ~7, CpB = (t.Cout + 7) & ~7;
   CUtensorMap tmA, tmB;
@@ -393,27 +411,27 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
   if (rc) return rc;
   const int tiles = ((t.Wo + kTW - 1) / kTW) * ((t.Ho + kTH - 1) / kTH) * t.B;
   const int n_ci = (t.Cin + kMC - 1) / kMC, n_co = (t.Cout + kNC - 1) / kNC;
-  int P = (2 * sm_count()) / (n_ci * n_co * kPasses);
+  const int T = t.KS * t.KS;
+  const int tap_groups = T <= 9 ? 1 : (T + 9) / 10;
+  int P = (2 * sm_count()) / (n_ci * n_co * kPasses * tap_groups);
   if (P < 1) P = 1;
   if (P > tiles) P = tiles;
-  dim3 grid(P, n_ci * n_co, kPasses);
-  if (t.KS == 3) {
-    const size_t smem = wg_smem<3>();
-    static bool attr = false;
-    if (!attr) {
-      PDES_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
-    wgrad_tc_kernel<3><<<grid, kThreads, smem, st>>>(tmA, tmB, t);
-  } else {
-    const size_t smem = wg_smem<1>();
-    static bool attr = false;
-    if (!attr) {
-      PDES_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
-    wgrad_tc_kernel<1><<<grid, kThreads, smem, st>>>(tmA, tmB, t);
+  dim3 grid(P, n_ci * n_co, kPasses * tap_groups);
+#define PDES_WG_LAUNCH(KSV)                                                                                  \
+  {                                                                                                          \
+    const size_t smem = wg_smem<KSV>();                                                                      \
+    static bool attr = false;                                                                                \
+    if (!attr) {                                                                                             \
+      PDES_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                     (int)smem));                                                            \
+      attr = true;                                                                                           \
+    }                                                                                                        \
+    wgrad_tc_kernel<KSV><<<grid, kThreads, smem, st>>>(tmA, tmB, t);                                         \
   }
+  if (t.KS == 3) PDES_WG_LAUNCH(3)
+  else if (t.KS == 1) PDES_WG_LAUNCH(1)
+  else PDES_WG_LAUNCH(5)
+#undef PDES_WG_LAUNCH
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

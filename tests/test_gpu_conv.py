@@ -51,6 +51,9 @@ TC_CASES = [
     (1, 16, 98, 49, 3, 1, 1, 1, 1),
     (1, 13, 20, 16, 3, 1, 1, 0, 1),    # ragged spatial size, partial tiles
     (3, 8, 8, 16, 3, 1, 1, 0, 1),      # image smaller than the 16-row tile
+    (2, 16, 49, 3, 5, 1, 2, 0, 1),     # last conv (5x5, 3 output channels)
+    (1, 32, 52, 16, 5, 1, 2, 0, 1),
+    (2, 16, 4, 48, 7, 1, 3, 0, 0),     # 7x7 taps
 ]
 
 
@@ -120,6 +123,8 @@ def _run_case(case, impl):
     da = torch.full((B, H, H, Cin), 7.0, device="cuda")
     _lib.check(L.pdes_conv2d_dgrad(byref(d), _lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(da), impl, st))
     assert rel(da, a.grad.permute(0, 2, 3, 1)) < (3e-6 if impl == 1 else 1e-5), rel(da, a.grad.permute(0, 2, 3, 1))
+    if impl == 2 and K == 7:
+        return  # 7x7 weight gradients stay on the SIMT kernel (49 accumulators do not fit TMEM)
     # wgrad (accumulates)
     dw = torch.ones(Cout, Cin, K, K, device="cuda")
     _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), _lib.ptr(sd) if bn else None,
