@@ -1,0 +1,131 @@
+"""Host-side logic of the reference-facing modules on CPU (oracle-backed executor, see
+tests/_cpu_backend.py): module tree / state_dict parity, flat storage, autograd wiring,
+loss memoisation, error behaviour, and the UNMODIFIED reference training script end to end."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdes_oracle as orc
+from tests._cpu_backend import cpu_backend
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("PDES_REFERENCE", "/root/reference")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def test_state_dict_matches_reference_layout(golden_dir):
+    from models.codec import DenseED
+    g = np.load(os.path.join(golden_dir, "densenet_full64.npz"))
+    torch.manual_seed(1)
+    m = DenseED(1, 3, 64, [6, 8, 6])
+    assert [n for n, _ in m.named_parameters()] == [str(s) for s in g["param_names"]]
+    assert tuple(m.model_size) == (740091, 28)
+    plan = orc.densenet_plan(1, 3, 64, [6, 8, 6])
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in orc.state_layout(plan)]
+    flat, gflat = m.flat_parameters()
+    assert all(p.data_ptr() >= flat.data_ptr() and p.data_ptr() < flat.data_ptr() + flat.numel() * 4
+               for p in m.parameters())
+    m2 = m.double()  # _apply re-flattens and keeps values
+    assert m2._flat.dtype == torch.float64 and len(m2.state_dict()) == 163
+    with pytest.raises(ValueError):
+        DenseED(1, 3, 64, [6, 8])
+    with pytest.raises(NotImplementedError):
+        DenseED(1, 3, 64, [6, 8, 6], upsample='bilinear')
+
+
+def test_no_cpu_fallback_in_product():
+    from models.codec import DenseED
+    from models.darcy import conv_boundary_condition
+    from utils.image_gradient import SobelFilter
+    m = DenseED(1, 3, 16, [1, 1, 1], growth_rate=4, init_features=8)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 1, 16, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        conv_boundary_condition(torch.zeros(2, 3, 16, 16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SobelFilter(16).grad_h(torch.zeros(1, 1, 16, 16))
+
+
+def test_autograd_wiring_and_memo(golden_dir):
+    g = np.load(os.path.join(golden_dir, "densenet_small16.npz"))
+    cfg = dict(in_channels=1, out_channels=3, imsize=16, blocks=[1, 2, 1], growth_rate=4, init_features=8)
+    with cpu_backend():
+        from models.codec import DenseED
+        from models import darcy
+        from pde_surrogate_b200 import darcy as pd
+        from utils.image_gradient import SobelFilter
+        model = DenseED(1, 3, 16, [1, 2, 1], growth_rate=4, init_features=8)
+        model.load_state_dict(orc.make_state(orc.densenet_plan(**cfg), int(g["seed"])))
+        K = orc.make_input(int(g["B"]), 16, int(g["seed"]))
+        sob = SobelFilter(16, correct=True, device="cpu")
+        model.train()
+        model.zero_grad()
+        out = model(K)
+        calls = []
+        real = pd._DarcyLossFn.apply
+        pd._DarcyLossFn.apply = staticmethod(lambda *a: (calls.append(1), real(*a))[1])
+        l_c = darcy.conv_constitutive_constraint(K, out, sob)
+        l_d = darcy.conv_continuity_constraint(out, sob)
+        l_dir, l_neu = darcy.conv_boundary_condition(out)
+        pd._DarcyLossFn.apply = staticmethod(real)
+        assert len(calls) == 1, "the three loss calls must share one fused evaluation"
+        loss = (l_c + l_d) + (l_dir + l_neu) * 10.0
+        loss.backward()
+        assert abs(float(loss) - float(g["loss"])) <= 2e-5 * float(g["loss"])
+        flat = np.concatenate([p.grad.numpy().ravel() for p in model.parameters()])
+        assert rel(flat, g["grads32"]) < 1e-4
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(model.parameters(), model._grad_views))
+        g1 = model.flat_parameters()[1].clone()
+        # a new tensor object (even at a recycled address) must not hit the memo
+        out2 = model(K)
+        assert darcy.conv_boundary_condition(out2)[0] is not l_dir
+        model.zero_grad()
+        assert all(p.grad is None for p in model.parameters())
+        out3 = model(K)
+        d, n = darcy.conv_boundary_condition(out3)
+        (d + n).backward()
+        assert model._params[0].grad is not None and float(model.flat_parameters()[1].abs().sum()) > 0
+        assert rel(model.flat_parameters()[1].numpy(), g1.numpy()) > 1e-3  # different loss, fresh buffer
+        model.eval()
+        with pytest.raises(NotImplementedError):
+            model(K).sum().backward()
+        with torch.no_grad():
+            assert model(K).requires_grad is False
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "train_codec_mixed_residual.py")),
+                    reason="reference checkout not present (only in the build container)")
+def test_unmodified_training_script_runs(tmp_path):
+    """BASELINE config 0 plumbing: the reference's own train_codec_mixed_residual.py, byte for byte,
+    against this repo's models/ and utils/ packages (oracle-backed executor on CPU)."""
+    from pde_surrogate_b200 import data
+    d = tmp_path / "datasets" / "32x32"
+    d.mkdir(parents=True)
+    rs = np.random.RandomState(0)
+    x = data.grf_kle(24, 32, 64, 0.2, seed=1, device="cpu").numpy()
+    data.write_hdf5(str(d / "kle512_lhs10000_train.hdf5"), x[:16])
+    data.write_hdf5(str(d / "kle512_lhs1000_val.hdf5"), x[16:], rs.standard_normal((8, 3, 32, 32)))
+    import run_reference_script
+    argv = ["--", "--data-dir", str(tmp_path / "datasets"), "--exp-dir", str(tmp_path / "exp"), "--imsize", "32",
+            "--ntrain", "16", "--ntest", "8", "--batch-size", "8", "--test-batch-size", "8", "--epochs", "1",
+            "--cuda", "0", "--plot-freq", "1", "--ckpt-freq", "1"]
+    old_argv, old_path = list(sys.argv), list(sys.path)
+    try:
+        with cpu_backend():
+            run_reference_script.main(argv)
+    finally:
+        sys.argv, sys.path[:] = old_argv, old_path
+    run_dirs = list((tmp_path / "exp").rglob("args.txt"))
+    assert len(run_dirs) == 1
+    run = run_dirs[0].parent
+    assert (run / "checkpoints" / "model_epoch1.pth").exists()
+    assert (run / "training" / "loss_train.txt").exists() and (run / "training" / "r2_test.txt").exists()
+    sd = torch.load(str(run / "checkpoints" / "model_epoch1.pth"))
+    assert len(sd) == 163 and "features.LastTransUp.conv3.weight" in sd
