@@ -208,9 +208,12 @@ def main():
         ts.broadcast_parameters()
     last = {}
 
+    use_graph = os.environ.get("PDES_BENCH_GRAPH", "1") != "0"
+
     def dev_step(i):
         K = dset[(i % n_batches) * BATCH:(i % n_batches + 1) * BATCH]
-        last["loss"] = ts.step(K, lr=sched.step((i + 1) / total_steps))
+        lr = sched.step((i + 1) / total_steps)
+        last["loss"] = ts.step_graph(K, lr=lr) if use_graph else ts.step(K, lr=lr)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -309,6 +312,7 @@ def main():
                     scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                     config=dict(workload=WORKLOAD, global_batch=BATCH * world,
                                 parallelism="dp%d" % world if world > 1 else "single",
+                                cuda_graph=bool(use_graph),
                                 l2="each step streams ~210 MB of activations+gradients (> 126 MB L2) and a "
                                    "different batch of the HBM-resident dataset; no explicit flush",
                                 grf="exp covariance, l=0.1, 512 KLE modes, seed 1"),

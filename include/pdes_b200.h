@@ -149,6 +149,15 @@ int pdes_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
                    float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                    int64_t step, void* stream);
 
+/* Same update with the step-dependent scalars read from DEVICE memory, so that the launch can be
+ * replayed from a CUDA graph: hyper = {lr/(1-beta1^t), 1/sqrt(1-beta2^t), beta1, beta2, eps,
+ * weight_decay, grad_scale} (7 floats, see pdes_adam_hyper). */
+int pdes_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                       void* stream);
+/* Fills the 7 host floats consumed by pdes_adam_step_dev for 1-based step `step`. */
+int pdes_adam_hyper(float* hyper7_host, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float grad_scale, int64_t step);
+
 /* ------------------------------------------------------------------------------------
  * Single convolution entry points (the building blocks the executor uses), exposed for
  * unit tests against torch.nn.functional.conv2d.  NHWC activations.

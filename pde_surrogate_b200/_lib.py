@@ -54,6 +54,8 @@ SIGNATURES = {
     "pdes_densenet_set_conv_impl": (c_int, [c_void_p, c_int]),
     "pdes_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                c_float, c_float, c_float, c_int64, c_void_p]),
+    "pdes_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "pdes_adam_hyper": (c_int, [c_void_p, c_float, c_float, c_float, c_float, c_float, c_float, c_int64]),
     "pdes_conv2d_fwd": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p]),
     "pdes_conv2d_dgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -72,6 +72,23 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   }
 }
 
+__global__ void __launch_bounds__(256)
+adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                float* __restrict__ v, int64_t n, const float* __restrict__ hyper) {
+  const float step_size = hyper[0], inv_sqrt_bc2 = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4],
+              wd = hyper[5], gscale = hyper[6];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    float gk = g[i] * gscale;
+    if (wd != 0.f) gk += wd * p[i];
+    const float mk = b1 * m[i] + (1.f - b1) * gk;
+    const float vk = b2 * v[i] + (1.f - b2) * gk * gk;
+    m[i] = mk;
+    v[i] = vk;
+    p[i] -= step_size * (mk / (sqrtf(vk) * inv_sqrt_bc2 + eps));
+  }
+}
+
 }  // namespace pdes
 
 using namespace pdes;
@@ -109,6 +126,33 @@ extern "C" int pdes_adam_step(float* p, const float* g, float* m, float* v, int6
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                         weight_decay, grad_scale, step_size,
                                                         inv_sqrt_bc2);
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+extern "C" int pdes_adam_hyper(float* h, float lr, float beta1, float beta2, float eps, float weight_decay,
+                               float grad_scale, int64_t step) {
+  PDES_REQUIRE(h != nullptr && step >= 1, PDES_ERR_INVALID, "pdes_adam_hyper: null pointer or step < 1");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  h[0] = (float)((double)lr / bc1);
+  h[1] = (float)(1.0 / sqrt(bc2));
+  h[2] = beta1;
+  h[3] = beta2;
+  h[4] = eps;
+  h[5] = weight_decay;
+  h[6] = grad_scale;
+  return PDES_OK;
+}
+
+extern "C" int pdes_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper,
+                                  void* stream) {
+  PDES_REQUIRE(p && g && m && v && hyper, PDES_ERR_INVALID, "pdes_adam_step_dev: null pointer");
+  if (n <= 0) return PDES_OK;
+  int blocks = (int)((n + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper);
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

@@ -25,6 +25,11 @@ class TrainStep(object):
         self.steps = 0
         self.kernel_launches = 0
         self.l4 = torch.zeros(4, device=self.flat.device)
+        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        self.hyper_dev = torch.zeros(8, dtype=torch.float32, device=self.flat.device)
+        self.graph = None
+        self.static_K = None
+        self.static_loss = None
         model.train()
         for p, v in zip(model._params, model._grad_views):
             p.grad = v
@@ -34,6 +39,74 @@ class TrainStep(object):
         import torch.distributed as dist
         dist.broadcast(self.flat, 0, group=self.pg)
         dist.broadcast(self.model._flat_running, 0, group=self.pg)
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    def _device_work(self, K):
+        """Everything of a step that is pure device work with step-independent launch arguments
+        (the Adam scalars are read from self.hyper_dev): capturable into a CUDA graph."""
+        L = _lib.lib()
+        ex = self.model._ex
+        st = _lib.stream_ptr()
+        B, _, H, W = K.shape
+        self.gflat.zero_()
+        out = ex.forward(K, True)
+        n = L.pdes_densenet_last_launches(ex.handle.h)
+        _lib.check(L.pdes_darcy_loss_fwd(_lib.ptr(K), _lib.ptr(out), B, H, W, 1, _lib.ptr(self.l4),
+                                         _lib.ptr(_darcy._workspace(K.device)), st), "pdes_darcy_loss_fwd")
+        dout = torch.empty_like(out)
+        _lib.check(L.pdes_darcy_loss_bwd(_lib.ptr(K), _lib.ptr(out), _lib.ptr(self.gw), B, H, W, 1,
+                                         _lib.ptr(dout), st), "pdes_darcy_loss_bwd")
+        ex.backward(dout)
+        n += L.pdes_densenet_last_launches(ex.handle.h) + 2
+        if self.world == 1:
+            _lib.check(L.pdes_adam_step_dev(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m),
+                                            _lib.ptr(self.v), self.flat.numel(), _lib.ptr(self.hyper_dev), st),
+                       "pdes_adam_step_dev")
+            n += 1
+        self.model._flat_nbt.add_(1)
+        self.kernel_launches = n
+        return torch.dot(self.l4, self.gw)
+
+    def capture(self, K_example):
+        """Record the whole step into one CUDA graph (single-GPU: including Adam; data-parallel: up to
+        the gradient bucket, the NCCL all-reduce and Adam follow eagerly)."""
+        self.static_K = torch.empty_like(K_example)
+        self.static_K.copy_(K_example)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._set_hyper(self.lr)
+            for _ in range(2):  # warm-up: lazily-set kernel attributes, workspaces, tensor maps
+                self._device_work(self.static_K)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._device_work(self.static_K)
+        self.steps += 2 if self.world == 1 else 0
+
+    def _set_hyper(self, lr):
+        L = _lib.lib()
+        _lib.check(L.pdes_adam_hyper(self.hyper_host.data_ptr(), float(lr), self.betas[0], self.betas[1], self.eps,
+                                     self.wd, 1.0 / self.world, self.steps + 1), "pdes_adam_hyper")
+        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+
+    def step_graph(self, K, lr=None):
+        """Replay the captured step on batch K (copied into the graph's static input)."""
+        if self.graph is None:
+            self.capture(K)
+        self.static_K.copy_(K, non_blocking=True)
+        self._set_hyper(self.lr if lr is None else lr)
+        self.graph.replay()
+        self.steps += 1
+        if self.world > 1:
+            import torch.distributed as dist
+            L = _lib.lib()
+            dist.all_reduce(self.gflat, group=self.pg)
+            _lib.check(L.pdes_adam_step_dev(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m),
+                                            _lib.ptr(self.v), self.flat.numel(), _lib.ptr(self.hyper_dev),
+                                            _lib.stream_ptr()), "pdes_adam_step_dev")
+        return self.static_loss
 
     def step(self, K, lr=None):
         """One optimisation step on the (B,1,H,W) device batch K; returns the 0-d device loss."""
