@@ -2,6 +2,8 @@
 // the DenseED executor launches).  These three calls are the only ones in the library that
 // allocate: a stream-ordered scratch buffer for the packed weights.
 #include <string.h>
+#include <stdlib.h>
+#include <stdio.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
 
@@ -120,7 +122,29 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
     t.AST = p.AST;
     t.NB = p.NB;
     t.TPB = p.TPB;
+    long long* dbg = nullptr;
+    const char* e = getenv("PDES_TC2_DBG");
+    if (e && atoi(e)) {
+      PDES_CUDA(cudaMallocAsync((void**)&dbg, sizeof(long long) * 16 * 256, st));
+      PDES_CUDA(cudaMemsetAsync(dbg, 0, sizeof(long long) * 16 * 256, st));
+      t.dbg = dbg;
+      // warm-up launch so that the timed one sees warm L2 / instruction cache
+      rc = launch_conv_tc2(t, planes, Hv, Wv, Cin_k, st);
+    }
     rc = launch_conv_tc2(t, planes, Hv, Wv, Cin_k, st);
+    if (dbg) {
+      long long h[16 * 4];
+      PDES_CUDA(cudaMemcpyAsync(h, dbg, sizeof(h), cudaMemcpyDeviceToHost, st));
+      PDES_CUDA(cudaStreamSynchronize(st));
+      const char* names[11] = {"setup", "mma:acc_empty", "mma:a_full0", "mma:a_full1", "mma:tile0 issued", "mma:last issued",
+                               "epi:acc_full0", "epi:tile0 done", "epi:last done", "epi:exit", "cta:exit"};
+      for (int c = 0; c < 2; ++c) {
+        fprintf(stderr, "[tc2 dbg] CTA %d (N=%d KC=%d chunks=%d TPB=%d NB=%d AST=%d S=%d TS=%d):", c, N, p.KC, p.nchunks, p.TPB, p.NB, p.AST, p.S, p.TS);
+        for (int i = 1; i < 11; ++i) fprintf(stderr, " %s=+%lld", names[i], h[c * 16 + i] ? h[c * 16 + i] - h[c * 16] : -1);
+        fprintf(stderr, "\n");
+      }
+      cudaFreeAsync(dbg, st);
+    }
   }
   cudaFreeAsync(buf, st);
   return rc;

@@ -36,13 +36,13 @@ struct ActSplitArgs {
   int nchw;              // 1: x is planar (B,C,Hs,Ws)
   int pro;               // 1: a = max(0, x*scale+shift) first
   BnSrc bn;
-  __nv_bfloat16* out;    // [3][B][Hv][Wv][Cp]
+  __nv_bfloat16* out;    // [3][B][Hv][Cp/8][Wv][8]
   int Cp;                // C rounded up to 8
 };
 
 struct TcWgradArgs {
-  const __nv_bfloat16* planesA;  // [3][B][Hv][Wv][CpA]  activation pieces (after BN+ReLU / upsampling)
-  const __nv_bfloat16* planesB;  // [3][B][Ho][Wo][CpB]  dY pieces
+  const __nv_bfloat16* planesA;  // [3][B][Hv][CpA/8][Wv][8]  activation pieces (after BN+ReLU / upsampling)
+  const __nv_bfloat16* planesB;  // [3][B][Ho][CpB/8][Wo][8]  dY pieces
   float* dwp;                    // staging gradient [tap][ci_pad][co_pad] (vector reductions)
   int B, Hv, Wv, Ho, Wo, Cin, Cout, KS, pad;
   int ci_pad, co_pad;
@@ -70,6 +70,7 @@ struct Tc2Args {
   ConvArgs c;                  // geometry (B, Ho, Wo, KS, pad, Cout) and epilogue; x/w/prologue unused
   const __nv_bfloat16* wpk;    // [chunk][tap][k-octet][piece][N][8]
   int N, KC, nchunks, ngroups, S, TS, AST, NB, TPB;
+  long long* dbg;              // optional per-CTA phase timestamps (debug), 16 slots per CTA
   int osub;                    // 1: store only even output positions at (y/2, x/2)  (stride-2 as stride-1)
 };
 struct Tc2PackDesc {
@@ -79,7 +80,7 @@ struct Tc2PackDesc {
 };
 void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p);
 bool tc2_supported(int KS, int stride, int Cin_k, int N);
-// planes: [3][B][Hv][Wv][round8(Cin_k)] bf16 pieces of the GEMM-K operand (act_split_kernel)
+// planes: [3][B][Hv][round8(Cin_k)/8][Wv][8] bf16 pieces of the GEMM-K operand (act_split_kernel)
 int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int Wv, int Cin_k, cudaStream_t st);
 int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st);
 

@@ -3,7 +3,7 @@
 //
 // Operands never pass through registers: the activation side (BN+ReLU'd, optionally nearest-
 // upsampled input — or the corrected dY slice for dgrad) is pre-split once per layer into three
-// bf16 planes by act_split_kernel; 5-D TMA boxes (cp.async.bulk.tensor, zero fill outside the
+// bf16 planes by act_split_kernel; 4-D TMA boxes (cp.async.bulk.tensor, zero fill outside the
 // image = convolution padding) drop a (TH+2)x(TW+2) halo tile of one channel chunk into shared
 // memory as [channel octet][halo pixel][16 B] — the canonical no-swizzle K-major UMMA layout —
 // and the KSxKS filter taps are shifted descriptors into that one tile (im2col-free).  Filter
@@ -50,12 +50,39 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
-                                            int c3, int c4, uint64_t* bar) {
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
-      "%5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
-      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// same instruction with the 64-bit descriptors given as (lo, hi) words: all per-MMA address
+// arithmetic happens on the 32-bit low words (start address / LBO fields)
+__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+      "%5}], [%6];" ::"r"(smem_u32(smem_dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void bf16_split3(float x, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
@@ -154,6 +181,8 @@ template <> struct Ops<3> {
   static constexpr uint32_t A = 0x211000u, Bp = 0x10210u, NP = 0x111111u, G = 0x111110u;
 };
 #define OPF(tab, i) ((int)(((tab) >> (4 * (i))) & 0xFu))
+// ops that are the first writer of (all of) their column groups within one k16 step
+template <int MODE> struct FirstW { static constexpr uint32_t mask = MODE == 0 ? 0x1u : (MODE == 1 ? 0x3u : (MODE == 2 ? 0x7u : 0x3u)); };
 
 template <int KS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -231,6 +260,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+#define DBG(slot) do { if (t.dbg) t.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
+  if (threadIdx.x == 0) DBG(0);
 
   if (warp == 0) {
     // ===== TMA producer: activation halo tiles (three bf16 pieces per chunk) =====
@@ -250,7 +281,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
           mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
 #pragma unroll
           for (int p = 0; p < 3; ++p)
-            tma_load_5d(st + (size_t)p * a_piece_bytes, &tmA, 0, ix0, iy0, ch * koct, p * a.B + b, &a_full[s]);
+            tma_load_4d(st + (size_t)p * a_piece_bytes, &tmA, ix0 * 8, iy0, ch * koct, p * a.B + b, &a_full[s]);
         }
       }
     }
@@ -270,61 +301,94 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       }
     }
   } else if (warp == 2) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+    // ===== MMA issuer: the whole warp walks the (warp-uniform) loop so that descriptors live in
+    // uniform registers; one elected lane issues the tcgen05 instructions =====
+    {
       using OP = Ops<MODE>;
       uint32_t idesc[OP::n];
 #pragma unroll
       for (int i = 0; i < OP::n; ++i) idesc[i] = make_idesc_bf16(128, OPF(OP::NP, i) * N);
       const uint32_t lbo_a = HP * 16u, sbo_a = HWp * 16u;            // K-major: LBO = next channel octet
       const uint32_t lbo_b = 3u * (uint32_t)N * 16u, sbo_b = 128u;   // [koct][piece][n][16 B]
-      int qa = 0, qb = 0, tile_it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
-        const int ts = tile_it % TS;
-        mbar_wait(&acc_empty[ts], (uint32_t)(((tile_it / TS) & 1) ^ 1));
-        tc_fence_after();
-        const uint32_t d_base = tmem_base + (uint32_t)ts * ts_cols;
-        uint32_t used = 0;  // bit (set*3+group)
-        for (int ch = 0; ch < nchunks; ++ch, ++qa) {
-          const int sa = qa % AST;
-          const int set = ch % t.S;
-          mbar_wait(&a_full[sa], (uint32_t)((qa / AST) & 1));
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(A_s + (size_t)sa * a_stage_bytes);
-          uint64_t adesc[3];
+      // per-op loop invariants: filter-piece offset (16-byte units) inside a k-octet block
+      uint32_t boff[OP::n];
 #pragma unroll
-          for (int p = 0; p < 3; ++p) adesc[p] = make_desc(a_base + (uint32_t)p * a_piece_bytes, lbo_a, sbo_a);
+      for (int i = 0; i < OP::n; ++i) boff[i] = (uint32_t)(OPF(OP::Bp, i) * N);
+      const uint32_t kstep_a = (2u * lbo_a) >> 4, kstep_b = (2u * lbo_b) >> 4;  // one k16 step, 16-byte units
+      const uint32_t a_piece_u = a_piece_bytes >> 4;
+      const int kc16 = KC / 16;
+      // ring positions are kept as (stage, phase) counters: no integer division in the issue loop
+      int sa = 0, sb = 0, ts = 0, tin = 0, tile_it = 0;
+      uint32_t pa = 0, pb = 0, pt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
+        mbar_wait(&acc_empty[ts], pt ^ 1u);
+        tc_fence_after();
+        if (tile_it == 0 && lane == 0) DBG(1);
+        const uint32_t d_base = tmem_base + (uint32_t)ts * ts_cols;
+        int set = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const bool fresh = ch < t.S;  // first visit of this accumulator set in this tile
+          uint32_t dcol[OP::n];
+#pragma unroll
+          for (int i = 0; i < OP::n; ++i) dcol[i] = d_base + (uint32_t)((set * t.ngroups + OPF(OP::G, i)) * N);
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          if (tile_it == 0 && ch == 0 && lane == 0) DBG(2);
+          if (tile_it == 0 && ch == 1 && lane == 0) DBG(3);
+          const uint64_t ad0 = make_desc(smem_u32(A_s + (size_t)sa * a_stage_bytes), lbo_a, sbo_a);
+          const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32);
+#pragma unroll(KS <= 3 ? T : 1)
           for (int tap = 0; tap < T; ++tap) {
-            const int sb = qb % NB;
-            const int tin = tap % TPB;
             if (tin == 0) {
-              mbar_wait(&b_full[sb], (uint32_t)((qb / NB) & 1));
+              mbar_wait(&b_full[sb], pb);
               tc_fence_after();
             }
-            const uint64_t bdesc0 =
+            const uint64_t bd0 =
                 make_desc(smem_u32(B_s + (size_t)sb * b_stage_bytes) + (uint32_t)tin * b_tap_bytes, lbo_b, sbo_b);
-            const uint64_t tapoff = (uint64_t)((tap / KS) * HWp + (tap % KS));
-            for (int k16 = 0; k16 < KC / 16; ++k16) {
-              const uint64_t ka = tapoff + (uint64_t)((2u * k16 * lbo_a) >> 4);
-              const uint64_t kb = (uint64_t)((2u * k16 * lbo_b) >> 4);
+            const uint32_t b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+            const uint32_t a_tap = a_lo0 + (uint32_t)((tap / KS) * HWp + (tap % KS));
+            if (elect_one()) {
 #pragma unroll
-              for (int i = 0; i < OP::n; ++i) {
-                // accumulate iff every group this instruction writes already holds data
-                const uint32_t bits = ((1u << OPF(OP::NP, i)) - 1u) << (set * 3 + OPF(OP::G, i));
-                const uint32_t acc = (used & bits) == bits ? 1u : 0u;
-                umma_bf16(d_base + (uint32_t)((set * t.ngroups + OPF(OP::G, i)) * N), adesc[OPF(OP::A, i)] + ka,
-                          bdesc0 + kb + (uint64_t)(OPF(OP::Bp, i) * N), idesc[i], acc);
-                used |= bits;
+              for (int k16 = 0; k16 < 2; ++k16) {
+                if (k16 < kc16) {
+                  const uint32_t a_k = a_tap + (uint32_t)k16 * kstep_a;
+                  const uint32_t b_k = b_lo0 + (uint32_t)k16 * kstep_b;
+#pragma unroll
+                  for (int i = 0; i < OP::n; ++i) {
+                    const bool first = fresh && tap == 0 && k16 == 0 && ((FirstW<MODE>::mask >> i) & 1u);
+                    umma_bf16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
+                                idesc[i], first ? 0u : 1u);
+                  }
+                }
+              }
+              if (tin == TPB - 1) umma_commit(&b_empty[sb]);
+              if (tap == T - 1) umma_commit(&a_empty[sa]);
+            }
+            __syncwarp();
+            if (++tin == TPB) {
+              tin = 0;
+              if (++sb == NB) {
+                sb = 0;
+                pb ^= 1u;
               }
             }
-            if (tin == TPB - 1) {
-              umma_commit(&b_empty[sb]);
-              ++qb;
-            }
           }
-          umma_commit(&a_empty[sa]);
+          if (++sa == AST) {
+            sa = 0;
+            pa ^= 1u;
+          }
+          if (++set == t.S) set = 0;
         }
-        umma_commit(&acc_full[ts]);
+        if (elect_one()) umma_commit(&acc_full[ts]);
+        __syncwarp();
+        if (lane == 0) {
+          if (tile_it == 0) DBG(4);
+          DBG(5);
+        }
+        if (++ts == TS) {
+          ts = 0;
+          pt ^= 1u;
+        }
       }
     }
   } else if (warp >= kEpiWarp0) {
@@ -360,6 +424,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       const size_t pix = ((size_t)b * Hd + oy) * Wd + ox;
       mbar_wait(&acc_full[ts], (uint32_t)((tile_it / TS) & 1));
       tc_fence_after();
+      if (ew == 0 && lane == 0 && tile_it == 0) DBG(6);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ts * ts_cols;
       for (int n0 = half * 16; n0 < N; n0 += 32) {
         // operands of the BatchNorm-backward epilogue do not depend on the accumulator: fetch first
@@ -471,6 +536,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ts]);
+      if (ew == 0 && lane == 0) { if (tile_it == 0) DBG(7); DBG(8); }
     }
     if (want_red) {
       named_bar_sync(1, kEpiWarps * 32);
@@ -491,12 +557,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       }
     }
   }
+  if (threadIdx.x == kEpiWarp0 * 32) DBG(9);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG(10);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+#undef DBG
 }
 
 // ---------------------------------------------------------------------------------------
@@ -611,14 +680,15 @@ int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int W
   const int Cp = (Cin_k + 7) & ~7;
   CUtensorMap tm;
   {
-    const cuuint64_t gdim[5] = {8, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)(Cp / 8), (cuuint64_t)3 * a.B};
-    const cuuint64_t gstr[4] = {(cuuint64_t)Cp * 2, (cuuint64_t)Wv * Cp * 2, 16, (cuuint64_t)Hv * Wv * Cp * 2};
-    const cuuint32_t box[5] = {8, (cuuint32_t)(kTW + a.KS - 1), (cuuint32_t)(kTH + a.KS - 1),
-                               (cuuint32_t)(t.KC / 8), 1};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(planes), gdim,
+    // planes [3*B][Hv][Cp/8][Wv][8] viewed as (x*8+c8, y, octet, piece*B+b)
+    const cuuint64_t oct = (cuuint64_t)(Cp / 8);
+    const cuuint64_t gdim[4] = {(cuuint64_t)Wv * 8, (cuuint64_t)Hv, oct, (cuuint64_t)3 * a.B};
+    const cuuint64_t gstr[3] = {oct * Wv * 16, (cuuint64_t)Wv * 16, (cuuint64_t)Hv * oct * Wv * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)(kTW + a.KS - 1) * 8, (cuuint32_t)(kTH + a.KS - 1), (cuuint32_t)(t.KC / 8), 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(planes), gdim,
                            gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
   }
   const size_t smem = tc2_smem(a.KS, t.N, t.KC, t.AST, t.NB, t.TPB);

@@ -11,9 +11,10 @@
 // Operands are NOT transformed inside this kernel.  A small elementwise pre-pass
 // (act_split_kernel) writes the BN+ReLU'd (and nearest-upsampled) activations — and the
 // corrected dY slice — once per layer as three bf16 planes (exact split x = b1 + b2 + b3,
-// 8+8+8 mantissa bits).  The kernel then streams 5-D TMA boxes (cp.async.bulk.tensor, zero fill
+// 8+8+8 mantissa bits).  The kernel then streams 4-D TMA boxes (cp.async.bulk.tensor, zero fill
 // outside the image = the convolution's padding) whose shared-memory image IS the UMMA layout:
-// box (8 ch, 10 x, 18 y, 16 octets, 1) -> [octet][pixel][16 B].
+// planes are stored [b][y][octet][x][8]; box (10 x * 8 ch, 18 y, 16 octets, 1) -> [octet][pixel][16 B],
+// each box row 160 contiguous bytes.
 //
 // Precision: tcgen05 only transposes 16-bit operands (kind::tf32 with MN-major operands returns
 // zeros on sm_100a — measured), hence bf16 pieces and the six products of weight >= 2^-16:
@@ -75,12 +76,37 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
-                                            int c3, int c4, uint64_t* bar) {
+__device__ __forceinline__ bool elect_one_w() {
+  uint32_t pred;
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
-      "%5, %6}], [%7];" ::"r"(smem_u32(smem_dst)),
-      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                            uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+      "%5}], [%6];" ::"r"(smem_u32(smem_dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
 
@@ -105,8 +131,9 @@ __device__ __forceinline__ void bn_consts_w(const BnSrc& s, int c, float& scale,
 }
 
 // ---------------------------------------------------------------------------------------
-// pre-pass: planes[piece][b][y][x][Cp] (bf16) = split3( pro ? relu(x*scale+shift) : x ),
-// optionally nearest-upsampled x2.  One thread per (pixel, channel octet).
+// pre-pass: planes[piece][b][y][octet][x][8] (bf16) = split3( pro ? relu(x*scale+shift) : x ),
+// optionally nearest-upsampled / zero-inserted x2.  One thread per (pixel, channel octet).  Rows of
+// one channel octet are x-contiguous so that a TMA box row is (TW+K-1)*16 contiguous bytes.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   __shared__ float sc_s[256], sh_s[256];
@@ -127,10 +154,11 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   const size_t plane = npix * Cp;  // elements per piece plane
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % oct);
-    const size_t pix = i / oct;
-    const int vx = (int)(pix % Wv);
-    const size_t r = pix / Wv;
+    // thread order (b, y, octet, x): 16-byte stores of consecutive threads are contiguous
+    const int vx = (int)(i % Wv);
+    size_t r = i / Wv;
+    const int q = (int)(r % oct);
+    r /= oct;
     const int vy = (int)(r % Hv);
     const int b = (int)(r / Hv);
     const int sy = a.up ? (vy >> 1) : vy, sx = a.up ? (vx >> 1) : vx;
@@ -164,7 +192,7 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
     uint32_t o[3][8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) bf16_split3(v[k], o[0][k], o[1][k], o[2][k]);
-    __nv_bfloat16* dst = a.out + pix * Cp + c;
+    __nv_bfloat16* dst = a.out + ((((size_t)b * Hv + vy) * oct + q) * Wv + vx) * 8;
 #pragma unroll
     for (int piece = 0; piece < 3; ++piece)
       *reinterpret_cast<uint4*>(dst + (size_t)piece * plane) =
@@ -249,42 +277,53 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(&empty[s], (uint32_t)(((it / kStages) & 1) ^ 1));
         unsigned char* st = stage0 + (size_t)s * STAGE;
         mbar_arrive_expect_tx(&full[s], A_BYTES + (uint32_t)NP * B_PIECE);
-        tma_load_5d(st, &tmA, 0, ox0 - t.pad, oy0 - t.pad, c0 >> 3, pass * t.B + b, &full[s]);
+        tma_load_4d(st, &tmA, (ox0 - t.pad) * 8, oy0 - t.pad, c0 >> 3, pass * t.B + b, &full[s]);
         for (int piece = 0; piece < NP; ++piece)
-          tma_load_5d(st + A_BYTES + (size_t)piece * B_PIECE, &tmB, 0, ox0, oy0, n0 >> 3, piece * t.B + b,
+          tma_load_4d(st + A_BYTES + (size_t)piece * B_PIECE, &tmB, ox0 * 8, oy0, n0 >> 3, piece * t.B + b,
                       &full[s]);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0 && my_tiles > 0) {
+    // ===== MMA issuer: whole warp walks the uniform loop, one elected lane issues =====
+    if (my_tiles > 0) {
       const uint32_t idesc = make_idesc_bf16_mn(128, NW);
       // MN-major canonical layout ((8,1,m),(8,k)) : ((1,8,SBO),(8,LBO)): SBO strides along the
       // channels (next octet), LBO along the pixels (next 8-pixel tile row)
       const uint32_t sbo_a = HP * 16u, lbo_a = HWp * 16u;
       const uint32_t sbo_b = B_OCT, lbo_b = 128u;
+      int s = 0;
+      uint32_t ph = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % kStages;
-        mbar_wait(&full[s], (uint32_t)((it / kStages) & 1));
+        mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(stage0 + (size_t)s * STAGE);
-        const uint64_t a_desc0 = make_desc(a_base, lbo_a, sbo_a);
-        const uint64_t b_desc0 = make_desc(a_base + A_BYTES, lbo_b, sbo_b);
+        const uint64_t ad0 = make_desc(a_base, lbo_a, sbo_a);
+        const uint64_t bd0 = make_desc(a_base + A_BYTES, lbo_b, sbo_b);
+        const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32);
+        const uint32_t b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+        if (elect_one_w()) {
 #pragma unroll 1
-        for (int r = 0; r < kTH; r += 2) {
-          const uint64_t bd = b_desc0 + (uint64_t)(r * 8);  // r * 128 B
+          for (int r = 0; r < kTH; r += 2) {
+            const uint32_t b_lo = b_lo0 + (uint32_t)(r * 8);  // r * 128 B
+            const uint32_t acc = (it | r) != 0 ? 1u : 0u;
 #pragma unroll
-          for (int j = 0; j < TG; ++j) {
-            const int tap = tap0 + j;
-            if (j < ntap) {
-              const uint64_t ad = a_desc0 + (uint64_t)((r + tap / KS) * HWp + (tap % KS));
-              umma_bf16(tmem_base + (uint32_t)(j * NW), ad, bd, idesc, (it | r) != 0 ? 1u : 0u);
+            for (int j = 0; j < TG; ++j) {
+              const int tap = tap0 + j;
+              if (j < ntap) {
+                const uint32_t a_lo = a_lo0 + (uint32_t)((r + tap / KS) * HWp + (tap % KS));
+                umma_bf16_w(tmem_base + (uint32_t)(j * NW), a_lo, a_hi, b_lo, b_hi, idesc, acc);
+              }
             }
           }
+          umma_commit(&empty[s]);
+          if (it == my_tiles - 1) umma_commit(acc_full);
         }
-        umma_commit(&empty[s]);
+        __syncwarp();
+        if (++s == kStages) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
-      umma_commit(acc_full);
     }
   } else if (my_tiles > 0) {
     // ===== epilogue: TMEM -> coalesced vector reductions into dWp[tap][ci][co] =====
@@ -349,18 +388,20 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// planes [3*B][H][W][Cp] bf16 viewed as (c8, x, y, octet, plane*B+b); box (8, bx, by, boct, 1)
+// planes [3*B][H][Cp/8][W][8] bf16 viewed as (x*8+c8, y, octet, plane*B+b); box (bx*8, by, boct, 1)
+// -> shared memory [octet][y][x][16 B]
 int make_plane_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int H, int W, int Cp, int bx, int by,
                    int boct) {
   EncodeFn enc = get_encode();
   PDES_REQUIRE(enc != nullptr, PDES_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t gdim[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cp / 8), (cuuint64_t)3 * B};
-  const cuuint64_t gstr[4] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, 16, (cuuint64_t)H * W * Cp * 2};
-  const cuuint32_t box[5] = {8, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)boct, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<__nv_bfloat16*>(base), gdim, gstr,
+  const cuuint64_t oct = (cuuint64_t)(Cp / 8);
+  const cuuint64_t gdim[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, oct, (cuuint64_t)3 * B};
+  const cuuint64_t gstr[3] = {oct * W * 16, (cuuint64_t)W * 16, (cuuint64_t)H * oct * W * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)bx * 8, (cuuint32_t)by, (cuuint32_t)boct, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), gdim, gstr,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
   return PDES_OK;
 }
