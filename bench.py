@@ -173,8 +173,10 @@ def main():
     n_batches = n_local // BATCH
 
     def make_model():
+        import contextlib
         torch.manual_seed(1)
-        return DenseED(1, 3, IMSIZE, [6, 8, 6]).to(dev)
+        with contextlib.redirect_stdout(sys.stderr):  # the constructor prints '# params ...' like the reference
+            return DenseED(1, 3, IMSIZE, [6, 8, 6]).to(dev)
 
     def barrier():
         torch.cuda.synchronize()

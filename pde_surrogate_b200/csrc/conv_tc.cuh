@@ -38,6 +38,10 @@ struct ActSplitArgs {
   BnSrc bn;
   __nv_bfloat16* out;    // [3][B][Hv][Cp/8][Wv][8]
   int Cp;                // C rounded up to 8
+  // fused dY correction (replaces a separate fix_dy launch): x is the gradient slice G, rewritten in
+  // place as G - c1[c] - xhat*c2[c] before the split; fx.G is ignored
+  int fix;
+  FixDyArgs fx;
 };
 
 struct TcWgradArgs {

@@ -337,6 +337,41 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
           if (tile_it == 0 && ch == 1 && lane == 0) DBG(3);
           const uint64_t ad0 = make_desc(smem_u32(A_s + (size_t)sa * a_stage_bytes), lbo_a, sbo_a);
           const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32);
+          if (TPB == T) {
+            // the whole chunk's filter taps sit in one TMA stage: one wait, one elected issue block
+            mbar_wait(&b_full[sb], pb);
+            tc_fence_after();
+            const uint64_t bd0 = make_desc(smem_u32(B_s + (size_t)sb * b_stage_bytes), lbo_b, sbo_b);
+            const uint32_t b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+            const uint32_t b_tap_u = b_tap_bytes >> 4;
+            if (elect_one()) {
+#pragma unroll(KS <= 3 ? T : 1)
+              for (int tap = 0; tap < T; ++tap) {
+                const uint32_t a_tap = a_lo0 + (uint32_t)((tap / KS) * HWp + (tap % KS));
+                const uint32_t b_tap = b_lo0 + (uint32_t)tap * b_tap_u;
+#pragma unroll
+                for (int k16 = 0; k16 < 2; ++k16) {
+                  if (k16 < kc16) {
+                    const uint32_t a_k = a_tap + (uint32_t)k16 * kstep_a;
+                    const uint32_t b_k = b_tap + (uint32_t)k16 * kstep_b;
+#pragma unroll
+                    for (int i = 0; i < OP::n; ++i) {
+                      const bool first = fresh && tap == 0 && k16 == 0 && ((FirstW<MODE>::mask >> i) & 1u);
+                      umma_bf16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
+                                  idesc[i], first ? 0u : 1u);
+                    }
+                  }
+                }
+              }
+              umma_commit(&b_empty[sb]);
+              umma_commit(&a_empty[sa]);
+            }
+            __syncwarp();
+            if (++sb == NB) {
+              sb = 0;
+              pb ^= 1u;
+            }
+          } else {
 #pragma unroll(KS <= 3 ? T : 1)
           for (int tap = 0; tap < T; ++tap) {
             if (tin == 0) {
@@ -372,6 +407,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
                 pb ^= 1u;
               }
             }
+          }
           }
           if (++sa == AST) {
             sa = 0;

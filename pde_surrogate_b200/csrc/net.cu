@@ -729,6 +729,8 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
     const Layer& L = n->layers[li];
     const float* dy;
     int lddy = 0, dy_nchw = 0;
+    FixDyArgs fixargs;
+    bool have_fix = false;
     if (L.out_buf < 0) {
       dy = dout;
       dy_nchw = 1;
@@ -753,9 +755,15 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         f.cons_C[f.n_cons] = M.Cin;
         f.n_cons++;
       }
-      rc = launch_fix_dy(f, st);
-      if (rc) return rc;
-      n->launches++;
+      const bool fuse_fix = n->conv_impl == 0 && ((L.tc_wg && (n->tc_mask & 4)) || (L.tc2_bwd && (n->tc_mask & 2)));
+      if (!fuse_fix) {
+        rc = launch_fix_dy(f, st);
+        if (rc) return rc;
+        n->launches++;
+      } else {
+        fixargs = f;
+        have_fix = true;
+      }
       dy = f.G;
       lddy = ob.ld;
     }
@@ -807,6 +815,10 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
         sb.up = L.stride == 2 ? 2 : 0;  // zero-insert: stride-2 layers run as stride-1 kernels
         sb.out = reinterpret_cast<__nv_bfloat16*>(wsf(n, n->planesB));
         sb.Cp = (L.Cout + 7) & ~7;
+        if (have_fix) {
+          sb.fix = 1;
+          sb.fx = fixargs;
+        }
         rc = launch_act_split(sb, st);
         if (rc) return rc;
         n->launches++;

@@ -137,7 +137,35 @@ __device__ __forceinline__ void bn_consts_w(const BnSrc& s, int c, float& scale,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
   __shared__ float sc_s[256], sh_s[256];
+  __shared__ float mean_s[256], is_s[256];  // fused dY correction: c1 -> sc_s, c2 -> sh_s
   const int Cp = a.Cp;
+  if (a.fix) {
+    const FixDyArgs& f = a.fx;
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+      float c1 = 0.f, c2 = 0.f, mean = 0.f, is = 0.f;
+      if (c < a.C) {
+        const double m = f.sum[c] * f.inv_count;
+        double var = f.sumsq[c] * f.inv_count - m * m;
+        if (var < 0.0) var = 0.0;
+        const double isd = 1.0 / sqrt(var + (double)f.eps);
+        double d1 = 0.0, d2 = 0.0;
+        for (int l = 0; l < f.n_cons; ++l) {
+          const double sc = (double)f.cons_gamma[l][c] * (double)(float)isd;
+          d1 += sc * f.cons_bsum[l][c];
+          d2 += sc * f.cons_bsum[l][f.cons_C[l] + c];
+        }
+        c1 = (float)(d1 * f.inv_count);
+        c2 = (float)(d2 * f.inv_count);
+        mean = (float)m;
+        is = (float)isd;
+      }
+      sc_s[c] = c1;
+      sh_s[c] = c2;
+      mean_s[c] = mean;
+      is_s[c] = is;
+    }
+    __syncthreads();
+  }
   if (a.pro) {
     for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
       float s = 0.f, h = 0.f;
@@ -188,6 +216,20 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         v[k] = (!hole && c + k < a.C) ? fmaxf(0.f, fmaf(v[k], sc_s[c + k], sh_s[c + k])) : 0.f;
+    }
+    if (a.fix && !hole) {
+      // dY = G - c1 - xhat*c2 (lazy BatchNorm-backward mean corrections of every consumer), written
+      // back in fp32 for the non-tensor-core consumers of the slice
+      const float* xp = a.fx.X + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.fx.ldX + c;
+      float* gp = const_cast<float*>(a.x) + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (c + k < a.C) {
+          const float xh = (xp[k] - mean_s[c + k]) * is_s[c + k];
+          v[k] = v[k] - sc_s[c + k] - xh * sh_s[c + k];
+          gp[k] = v[k];
+        }
+      }
     }
     uint32_t o[3][8];
 #pragma unroll
