@@ -595,9 +595,15 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
     PDES_CUDA(cudaMemsetAsync(wsd(n, 0), 0, n->ws_doubles * sizeof(double), st));
     n->launches++;
   }
-  int rc = launch_pack_weights(pack_table(n), (int)n->layers.size(), n->max_pack, st);
-  if (rc) return rc;
-  n->launches++;
+  int rc = PDES_OK;
+  bool need_simt_pack = n->conv_impl != 0 || n->tc_mask != 7;
+  for (const auto& L : n->layers)
+    if (!L.tc2_fwd || (L.in_buf >= 0 && !L.tc2_bwd)) need_simt_pack = true;
+  if (need_simt_pack) {
+    rc = launch_pack_weights(pack_table(n), (int)n->layers.size(), n->max_pack, st);
+    if (rc) return rc;
+    n->launches++;
+  }
   if (n->conv_impl == 0 && n->n_tc2 > 0) {
     rc = launch_pack_tc2(tc2_table(n), n->n_tc2, n->max_tc2_pack, st);
     if (rc) return rc;

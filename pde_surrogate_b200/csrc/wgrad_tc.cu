@@ -399,18 +399,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
-// dW_OIHW[co][ci][tap] += dWp[tap][ci][co]; dWp is cleared for the next step
+// dW_OIHW[co][ci][tap] += dWp[tap][ci][co]; dWp is cleared for the next step.  One thread per
+// (ci, co): coalesced reads along co, KS*KS contiguous floats written per thread.
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const TcWgradUnpack* tab) {
   const TcWgradUnpack d = tab[blockIdx.y];
   const int T = d.KS * d.KS;
-  const int total = d.Cout * d.Cin * T;
+  const int total = d.Cout * d.Cin;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int tap = i % T;
-    const int r = i / T;
-    const int ci = r % d.Cin, co = r / d.Cin;
-    float* src = d.dwp + ((size_t)tap * d.ci_pad + ci) * d.co_pad + co;
-    d.dw[i] += *src;
-    *src = 0.f;
+    const int co = i % d.Cout, ci = i / d.Cout;
+    float* dst = d.dw + ((size_t)co * d.Cin + ci) * T;
+    float* src = d.dwp + (size_t)ci * d.co_pad + co;
+    const size_t tap_stride = (size_t)d.ci_pad * d.co_pad;
+    for (int tap = 0; tap < T; ++tap) {
+      dst[tap] += src[tap * tap_stride];
+      src[tap * tap_stride] = 0.f;
+    }
   }
 }
 
@@ -521,8 +524,8 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
 
 int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_elems, cudaStream_t st) {
   if (n == 0) return PDES_OK;
-  int bx = (max_elems + 255) / 256;
-  if (bx > 64) bx = 64;
+  int bx = (max_elems / 9 + 255) / 256;
+  if (bx > 96) bx = 96;
   if (bx < 1) bx = 1;
   wgrad_unpack_kernel<<<dim3(bx, n), 256, 0, st>>>(dev_table);
   PDES_LAUNCH_CHECK();
