@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <string.h>
 #include "../../include/pdes_b200.h"
 
 #ifndef PDES_HD
@@ -33,6 +34,26 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 #define PDES_LAUNCH_CHECK() PDES_CUDA(cudaGetLastError())
 
 int sm_count();
+bool pdl_enabled();  // programmatic dependent launch of the kernel chain (opt-in: env PDES_PDL=1)
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start (and run its
+// prologue up to griddep_wait()) while the previous kernel in the stream is still draining.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // ---- device helpers ----------------------------------------------------------------
 #ifdef __CUDACC__
@@ -96,6 +117,10 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_all() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
+
+// programmatic dependent launch: wait for the previous grid's results / let the next grid start
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll

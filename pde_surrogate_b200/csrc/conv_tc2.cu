@@ -244,6 +244,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
+  griddep_wait();  // everything below reads what earlier kernels of the step produced
   if (warp >= kEpiWarp0) {
     const int tt = threadIdx.x - kEpiWarp0 * 32;
     for (int n = tt; n < N; n += kEpiWarps * 32) {
@@ -426,6 +427,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
           pt ^= 1u;
         }
       }
+      griddep_launch();  // all MMAs of this CTA are issued: the next kernel may start its prologue
     }
   } else if (warp >= kEpiWarp0) {
     // ===== epilogue =====
@@ -741,7 +743,7 @@ int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int W
                                      (int)smem));                                                            \
       attr = smem;                                                                                           \
     }                                                                                                        \
-    conv_tc2_kernel<KSV, MODEV><<<grid, kThreads, smem, st>>>(tm, t);                                        \
+    PDES_CUDA(launch_pdl(conv_tc2_kernel<KSV, MODEV>, dim3(grid), dim3(kThreads), smem, st, tm, t));         \
   }
 #define PDES_TC2_MODES(KSV)                        \
   {                                                \

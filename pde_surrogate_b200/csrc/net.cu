@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
 
@@ -80,6 +81,15 @@ struct pdes_net {
   size_t max_tc_pack = 0;
   int max_wg_elems = 0;
   int prec = 0;
+  // executor-level CUDA graphs: the launch sequence of one forward / backward at a given batch size is
+  // captured once (second call) and replayed afterwards; static input/output staging keeps pointers stable
+  struct GraphSlot {
+    int B = 0, training = -1, calls = 0, launches = 0;
+    cudaGraphExec_t exec = nullptr;
+  };
+  GraphSlot gfwd[4], gbwd[2];
+  int use_graph = 0;
+  size_t xs = 0, outs = 0, douts = 0;  // float offsets of the static x / out / dout buffers
   int n_wg_bound = 0;
   int tc_mask = 7;  // bit 0: forward, bit 1: dgrad, bit 2: wgrad on tcgen05
   // bound
@@ -334,6 +344,12 @@ int build(pdes_net* n) {
   }
   n->xin = f;
   f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
+  n->xs = f;
+  f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
+  n->outs = f;
+  f += pad4((int64_t)B * c.out_channels * c.imsize * c.imsize);
+  n->douts = f;
+  f += pad4((int64_t)B * c.out_channels * c.imsize * c.imsize);
   n->ws_floats = f;
   size_t d = 0;
   for (auto& b : n->bufs) {
@@ -411,7 +427,14 @@ extern "C" int pdes_densenet_create(const pdes_densenet_config* cfg, pdes_net_t*
   return PDES_OK;
 }
 
-extern "C" void pdes_densenet_destroy(pdes_net_t* net) { delete net; }
+extern "C" void pdes_densenet_destroy(pdes_net_t* net) {
+  if (!net) return;
+  for (auto& gs : net->gfwd)
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+  for (auto& gs : net->gbwd)
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+  delete net;
+}
 
 extern "C" int pdes_densenet_num_params(const pdes_net_t* n) { return n ? (int)n->params.size() : 0; }
 extern "C" int64_t pdes_densenet_param_floats(const pdes_net_t* n) { return n ? n->param_floats : 0; }
@@ -464,6 +487,19 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
                "pdes_densenet_bind: workspace %zu < %zu bytes", workspace_bytes, n->ws_bytes);
   PDES_REQUIRE((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)running | (uintptr_t)workspace) & 15u) == 0,
                PDES_ERR_INVALID, "pdes_densenet_bind: buffers must be 16-byte aligned");
+  for (auto& gs : n->gfwd) {
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+    gs = pdes_net::GraphSlot();
+  }
+  for (auto& gs : n->gbwd) {
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+    gs = pdes_net::GraphSlot();
+  }
+  {
+    // opt-in (PDES_EXEC_GRAPH=1): measured no gain for the per-step-synchronising script loop
+    const char* e = getenv("PDES_EXEC_GRAPH");
+    n->use_graph = (e && e[0] == '1') ? 1 : 0;
+  }
   n->p = params;
   n->g = grads;
   n->run = running;
@@ -582,8 +618,7 @@ extern "C" double pdes_densenet_flops(const pdes_net_t* n, int B, int training) 
   return f;
 }
 
-extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, int B, int training,
-                                     void* stream) {
+static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int training, void* stream) {
   PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_forward: bind() first");
   PDES_REQUIRE(x && out, PDES_ERR_INVALID, "pdes_densenet_forward: null pointer");
   PDES_REQUIRE(B >= 1 && B <= n->cfg.max_batch, PDES_ERR_INVALID,
@@ -720,7 +755,7 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   return PDES_OK;
 }
 
-extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* stream) {
+static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
   PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_backward: bind() first");
   PDES_REQUIRE(n->fwd_train_done, PDES_ERR_STATE,
                "pdes_densenet_backward: needs a preceding training-mode forward");
@@ -921,6 +956,132 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
   rc = launch_bn_param_grad(bn_table(n), n->n_bn, n->maxC, st);
   if (rc) return rc;
   n->launches++;
+  n->fwd_train_done = false;
+  return PDES_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// public entry points: eager on the first call of a (batch, mode), captured into a CUDA graph on the
+// second, replayed afterwards.  When the caller's stream is itself being captured (e.g. the whole
+// training step in one outer graph) the launches are issued directly.
+// ---------------------------------------------------------------------------------------
+namespace {
+bool stream_is_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return cs != cudaStreamCaptureStatusNone;
+}
+template <class F>
+int capture_into(pdes_net::GraphSlot& gs, pdes_net* n, cudaStream_t st, F&& body) {
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  const int rc = body();
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(st, &g);
+  if (rc != PDES_OK || e != cudaSuccess || g == nullptr) {
+    if (g) cudaGraphDestroy(g);
+    cudaGetLastError();
+    return -1;
+  }
+  cudaGraphExec_t ex = nullptr;
+  const cudaError_t ei = cudaGraphInstantiate(&ex, g, 0);
+  cudaGraphDestroy(g);
+  if (ei != cudaSuccess || ex == nullptr) {
+    cudaGetLastError();
+    return -1;
+  }
+  gs.exec = ex;
+  gs.launches = n->launches;
+  return 0;
+}
+}  // namespace
+
+extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, int B, int training,
+                                     void* stream) {
+  PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_forward: bind() first");
+  PDES_REQUIRE(x && out, PDES_ERR_INVALID, "pdes_densenet_forward: null pointer");
+  PDES_REQUIRE(B >= 1 && B <= n->cfg.max_batch, PDES_ERR_INVALID,
+               "pdes_densenet_forward: batch %d outside 1..%d", B, n->cfg.max_batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!n->use_graph || stream_is_capturing(st)) return forward_impl(n, x, out, B, training, stream);
+  const int tr = training != 0;
+  pdes_net::GraphSlot* gs = nullptr;
+  for (auto& s : n->gfwd)
+    if (s.B == B && s.training == tr) gs = &s;
+  if (!gs) {
+    gs = &n->gfwd[0];
+    for (auto& s : n->gfwd)
+      if (s.calls < gs->calls) gs = &s;
+    if (gs->exec) cudaGraphExecDestroy(gs->exec);
+    *gs = pdes_net::GraphSlot();
+    gs->B = B;
+    gs->training = tr;
+  }
+  gs->calls++;
+  if (gs->calls == 1) return forward_impl(n, x, out, B, training, stream);  // warm-up (lazy attributes)
+  const size_t xbytes = sizeof(float) * (size_t)B * n->cfg.in_channels * n->cfg.imsize * n->cfg.imsize;
+  const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->cfg.imsize * n->cfg.imsize;
+  if (!gs->exec) {
+    pdes_net* nn = n;
+    const int rc = capture_into(*gs, n, st, [&]() {
+      return forward_impl(nn, wsf(nn, nn->xs), wsf(nn, nn->outs), B, training, stream);
+    });
+    if (rc != 0) {  // capture unavailable: stay on direct launches
+      n->use_graph = 0;
+      return forward_impl(n, x, out, B, training, stream);
+    }
+  }
+  PDES_CUDA(cudaMemcpyAsync(wsf(n, n->xs), x, xbytes, cudaMemcpyDeviceToDevice, st));
+  PDES_CUDA(cudaGraphLaunch(gs->exec, st));
+  PDES_CUDA(cudaMemcpyAsync(out, wsf(n, n->outs), obytes, cudaMemcpyDeviceToDevice, st));
+  n->launches = gs->launches + 2;
+  if (tr) {
+    n->last_B = B;
+    n->fwd_train_done = true;
+  }
+  return PDES_OK;
+}
+
+extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* stream) {
+  PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_backward: bind() first");
+  PDES_REQUIRE(n->fwd_train_done, PDES_ERR_STATE,
+               "pdes_densenet_backward: needs a preceding training-mode forward");
+  PDES_REQUIRE(n->g != nullptr, PDES_ERR_STATE, "pdes_densenet_backward: no gradient buffer bound");
+  PDES_REQUIRE(dout != nullptr, PDES_ERR_INVALID, "pdes_densenet_backward: null dout");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!n->use_graph || stream_is_capturing(st)) return backward_impl(n, dout, stream);
+  const int B = n->last_B;
+  pdes_net::GraphSlot* gs = nullptr;
+  for (auto& s : n->gbwd)
+    if (s.B == B) gs = &s;
+  if (!gs) {
+    gs = &n->gbwd[0];
+    for (auto& s : n->gbwd)
+      if (s.calls < gs->calls) gs = &s;
+    if (gs->exec) cudaGraphExecDestroy(gs->exec);
+    *gs = pdes_net::GraphSlot();
+    gs->B = B;
+  }
+  gs->calls++;
+  if (gs->calls == 1) return backward_impl(n, dout, stream);
+  const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->cfg.imsize * n->cfg.imsize;
+  if (!gs->exec) {
+    pdes_net* nn = n;
+    const int rc = capture_into(*gs, n, st, [&]() { return backward_impl(nn, wsf(nn, nn->douts), stream); });
+    n->fwd_train_done = true;  // the captured body cleared it on the host
+    if (rc != 0) {
+      n->use_graph = 0;
+      return backward_impl(n, dout, stream);
+    }
+  }
+  PDES_CUDA(cudaMemcpyAsync(wsf(n, n->douts), dout, obytes, cudaMemcpyDeviceToDevice, st));
+  PDES_CUDA(cudaGraphLaunch(gs->exec, st));
+  n->launches = gs->launches + 1;
   n->fwd_train_done = false;
   return PDES_OK;
 }

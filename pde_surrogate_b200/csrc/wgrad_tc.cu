@@ -136,6 +136,7 @@ __device__ __forceinline__ void bn_consts_w(const BnSrc& s, int c, float& scale,
 // one channel octet are x-contiguous so that a TMA box row is (TW+K-1)*16 contiguous bytes.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
+  griddep_wait();
   __shared__ float sc_s[256], sh_s[256];
   __shared__ float mean_s[256], is_s[256];  // fused dY correction: c1 -> sc_s, c2 -> sh_s
   const int Cp = a.Cp;
@@ -300,6 +301,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // operand planes / staging gradient come from earlier kernels of the step
 
   int my_tiles = 0;
   for (int pt = blockIdx.x; pt < n_tiles; pt += gridDim.x) ++my_tiles;
@@ -367,6 +369,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+    griddep_launch();
   } else if (my_tiles > 0) {
     // ===== epilogue: TMEM -> coalesced vector reductions into dWp[tap][ci][co] =====
     mbar_wait(acc_full, 0);
@@ -481,8 +484,7 @@ int launch_act_split(const ActSplitArgs& a, cudaStream_t st) {
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  act_split_kernel<<<blocks, 256, 0, st>>>(a);
-  PDES_LAUNCH_CHECK();
+  PDES_CUDA(launch_pdl(act_split_kernel, dim3(blocks), dim3(256), 0, st, a));
   return PDES_OK;
 }
 
@@ -512,7 +514,7 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
                                      (int)smem));                                                            \
       attr = true;                                                                                           \
     }                                                                                                        \
-    wgrad_tc_kernel<KSV><<<grid, kThreads, smem, st>>>(tmA, tmB, t);                                         \
+    PDES_CUDA(launch_pdl(wgrad_tc_kernel<KSV>, grid, dim3(kThreads), smem, st, tmA, tmB, t));                \
   }
   if (t.KS == 3) PDES_WG_LAUNCH(3)
   else if (t.KS == 1) PDES_WG_LAUNCH(1)
