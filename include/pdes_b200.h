@@ -73,7 +73,8 @@ int pdes_darcy_loss_bwd(const float* K, const float* out, const float* gw4, int 
                         int W, int use_tb, float* dout, void* stream);
 /* Selects the implementation of the two calls above: 0 = auto, 1 = force the generic
  * (any H,W) kernels, 2 / 3 = force the whole-image-in-shared-memory TMA kernels with 256 / 512
- * threads per CTA. Test hook. */
+ * threads per CTA (unrolled 4- / 2-row strips when they tile the image exactly, else rolling
+ * strips), 4 / 5 = the same thread counts with rolling strips always. Test / A-B hook. */
 int pdes_darcy_loss_set_impl(int impl);
 
 /* ------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 // Reference semantics: utils/image_gradient.py:24-92 (SobelFilter), models/darcy.py:162-176,
 // 210-224, 226-233.
 #include "common.cuh"
+#include <stdlib.h>
 #include "stencil_core.cuh"
 
 namespace pdes {
@@ -283,7 +284,8 @@ darcy_bwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ 
 // tile kernels: whole sample in shared memory, TMA-fed, persistent over samples
 // ---------------------------------------------------------------------------------------
 // smem: [mbar x2 (16 B)] pad to 128 | stage0: K,u,s1,s2 | stage1: K,u,s1,s2 | (bwd) P1,P2,P3,Q1,Q2
-template <int NT>
+// R > 0: exact-fit unrolled strips (H % R == 0 and NT == (H/R)*(W/4)); R == 0: rolling strips, any fit.
+template <int NT, int R>
 __global__ void __launch_bounds__(NT, 1)
 darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out, int B, int H,
                       int W, int use_tb, float* loss4, LossWs* ws, LossNorm nrm) {
@@ -321,9 +323,16 @@ darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
     const int s = it & 1;
     mbar_wait(&bars[s], (uint32_t)((it >> 1) & 1));
     const float* st = stage_base + (size_t)s * 4 * HW;
-    const FwdPartial p = fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W,
-                                   threadIdx.x, NT, true, use_tb != 0, 0.f, 0.f,
-                                   nullptr, nullptr, nullptr, nullptr, nullptr);
+    FwdPartial p;
+    if (R > 0) {
+      const int W4 = W >> 2;
+      p = fwd_strip_r<(R > 0 ? R : 2), false, true>(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H,
+                                                    W, threadIdx.x % W4, (threadIdx.x / W4) * R, use_tb != 0,
+                                                    0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
+    } else {
+      p = fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W, threadIdx.x, NT, true,
+                    use_tb != 0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
+    }
     part.c += p.c;
     part.d += p.d;
     part.dir += p.dir;
@@ -335,7 +344,7 @@ darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
   loss_block_reduce_and_finish(part, ws, loss4, nrm);
 }
 
-template <int NT>
+template <int NT, int R>
 __global__ void __launch_bounds__(NT, 1)
 darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out,
                       const float* __restrict__ gw4, int B, int H, int W, int use_tb, float* dout,
@@ -381,12 +390,22 @@ darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
     float* P3 = scratch + 2 * HW;
     float* Q1 = scratch + 3 * HW;
     float* Q2 = scratch + 4 * HW;
-    (void)fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W, threadIdx.x,
-                    NT, true, use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
+    const int W4 = W >> 2;
+    const int cs = threadIdx.x % W4, y0 = (threadIdx.x / W4) * R;
+    if (R > 0)
+      (void)fwd_strip_r<(R > 0 ? R : 2), true, false>(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW,
+                                                      H, W, cs, y0, use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
+    else
+      (void)fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W, threadIdx.x, NT, true,
+                      use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
     __syncthreads();  // residual planes complete; nobody reads neighbours of u/s1/s2 any more
     // gradient planes overwrite u, s1, s2 in place (own-position reads only)
-    bwd_strip_pass2(P1, P2, P3, Q1, Q2, st + HW, st + 3 * HW, st + HW, st + 2 * HW, st + 3 * HW, H,
-                    W, threadIdx.x, NT, true, cdir, cneu);
+    if (R > 0)
+      bwd_strip_pass2_r<(R > 0 ? R : 2)>(P1, P2, P3, Q1, Q2, st + HW, st + 3 * HW, st + HW, st + 2 * HW,
+                                         st + 3 * HW, H, W, cs, y0, cdir, cneu);
+    else
+      bwd_strip_pass2(P1, P2, P3, Q1, Q2, st + HW, st + 3 * HW, st + HW, st + 2 * HW, st + 3 * HW, H, W,
+                      threadIdx.x, NT, true, cdir, cneu);
     fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -400,6 +419,31 @@ darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
     }
   }
   if (threadIdx.x == 0) tma_store_wait_all<0>();
+}
+
+// Tile-kernel variant for pdes_darcy_loss_set_impl(): 0 auto, 2/3 = 256/512 threads (unrolled exact-fit
+// strips when the image tiles exactly, else rolling strips), 4/5 = 256/512 threads, rolling strips always.
+struct TileVariant {
+  int nt, R;  // R == 0: rolling strips
+};
+TileVariant pick_variant(int impl, int H, int W4, bool bwd) {
+  const bool fit4 = (H % 4 == 0) && (H / 4) * W4 == 256;
+  const bool fit2 = (H % 2 == 0) && (H / 2) * W4 == 512;
+  TileVariant v;
+  switch (impl) {
+    case 2: v.nt = 256; v.R = fit4 ? 4 : 0; break;
+    case 3: v.nt = 512; v.R = fit2 ? 2 : 0; break;
+    case 4: v.nt = 256; v.R = 0; break;
+    case 5: v.nt = 512; v.R = 0; break;
+    default:
+      // measured on B200 (8192 cold 64x64 samples): 256 threads x 4 rows beats 512 x 2 in both directions
+      // (fwd 5.54 vs 5.12 TB/s, bwd 4.62 vs 4.12 TB/s); compile-time H = W = 64 was tried and is slower
+      // (the compiler turns the column-edge selects into divergent branches: bwd 3.48 TB/s)
+      if (fit4) { v.nt = 256; v.R = 4; }
+      else if (fit2) { v.nt = 512; v.R = 2; }
+      else { v.nt = (bwd && H * W4 * 4 >= 2048) ? 512 : 256; v.R = 0; }
+  }
+  return v;
 }
 
 bool tile_ok(int H, int W, const void* a, const void* b, bool bwd) {
@@ -440,7 +484,7 @@ extern "C" int pdes_sobel_grad(const float* img, float* out, int64_t n_img, int 
 extern "C" size_t pdes_darcy_loss_workspace_bytes(void) { return sizeof(LossWs); }
 
 extern "C" int pdes_darcy_loss_set_impl(int impl) {
-  PDES_REQUIRE(impl >= 0 && impl <= 3, PDES_ERR_INVALID, "pdes_darcy_loss_set_impl: impl in 0..3");
+  PDES_REQUIRE(impl >= 0 && impl <= 5, PDES_ERR_INVALID, "pdes_darcy_loss_set_impl: impl in 0..5");
   g_loss_impl = impl;
   return PDES_OK;
 }
@@ -469,21 +513,24 @@ extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int 
                "pdes_darcy_loss_fwd: tile kernel forced but %dx%d does not qualify", H, W);
   if (g_loss_impl != 1 && can_tile) {
     const size_t smem = 128 + (size_t)H * W * 4 * 8;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel<256>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel<512>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
-    }
     int grid = sm_count();
     if (grid > B) grid = B;
-    const bool big = g_loss_impl == 3;  // measured: 256 threads stream faster in the forward
-    if (big)
-      darcy_fwd_tile_kernel<512><<<grid, 512, smem, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm);
-    else
-      darcy_fwd_tile_kernel<256><<<grid, 256, smem, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm);
+    const TileVariant tv = pick_variant(g_loss_impl, H, W / 4, false);
+#define PDES_FWD_TILE(NT, R)                                                                              \
+  do {                                                                                                    \
+    static size_t attr_smem = 0; /* one per variant; not re-set while a graph is being captured */        \
+    if (smem > attr_smem) {                                                                               \
+      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel<NT, R>,                                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      attr_smem = smem;                                                                                   \
+    }                                                                                                     \
+    darcy_fwd_tile_kernel<NT, R><<<grid, NT, smem, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm); \
+  } while (0)
+    if (tv.nt == 512 && tv.R == 2) PDES_FWD_TILE(512, 2);
+    else if (tv.nt == 256 && tv.R == 4) PDES_FWD_TILE(256, 4);
+    else if (tv.nt == 512) PDES_FWD_TILE(512, 0);
+    else PDES_FWD_TILE(256, 0);
+#undef PDES_FWD_TILE
   } else {
     const int64_t total = (int64_t)B * H * W;
     int blocks = (int)((total + 255) / 256);
@@ -513,21 +560,24 @@ extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float
                "pdes_darcy_loss_bwd: tile kernel forced but %dx%d does not qualify", H, W);
   if (g_loss_impl != 1 && can_tile) {
     const size_t smem = 128 + (size_t)H * W * 4 * 13;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel<256>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel<512>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_smem = smem;
-    }
     int grid = sm_count();
     if (grid > B) grid = B;
-    const bool big = g_loss_impl == 3 || (g_loss_impl == 0 && H * W >= 2048);
-    if (big)
-      darcy_bwd_tile_kernel<512><<<grid, 512, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
-    else
-      darcy_bwd_tile_kernel<256><<<grid, 256, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
+    const TileVariant tv = pick_variant(g_loss_impl, H, W / 4, true);
+#define PDES_BWD_TILE(NT, R)                                                                              \
+  do {                                                                                                    \
+    static size_t attr_smem = 0; /* one per variant; not re-set while a graph is being captured */        \
+    if (smem > attr_smem) {                                                                               \
+      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel<NT, R>,                                        \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
+      attr_smem = smem;                                                                                   \
+    }                                                                                                     \
+    darcy_bwd_tile_kernel<NT, R><<<grid, NT, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);           \
+  } while (0)
+    if (tv.nt == 512 && tv.R == 2) PDES_BWD_TILE(512, 2);
+    else if (tv.nt == 256 && tv.R == 4) PDES_BWD_TILE(256, 4);
+    else if (tv.nt == 512) PDES_BWD_TILE(512, 0);
+    else PDES_BWD_TILE(256, 0);
+#undef PDES_BWD_TILE
   } else {
     const int64_t total = (int64_t)B * H * W;
     PDES_CUDA(cudaMemsetAsync(dout, 0, (size_t)total * 3 * sizeof(float), st));

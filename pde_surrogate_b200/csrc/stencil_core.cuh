@@ -366,5 +366,324 @@ PDES_HD void bwd_strip_pass2(const float* P1, const float* P2, const float* P3, 
   }
 }
 
+
+// =======================================================================================
+// Exact-fit fast path: every thread owns R rows (compile-time) x 4 columns, the strips tile the
+// image exactly (H % R == 0, nthreads == (H/R)*(W/4)) and `correct` is true.  Same operators as
+// fwd_strip / bwd_strip_pass2 above, but the R+2 row window is loaded once into registers and the
+// row loop is fully unrolled, so each horizontal difference is formed once (the rolling version
+// recomputes it three times and pays a register rotation per row) and the top/bottom one-sided
+// rows come out of the window instead of extra loads.  Measured effect on B200: see DESIGN.md §4.
+// =======================================================================================
+PDES_HD void load6_cols(const float* r, int x0, int xl, int xr, float e[6]) {
+  const float4 c = *reinterpret_cast<const float4*>(r + x0);
+  e[1] = c.x;
+  e[2] = c.y;
+  e[3] = c.z;
+  e[4] = c.w;
+  e[0] = r[xl];
+  e[5] = r[xr];
+}
+// zero-extended columns: the halo words are always loaded from an in-range (clamped) address and
+// then masked, which keeps the loads unconditional (no branches around predicated LDS)
+PDES_HD void load6_zcols(const float* r, int x0, int xl, int xr, float ml, float mr, float e[6]) {
+  const float4 c = *reinterpret_cast<const float4*>(r + x0);
+  e[1] = c.x;
+  e[2] = c.y;
+  e[3] = c.z;
+  e[4] = c.w;
+  e[0] = ml * r[xl];
+  e[5] = mr * r[xr];
+}
+PDES_HD void zero6(float e[6]) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) e[j] = 0.f;
+}
+// d_x with the one-sided first/last column (first/last are thread-uniform flags)
+PDES_HD void hdiff_c(const float e[6], bool first, bool last, float h[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = e[k + 2] - e[k];
+  if (first) h[0] = 4.f * (e[2] - e[1]) - (e[3] - e[1]);
+  if (last) h[3] = 4.f * (e[4] - e[3]) - (e[4] - e[2]);
+}
+PDES_HD void hdiff_Tc(const float e[6], bool first, bool last, float t[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) t[k] = e[k] - e[k + 2];
+  if (first) {
+    const float p0 = e[1];
+    t[0] -= 3.f * p0;
+    t[1] += 3.f * p0;
+    t[2] -= p0;
+  }
+  if (last) {
+    const float pl = e[4];
+    t[1] += pl;
+    t[2] -= 3.f * pl;
+    t[3] += 3.f * pl;
+  }
+}
+
+template <int R, bool WRITE, bool SUMS>
+PDES_HD FwdPartial fwd_strip_r(const float* Kp, const float* up, const float* s1p, const float* s2p,
+                               int H, int W, int cs, int y0, bool use_tb, float a, float b,
+                               float* P1, float* P2, float* P3, float* Q1, float* Q2) {
+  static_assert(R >= 2, "the one-sided boundary rows must lie inside the window");
+  FwdPartial acc;
+  acc.c = acc.d = acc.dir = acc.neu = 0.f;
+  const int W4 = W >> 2;
+  const bool first = (cs == 0), last = (cs == W4 - 1);
+  const bool top = (y0 == 0), bot = (y0 + R == H);
+  const int x0 = 4 * cs;
+  const int xl = first ? 0 : x0 - 1, xr = last ? W - 1 : x0 + 4;
+  const float cW = (float)W * 0.125f, cH = (float)H * 0.125f;
+  const bool hasK = (Kp != nullptr);
+  // window row r <-> image row clamp(y0 - 1 + r)
+  const int rtop = top ? 0 : y0 - 1, rbot = bot ? H - 1 : y0 + R;
+
+  float dxu[R][4], dyu[R][4], dxs1[R][4], dys2[R][4];
+  float uc[R][2], s1c[R][4], s2c[R][4];  // u at columns 4cs / 4cs+3 (Dirichlet), centre sigma values
+  {
+    float e[R + 2][6];
+    load6_cols(up + (size_t)rtop * W, x0, xl, xr, e[0]);
+#pragma unroll
+    for (int r = 1; r <= R; ++r) load6_cols(up + (size_t)(y0 - 1 + r) * W, x0, xl, xr, e[r]);
+    load6_cols(up + (size_t)rbot * W, x0, xl, xr, e[R + 1]);
+    float h[R + 2][4];
+#pragma unroll
+    for (int r = 0; r < R + 2; ++r) hdiff_c(e[r], first, last, h[r]);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float v[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[j] = e[i + 2][j] - e[i][j];
+      if (i == 0 && top) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = 4.f * (e[2][j] - e[1][j]) - (e[3][j] - e[1][j]);
+      }
+      if (i == R - 1 && bot) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = 4.f * (e[R][j] - e[R - 1][j]) - (e[R][j] - e[R - 2][j]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dxu[i][k] = cW * (h[i][k] + 2.f * h[i + 1][k] + h[i + 2][k]);
+        dyu[i][k] = cH * (v[k] + 2.f * v[k + 1] + v[k + 2]);
+      }
+      uc[i][0] = e[i + 1][1];
+      uc[i][1] = e[i + 1][4];
+    }
+  }
+  {
+    float e[R + 2][6];
+    load6_cols(s1p + (size_t)rtop * W, x0, xl, xr, e[0]);
+#pragma unroll
+    for (int r = 1; r <= R; ++r) load6_cols(s1p + (size_t)(y0 - 1 + r) * W, x0, xl, xr, e[r]);
+    load6_cols(s1p + (size_t)rbot * W, x0, xl, xr, e[R + 1]);
+    float h[R + 2][4];
+#pragma unroll
+    for (int r = 0; r < R + 2; ++r) hdiff_c(e[r], first, last, h[r]);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dxs1[i][k] = cW * (h[i][k] + 2.f * h[i + 1][k] + h[i + 2][k]);
+        s1c[i][k] = e[i + 1][k + 1];
+      }
+    }
+  }
+  {
+    float e[R + 2][6];
+    load6_cols(s2p + (size_t)rtop * W, x0, xl, xr, e[0]);
+#pragma unroll
+    for (int r = 1; r <= R; ++r) load6_cols(s2p + (size_t)(y0 - 1 + r) * W, x0, xl, xr, e[r]);
+    load6_cols(s2p + (size_t)rbot * W, x0, xl, xr, e[R + 1]);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float v[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[j] = e[i + 2][j] - e[i][j];
+      if (i == 0 && top) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = 4.f * (e[2][j] - e[1][j]) - (e[3][j] - e[1][j]);
+      }
+      if (i == R - 1 && bot) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = 4.f * (e[R][j] - e[R - 1][j]) - (e[R][j] - e[R - 2][j]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        dys2[i][k] = cH * (v[k] + 2.f * v[k + 1] + v[k + 2]);
+        s2c[i][k] = e[i + 1][k + 1];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int y = y0 + i;
+    float kk[4] = {0.f, 0.f, 0.f, 0.f};
+    if (hasK) {
+      const float4 kv = *reinterpret_cast<const float4*>(Kp + (size_t)y * W + x0);
+      kk[0] = kv.x;
+      kk[1] = kv.y;
+      kk[2] = kv.z;
+      kk[3] = kv.w;
+    }
+    const bool yedge = (i == 0 && top) || (i == R - 1 && bot);
+    const bool row_in = use_tb || !yedge;
+    float p1[4], p2[4], p3[4], q1[4], q2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float r1 = 0.f, r2 = 0.f;
+      if (hasK) {
+        r1 = s1c[i][k] + kk[k] * dxu[i][k];
+        r2 = s2c[i][k] + kk[k] * dyu[i][k];
+      }
+      const float r3 = row_in ? (dxs1[i][k] + dys2[i][k]) : 0.f;
+      if (SUMS) {
+        acc.c += r1 * r1 + r2 * r2;
+        acc.d += r3 * r3;
+      }
+      if (WRITE) {
+        q1[k] = a * r1;
+        q2[k] = a * r2;
+        p1[k] = kk[k] * q1[k];
+        p2[k] = kk[k] * q2[k];
+        p3[k] = b * r3;
+      }
+    }
+    if (SUMS) {
+      if (first) {
+        const float t = uc[i][0] - 1.f;
+        acc.dir += t * t;
+      }
+      if (last) acc.dir += uc[i][1] * uc[i][1];
+      if (yedge) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc.neu += s2c[i][k] * s2c[i][k];
+      }
+    }
+    if (WRITE) {
+      const size_t o = (size_t)y * W + x0;
+      *reinterpret_cast<float4*>(P1 + o) = make_float4(p1[0], p1[1], p1[2], p1[3]);
+      *reinterpret_cast<float4*>(P2 + o) = make_float4(p2[0], p2[1], p2[2], p2[3]);
+      *reinterpret_cast<float4*>(P3 + o) = make_float4(p3[0], p3[1], p3[2], p3[3]);
+      *reinterpret_cast<float4*>(Q1 + o) = make_float4(q1[0], q1[1], q1[2], q1[3]);
+      *reinterpret_cast<float4*>(Q2 + o) = make_float4(q2[0], q2[1], q2[2], q2[3]);
+    }
+  }
+  return acc;
+}
+
+// adjoint pass of the exact-fit path; du/ds1/ds2 may alias up/s1p/s2p (own-position reads only)
+template <int R>
+PDES_HD void bwd_strip_pass2_r(const float* P1, const float* P2, const float* P3, const float* Q1,
+                               const float* Q2, const float* up, const float* s2p, float* du, float* ds1,
+                               float* ds2, int H, int W, int cs, int y0, float cdir, float cneu) {
+  static_assert(R >= 2, "R >= 2");
+  const int W4 = W >> 2;
+  const bool first = (cs == 0), last = (cs == W4 - 1);
+  const bool top = (y0 == 0), bot = (y0 + R == H);
+  const int x0 = 4 * cs;
+  const float cW = (float)W * 0.125f, cH = (float)H * 0.125f;
+  const int xl = first ? x0 : x0 - 1, xr = last ? x0 + 3 : x0 + 4;
+  const float ml = first ? 0.f : 1.f, mr = last ? 0.f : 1.f;
+
+  float tx1[R + 2][4], tx3[R + 2][4], e2[R + 2][6], e3[R + 2][6];
+#pragma unroll
+  for (int r = 0; r < R + 2; ++r) {
+    const int yy = y0 - 1 + r;
+    const bool valid = !((r == 0 && top) || (r == R + 1 && bot));
+    if (valid) {
+      float e[6];
+      load6_zcols(P1 + (size_t)yy * W, x0, xl, xr, ml, mr, e);
+      hdiff_Tc(e, first, last, tx1[r]);
+      load6_zcols(P3 + (size_t)yy * W, x0, xl, xr, ml, mr, e3[r]);
+      hdiff_Tc(e3[r], first, last, tx3[r]);
+      load6_zcols(P2 + (size_t)yy * W, x0, xl, xr, ml, mr, e2[r]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tx1[r][k] = tx3[r][k] = 0.f;
+      zero6(e2[r]);
+      zero6(e3[r]);
+    }
+  }
+  float ty2[R][6], ty3[R][6];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      ty2[i][j] = e2[i][j] - e2[i + 2][j];
+      ty3[i][j] = e3[i][j] - e3[i + 2][j];
+    }
+  }
+  // one-sided first/last image row of d_y: extra taps on rows 0 and H-1 for y <= 2 / y >= H-3
+  if (y0 <= 2) {
+    float r2[6], r3[6];
+    load6_zcols(P2, x0, xl, xr, ml, mr, r2);
+    load6_zcols(P3, x0, xl, xr, ml, mr, r3);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int y = y0 + i;
+      const float c = (y == 0) ? -3.f : (y == 1) ? 3.f : (y == 2) ? -1.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        ty2[i][j] += c * r2[j];
+        ty3[i][j] += c * r3[j];
+      }
+    }
+  }
+  if (y0 + R - 1 >= H - 3) {
+    float r2[6], r3[6];
+    load6_zcols(P2 + (size_t)(H - 1) * W, x0, xl, xr, ml, mr, r2);
+    load6_zcols(P3 + (size_t)(H - 1) * W, x0, xl, xr, ml, mr, r3);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int y = y0 + i;
+      const float c = (y == H - 3) ? 1.f : (y == H - 2) ? -3.f : (y == H - 1) ? 3.f : 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        ty2[i][j] += c * r2[j];
+        ty3[i][j] += c * r3[j];
+      }
+    }
+  }
+  const float wx0 = first ? 3.f : 2.f, wx3 = last ? 3.f : 2.f;
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int y = y0 + i;
+    const bool yedge = (i == 0 && top) || (i == R - 1 && bot);
+    const float wy = yedge ? 3.f : 2.f;
+    const size_t o = (size_t)y * W + x0;
+    const float4 q1 = *reinterpret_cast<const float4*>(Q1 + o);
+    const float4 q2 = *reinterpret_cast<const float4*>(Q2 + o);
+    const float q1a[4] = {q1.x, q1.y, q1.z, q1.w};
+    const float q2a[4] = {q2.x, q2.y, q2.z, q2.w};
+    float gu[4], g1[4], g2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float wx = (k == 0) ? wx0 : (k == 3) ? wx3 : 2.f;
+      const float ox1 = tx1[i][k] + wy * tx1[i + 1][k] + tx1[i + 2][k];
+      const float ox3 = tx3[i][k] + wy * tx3[i + 1][k] + tx3[i + 2][k];
+      const float oy2 = ty2[i][k] + wx * ty2[i][k + 1] + ty2[i][k + 2];
+      const float oy3 = ty3[i][k] + wx * ty3[i][k + 1] + ty3[i][k + 2];
+      gu[k] = cW * ox1 + cH * oy2;
+      g1[k] = q1a[k] + cW * ox3;
+      g2[k] = q2a[k] + cH * oy3;
+    }
+    if (first) gu[0] += cdir * (up[o] - 1.f);
+    if (last) gu[3] += cdir * up[o + 3];
+    if (yedge) {
+      const float4 ss = *reinterpret_cast<const float4*>(s2p + o);
+      g2[0] += cneu * ss.x;
+      g2[1] += cneu * ss.y;
+      g2[2] += cneu * ss.z;
+      g2[3] += cneu * ss.w;
+    }
+    *reinterpret_cast<float4*>(du + o) = make_float4(gu[0], gu[1], gu[2], gu[3]);
+    *reinterpret_cast<float4*>(ds1 + o) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+    *reinterpret_cast<float4*>(ds2 + o) = make_float4(g2[0], g2[1], g2[2], g2[3]);
+  }
+}
+
 }  // namespace stencil
 }  // namespace pdes

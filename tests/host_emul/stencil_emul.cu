@@ -11,7 +11,29 @@ extern "C" void pdes_oracle_darcy(const float* K, const float* out, int B, int H
 
 static double frand() { return (double)rand() / RAND_MAX * 2.0 - 1.0; }
 
-static int run_case(int B, int H, int W, int use_tb, int hasK, int nthreads) {
+// fitR > 0: drive the exact-fit unrolled strips (fwd_strip_r / bwd_strip_pass2_r) instead
+template <int R>
+static void fast_sample(const float* st, int hasK, int H, int W, int use_tb, float a, float b, float cdir,
+                        float cneu, float* scratch, double acc[4]) {
+  using namespace pdes::stencil;
+  const int HW = H * W, W4 = W / 4, nthreads = (H / R) * W4;
+  float* s = const_cast<float*>(st);
+  for (int t = 0; t < nthreads; ++t) {
+    FwdPartial p = fwd_strip_r<R, false, true>(hasK ? s : nullptr, s + HW, s + 2 * HW, s + 3 * HW, H, W, t % W4,
+                                               (t / W4) * R, use_tb != 0, 0.f, 0.f, nullptr, nullptr, nullptr,
+                                               nullptr, nullptr);
+    acc[0] += p.c; acc[1] += p.d; acc[2] += p.dir; acc[3] += p.neu;
+  }
+  float *P1 = scratch, *P2 = P1 + HW, *P3 = P2 + HW, *Q1 = P3 + HW, *Q2 = Q1 + HW;
+  for (int t = 0; t < nthreads; ++t)
+    (void)fwd_strip_r<R, true, false>(hasK ? s : nullptr, s + HW, s + 2 * HW, s + 3 * HW, H, W, t % W4,
+                                      (t / W4) * R, use_tb != 0, a, b, P1, P2, P3, Q1, Q2);
+  for (int t = 0; t < nthreads; ++t)
+    bwd_strip_pass2_r<R>(P1, P2, P3, Q1, Q2, s + HW, s + 3 * HW, s + HW, s + 2 * HW, s + 3 * HW, H, W, t % W4,
+                         (t / W4) * R, cdir, cneu);
+}
+
+static int run_case(int B, int H, int W, int use_tb, int hasK, int nthreads, int fitR = 0) {
   using namespace pdes::stencil;
   const int HW = H * W;
   std::vector<float> K((size_t)B * HW), out((size_t)B * 3 * HW);
@@ -35,6 +57,12 @@ static int run_case(int B, int H, int W, int use_tb, int hasK, int nthreads) {
       for (int c = 0; c < 3; ++c) stage[(size_t)(c + 1) * HW + p] = out[((size_t)s * 3 + c) * HW + p];
     }
     float* st = stage.data();
+    if (fitR > 0) {
+      if (fitR == 2) fast_sample<2>(st, hasK, H, W, use_tb, a, b, cdir, cneu, scratch.data(), acc);
+      else fast_sample<4>(st, hasK, H, W, use_tb, a, b, cdir, cneu, scratch.data(), acc);
+      for (int p = 0; p < 3 * HW; ++p) dout[(size_t)s * 3 * HW + p] = st[HW + p];
+      continue;
+    }
     for (int t = 0; t < nthreads; ++t) {
       FwdPartial p = fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W, t, nthreads,
                                true, use_tb != 0, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -63,8 +91,8 @@ static int run_case(int B, int H, int W, int use_tb, int hasK, int nthreads) {
   }
   const double ge = std::sqrt(num / std::fmax(den, 1e-300));
   const int ok = worst < 2e-5 && ge < 2e-5;
-  printf("B=%d H=%d W=%d use_tb=%d hasK=%d nthr=%d : loss rel err %.2e, grad rel-L2 %.2e %s\n", B, H, W,
-         use_tb, hasK, nthreads, worst, ge, ok ? "ok" : "FAIL");
+  printf("B=%d H=%d W=%d use_tb=%d hasK=%d nthr=%d fitR=%d : loss rel err %.2e, grad rel-L2 %.2e %s\n", B, H, W,
+         use_tb, hasK, nthreads, fitR, worst, ge, ok ? "ok" : "FAIL");
   return ok ? 0 : 1;
 }
 
@@ -75,6 +103,14 @@ int main() {
   for (auto& s : shapes)
     for (int tb = 0; tb < 2; ++tb)
       for (int hk = 0; hk < 2; ++hk) fails += run_case(2, s[0], s[1], tb, hk, 256);
+  // exact-fit unrolled strips: the shapes the kernels use (64x64) and small/edge-heavy ones
+  const int fshapes[][2] = {{64, 64}, {32, 32}, {4, 4}, {8, 12}, {6, 8}, {12, 16}, {64, 32}};
+  for (auto& s : fshapes)
+    for (int tb = 0; tb < 2; ++tb)
+      for (int hk = 0; hk < 2; ++hk) {
+        if (s[0] % 2 == 0) fails += run_case(2, s[0], s[1], tb, hk, 0, 2);
+        if (s[0] % 4 == 0) fails += run_case(2, s[0], s[1], tb, hk, 0, 4);
+      }
   fails += run_case(1, 64, 64, 1, 1, 128);
   fails += run_case(1, 32, 32, 1, 1, 64);
   printf("%s\n", fails ? "EMUL FAILED" : "EMUL PASSED");

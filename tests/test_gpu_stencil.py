@@ -36,7 +36,7 @@ def test_sobel_matches_reference_fixture(G):
             assert rel(av.cpu().numpy(), G[f"{tag}{c}_av"]) < 2e-6
 
 
-@pytest.mark.parametrize("impl", [1, 2, 3])
+@pytest.mark.parametrize("impl", [1, 2, 3, 4, 5])
 def test_darcy_loss_matches_reference_fixture(G, impl):
     from pde_surrogate_b200 import _lib, darcy
     from utils.image_gradient import SobelFilter
@@ -92,7 +92,7 @@ def test_darcy_generic_equals_tile():
     rs = np.random.RandomState(7)
     K = torch.tensor(np.exp(0.5 * rs.standard_normal((19, 1, 64, 64))), dtype=torch.float32, device="cuda")
     res = {}
-    for impl in (1, 2, 3):
+    for impl in (1, 2, 3, 4, 5):
         _lib.lib().pdes_darcy_loss_set_impl(impl)
         try:
             out = torch.tensor(np.random.RandomState(8).standard_normal((19, 3, 64, 64)), dtype=torch.float32,
@@ -102,7 +102,7 @@ def test_darcy_generic_equals_tile():
             res[impl] = (l4.detach().cpu().numpy(), out.grad.cpu().numpy())
         finally:
             _lib.lib().pdes_darcy_loss_set_impl(0)
-    for impl in (2, 3):
+    for impl in (2, 3, 4, 5):
         assert rel(res[impl][0], res[1][0]) < 2e-6
         assert rel(res[impl][1], res[1][1]) < 5e-6
 
