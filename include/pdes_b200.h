@@ -139,6 +139,10 @@ int pdes_densenet_last_launches(const pdes_net_t* net);
 /* Implementation selector for the convolutions: 0 = auto (tensor-core kernels where
  * available), 1 = force the SIMT fp32 kernels everywhere. Test hook. */
 int pdes_densenet_set_conv_impl(pdes_net_t* net, int impl);
+/* Diagnostics: set_timing(net, 1) records one CUDA event after every eager launch of the executor;
+ * timing_report synchronises the device and prints one "<us> <label>" line per launch to stderr. */
+int pdes_densenet_set_timing(pdes_net_t* net, int on);
+int pdes_densenet_timing_report(pdes_net_t* net);
 
 /* ------------------------------------------------------------------------------------
  * Fused Adam over a flat buffer; replaces torch.optim.Adam.step() as used at

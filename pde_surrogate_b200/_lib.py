@@ -52,6 +52,8 @@ SIGNATURES = {
     "pdes_densenet_flops": (c_double, [c_void_p, c_int, c_int]),
     "pdes_densenet_last_launches": (c_int, [c_void_p]),
     "pdes_densenet_set_conv_impl": (c_int, [c_void_p, c_int]),
+    "pdes_densenet_set_timing": (c_int, [c_void_p, c_int]),
+    "pdes_densenet_timing_report": (c_int, [c_void_p]),
     "pdes_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                c_float, c_float, c_float, c_int64, c_void_p]),
     "pdes_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -101,11 +101,24 @@ struct pdes_net {
   bool fwd_train_done = false;
   int launches = 0;
   int conv_impl = 0;
+  // PDES_TIMING=1: one CUDA event after every launch of the eager executor (diagnostics)
+  bool timing = false;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
 };
 
 namespace {
 
 int64_t pad4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
+void mark(pdes_net* n, cudaStream_t st, const std::string& label) {
+  if (!n->timing) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  n->marks.push_back(std::make_pair(label, e));
+}
 int rup(int v, int m) { return (v + m - 1) / m * m; }
 
 int add_buf(pdes_net* n, int H, int W, int C) {
@@ -605,6 +618,29 @@ extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
   return PDES_OK;
 }
 
+extern "C" int pdes_densenet_set_timing(pdes_net_t* n, int on) {
+  PDES_REQUIRE(n, PDES_ERR_INVALID, "pdes_densenet_set_timing: null net");
+  for (auto& m : n->marks) cudaEventDestroy(m.second);
+  n->marks.clear();
+  n->timing = on != 0;
+  return PDES_OK;
+}
+
+// Synchronises the device and prints "<us> <label>" per launch since set_timing(1) to stderr.
+extern "C" int pdes_densenet_timing_report(pdes_net_t* n) {
+  PDES_REQUIRE(n, PDES_ERR_INVALID, "pdes_densenet_timing_report: null net");
+  PDES_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 1; i < n->marks.size(); ++i) {
+    if (n->marks[i].first[0] == '@') continue;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, n->marks[i - 1].second, n->marks[i].second);
+    fprintf(stderr, "[pdes timing] %9.2f us  %s\n", ms * 1e3f, n->marks[i].first.c_str());
+  }
+  for (auto& m : n->marks) cudaEventDestroy(m.second);
+  n->marks.clear();
+  return PDES_OK;
+}
+
 extern "C" int pdes_densenet_last_launches(const pdes_net_t* n) { return n ? n->launches : 0; }
 
 extern "C" double pdes_densenet_flops(const pdes_net_t* n, int B, int training) {
@@ -626,9 +662,11 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
   cudaStream_t st = (cudaStream_t)stream;
   n->launches = 0;
   const bool tr = training != 0;
+  mark(n, st, "@forward");
   if (tr) {
     PDES_CUDA(cudaMemsetAsync(wsd(n, 0), 0, n->ws_doubles * sizeof(double), st));
     n->launches++;
+    mark(n, st, "memset stats");
   }
   int rc = PDES_OK;
   bool need_simt_pack = n->conv_impl != 0 || n->tc_mask != 7;
@@ -638,17 +676,20 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     rc = launch_pack_weights(pack_table(n), (int)n->layers.size(), n->max_pack, st);
     if (rc) return rc;
     n->launches++;
+    mark(n, st, "pack_weights");
   }
   if (n->conv_impl == 0 && n->n_tc2 > 0) {
     rc = launch_pack_tc2(tc2_table(n), n->n_tc2, n->max_tc2_pack, st);
     if (rc) return rc;
     n->launches++;
+    mark(n, st, "pack_tc2");
   }
   if (tr) {
     PDES_CUDA(cudaMemcpyAsync(wsf(n, n->xin), x,
                               sizeof(float) * (size_t)B * n->cfg.in_channels * n->cfg.imsize * n->cfg.imsize,
                               cudaMemcpyDeviceToDevice, st));
     n->launches++;
+    mark(n, st, "copy xin");
   }
   for (const auto& L : n->layers) {
     ConvArgs a;
@@ -716,6 +757,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       rc = launch_act_split(sa, st);
       if (rc) return rc;
       n->launches++;
+      mark(n, st, "split.f " + L.conv_name);
     }
     if (n->conv_impl == 0 && L.tc2_fwd && (n->tc_mask & 1)) {
       const int Hv = L.up ? 2 * Hs_l : Hs_l, Wv = L.up ? 2 * Ws_l : Ws_l;
@@ -744,11 +786,13 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     }
     if (rc) return rc;
     n->launches++;
+    mark(n, st, "conv.f " + L.conv_name);
   }
   if (tr) {
     rc = launch_bn_running_update(bn_table(n), n->n_bn, n->maxC, 0.1f, B, st);
     if (rc) return rc;
     n->launches++;
+    mark(n, st, "bn_running_update");
     n->last_B = B;
     n->fwd_train_done = true;
   }
@@ -766,6 +810,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
   n->launches = 0;
   int rc;
   bool used_wg = false;
+  mark(n, st, "@backward");
   for (int li = (int)n->layers.size() - 1; li >= 0; --li) {
     const Layer& L = n->layers[li];
     const float* dy;
@@ -801,6 +846,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         rc = launch_fix_dy(f, st);
         if (rc) return rc;
         n->launches++;
+        mark(n, st, "fix_dy " + L.conv_name);
       } else {
         fixargs = f;
         have_fix = true;
@@ -863,6 +909,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         rc = launch_act_split(sb, st);
         if (rc) return rc;
         n->launches++;
+        mark(n, st, "split.b " + L.conv_name);
       }
       if (use_wg) {
         const Buf& ib = n->bufs[L.in_buf];
@@ -889,6 +936,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       }
       if (rc) return rc;
       n->launches++;
+      mark(n, st, "wgrad " + L.conv_name);
     }
     // ---- dgrad (not needed for the first conv: the input does not require grad) ------
     if (L.in_buf >= 0) {
@@ -946,16 +994,19 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       }
       if (rc) return rc;
       n->launches++;
+      mark(n, st, "dgrad " + L.conv_name);
     }
   }
   if (used_wg) {
     rc = launch_wgrad_unpack(wg_table(n), n->n_wg_bound, n->max_wg_elems, st);
     if (rc) return rc;
     n->launches++;
+    mark(n, st, "wgrad_unpack");
   }
   rc = launch_bn_param_grad(bn_table(n), n->n_bn, n->maxC, st);
   if (rc) return rc;
   n->launches++;
+  mark(n, st, "bn_param_grad");
   n->fwd_train_done = false;
   return PDES_OK;
 }
