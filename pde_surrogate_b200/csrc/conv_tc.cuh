@@ -76,6 +76,7 @@ struct Tc2Args {
   int N, KC, nchunks, ngroups, S, TS, AST, NB, TPB;
   long long* dbg;              // optional per-CTA phase timestamps (debug), 16 slots per CTA
   int osub;                    // 1: store only even output positions at (y/2, x/2)  (stride-2 as stride-1)
+  int exp;                     // timing experiments (PDES_TC2_EXP): 1 = skip activation loads, 2 = skip filter loads
 };
 struct Tc2PackDesc {
   const float* w;  // OIHW

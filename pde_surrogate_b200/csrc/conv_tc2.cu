@@ -279,6 +279,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
           const int s = q % AST;
           mbar_wait(&a_empty[s], (uint32_t)(((q / AST) & 1) ^ 1));
           unsigned char* st = A_s + (size_t)s * a_stage_bytes;
+          if (t.exp == 1) {  // timing experiment: no activation loads
+            mbar_arrive(&a_full[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
 #pragma unroll
           for (int p = 0; p < 3; ++p)
@@ -294,6 +298,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
         for (int st = 0; st < nchunks * bstages_per_chunk; ++st, ++q) {
           const int s = q % NB;
           mbar_wait(&b_empty[s], (uint32_t)(((q / NB) & 1) ^ 1));
+          if (t.exp == 2) {  // timing experiment: no filter loads
+            mbar_arrive(&b_full[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&b_full[s], b_stage_bytes);
           tma_load_1d(B_s + (size_t)s * b_stage_bytes,
                       reinterpret_cast<const unsigned char*>(t.wpk) + (size_t)st * b_stage_bytes, b_stage_bytes,

@@ -176,11 +176,12 @@ def test_engine_graph_replay_matches_eager(golden_dir):
         model, K, cfg = _model(g)
         ts = TrainStep(model, lr=2e-3)
         out = []
-        for i in range(4):
+        for i in range(6 if mode == "eager" else 4):
             loss = ts.step_graph(K, lr=2e-3) if mode == "graph" else ts.step(K, lr=2e-3)
             out.append(float(loss))
         losses[mode] = out
-    # the graph path spends two warm-up steps before capture: compare the overlapping part loosely
     assert np.all(np.isfinite(losses["graph"])) and np.all(np.isfinite(losses["eager"]))
     assert abs(losses["eager"][0] - float(g["loss"])) <= 1e-4 * float(g["loss"])
-    assert losses["graph"][-1] < losses["eager"][0]  # it trains
+    # the graph path spends two real optimisation steps on warm-up before capture: replay i is step i+2
+    for i in range(4):
+        assert abs(losses["graph"][i] - losses["eager"][i + 2]) <= 2e-2 * abs(losses["eager"][i + 2]), (i, losses)
