@@ -132,6 +132,45 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// column sums over the 32 lanes of a warp for 16 values per lane, by recursive halving:
+// 8+4+2+1+1 = 16 shuffles.  On return lane l holds in `out` the sum of column col_of_lane(l).
+__device__ __forceinline__ float colsum16(const float v[16], int lane) {
+  float a[8];
+  const bool up16 = lane & 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = up16 ? v[i] : v[i + 8];
+    const float keep = up16 ? v[i + 8] : v[i];
+    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float b[4];
+  const bool up8 = lane & 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = up8 ? a[i] : a[i + 4];
+    const float keep = up8 ? a[i + 4] : a[i];
+    b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float c[2];
+  const bool up4 = lane & 4;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = up4 ? b[i] : b[i + 2];
+    const float keep = up4 ? b[i + 2] : b[i];
+    c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const bool up2 = lane & 2;
+  const float send = up2 ? c[0] : c[1];
+  const float keep = up2 ? c[1] : c[0];
+  float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  return d;
+}
+// column index held by `lane` after colsum16
+__device__ __forceinline__ int colsum16_col(int lane) {
+  return ((lane & 16) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 4) ? 2 : 0) + ((lane & 2) ? 1 : 0);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace pdes

@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "first_conv.cuh"
 
 using namespace pdes;
 
@@ -153,6 +154,28 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
 }
 }  // namespace
 
+namespace {
+// impl 3: the dedicated first-convolution kernels; x is the PLANAR (B, Cin, H, W) network input
+int first_args(const pdes_conv_desc* d, FirstConvArgs& fa, const char* fn) {
+  PDES_REQUIRE(!d->bn_relu && !d->upsample && !d->out_nchw, PDES_ERR_UNSUPPORTED,
+               "%s: impl 3 is the plain first convolution (no BatchNorm prologue, no upsampling, NHWC output)", fn);
+  PDES_REQUIRE(first_conv_supported(d->Cin, d->Cout, d->KH, d->stride), PDES_ERR_UNSUPPORTED,
+               "%s: impl 3 supports k7 s2 convolutions with at most 4 input channels", fn);
+  memset(&fa, 0, sizeof(fa));
+  fa.B = d->B;
+  fa.Cin = d->Cin;
+  fa.H = d->Hin;
+  fa.W = d->Win;
+  fa.Cout = d->Cout;
+  fa.KS = d->KH;
+  fa.stride = d->stride;
+  fa.pad = d->pad;
+  fa.Ho = d->Hout;
+  fa.Wo = d->Wout;
+  return PDES_OK;
+}
+}  // namespace
+
 extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const float* w,
                                const float* scale, const float* shift, float* y, double* ch_sum,
                                double* ch_sumsq, int impl, void* stream) {
@@ -160,8 +183,21 @@ extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const fl
   if (rc) return rc;
   PDES_REQUIRE(x && w && y, PDES_ERR_INVALID, "pdes_conv2d_fwd: null pointer");
   PDES_REQUIRE(!d->bn_relu || (scale && shift), PDES_ERR_INVALID, "pdes_conv2d_fwd: bn_relu needs scale/shift");
-  PDES_REQUIRE(impl >= 0 && impl <= 2, PDES_ERR_UNSUPPORTED, "pdes_conv2d_fwd: impl %d not available", impl);
+  PDES_REQUIRE(impl >= 0 && impl <= 3, PDES_ERR_UNSUPPORTED, "pdes_conv2d_fwd: impl %d not available", impl);
   cudaStream_t st = (cudaStream_t)stream;
+  if (impl == 3) {
+    FirstConvArgs fa;
+    rc = first_args(d, fa, "pdes_conv2d_fwd");
+    if (rc) return rc;
+    fa.x = x;
+    fa.w = w;
+    fa.y = y;
+    fa.ldy = d->ld_out;
+    fa.coff = d->c_off_out;
+    fa.o_sum = ch_sum;
+    fa.o_sumsq = ch_sumsq;
+    return launch_first_conv_fwd(fa, st);
+  }
   Packed pk;
   rc = pack(d, w, st, pk);
   if (rc) return rc;
@@ -249,7 +285,17 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   if (rc) return rc;
   PDES_REQUIRE(x && dy && dw, PDES_ERR_INVALID, "pdes_conv2d_wgrad: null pointer");
   PDES_REQUIRE(!d->bn_relu || (scale && shift), PDES_ERR_INVALID, "pdes_conv2d_wgrad: bn_relu needs scale/shift");
-  PDES_REQUIRE(impl >= 0 && impl <= 2, PDES_ERR_UNSUPPORTED, "pdes_conv2d_wgrad: impl %d not available", impl);
+  PDES_REQUIRE(impl >= 0 && impl <= 3, PDES_ERR_UNSUPPORTED, "pdes_conv2d_wgrad: impl %d not available", impl);
+  if (impl == 3) {
+    FirstConvArgs fa;
+    rc = first_args(d, fa, "pdes_conv2d_wgrad");
+    if (rc) return rc;
+    fa.x = x;
+    fa.dy = dy + d->c_off_out;
+    fa.lddy = d->ld_out;
+    fa.dw = dw;
+    return launch_first_conv_wgrad(fa, (cudaStream_t)stream);
+  }
   WgradArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x;

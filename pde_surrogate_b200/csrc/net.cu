@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
+#include "first_conv.cuh"
 
 namespace pdes {
 
@@ -51,6 +52,7 @@ struct Layer {
   size_t planes;     // float offset of this layer's activation piece planes [3][B][Hv][Wv][Cp] bf16
   size_t planesB;    // float offset of this layer's dY piece planes (read by its dgrad and, concurrently, its wgrad)
   bool tc_wg;        // weight gradient on tcgen05
+  bool first_k;      // dedicated CUDA-core kernels of the first convolution (first_conv.cu)
   int ci_pad, co_pad;
   size_t dwp;        // float offset of the [tap][ci_pad][co_pad] staging gradient
 };
@@ -176,6 +178,7 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   memset(&L.p2f, 0, sizeof(L.p2f));
   memset(&L.p2b, 0, sizeof(L.p2b));
   L.tc_wg = false;
+  L.first_k = false;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
   memset(&L.pf, 0, sizeof(L.pf));
@@ -317,6 +320,10 @@ int build(pdes_net* n) {
     const bool out_ok = L.out_buf < 0 || ((n->bufs[L.out_buf].ld % 4 == 0) && (L.coff % 4 == 0));
     const bool sub_ok = L.stride == 1 || (L.stride == 2 && !L.up);
     const bool aligned = in_ok && out_ok && sub_ok;
+    if (L.in_buf < 0 && L.out_buf >= 0 && first_conv_supported(L.Cin, L.Cout, L.KS, L.stride)) {
+      L.first_k = true;
+      continue;
+    }
     if (aligned && tc2_supported(L.KS, 1, L.Cin, L.Nf)) {
       L.tc2_fwd = true;
       tc2_plan(L.KS, L.Cin, L.Nf, &L.p2f);
@@ -703,7 +710,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
   int rc = PDES_OK;
   bool need_simt_pack = n->conv_impl != 0 || n->tc_mask != 7;
   for (const auto& L : n->layers)
-    if (!L.tc2_fwd || (L.in_buf >= 0 && !L.tc2_bwd)) need_simt_pack = true;
+    if (!(L.tc2_fwd || L.first_k) || (L.in_buf >= 0 && !L.tc2_bwd)) need_simt_pack = true;
   if (need_simt_pack) {
     rc = launch_pack_weights(pack_table(n), (int)n->layers.size(), n->max_pack, st);
     if (rc) return rc;
@@ -791,7 +798,28 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       n->launches++;
       mark(n, st, "split.f " + L.conv_name);
     }
-    if (n->conv_impl == 0 && L.tc2_fwd && (n->tc_mask & 1)) {
+    if (n->conv_impl == 0 && L.first_k) {
+      FirstConvArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.x = a.x;
+      fa.w = n->p + L.w_off;
+      fa.y = a.y;
+      fa.ldy = a.ldy;
+      fa.coff = a.coff;
+      fa.o_sum = a.o_sum;
+      fa.o_sumsq = a.o_sumsq;
+      fa.B = B;
+      fa.Cin = L.Cin;
+      fa.H = L.Hs;
+      fa.W = L.Ws;
+      fa.Cout = L.Cout;
+      fa.KS = L.KS;
+      fa.stride = L.stride;
+      fa.pad = L.pad;
+      fa.Ho = L.Ho;
+      fa.Wo = L.Wo;
+      rc = launch_first_conv_fwd(fa, st);
+    } else if (n->conv_impl == 0 && L.tc2_fwd && (n->tc_mask & 1)) {
       const int Hv = L.up ? 2 * Hs_l : Hs_l, Wv = L.up ? 2 * Ws_l : Ws_l;
       Tc2Args t;
       memset(&t, 0, sizeof(t));
@@ -973,6 +1001,24 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
           rc = launch_wgrad_tc(tw, st);
         }
         used_wg = true;
+      } else if (n->conv_impl == 0 && L.first_k) {
+        FirstConvArgs fa;
+        memset(&fa, 0, sizeof(fa));
+        fa.x = w.x;
+        fa.dy = w.dy;
+        fa.lddy = w.lddy;
+        fa.dw = w.dw;
+        fa.B = B;
+        fa.Cin = L.Cin;
+        fa.H = L.Hs;
+        fa.W = L.Ws;
+        fa.Cout = L.Cout;
+        fa.KS = L.KS;
+        fa.stride = L.stride;
+        fa.pad = L.pad;
+        fa.Ho = L.Ho;
+        fa.Wo = L.Wo;
+        rc = launch_first_conv_wgrad(fa, st);
       } else {
         rc = launch_wgrad_simt(w, st);
       }

@@ -75,15 +75,16 @@ class TrainStep(object):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            self._set_hyper(self.lr)
             for _ in range(2):  # warm-up: lazily-set kernel attributes, workspaces, tensor maps
+                self._set_hyper(self.lr)
                 self._device_work(self.static_K)
+                if self.world == 1:  # these are real optimisation steps (Adam is part of the device work)
+                    self.steps += 1
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._device_work(self.static_K)
-        self.steps += 2 if self.world == 1 else 0
 
     def _set_hyper(self, lr):
         L = _lib.lib()

@@ -130,3 +130,49 @@ def _run_case(case, impl):
     _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), _lib.ptr(sd) if bn else None,
                                    _lib.ptr(hd) if bn else None, _lib.ptr(dyd), _lib.ptr(dw), impl, st))
     assert rel(dw - 1.0, wr.grad) < 1e-5, rel(dw - 1.0, wr.grad)
+
+
+FIRST_CASES = [
+    # B, H, Cin, Cout, pad   (k7 s2; models/codec.py:238-243: pad 3 for even imsize, 2 for odd)
+    (3, 64, 1, 48, 3),
+    (2, 32, 1, 48, 3),
+    (2, 33, 1, 48, 2),      # odd image: ragged tiles
+    (1, 20, 3, 20, 3),      # several input channels, Cout not a multiple of 16
+    (2, 16, 2, 6, 3),       # Cout not a multiple of 4: scalar stores
+]
+
+
+@pytest.mark.parametrize("case", FIRST_CASES)
+def test_first_conv_kernels(case):
+    """Dedicated CUDA-core kernels of In_conv (impl 3: planar input, forward + batch statistics,
+    weight gradient) against torch fp64."""
+    from pde_surrogate_b200 import _lib
+    L = _lib.lib()
+    B, H, Cin, Cout, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    coff = 4 if Cout % 4 == 0 else 3
+    ld_out = coff + Cout + (5 if Cout % 4 else 4)
+    x = torch.exp(0.5 * torch.randn(B, Cin, H, H, generator=g))
+    w = torch.randn(Cout, Cin, 7, 7, generator=g) / (Cin * 49) ** 0.5
+    d, Ho = _desc(B, H, Cin, Cout, 7, 2, p, 0, 0, Cin, ld_out, coff)
+    xr, wr = x.double(), w.double().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, 2, p)
+    dy = torch.randn(yr.shape, generator=g, dtype=torch.float64)
+    yr.backward(dy)
+    st = _lib.stream_ptr()
+    xd, wd = x.cuda(), w.cuda()
+    y = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
+    csum = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    csq = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    _lib.check(L.pdes_conv2d_fwd(byref(d), _lib.ptr(xd), _lib.ptr(wd), None, None, _lib.ptr(y), _lib.ptr(csum),
+                                 _lib.ptr(csq), 3, st))
+    ynhwc = yr.detach().permute(0, 2, 3, 1)
+    assert rel(y[..., coff:coff + Cout], ynhwc) < 2e-6, rel(y[..., coff:coff + Cout], ynhwc)
+    assert float(y[..., :coff].abs().max()) == 0.0 and float(y[..., coff + Cout:].abs().max()) == 0.0
+    assert rel(csum, ynhwc.sum((0, 1, 2))) < 1e-5
+    assert rel(csq, (ynhwc ** 2).sum((0, 1, 2))) < 1e-5
+    dyd = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
+    dyd[..., coff:coff + Cout] = dy.permute(0, 2, 3, 1).float().cuda()
+    dw = torch.ones(Cout, Cin, 7, 7, device="cuda")
+    _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), None, None, _lib.ptr(dyd), _lib.ptr(dw), 3, st))
+    assert rel(dw - 1.0, wr.grad) < 1e-5, rel(dw - 1.0, wr.grad)
