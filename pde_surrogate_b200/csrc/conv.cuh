@@ -52,6 +52,7 @@ struct ConvArgs {
   float* G;        // gradient buffer of the same tensor (ldG)
   int ldG, g_accum;
   double* bsum;    // [0,C): sum dZ ; [C,2C): sum dZ*xhat   (C = Cout of this "conv")
+  unsigned* gmax;  // EPI_BNBWD: running max |G| written (float bits, atomicMax) or null
 };
 
 struct WgradArgs {

@@ -89,11 +89,22 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
   const size_t pack_bytes = (p.pack_elems * 2 + 255) & ~(size_t)255;
   unsigned char* buf = nullptr;
   PDES_CUDA(cudaMallocAsync((void**)&buf, pack_bytes + ((plane_bytes + 255) & ~(size_t)255) + 512, st));
-  __nv_bfloat16* wpk = reinterpret_cast<__nv_bfloat16*>(buf);
-  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>(buf + pack_bytes);
+  op16* wpk = reinterpret_cast<op16*>(buf);
+  op16* planes = reinterpret_cast<op16*>(buf + pack_bytes);
   Tc2PackDesc* tab = reinterpret_cast<Tc2PackDesc*>(buf + pack_bytes + ((plane_bytes + 255) & ~(size_t)255));
+  unsigned* dmax = reinterpret_cast<unsigned*>(tab + 1);  // dynamic scale of a gradient operand (dgrad)
+  float* dinv = reinterpret_cast<float*>(dmax + 1);
   sa.out = planes;
-  int rc = launch_act_split(sa, st);
+  sa.scale = pow2f(kActScaleLog2);
+  int rc = PDES_OK;
+  if (transpose) {
+    PDES_CUDA(cudaMemsetAsync(dmax, 0, 8, st));
+    rc = launch_absmax(a.x, (size_t)a.B * a.Hs * a.Ws * a.ldx - (size_t)(a.ldx - Cin_k), dmax, st);
+    if (rc) return rc;
+    sa.dyn_max = dmax;
+    sa.dyn_inv = dinv;
+  }
+  rc = launch_act_split(sa, st);
   Tc2PackDesc h;
   h.w = w;
   h.dst = wpk;
@@ -114,6 +125,8 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
     memset(&t, 0, sizeof(t));
     t.c = a;
     t.wpk = wpk;
+    t.out_scale = transpose ? pow2f(-kWScaleLog2) : pow2f(-(kActScaleLog2 + kWScaleLog2));
+    t.dyn_scale = transpose ? dinv : nullptr;
     t.N = N;
     t.KC = p.KC;
     t.nchunks = p.nchunks;
@@ -329,12 +342,12 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   const size_t nf = (size_t)d->KH * d->KW * tw.ci_pad * tw.co_pad;
   const int Hv = d->upsample ? 2 * d->Hin : d->Hin, Wv = d->upsample ? 2 * d->Win : d->Win;
   const size_t bytesA = act_planes_bytes(d->B, Hv, Wv, d->Cin), bytesB = act_planes_bytes(d->B, d->Hout, d->Wout, d->Cout);
-  const size_t offA = (nf * sizeof(float) + 512 + 255) & ~(size_t)255, offB = (offA + bytesA + 255) & ~(size_t)255;
+  const size_t offA = (nf * sizeof(float) + 1024 + 255) & ~(size_t)255, offB = (offA + bytesA + 255) & ~(size_t)255;
   float* buf = nullptr;
   PDES_CUDA(cudaMallocAsync((void**)&buf, offB + bytesB + 256, st));
   PDES_CUDA(cudaMemsetAsync(buf, 0, nf * sizeof(float), st));
-  __nv_bfloat16* pa = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(buf) + offA);
-  __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<unsigned char*>(buf) + offB);
+  op16* pa = reinterpret_cast<op16*>(reinterpret_cast<unsigned char*>(buf) + offA);
+  op16* pb = reinterpret_cast<op16*>(reinterpret_cast<unsigned char*>(buf) + offB);
   ActSplitArgs sa;
   memset(&sa, 0, sizeof(sa));
   sa.x = a.x;
@@ -348,7 +361,13 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   sa.bn = a.bn;
   sa.out = pa;
   sa.Cp = (d->Cin + 7) & ~7;
+  sa.scale = pow2f(kActScaleLog2);
   rc = launch_act_split(sa, st);
+  if (rc) return rc;
+  unsigned* dmax = reinterpret_cast<unsigned*>(buf + nf) + 64;  // behind the unpack table slot
+  float* dinv = reinterpret_cast<float*>(dmax + 1);
+  PDES_CUDA(cudaMemsetAsync(dmax, 0, 8, st));
+  rc = launch_absmax(a.dy, (size_t)d->B * d->Hout * d->Wout * a.lddy - (size_t)(a.lddy - d->Cout), dmax, st);
   if (rc) return rc;
   ActSplitArgs sb;
   memset(&sb, 0, sizeof(sb));
@@ -360,6 +379,9 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   sb.B = d->B;
   sb.out = pb;
   sb.Cp = (d->Cout + 7) & ~7;
+  sb.scale = 1.f;
+  sb.dyn_max = dmax;
+  sb.dyn_inv = dinv;
   rc = launch_act_split(sb, st);
   if (rc) return rc;
   tw.planesA = pa;
@@ -374,6 +396,8 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   tw.Cout = d->Cout;
   tw.KS = d->KH;
   tw.pad = d->pad;
+  tw.out_scale = pow2f(-kActScaleLog2);
+  tw.dyn_scale = dinv;
   rc = launch_wgrad_tc(tw, st);
   if (rc == PDES_OK) {
     TcWgradUnpack u;

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_simt_kernel(ConvArgs a) {
   int npx = 2;
   int py[2], px[2];
   bool act = true;
+  float gmx = 0.f;
   if (a.pool) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
@@ -279,12 +280,18 @@ __global__ void __launch_bounds__(kConvThreads) conv_simt_kernel(ConvArgs a) {
           s1[j][i] += dz;
           s2[j][i] += dz * xh;
           const float g = ep_s[nl + i] * dz;
-          gp[i] = a.g_accum ? gp[i] + g : g;
+          const float o = a.g_accum ? gp[i] + g : g;
+          gp[i] = o;
+          gmx = fmaxf(gmx, fabsf(o));
         }
       }
     }
   }
 
+  if (a.epi == EPI_BNBWD && a.gmax != nullptr) {  // running |G| maximum (dynamic fp16 scale of the dY pieces)
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(gmx));
+    if ((t & 31) == 0 && m != 0u) atomicMax(a.gmax, m);
+  }
   const bool want_red = (a.epi == EPI_NHWC && a.o_sum != nullptr) || a.epi == EPI_BNBWD;
   if (want_red) {
 #pragma unroll

@@ -1,9 +1,30 @@
 // conv_tc.cuh — interface of the tcgen05 convolution kernels.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "conv.cuh"
 
 namespace pdes {
+
+// ---- fp32-accurate tensor-core operands -----------------------------------------------------
+// Every GEMM operand x is stored as TWO fp16 pieces of the power-of-two scaled value:
+//   x * 2^s = h1 + h2,   h1 = fp16(x * 2^s),  h2 = fp16(x * 2^s - h1)      (11 + 11 significand bits)
+// and a product a*w is evaluated as the three tensor-core products a1*w1 + a1*w2 + a2*w1 (the dropped
+// a2*w2 is 2^-22 relative), accumulated in fp32 in separate TMEM column groups for the leading and
+// the cross terms.  fp16 has 5 exponent bits, hence the scaling: static powers of two for
+// activations and filters, a per-layer dynamic power of two for gradients (derived on the device
+// from the running maximum of the gradient buffer the slice lives in); the epilogues multiply by
+// the exact inverse.  Below 2^-2 (scaled) the second piece is subnormal: the absolute error of an
+// element is max(2^-23 |x|, 2^-25 / 2^s).
+using op16 = __half;
+constexpr int kPieces = 2;
+constexpr int kActScaleLog2 = 4;    // activations (post BatchNorm+ReLU, O(1)):   x * 16
+constexpr int kWScaleLog2 = 8;      // filters (|w| << 256):                      w * 256
+constexpr int kDyTargetLog2 = 10;   // gradients: buffer maximum scaled into [2^10, 2^11)
+inline float pow2f(int e) {
+  union { uint32_t u; float f; } v;
+  v.u = (uint32_t)(e + 127) << 23;
+  return v.f;
+}
 
 struct TcConvArgs {
   ConvArgs c;        // geometry, prologue, epilogue (weights pointer `w` unused)
@@ -28,7 +49,7 @@ struct TcPackDesc {
   int Cout, Cin, KS, N, KC, nchunks, transpose;
 };
 
-// elementwise pre-pass of the tensor-core wgrad: three bf16 piece planes of the operand
+// elementwise pre-pass of the tensor-core wgrad: two fp16 piece planes of the operand
 struct ActSplitArgs {
   const float* x;        // NHWC, ldx floats per pixel (channel offset already applied)
   int ldx, C, Hs, Ws, B;
@@ -36,20 +57,29 @@ struct ActSplitArgs {
   int nchw;              // 1: x is planar (B,C,Hs,Ws)
   int pro;               // 1: a = max(0, x*scale+shift) first
   BnSrc bn;
-  __nv_bfloat16* out;    // [3][B][Hv][Cp/8][Wv][8]
+  op16* out;    // [2][B][Hv][Cp/8][Wv][8]
   int Cp;                // C rounded up to 8
   // fused dY correction (replaces a separate fix_dy launch): x is the gradient slice G, rewritten in
   // place as G - c1[c] - xhat*c2[c] before the split; fx.G is ignored
   int fix;
   FixDyArgs fx;
+  // scaling of the pieces: x * scale, with scale = 2^kActScaleLog2 style constants, or — when dyn_max
+  // is set — the power of two that brings the float whose bits are *dyn_max (running |gradient|
+  // maximum of the buffer) to 2^kDyTargetLog2; the inverse is published in *dyn_inv for the
+  // consumers' epilogues
+  float scale;
+  const unsigned* dyn_max;
+  float* dyn_inv;
 };
 
 struct TcWgradArgs {
-  const __nv_bfloat16* planesA;  // [3][B][Hv][CpA/8][Wv][8]  activation pieces (after BN+ReLU / upsampling)
-  const __nv_bfloat16* planesB;  // [3][B][Ho][CpB/8][Wo][8]  dY pieces
+  const op16* planesA;  // [2][B][Hv][CpA/8][Wv][8]  activation pieces (after BN+ReLU / upsampling)
+  const op16* planesB;  // [2][B][Ho][CpB/8][Wo][8]  dY pieces
   float* dwp;                    // staging gradient [tap][ci_pad][co_pad] (vector reductions)
   int B, Hv, Wv, Ho, Wo, Cin, Cout, KS, pad;
   int ci_pad, co_pad;
+  float out_scale;               // exact inverse of the static operand scales
+  const float* dyn_scale;        // optional device scalar multiplied in as well (dynamic dY scale)
 };
 
 struct TcWgradUnpack {
@@ -63,6 +93,8 @@ void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad);
 int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st);
 int launch_act_split(const ActSplitArgs& a, cudaStream_t st);
 size_t act_planes_bytes(int B, int H, int W, int C);
+// max |x| over n floats as float bits, atomicMax-ed into *out (the caller clears it)
+int launch_absmax(const float* x, size_t n, unsigned* out, cudaStream_t st);
 int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_elems, cudaStream_t st);
 
 // ---- TMA-fed bf16x3 convolution (conv_tc2.cu) -----------------------------------------------
@@ -72,21 +104,23 @@ struct Tc2Plan {
 };
 struct Tc2Args {
   ConvArgs c;                  // geometry (B, Ho, Wo, KS, pad, Cout) and epilogue; x/w/prologue unused
-  const __nv_bfloat16* wpk;    // [chunk][tap][k-octet][piece][N][8]
+  const op16* wpk;    // [chunk][tap][k-octet][piece][N][8]
   int N, KC, nchunks, ngroups, S, TS, AST, NB, TPB;
   long long* dbg;              // optional per-CTA phase timestamps (debug), 16 slots per CTA
   int osub;                    // 1: store only even output positions at (y/2, x/2)  (stride-2 as stride-1)
+  float out_scale;             // exact inverse of the static operand scales, applied to the accumulator
+  const float* dyn_scale;      // optional device scalar multiplied in as well (dynamic dY scale)
   int exp;                     // timing experiments (PDES_TC2_EXP): 1 = skip activation loads, 2 = skip filter loads
 };
 struct Tc2PackDesc {
   const float* w;  // OIHW
-  __nv_bfloat16* dst;
+  op16* dst;
   int Cout, Cin, KS, N, KC, nchunks, transpose;
 };
 void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p);
 bool tc2_supported(int KS, int stride, int Cin_k, int N);
-// planes: [3][B][Hv][round8(Cin_k)/8][Wv][8] bf16 pieces of the GEMM-K operand (act_split_kernel)
-int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int Wv, int Cin_k, cudaStream_t st);
+// planes: [2][B][Hv][round8(Cin_k)/8][Wv][8] bf16 pieces of the GEMM-K operand (act_split_kernel)
+int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Cin_k, cudaStream_t st);
 int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st);
 
 // tiling for a convolution whose GEMM-K operand has Cin_k channels and GEMM-N is N

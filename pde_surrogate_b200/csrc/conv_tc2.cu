@@ -9,20 +9,22 @@
 // and the KSxKS filter taps are shifted descriptors into that one tile (im2col-free).  Filter
 // tiles are pre-packed per (chunk, tap) in their shared-memory image and arrive by 1-D bulk TMA.
 //
-// fp32 parity: x = b1 + b2 + b3 exactly (8+8+8 mantissa bits); the six products of weight >= 2^-16
-//   a1*[w1|w2|w3], a2*[w1|w2], a3*[w1]
-// are issued as (up to) three tcgen05.mma.kind::f16 instructions whose N-concatenated filter
-// operand sends each product class to its own TMEM column group (G0 = a1w1, G1 = a1w2+a2w1,
-// G2 = a1w3+a2w2+a3w1): tensor-core accumulation truncates, so big and small terms never share
-// an accumulator, the K range is spread over S accumulator sets, and the epilogue adds everything
-// with round-to-nearest fp32.
+// fp32 parity: every operand is two fp16 pieces of its power-of-two scaled value (conv_tc.cuh); the
+// three products of weight >= 2^-11
+//   a1*[w1|w2], a2*[w1]
+// are issued as two tcgen05.mma.kind::f16 instructions (three when 2N > 256) whose N-concatenated
+// filter operand sends each product class to its own TMEM column group (G0 = a1w1,
+// G1 = a1w2 + a2w1): tensor-core accumulation truncates, so big and small terms never share an
+// accumulator, the K range is spread over S accumulator sets, and the epilogue adds everything
+// with round-to-nearest fp32 and multiplies by the exact inverse of the operand scales.
 //
 // Warp roles (384 threads, persistent over pixel tiles): warp 0 = TMA producer of activation
 // tiles, warp 1 = TMA producer of filter tiles, warp 2 = TMEM allocator + MMA issuer (one lane),
 // warps 4-11 = epilogue (two warps per TMEM lane quarter).  With two TMEM accumulator stages the
 // epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <stdlib.h>
+#include <cuda_fp16.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
@@ -36,8 +38,8 @@ constexpr int kThreads = 384;
 constexpr int kTH = 16, kTW = 8;
 constexpr int kEpiWarp0 = 4, kEpiWarps = 8;
 
-__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {  // D fp32, A/B bf16, K-major
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {  // D fp32, A/B fp16 (format 0), K-major
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -85,14 +87,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void bf16_split3(float x, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-  const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(b1);
-  const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(b2);
-  p0 = (uint32_t)__bfloat16_as_ushort(b1);
-  p1 = (uint32_t)__bfloat16_as_ushort(b2);
-  p2 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(r2));
+__device__ __forceinline__ uint32_t f2h_sat(float x) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return (uint32_t)h;
 }
 __device__ __forceinline__ void bn_consts2(const BnSrc& s, int c, float& scale, float& shift, float& mean,
                                            float& invstd) {
@@ -119,31 +117,21 @@ __device__ __forceinline__ void bn_consts2(const BnSrc& s, int c, float& scale, 
 }
 
 // instruction list of one k16 step per MODE: (a piece, first filter piece, #pieces, first group)
-//  MODE 0: 3N <= 256            a1x[w1|w2|w3]->G0..2, a2x[w1|w2]->G1..2, a3xw1->G2
-//  MODE 1: 2N <= 256 < 3N       a1x[w1|w2]->G0..1, a1xw3->G2, a2x[w1|w2]->G1..2, a3xw1->G2
-//  MODE 2: 3 groups, N > 128    six single-piece instructions
-//  MODE 3: 2 groups (3N > 512)  six single-piece instructions, all cross terms in G1
+//  MODE 0: 2N <= 256   a1x[w1|w2] -> G0..1, a2xw1 -> G1
+//  MODE 1: 2N >  256   three single-piece instructions a1xw1 -> G0, a1xw2 -> G1, a2xw1 -> G1
 // nibble-packed tables (entry i = bits [4i, 4i+4)) so that they fold to constants in device code
 template <int MODE> struct Ops;
 template <> struct Ops<0> {
-  static constexpr int n = 3;
-  static constexpr uint32_t A = 0x210u, Bp = 0x0u, NP = 0x123u, G = 0x210u;
+  static constexpr int n = 2;
+  static constexpr uint32_t A = 0x10u, Bp = 0x00u, NP = 0x12u, G = 0x10u;
 };
 template <> struct Ops<1> {
-  static constexpr int n = 4;
-  static constexpr uint32_t A = 0x2100u, Bp = 0x20u, NP = 0x1212u, G = 0x2120u;
-};
-template <> struct Ops<2> {
-  static constexpr int n = 6;
-  static constexpr uint32_t A = 0x211000u, Bp = 0x10210u, NP = 0x111111u, G = 0x221210u;
-};
-template <> struct Ops<3> {
-  static constexpr int n = 6;
-  static constexpr uint32_t A = 0x211000u, Bp = 0x10210u, NP = 0x111111u, G = 0x111110u;
+  static constexpr int n = 3;
+  static constexpr uint32_t A = 0x100u, Bp = 0x010u, NP = 0x111u, G = 0x110u;
 };
 #define OPF(tab, i) ((int)(((tab) >> (4 * (i))) & 0xFu))
 // ops that are the first writer of (all of) their column groups within one k16 step
-template <int MODE> struct FirstW { static constexpr uint32_t mask = MODE == 0 ? 0x1u : (MODE == 1 ? 0x3u : (MODE == 2 ? 0x7u : 0x3u)); };
+template <int MODE> struct FirstW { static constexpr uint32_t mask = MODE == 0 ? 0x1u : 0x3u; };
 
 template <int KS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -156,8 +144,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
   const int N = t.N, KC = t.KC, NB = t.NB, TPB = t.TPB, AST = t.AST;
   const int koct = KC >> 3;
   const uint32_t a_piece_bytes = (uint32_t)koct * HP * 16u;
-  const uint32_t a_stage_bytes = 3u * a_piece_bytes;
-  const uint32_t b_tap_bytes = (uint32_t)koct * 3u * (uint32_t)N * 16u;
+  const uint32_t a_stage_bytes = (uint32_t)kPieces * a_piece_bytes;
+  const uint32_t b_tap_bytes = (uint32_t)koct * (uint32_t)kPieces * (uint32_t)N * 16u;
   const uint32_t b_stage_bytes = (uint32_t)TPB * b_tap_bytes;
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -226,7 +214,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
   if (threadIdx.x == 0) DBG(0);
 
   if (warp == 0) {
-    // ===== TMA producer: activation halo tiles (three bf16 pieces per chunk) =====
+    // ===== TMA producer: activation halo tiles (two fp16 pieces per chunk) =====
     if (lane == 0) {
       int q = 0;  // global chunk counter
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -246,7 +234,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
           }
           mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
 #pragma unroll
-          for (int p = 0; p < 3; ++p)
+          for (int p = 0; p < kPieces; ++p)
             tma_load_4d(st + (size_t)p * a_piece_bytes, &tmA, ix0 * 8, iy0, ch * koct, p * a.B + b, &a_full[s]);
         }
       }
@@ -277,9 +265,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       using OP = Ops<MODE>;
       uint32_t idesc[OP::n];
 #pragma unroll
-      for (int i = 0; i < OP::n; ++i) idesc[i] = make_idesc_bf16(128, OPF(OP::NP, i) * N);
+      for (int i = 0; i < OP::n; ++i) idesc[i] = make_idesc_f16(128, OPF(OP::NP, i) * N);
       const uint32_t lbo_a = HP * 16u, sbo_a = HWp * 16u;            // K-major: LBO = next channel octet
-      const uint32_t lbo_b = 3u * (uint32_t)N * 16u, sbo_b = 128u;   // [koct][piece][n][16 B]
+      const uint32_t lbo_b = (uint32_t)kPieces * (uint32_t)N * 16u, sbo_b = 128u;   // [koct][piece][n][16 B]
       // per-op loop invariants: filter-piece offset (16-byte units) inside a k-octet block
       uint32_t boff[OP::n];
 #pragma unroll
@@ -408,6 +396,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
     const bool want_red = (a.epi == EPI_NHWC && a.o_sum != nullptr) || a.epi == EPI_BNBWD;
     const int my_col = colsum16_col(lane);
     const int nsets = nchunks < t.S ? nchunks : t.S;
+    const float osc = t.out_scale * (t.dyn_scale != nullptr ? *t.dyn_scale : 1.f);
+    float gmx = 0.f;  // running max |G| written by this thread (dynamic fp16 scale of the next layers)
     int tile_it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
       const int ts = tile_it % TS;
@@ -472,6 +462,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
             for (int i = 0; i < 16; ++i) v[i] += w1[i];
           }
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= osc;
         if (a.pool) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
@@ -518,6 +510,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
               s1[i] = dz;
               s2[i] = dz * xh;
               o[i] = gv[i] + ep_s[nl] * dz;
+              gmx = fmaxf(gmx, fabsf(o[i]));
             }
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
@@ -544,6 +537,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ts]);
       if (ew == 0 && lane == 0) { if (tile_it == 0) DBG(7); DBG(8); }
+    }
+    if (a.epi == EPI_BNBWD && a.gmax != nullptr) {
+      const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(gmx));
+      if (lane == 0 && m != 0u) atomicMax(a.gmax, m);
     }
     if (want_red) {
       named_bar_sync(1, kEpiWarps * 32);
@@ -576,7 +573,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
 }
 
 // ---------------------------------------------------------------------------------------
-// filter packing: OIHW fp32 -> [chunk][tap][k-octet][piece][n][8] bf16 pieces
+// filter packing: OIHW fp32 -> [chunk][tap][k-octet][piece][n][8] fp16 pieces of w * 2^kWScaleLog2
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
   const Tc2PackDesc d = tab[blockIdx.y];
@@ -599,11 +596,13 @@ __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
     } else {
       if (n < d.Cin && k < d.Cout) v = d.w[((size_t)k * d.Cin + n) * T + (T - 1 - tap)];
     }
-    uint32_t p[3];
-    bf16_split3(v, p[0], p[1], p[2]);
-    __nv_bfloat16* base = d.dst + step * per_tap * 3 + (size_t)ko * 3 * d.N * 8 + (size_t)n * 8 + k8;
+    uint32_t p[kPieces];
+    v *= (float)(1 << kWScaleLog2);
+    p[0] = f2h_sat(v);
+    p[1] = f2h_sat(v - __half2float(__ushort_as_half((unsigned short)p[0])));
+    op16* base = d.dst + step * per_tap * kPieces + (size_t)ko * kPieces * d.N * 8 + (size_t)n * 8 + k8;
 #pragma unroll
-    for (int pc = 0; pc < 3; ++pc) base[(size_t)pc * d.N * 8] = __ushort_as_bfloat16((unsigned short)p[pc]);
+    for (int pc = 0; pc < kPieces; ++pc) base[(size_t)pc * d.N * 8] = __ushort_as_half((unsigned short)p[pc]);
   }
 }
 
@@ -625,7 +624,7 @@ EncodeFn get_encode2() {
 size_t tc2_smem(int KS, int N, int KC, int AST, int NB, int TPB) {
   const int HP = (kTH + KS - 1) * (kTW + KS - 1);
   const size_t hdr = (256 + sizeof(float) * (size_t)(4 + 2 * kEpiWarps) * N + 127) & ~(size_t)127;
-  return hdr + (size_t)AST * 3 * (KC / 8) * HP * 16 + (size_t)NB * TPB * (KC / 8) * 3 * N * 16;
+  return hdr + (size_t)AST * kPieces * (KC / 8) * HP * 16 + (size_t)NB * TPB * (KC / 8) * kPieces * N * 16;
 }
 
 }  // namespace
@@ -635,18 +634,30 @@ void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p) {
   int KC = Cin_k >= 32 ? 32 : 16;
   p->KC = KC;
   p->nchunks = (Cin_k + KC - 1) / KC;
-  p->ngroups = (3 * N <= 512) ? 3 : 2;
+  p->ngroups = 2;  // G0 = a1*w1, G1 = a1*w2 + a2*w1
   int S = 256 / (p->ngroups * N), TS = 2;
   if (S < 1) {
     S = 512 / (p->ngroups * N);
     TS = 1;
   }
+  {
+    const char* e = getenv("PDES_TC2_TS1");  // experiment: one accumulator stage, more K-spreading sets
+    if (e && e[0] == '1') {
+      S = 512 / (p->ngroups * N);
+      TS = 1;
+    }
+  }
+  int smax = 4;
+  {
+    const char* e = getenv("PDES_TC2_SMAX");
+    if (e) smax = atoi(e);
+  }
   if (S > p->nchunks) S = p->nchunks;
-  if (S > 4) S = 4;
+  if (S > smax) S = smax;
   if (S < 1) S = 1;
   p->S = S;
   p->TS = TS;
-  const size_t tap_bytes = (size_t)(KC / 8) * 3 * N * 16;
+  const size_t tap_bytes = (size_t)(KC / 8) * kPieces * N * 16;
   int TPB = 1;
   for (int d = 1; d <= T; ++d)
     if (T % d == 0 && d * tap_bytes <= 32 * 1024) TPB = d;
@@ -660,7 +671,7 @@ void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p) {
   p->NB = NB;
   p->TPB = TPB;
   p->smem = tc2_smem(KS, N, KC, AST, NB, TPB);
-  p->pack_elems = (size_t)p->nchunks * T * (KC / 8) * 3 * N * 8;
+  p->pack_elems = (size_t)p->nchunks * T * (KC / 8) * kPieces * N * 8;
 }
 
 bool tc2_supported(int KS, int stride, int Cin_k, int N) {
@@ -671,7 +682,7 @@ bool tc2_supported(int KS, int stride, int Cin_k, int N) {
   return p.smem <= 225 * 1024 && (uint32_t)(p.S * p.ngroups * N * p.TS) <= 512u;
 }
 
-int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int Wv, int Cin_k,
+int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Cin_k,
                     cudaStream_t st) {
   const ConvArgs& a = t.c;
   PDES_REQUIRE(a.KS == 1 || a.KS == 3 || a.KS == 5 || a.KS == 7, PDES_ERR_UNSUPPORTED, "conv_tc2: kernel size %d", a.KS);
@@ -687,13 +698,13 @@ int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int W
   const int Cp = (Cin_k + 7) & ~7;
   CUtensorMap tm;
   {
-    // planes [3*B][Hv][Cp/8][Wv][8] viewed as (x*8+c8, y, octet, piece*B+b)
+    // planes [2*B][Hv][Cp/8][Wv][8] viewed as (x*8+c8, y, octet, piece*B+b)
     const cuuint64_t oct = (cuuint64_t)(Cp / 8);
-    const cuuint64_t gdim[4] = {(cuuint64_t)Wv * 8, (cuuint64_t)Hv, oct, (cuuint64_t)3 * a.B};
+    const cuuint64_t gdim[4] = {(cuuint64_t)Wv * 8, (cuuint64_t)Hv, oct, (cuuint64_t)kPieces * a.B};
     const cuuint64_t gstr[3] = {oct * Wv * 16, (cuuint64_t)Wv * 16, (cuuint64_t)Hv * oct * Wv * 16};
     const cuuint32_t box[4] = {(cuuint32_t)(kTW + a.KS - 1) * 8, (cuuint32_t)(kTH + a.KS - 1), (cuuint32_t)(t.KC / 8), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(planes), gdim,
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<op16*>(planes), gdim,
                            gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
@@ -703,7 +714,7 @@ int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int W
   const int tiles = ((a.Wo + kTW - 1) / kTW) * ((a.Ho + kTH - 1) / kTH) * a.B;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  const int mode = t.ngroups == 2 ? 3 : (3 * t.N <= 256 ? 0 : (2 * t.N <= 256 ? 1 : 2));
+  const int mode = 2 * t.N <= 256 ? 0 : 1;
 #define PDES_TC2_LAUNCH(KSV, MODEV)                                                                          \
   {                                                                                                          \
     static size_t attr = 0;                                                                                  \
@@ -717,9 +728,7 @@ int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int W
 #define PDES_TC2_MODES(KSV)                        \
   {                                                \
     if (mode == 0) PDES_TC2_LAUNCH(KSV, 0)         \
-    else if (mode == 1) PDES_TC2_LAUNCH(KSV, 1)    \
-    else if (mode == 2) PDES_TC2_LAUNCH(KSV, 2)    \
-    else PDES_TC2_LAUNCH(KSV, 3)                   \
+    else PDES_TC2_LAUNCH(KSV, 1)                   \
   }
   if (a.KS == 3) PDES_TC2_MODES(3)
   else if (a.KS == 1) PDES_TC2_MODES(1)
@@ -733,7 +742,7 @@ int launch_conv_tc2(const Tc2Args& t, const __nv_bfloat16* planes, int Hv, int W
 
 int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st) {
   if (n == 0) return PDES_OK;
-  int bx = (int)((max_elems / 3 + 255) / 256);
+  int bx = (int)((max_elems / kPieces + 255) / 256);
   if (bx > 128) bx = 128;
   if (bx < 1) bx = 1;
   pack_tc2_kernel<<<dim3(bx, n), 256, 0, st>>>(dev_table);

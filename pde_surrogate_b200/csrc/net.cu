@@ -48,8 +48,8 @@ struct Layer {
   size_t wtf, wtb;   // float offsets of the packed filter tiles
   bool tc2_fwd, tc2_bwd;  // TMA-fed bf16x3 tcgen05 path (conv_tc2.cu)
   Tc2Plan p2f, p2b;
-  size_t w2f, w2b;   // float offsets of the packed bf16 filter pieces
-  size_t planes;     // float offset of this layer's activation piece planes [3][B][Hv][Wv][Cp] bf16
+  size_t w2f, w2b;   // float offsets of the packed fp16 filter pieces
+  size_t planes;     // float offset of this layer's activation piece planes [2][B][Hv][Wv][Cp] fp16
   size_t planesB;    // float offset of this layer's dY piece planes (read by its dgrad and, concurrently, its wgrad)
   bool tc_wg;        // weight gradient on tcgen05
   bool first_k;      // dedicated CUDA-core kernels of the first convolution (first_conv.cu)
@@ -77,6 +77,8 @@ struct pdes_net {
   int64_t param_floats = 0, running_floats = 0;
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
   size_t xin = 0;
+  size_t gmax_off = 0;  // double offset: running |G| maxima (unsigned float bits), one per buffer + one for dout
+  size_t dyinv = 0;     // float offset: per-layer inverse of the dynamic dY scale (written by the dY split)
   // side streams for the weight-gradient kernels: they are off the critical path of the backward
   // pass (nothing but the final unpack reads them), so they overlap with the dgrad chain
   cudaStream_t side[2] = {nullptr, nullptr};
@@ -366,6 +368,8 @@ int build(pdes_net* n) {
       }
     }
   }
+  n->dyinv = f;
+  f += pad4((int64_t)n->layers.size());
   n->xin = f;
   f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
   n->xs = f;
@@ -384,6 +388,8 @@ int build(pdes_net* n) {
     L.bsum = d;
     d += 2 * (size_t)L.Cin;
   }
+  n->gmax_off = d;
+  d += (n->bufs.size() + 1 + 1) / 2;  // two unsigned words per double slot
   n->ws_doubles = d;
   n->off_doubles = (n->ws_floats * sizeof(float) + 255) & ~(size_t)255;
   n->off_tables = (n->off_doubles + n->ws_doubles * sizeof(double) + 255) & ~(size_t)255;
@@ -396,6 +402,9 @@ int build(pdes_net* n) {
 inline float* wsf(const pdes_net* n, size_t off) { return reinterpret_cast<float*>(n->ws) + off; }
 inline double* wsd(const pdes_net* n, size_t off) {
   return reinterpret_cast<double*>(n->ws + n->off_doubles) + off;
+}
+inline unsigned* gmax_slot(const pdes_net* n, int buf) {  // buf < 0: the network output gradient
+  return reinterpret_cast<unsigned*>(wsd(n, n->gmax_off)) + (buf < 0 ? (int)n->bufs.size() : buf);
 }
 inline PackDesc* pack_table(const pdes_net* n) { return reinterpret_cast<PackDesc*>(n->ws + n->off_tables); }
 inline BnLayerDesc* bn_table(const pdes_net* n) {
@@ -612,7 +621,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       if (!(dir == 0 ? L.tc2_fwd : L.tc2_bwd)) continue;
       Tc2PackDesc d;
       d.w = n->p + L.w_off;
-      d.dst = reinterpret_cast<__nv_bfloat16*>(wsf(n, dir == 0 ? L.w2f : L.w2b));
+      d.dst = reinterpret_cast<op16*>(wsf(n, dir == 0 ? L.w2f : L.w2b));
       d.Cout = L.Cout;
       d.Cin = L.Cin;
       d.KS = L.KS;
@@ -777,7 +786,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     const bool want_planes = n->conv_impl == 0 && (L.tc2_fwd || (tr && L.tc_wg));
     const int Hs_l = L.in_buf >= 0 ? n->bufs[L.in_buf].H : L.Hs, Ws_l = L.in_buf >= 0 ? n->bufs[L.in_buf].W : L.Ws;
     if (want_planes) {
-      // bf16 pieces of relu(bn(x)) (nearest-upsampled if needed): read by the forward conv and,
+      // fp16 pieces of relu(bn(x)) (nearest-upsampled if needed): read by the forward conv and,
       // in training, again by the weight-gradient kernel
       ActSplitArgs sa;
       memset(&sa, 0, sizeof(sa));
@@ -791,8 +800,9 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       sa.up = L.up;
       sa.pro = a.pro;
       sa.bn = a.bn;
-      sa.out = reinterpret_cast<__nv_bfloat16*>(wsf(n, L.planes));
+      sa.out = reinterpret_cast<op16*>(wsf(n, L.planes));
       sa.Cp = (L.Cin + 7) & ~7;
+      sa.scale = pow2f(kActScaleLog2);
       rc = launch_act_split(sa, st);
       if (rc) return rc;
       n->launches++;
@@ -830,7 +840,8 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
         t.c.Wo = Wv + 2 * L.pad - L.KS + 1;
         t.osub = 1;
       }
-      t.wpk = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.w2f));
+      t.wpk = reinterpret_cast<const op16*>(wsf(n, L.w2f));
+      t.out_scale = pow2f(-(kActScaleLog2 + kWScaleLog2));
       t.N = L.Nf;
       t.KC = L.p2f.KC;
       t.nchunks = L.p2f.nchunks;
@@ -840,7 +851,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       t.AST = L.p2f.AST;
       t.NB = L.p2f.NB;
       t.TPB = L.p2f.TPB;
-      rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planes)), Hv, Wv, L.Cin, st);
+      rc = launch_conv_tc2(t, reinterpret_cast<const op16*>(wsf(n, L.planes)), Hv, Wv, L.Cin, st);
     } else {
       rc = launch_conv_simt(a, st);
     }
@@ -872,6 +883,14 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
   bool used_wg = false;
   int wg_rr = 0, side_used = 0;
   mark(n, st, "@backward");
+  if (n->conv_impl == 0) {
+    // dynamic fp16 scale of the last layer's dY pieces: |dout| maximum (the other layers' slices take
+    // the running maximum their gradient buffer collected from the dgrad epilogues)
+    rc = launch_absmax(dout, (size_t)B * n->cfg.out_channels * n->cfg.imsize * n->cfg.imsize, gmax_slot(n, -1), st);
+    if (rc) return rc;
+    n->launches++;
+    mark(n, st, "absmax dout");
+  }
   for (int li = (int)n->layers.size() - 1; li >= 0; --li) {
     const Layer& L = n->layers[li];
     const float* dy;
@@ -950,7 +969,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       const bool use_wg = n->conv_impl == 0 && L.tc_wg && (n->tc_mask & 4);
       const bool use_dg = n->conv_impl == 0 && L.tc2_bwd && (n->tc_mask & 2) && L.in_buf >= 0;
       if (use_wg || use_dg) {
-        // bf16 pieces of the corrected dY slice: GEMM-K operand of dgrad, GEMM-N operand of wgrad
+        // fp16 pieces of the corrected dY slice: GEMM-K operand of dgrad, GEMM-N operand of wgrad
         ActSplitArgs sb;
         memset(&sb, 0, sizeof(sb));
         sb.x = dy;
@@ -961,8 +980,11 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         sb.Ws = L.Wo;
         sb.B = B;
         sb.up = L.stride == 2 ? 2 : 0;  // zero-insert: stride-2 layers run as stride-1 kernels
-        sb.out = reinterpret_cast<__nv_bfloat16*>(wsf(n, L.planesB));
+        sb.out = reinterpret_cast<op16*>(wsf(n, L.planesB));
         sb.Cp = (L.Cout + 7) & ~7;
+        sb.scale = 1.f;
+        sb.dyn_max = gmax_slot(n, L.out_buf);
+        sb.dyn_inv = wsf(n, n->dyinv) + li;
         if (have_fix) {
           sb.fix = 1;
           sb.fx = fixargs;
@@ -976,8 +998,8 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         const Buf& ib = n->bufs[L.in_buf];
         TcWgradArgs tw;
         memset(&tw, 0, sizeof(tw));
-        tw.planesA = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planes));
-        tw.planesB = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planesB));
+        tw.planesA = reinterpret_cast<const op16*>(wsf(n, L.planes));
+        tw.planesB = reinterpret_cast<const op16*>(wsf(n, L.planesB));
         tw.dwp = wsf(n, L.dwp);
         tw.B = B;
         tw.Hv = L.up ? 2 * ib.H : ib.H;
@@ -990,6 +1012,8 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         tw.pad = L.pad;
         tw.ci_pad = L.ci_pad;
         tw.co_pad = L.co_pad;
+        tw.out_scale = pow2f(-kActScaleLog2);
+        tw.dyn_scale = wsf(n, n->dyinv) + li;
         if (n->n_side > 0 && n->side[0]) {
           // fork: the wgrad kernel only needs the dY planes just written; it runs beside the dgrad chain
           const int k = wg_rr++ % n->n_side;
@@ -1059,11 +1083,14 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       a.ldG = ib.ld;
       a.g_accum = L.last_consumer ? 0 : 1;
       a.bsum = wsd(n, L.bsum);
+      a.gmax = gmax_slot(n, L.in_buf);
       if (n->conv_impl == 0 && L.tc2_bwd && (n->tc_mask & 2)) {
         Tc2Args t;
         memset(&t, 0, sizeof(t));
         t.c = a;
-        t.wpk = reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.w2b));
+        t.wpk = reinterpret_cast<const op16*>(wsf(n, L.w2b));
+        t.out_scale = pow2f(-kWScaleLog2);
+        t.dyn_scale = wsf(n, n->dyinv) + li;
         t.N = L.Nb;
         t.KC = L.p2b.KC;
         t.nchunks = L.p2b.nchunks;
@@ -1075,7 +1102,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         t.TPB = L.p2b.TPB;
         if (L.stride == 2) t.c.in_mode = IN_DIRECT;  // the zero insertion is in the dY planes
         const int zi = L.stride == 2 ? 2 : 1;
-        rc = launch_conv_tc2(t, reinterpret_cast<const __nv_bfloat16*>(wsf(n, L.planesB)), zi * L.Ho,
+        rc = launch_conv_tc2(t, reinterpret_cast<const op16*>(wsf(n, L.planesB)), zi * L.Ho,
                              zi * L.Wo, L.Cout, st);
       } else {
         rc = launch_conv_simt(a, st);

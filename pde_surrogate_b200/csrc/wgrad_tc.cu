@@ -17,15 +17,15 @@
 // each box row 160 contiguous bytes.
 //
 // Precision: tcgen05 only transposes 16-bit operands (kind::tf32 with MN-major operands returns
-// zeros on sm_100a — measured), hence bf16 pieces and the six products of weight >= 2^-16:
-//   pass 0 CTAs stream a1 and multiply by [d1|d2|d3]   (one N'=48 instruction per tap)
-//   pass 1 CTAs stream a2 and multiply by [d1|d2]      (N'=32)
-//   pass 2 CTAs stream a3 and multiply by  d1          (N =16)
+// zeros on sm_100a — measured), hence 16-bit pieces: two fp16 pieces per (power-of-two scaled)
+// operand and the three products of weight >= 2^-11 (conv_tc.cuh):
+//   pass 0 CTAs stream a1 and multiply by [d1|d2]   (one N'=32 instruction per tap)
+//   pass 1 CTAs stream a2 and multiply by  d1       (N =16)
 // Every product lands in its own TMEM columns and the epilogue adds them in fp32.  CTAs split the
 // pixel range (split-K) and finish with coalesced vector reductions (red.global.add.v4.f32) into a
 // [tap][ci][co] staging buffer that a small kernel folds into the OIHW gradient.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
@@ -40,7 +40,7 @@ constexpr int kThreads = 192;
 constexpr int kTH = 16, kTW = 8;
 constexpr int kMC = 128;  // input channels per CTA (GEMM M)
 constexpr int kNC = 16;   // output channels per CTA (GEMM N)
-constexpr int kPasses = 3;
+constexpr int kPasses = kPieces;
 constexpr int kStages = 3;
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
@@ -48,22 +48,20 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
                : "memory");
 }
 
-// exact 3-way bf16 split
-__device__ __forceinline__ void bf16_split3(float x, uint32_t& p0, uint32_t& p1, uint32_t& p2) {
-  const __nv_bfloat16 b1 = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(b1);
-  const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(b2);
-  const __nv_bfloat16 b3 = __float2bfloat16_rn(r2);
-  p0 = (uint32_t)__bfloat16_as_ushort(b1);
-  p1 = (uint32_t)__bfloat16_as_ushort(b2);
-  p2 = (uint32_t)__bfloat16_as_ushort(b3);
+// two fp16 pieces of an (already scaled) value; saturating conversions keep overflow finite
+__device__ __forceinline__ uint32_t f2h_sat(float x) {
+  unsigned short h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(x));
+  return (uint32_t)h;
+}
+__device__ __forceinline__ void fp16_split2(float x, uint32_t& p0, uint32_t& p1) {
+  p0 = f2h_sat(x);
+  p1 = f2h_sat(x - __half2float(__ushort_as_half((unsigned short)p0)));
 }
 
-// instruction descriptor: D fp32, A/B bf16, both MN-major
-__device__ __forceinline__ uint32_t make_idesc_bf16_mn(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
+// instruction descriptor: D fp32, A/B fp16 (format 0), both MN-major
+__device__ __forceinline__ uint32_t make_idesc_f16_mn(int M, int N) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -131,7 +129,7 @@ __device__ __forceinline__ void bn_consts_w(const BnSrc& s, int c, float& scale,
 }
 
 // ---------------------------------------------------------------------------------------
-// pre-pass: planes[piece][b][y][octet][x][8] (bf16) = split3( pro ? relu(x*scale+shift) : x ),
+// pre-pass: planes[piece][b][y][octet][x][8] (fp16) = split2( scale * (pro ? relu(x*bn_scale+bn_shift) : x) ),
 // optionally nearest-upsampled / zero-inserted x2.  One thread per (pixel, channel octet).  Rows of
 // one channel octet are x-contiguous so that a TMA box row is (TW+K-1)*16 contiguous bytes.
 // ---------------------------------------------------------------------------------------
@@ -175,6 +173,15 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
       sh_s[c] = h;
     }
     __syncthreads();
+  }
+  float mul = a.scale;
+  if (a.dyn_max != nullptr) {
+    // power of two that brings the buffer's running |gradient| maximum to 2^kDyTargetLog2
+    const unsigned m = *a.dyn_max;
+    int e = m == 0u ? 0 : kDyTargetLog2 - ((int)((m >> 23) & 0xffu) - 127);
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    mul = __uint_as_float((uint32_t)(e + 127) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.dyn_inv = __uint_as_float((uint32_t)(127 - e) << 23);
   }
   const int oct = Cp >> 3;
   const int Hv = a.up ? 2 * a.Hs : a.Hs, Wv = a.up ? 2 * a.Ws : a.Ws;
@@ -232,12 +239,12 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
         }
       }
     }
-    uint32_t o[3][8];
+    uint32_t o[kPieces][8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) bf16_split3(v[k], o[0][k], o[1][k], o[2][k]);
-    __nv_bfloat16* dst = a.out + ((((size_t)b * Hv + vy) * oct + q) * Wv + vx) * 8;
+    for (int k = 0; k < 8; ++k) fp16_split2(v[k] * mul, o[0][k], o[1][k]);
+    op16* dst = a.out + ((((size_t)b * Hv + vy) * oct + q) * Wv + vx) * 8;
 #pragma unroll
-    for (int piece = 0; piece < 3; ++piece)
+    for (int piece = 0; piece < kPieces; ++piece)
       *reinterpret_cast<uint4*>(dst + (size_t)piece * plane) =
           make_uint4(o[piece][0] | (o[piece][1] << 16), o[piece][2] | (o[piece][3] << 16),
                      o[piece][4] | (o[piece][5] << 16), o[piece][6] | (o[piece][7] << 16));
@@ -259,12 +266,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr uint32_t A_BYTES = QA * HP * 16u;       // one bf16 plane tile
   constexpr uint32_t B_OCT = 128u * 16u;            // one co-octet: 128 pixels x 16 B
   constexpr uint32_t B_PIECE = 2u * B_OCT;          // 16 output channels of one piece
-  constexpr uint32_t STAGE = (A_BYTES + 3u * B_PIECE + 127u) & ~127u;
+  constexpr uint32_t STAGE = (A_BYTES + (uint32_t)kPieces * B_PIECE + 127u) & ~127u;
   constexpr int TG = T <= 9 ? T : 10;               // filter taps per CTA (TMEM holds TG accumulators)
-  const int pass = blockIdx.z % kPasses;            // which bf16 piece of `a` this CTA streams
+  const int pass = blockIdx.z % kPasses;            // which fp16 piece of `a` this CTA streams
   const int tap0 = (blockIdx.z / kPasses) * TG;     // first tap of this CTA's tap group
   const int ntap = (T - tap0) < TG ? (T - tap0) : TG;
-  const int NP = kPasses - pass;                    // dY pieces multiplied: 3, 2, 1
+  const int NP = kPasses - pass;                    // dY pieces multiplied: 2, 1
   const int NW = NP * kNC;                          // accumulator columns per tap
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -330,7 +337,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer: whole warp walks the uniform loop, one elected lane issues =====
     if (my_tiles > 0) {
-      const uint32_t idesc = make_idesc_bf16_mn(128, NW);
+      const uint32_t idesc = make_idesc_f16_mn(128, NW);
       // MN-major canonical layout ((8,1,m),(8,k)) : ((1,8,SBO),(8,LBO)): SBO strides along the
       // channels (next octet), LBO along the pixels (next 8-pixel tile row)
       const uint32_t sbo_a = HP * 16u, lbo_a = HWp * 16u;
@@ -377,6 +384,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int quarter = warp & 3;
     const int ci = c0 + quarter * 32 + lane;
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float osc = t.out_scale * (t.dyn_scale != nullptr ? *t.dyn_scale : 1.f);
     for (int j = 0; j < ntap; ++j) {
       const int tap = tap0 + j;
       float v[16];
@@ -390,7 +398,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       if (ci < t.Cin) {
         float* dst = t.dwp + ((size_t)tap * t.ci_pad + ci) * t.co_pad + n0;
 #pragma unroll
-        for (int i = 0; i < 16; i += 4) red_add_v4(dst + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+        for (int i = 0; i < 16; i += 4)
+          red_add_v4(dst + i, v[i] * osc, v[i + 1] * osc, v[i + 2] * osc, v[i + 3] * osc);
       }
     }
     tc_fence_before();
@@ -400,6 +409,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+// max |x| as float bits (non-negative floats order like unsigned integers)
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
+  unsigned m = 0u;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned u = __float_as_uint(x[i]) & 0x7fffffffu;
+    m = u > m ? u : m;
+  }
+  m = __reduce_max_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
 }
 
 // dW_OIHW[co][ci][tap] += dWp[tap][ci][co]; dWp is cleared for the next step.  One thread per
@@ -436,18 +456,18 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// planes [3*B][H][Cp/8][W][8] bf16 viewed as (x*8+c8, y, octet, plane*B+b); box (bx*8, by, boct, 1)
+// planes [2*B][H][Cp/8][W][8] fp16 viewed as (x*8+c8, y, octet, plane*B+b); box (bx*8, by, boct, 1)
 // -> shared memory [octet][y][x][16 B]
-int make_plane_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int H, int W, int Cp, int bx, int by,
+int make_plane_map(CUtensorMap* tm, const op16* base, int B, int H, int W, int Cp, int bx, int by,
                    int boct) {
   EncodeFn enc = get_encode();
   PDES_REQUIRE(enc != nullptr, PDES_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t oct = (cuuint64_t)(Cp / 8);
-  const cuuint64_t gdim[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, oct, (cuuint64_t)3 * B};
+  const cuuint64_t gdim[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, oct, (cuuint64_t)kPieces * B};
   const cuuint64_t gstr[3] = {oct * W * 16, (cuuint64_t)W * 16, (cuuint64_t)H * oct * W * 16};
   const cuuint32_t box[4] = {(cuuint32_t)bx * 8, (cuuint32_t)by, (cuuint32_t)boct, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), gdim, gstr,
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<op16*>(base), gdim, gstr,
                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
@@ -457,7 +477,7 @@ int make_plane_map(CUtensorMap* tm, const __nv_bfloat16* base, int B, int H, int
 template <int KS>
 size_t wg_smem() {
   constexpr int HP = (kTH + KS - 1) * (kTW + KS - 1);
-  const size_t stage = ((size_t)(kMC / 8) * HP * 16 + 3 * 2 * 128 * 16 + 127) & ~(size_t)127;
+  const size_t stage = ((size_t)(kMC / 8) * HP * 16 + kPieces * 2 * 128 * 16 + 127) & ~(size_t)127;
   return 128 + kStages * stage;
 }
 
@@ -472,7 +492,16 @@ void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad) {
 
 size_t act_planes_bytes(int B, int H, int W, int C) {
   const int Cp = (C + 7) & ~7;
-  return (size_t)3 * B * H * W * Cp * sizeof(__nv_bfloat16);
+  return (size_t)kPieces * B * H * W * Cp * sizeof(op16);
+}
+
+int launch_absmax(const float* x, size_t n, unsigned* out, cudaStream_t st) {
+  int blocks = (int)((n / 4 + 255) / 256);
+  if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
+  if (blocks < 1) blocks = 1;
+  absmax_kernel<<<blocks, 256, 0, st>>>(x, n, out);
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
 }
 
 int launch_act_split(const ActSplitArgs& a, cudaStream_t st) {

@@ -9,7 +9,7 @@ cfg = dict(in_channels=1, out_channels=3, imsize=32, blocks=[6,8,6], growth_rate
 plan = orc.densenet_plan(**cfg)
 names = [str(s) for s in g['param_names']]
 res = {}
-for impl in (1, 0, 3, 4):
+for impl in (1, 0, 3, 4, 5):
     sd = orc.make_state(plan, int(g['seed']))
     model = DenseED(1, 3, 32, [6,8,6]); model.load_state_dict(sd); model = model.cuda(); model.conv_impl = impl
     K = orc.make_input(int(g['B']), 32, int(g['seed'])).cuda()
@@ -33,5 +33,5 @@ for impl in (1, 0, 3, 4):
           'dout rel', np.linalg.norm(out.grad.cpu().double().numpy()-g['dout64'])/np.linalg.norm(g['dout64']),
           'head err median %.2e max %.2e | norm err median %.2e max %.2e | ref fp32 floor median %.2e max %.2e' % (
           np.median(rows[:,0]), rows[:,0].max(), np.median(rows[:,1]), rows[:,1].max(), np.median(rows[:,2]), rows[:,2].max()))
-    worst = np.argsort(-rows[:,1])[:4]
+    worst = np.argsort(-rows[:,1])[:6]
     print('   worst norm errs:', [(names[j], '%.2e' % rows[j,1], '%.2e' % rows[j,2]) for j in worst])
