@@ -4,14 +4,14 @@
 //
 // GEMM view per filter tap: D[M = 128 input channels, N = 16 output channels] += A^T * B with the
 // reduction (GEMM-K) over PIXELS.  Both operands are pixel-major ([pixel][channel], what NHWC
-// gives for free), i.e. MN-major UMMA operands: core matrix = 8 pixels x 16 B (8 bf16 channels).
+// gives for free), i.e. MN-major UMMA operands: core matrix = 8 pixels x 16 B (8 fp16 channels).
 // One tcgen05.mma (K = 16) consumes two 8-pixel tile rows; the nine taps read the SAME staged halo
 // tile through shifted descriptors and own nine accumulators in TMEM.
 //
 // Operands are NOT transformed inside this kernel.  A small elementwise pre-pass
 // (act_split_kernel) writes the BN+ReLU'd (and nearest-upsampled) activations — and the
-// corrected dY slice — once per layer as three bf16 planes (exact split x = b1 + b2 + b3,
-// 8+8+8 mantissa bits).  The kernel then streams 4-D TMA boxes (cp.async.bulk.tensor, zero fill
+// corrected dY slice — once per layer as two fp16 planes of the power-of-two scaled values
+// (conv_tc.cuh).  The kernel then streams 4-D TMA boxes (cp.async.bulk.tensor, zero fill
 // outside the image = the convolution's padding) whose shared-memory image IS the UMMA layout:
 // planes are stored [b][y][octet][x][8]; box (10 x * 8 ch, 18 y, 16 octets, 1) -> [octet][pixel][16 B],
 // each box row 160 contiguous bytes.
@@ -130,14 +130,24 @@ __device__ __forceinline__ void bn_consts_w(const BnSrc& s, int c, float& scale,
 
 // ---------------------------------------------------------------------------------------
 // pre-pass: planes[piece][b][y][octet][x][8] (fp16) = split2( scale * (pro ? relu(x*bn_scale+bn_shift) : x) ),
-// optionally nearest-upsampled / zero-inserted x2.  One thread per (pixel, channel octet).  Rows of
-// one channel octet are x-contiguous so that a TMA box row is (TW+K-1)*16 contiguous bytes.
+// optionally nearest-upsampled / zero-inserted x2.  Rows of one channel octet are x-contiguous so that
+// a TMA box row is (TW+K-1)*16 contiguous bytes.
+//
+// Work item = one source image row (segment).  Phase 1 reads the NHWC row with consecutive threads on
+// consecutive float4 of a pixel (coalesced: a pixel's channels are contiguous), applies the
+// prologue / the lazy BatchNorm-backward correction, scales and splits, and drops the pieces into a
+// shared-memory tile [piece][octet][x][16 B] (rows padded by 16 B against bank conflicts); phase 2
+// streams every (piece, octet) row of the tile to global memory as x-contiguous 16-byte stores.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
+__global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int xs) {
   griddep_wait();
-  __shared__ float sc_s[256], sh_s[256];
-  __shared__ float mean_s[256], is_s[256];  // fused dY correction: c1 -> sc_s, c2 -> sh_s
+  extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cp = a.Cp;
+  float* sc_s = reinterpret_cast<float*>(sm_raw);  // fused dY correction: c1 -> sc_s, c2 -> sh_s
+  float* sh_s = sc_s + Cp;
+  float* mean_s = sh_s + Cp;
+  float* is_s = mean_s + Cp;
+  unsigned char* tile = sm_raw + 16 * (size_t)Cp;
   if (a.fix) {
     const FixDyArgs& f = a.fx;
     for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
@@ -163,16 +173,13 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
       mean_s[c] = mean;
       is_s[c] = is;
     }
-    __syncthreads();
-  }
-  if (a.pro) {
+  } else if (a.pro) {
     for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
       float s = 0.f, h = 0.f;
       if (c < a.C) bn_consts_w(a.bn, c, s, h);
       sc_s[c] = s;
       sh_s[c] = h;
     }
-    __syncthreads();
   }
   float mul = a.scale;
   if (a.dyn_max != nullptr) {
@@ -184,70 +191,117 @@ __global__ void __launch_bounds__(256) act_split_kernel(ActSplitArgs a) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.dyn_inv = __uint_as_float((uint32_t)(127 - e) << 23);
   }
   const int oct = Cp >> 3;
-  const int Hv = a.up ? 2 * a.Hs : a.Hs, Wv = a.up ? 2 * a.Ws : a.Ws;
-  const size_t npix = (size_t)a.B * Hv * Wv;
-  const size_t total = npix * oct;
-  const size_t plane = npix * Cp;  // elements per piece plane
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    // thread order (b, y, octet, x): 16-byte stores of consecutive threads are contiguous
-    const int vx = (int)(i % Wv);
-    size_t r = i / Wv;
-    const int q = (int)(r % oct);
-    r /= oct;
-    const int vy = (int)(r % Hv);
-    const int b = (int)(r / Hv);
-    const int sy = a.up ? (vy >> 1) : vy, sx = a.up ? (vx >> 1) : vx;
-    const int c = 8 * q;
-    const bool hole = a.up == 2 && ((vy | vx) & 1);  // zero-insert: odd positions are zero
-    float v[8];
-    if (hole) {
+  const int up = a.up;
+  const int Hv = up ? 2 * a.Hs : a.Hs, Wv = up ? 2 * a.Ws : a.Ws;
+  const size_t plane = (size_t)a.B * Hv * Wv * Cp;  // elements per piece plane
+  const int XO = up ? 2 * xs : xs;                  // output pixels per segment
+  const int rstride = XO * 16 + 16;                 // bytes per (piece, octet) row of the tile
+  const int nseg = (a.Ws + xs - 1) / xs;
+  const int n_work = a.B * a.Hs * nseg;
+  const bool vec_in = !a.nchw && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0;
+  const bool vec_fx = a.fix && (a.fx.ldX & 3) == 0 && (reinterpret_cast<uintptr_t>(a.fx.X) & 15u) == 0 && vec_in;
+  // phase-1 thread grid: qp (power of two >= octets) threads along the channels of a pixel, 256/qp pixels
+  // in flight; phase-2 thread grid: xp (power of two >= output pixels) threads along x
+  int qsh = 0;
+  while ((1 << qsh) < oct) ++qsh;
+  const int tq = threadIdx.x & ((1 << qsh) - 1), tp = threadIdx.x >> qsh, pstep = 256 >> qsh;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int seg = work % nseg, row = work / nseg;
+    const int sy = row % a.Hs, b = row / a.Hs;
+    const int x0 = seg * xs;
+    const int nx = (a.Ws - x0) < xs ? (a.Ws - x0) : xs;
+    __syncthreads();  // constants ready / previous tile drained
+    // ---- phase 1: load, transform, split -> shared tile ------------------------------------
+    if (tq < oct) {
+      const int c = 8 * tq;
+      for (int px = tp; px < nx; px += pstep) {
+        const int sx = x0 + px;
+        const size_t pix = ((size_t)b * a.Hs + sy) * a.Ws + sx;
+        float v[8];
+        if (a.nchw) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = 0.f;
-    } else if (a.nchw) {
+          for (int k = 0; k < 8; ++k)
+            v[k] = (c + k < a.C) ? a.x[(((size_t)b * a.C + c + k) * a.Hs + sy) * a.Ws + sx] : 0.f;
+        } else {
+          const float* p = a.x + pix * a.ldx + c;
+          if (vec_in && c + 7 < a.C) {
+            const float4 f0 = __ldg(reinterpret_cast<const float4*>(p));
+            const float4 f1 = __ldg(reinterpret_cast<const float4*>(p + 4));
+            v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w;
+            v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+          } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] = (c + k < a.C) ? a.x[(((size_t)b * a.C + c + k) * a.Hs + sy) * a.Ws + sx] : 0.f;
-    } else {
-      const float* p = a.x + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
-      if (c + 7 < a.C && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0)) {
-        const float4 f0 = __ldg(reinterpret_cast<const float4*>(p));
-        const float4 f1 = __ldg(reinterpret_cast<const float4*>(p + 4));
-        v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w;
-        v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
-      } else {
+            for (int k = 0; k < 8; ++k) v[k] = (c + k < a.C) ? p[k] : 0.f;
+          }
+        }
+        if (a.pro) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (c + k < a.C) ? p[k] : 0.f;
-      }
-    }
-    if (a.pro) {
+          for (int k = 0; k < 8; ++k)
+            v[k] = (c + k < a.C) ? fmaxf(0.f, fmaf(v[k], sc_s[c + k], sh_s[c + k])) : 0.f;
+        }
+        if (a.fix) {
+          // dY = G - c1 - xhat*c2 (lazy BatchNorm-backward mean corrections of every consumer), written
+          // back in fp32 for the non-tensor-core consumers of the slice
+          const float* xp = a.fx.X + pix * a.fx.ldX + c;
+          float* gp = const_cast<float*>(a.x) + pix * a.ldx + c;
+          if (vec_fx && c + 7 < a.C) {
+            const float4 x0q = __ldg(reinterpret_cast<const float4*>(xp));
+            const float4 x1q = __ldg(reinterpret_cast<const float4*>(xp + 4));
+            const float xv[8] = {x0q.x, x0q.y, x0q.z, x0q.w, x1q.x, x1q.y, x1q.z, x1q.w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        v[k] = (!hole && c + k < a.C) ? fmaxf(0.f, fmaf(v[k], sc_s[c + k], sh_s[c + k])) : 0.f;
-    }
-    if (a.fix && !hole) {
-      // dY = G - c1 - xhat*c2 (lazy BatchNorm-backward mean corrections of every consumer), written
-      // back in fp32 for the non-tensor-core consumers of the slice
-      const float* xp = a.fx.X + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.fx.ldX + c;
-      float* gp = const_cast<float*>(a.x) + (((size_t)b * a.Hs + sy) * a.Ws + sx) * a.ldx + c;
+            for (int k = 0; k < 8; ++k) {
+              const float xh = (xv[k] - mean_s[c + k]) * is_s[c + k];
+              v[k] = v[k] - sc_s[c + k] - xh * sh_s[c + k];
+            }
+            *reinterpret_cast<float4*>(gp) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(gp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (c + k < a.C) {
-          const float xh = (xp[k] - mean_s[c + k]) * is_s[c + k];
-          v[k] = v[k] - sc_s[c + k] - xh * sh_s[c + k];
-          gp[k] = v[k];
+            for (int k = 0; k < 8; ++k) {
+              if (c + k < a.C) {
+                const float xh = (xp[k] - mean_s[c + k]) * is_s[c + k];
+                v[k] = v[k] - sc_s[c + k] - xh * sh_s[c + k];
+                gp[k] = v[k];
+              }
+            }
+          }
+        }
+        uint32_t h0[8], h1[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fp16_split2(v[k] * mul, h0[k], h1[k]);
+        const uint4 w0 = make_uint4(h0[0] | (h0[1] << 16), h0[2] | (h0[3] << 16), h0[4] | (h0[5] << 16), h0[6] | (h0[7] << 16));
+        const uint4 w1 = make_uint4(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16), h1[4] | (h1[5] << 16), h1[6] | (h1[7] << 16));
+        const int ox = up ? 2 * px : px;
+        unsigned char* t0 = tile + (size_t)tq * rstride + ox * 16;
+        unsigned char* t1 = t0 + (size_t)oct * rstride;
+        *reinterpret_cast<uint4*>(t0) = w0;
+        *reinterpret_cast<uint4*>(t1) = w1;
+        if (up == 1) {  // nearest x2: the same value at 2x and 2x+1
+          *reinterpret_cast<uint4*>(t0 + 16) = w0;
+          *reinterpret_cast<uint4*>(t1 + 16) = w1;
+        } else if (up == 2) {  // zero insertion: odd positions are zero
+          *reinterpret_cast<uint4*>(t0 + 16) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(t1 + 16) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }
-    uint32_t o[kPieces][8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) fp16_split2(v[k] * mul, o[0][k], o[1][k]);
-    op16* dst = a.out + ((((size_t)b * Hv + vy) * oct + q) * Wv + vx) * 8;
-#pragma unroll
-    for (int piece = 0; piece < kPieces; ++piece)
-      *reinterpret_cast<uint4*>(dst + (size_t)piece * plane) =
-          make_uint4(o[piece][0] | (o[piece][1] << 16), o[piece][2] | (o[piece][3] << 16),
-                     o[piece][4] | (o[piece][5] << 16), o[piece][6] | (o[piece][7] << 16));
+    __syncthreads();
+    // ---- phase 2: tile rows -> global, x-contiguous 16-byte stores ---------------------------
+    const int nxo = up ? 2 * nx : nx, xo0 = up ? 2 * x0 : x0;
+    int xsh = 0;
+    while ((1 << xsh) < nxo) ++xsh;
+    const int ox = threadIdx.x & ((1 << xsh) - 1);
+    if (ox < nxo) {
+      for (int r = threadIdx.x >> xsh; r < kPieces * oct; r += 256 >> xsh) {  // r = piece * oct + q
+        const int piece = r >= oct ? 1 : 0, q = r - piece * oct;
+        const uint4 val = *reinterpret_cast<const uint4*>(tile + (size_t)r * rstride + ox * 16);
+        op16* dst = a.out + (size_t)piece * plane + ((((size_t)b * Hv + (up ? 2 * sy : sy)) * oct + q) * Wv + xo0 + ox) * 8;
+        *reinterpret_cast<uint4*>(dst) = val;
+        if (up) {  // second output row: a copy (nearest) or zeros (zero insertion)
+          *reinterpret_cast<uint4*>(dst + (size_t)oct * Wv * 8) = up == 1 ? val : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
   }
 }
 
@@ -263,7 +317,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr int HH = kTH + KS - 1;
   constexpr int HP = HH * HWp;
   constexpr int QA = kMC / 8;                       // channel octets of the A tile
-  constexpr uint32_t A_BYTES = QA * HP * 16u;       // one bf16 plane tile
+  constexpr uint32_t A_BYTES = QA * HP * 16u;       // one fp16 plane tile
   constexpr uint32_t B_OCT = 128u * 16u;            // one co-octet: 128 pixels x 16 B
   constexpr uint32_t B_PIECE = 2u * B_OCT;          // 16 output channels of one piece
   constexpr uint32_t STAGE = (A_BYTES + (uint32_t)kPieces * B_PIECE + 127u) & ~127u;
@@ -474,6 +528,17 @@ int make_plane_map(CUtensorMap* tm, const op16* base, int B, int H, int W, int C
   return PDES_OK;
 }
 
+// CTAs per SM-slot the pixel range is split over (one CTA fits per SM: 1 = a single wave)
+int wg_waves() {
+  static int w = 0;
+  if (w == 0) {
+    const char* e = getenv("PDES_WG_WAVES");
+    w = e ? atoi(e) : 1;
+    if (w < 1) w = 1;
+  }
+  return w;
+}
+
 template <int KS>
 size_t wg_smem() {
   constexpr int HP = (kTH + KS - 1) * (kTW + KS - 1);
@@ -505,15 +570,20 @@ int launch_absmax(const float* x, size_t n, unsigned* out, cudaStream_t st) {
 }
 
 int launch_act_split(const ActSplitArgs& a, cudaStream_t st) {
-  PDES_REQUIRE(a.Cp % 8 == 0 && a.Cp >= a.C && a.Cp <= 256, PDES_ERR_INVALID,
+  PDES_REQUIRE(a.Cp % 8 == 0 && a.Cp >= a.C && a.Cp <= 1024, PDES_ERR_INVALID,
                "act_split: padded channel count %d invalid", a.Cp);
-  const int Hv = a.up ? 2 * a.Hs : a.Hs, Wv = a.up ? 2 * a.Ws : a.Ws;
-  const size_t total = (size_t)a.B * Hv * Wv * (a.Cp / 8);
-  int blocks = (int)((total + 255) / 256);
+  // pixels of a source row per work item: the whole row unless its tile would not fit 40 KB
+  int xs = a.Ws;
+  auto tile_bytes = [&](int x) { return (size_t)kPieces * (a.Cp / 8) * ((size_t)(a.up ? 2 * x : x) * 16 + 16); };
+  while (xs > 1 && tile_bytes(xs) > 40 * 1024) xs = (xs + 1) / 2;
+  const size_t smem = 16 * (size_t)a.Cp + tile_bytes(xs);
+  PDES_REQUIRE(smem <= 48 * 1024, PDES_ERR_UNSUPPORTED, "act_split: %d channels need %zu bytes of shared memory", a.Cp, smem);
+  const int n_work = a.B * a.Hs * ((a.Ws + xs - 1) / xs);
+  int blocks = n_work;
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  PDES_CUDA(launch_pdl(act_split_kernel, dim3(blocks), dim3(256), 0, st, a));
+  PDES_CUDA(launch_pdl(act_split_kernel, dim3(blocks), dim3(256), smem, st, a, xs));
   return PDES_OK;
 }
 
@@ -530,7 +600,7 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
   const int n_ci = (t.Cin + kMC - 1) / kMC, n_co = (t.Cout + kNC - 1) / kNC;
   const int T = t.KS * t.KS;
   const int tap_groups = T <= 9 ? 1 : (T + 9) / 10;
-  int P = (2 * sm_count()) / (n_ci * n_co * kPasses * tap_groups);
+  int P = (wg_waves() * sm_count()) / (n_ci * n_co * kPasses * tap_groups);
   if (P < 1) P = 1;
   if (P > tiles) P = tiles;
   dim3 grid(P, n_ci * n_co, kPasses * tap_groups);
