@@ -276,7 +276,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       const uint32_t a_piece_u = a_piece_bytes >> 4;
       const int kc16 = KC / 16;
       // ring positions are kept as (stage, phase) counters: no integer division in the issue loop
-      int sa = 0, sb = 0, ts = 0, tin = 0, tile_it = 0;
+      int sa = 0, sb = 0, ts = 0, tile_it = 0;
       uint32_t pa = 0, pb = 0, pt = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_it) {
         mbar_wait(&acc_empty[ts], pt ^ 1u);
@@ -330,42 +330,43 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
               pb ^= 1u;
             }
           } else {
-#pragma unroll(KS <= 3 ? T : 1)
-          for (int tap = 0; tap < T; ++tap) {
-            if (tin == 0) {
+            // filter taps arrive in groups of TPB per ring stage: one wait and one elected issue block
+            // per stage (the tap loop stays rolled; its body is 2 x OP::n back-to-back MMAs)
+            const uint32_t b_tap_u = b_tap_bytes >> 4;
+            for (int tb = 0; tb < T; tb += TPB) {
               mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-            }
-            const uint64_t bd0 =
-                make_desc(smem_u32(B_s + (size_t)sb * b_stage_bytes) + (uint32_t)tin * b_tap_bytes, lbo_b, sbo_b);
-            const uint32_t b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
-            const uint32_t a_tap = a_lo0 + (uint32_t)((tap / KS) * HWp + (tap % KS));
-            if (elect_one()) {
+              const uint64_t bd0 = make_desc(smem_u32(B_s + (size_t)sb * b_stage_bytes), lbo_b, sbo_b);
+              const uint32_t b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+              if (elect_one()) {
+#pragma unroll 1
+                for (int j = 0; j < TPB; ++j) {
+                  const int tap = tb + j;
+                  const uint32_t a_tap = a_lo0 + (uint32_t)((tap / KS) * HWp + (tap % KS));
+                  const uint32_t b_tap = b_lo0 + (uint32_t)j * b_tap_u;
 #pragma unroll
-              for (int k16 = 0; k16 < 2; ++k16) {
-                if (k16 < kc16) {
-                  const uint32_t a_k = a_tap + (uint32_t)k16 * kstep_a;
-                  const uint32_t b_k = b_lo0 + (uint32_t)k16 * kstep_b;
+                  for (int k16 = 0; k16 < 2; ++k16) {
+                    if (k16 < kc16) {
+                      const uint32_t a_k = a_tap + (uint32_t)k16 * kstep_a;
+                      const uint32_t b_k = b_tap + (uint32_t)k16 * kstep_b;
 #pragma unroll
-                  for (int i = 0; i < OP::n; ++i) {
-                    const bool first = fresh && tap == 0 && k16 == 0 && ((FirstW<MODE>::mask >> i) & 1u);
-                    umma_bf16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
-                                idesc[i], first ? 0u : 1u);
+                      for (int i = 0; i < OP::n; ++i) {
+                        const bool first = fresh && tap == 0 && k16 == 0 && ((FirstW<MODE>::mask >> i) & 1u);
+                        umma_bf16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
+                                    idesc[i], first ? 0u : 1u);
+                      }
+                    }
                   }
                 }
+                umma_commit(&b_empty[sb]);
+                if (tb + TPB >= T) umma_commit(&a_empty[sa]);
               }
-              if (tin == TPB - 1) umma_commit(&b_empty[sb]);
-              if (tap == T - 1) umma_commit(&a_empty[sa]);
-            }
-            __syncwarp();
-            if (++tin == TPB) {
-              tin = 0;
+              __syncwarp();
               if (++sb == NB) {
                 sb = 0;
                 pb ^= 1u;
               }
             }
-          }
           }
           if (++sa == AST) {
             sa = 0;
@@ -660,7 +661,7 @@ void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p) {
   const size_t tap_bytes = (size_t)(KC / 8) * kPieces * N * 16;
   int TPB = 1;
   for (int d = 1; d <= T; ++d)
-    if (T % d == 0 && d * tap_bytes <= 32 * 1024) TPB = d;
+    if (T % d == 0 && d * tap_bytes <= (d == T ? 56 : 32) * 1024) TPB = d;
   int NB = TPB * tap_bytes >= 16 * 1024 ? 3 : 4;
   int AST = 3;
   while (tc2_smem(KS, N, KC, AST, NB, TPB) > 224 * 1024 && (NB > 2 || AST > 2)) {
