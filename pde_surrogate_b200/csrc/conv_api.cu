@@ -411,7 +411,7 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
     TcWgradUnpack* tab = reinterpret_cast<TcWgradUnpack*>(buf + nf);
     PDES_CUDA(cudaMemcpyAsync(tab, &u, sizeof(u), cudaMemcpyHostToDevice, st));
     PDES_CUDA(cudaStreamSynchronize(st));
-    rc = launch_wgrad_unpack(tab, 1, d->Cout * d->Cin * d->KH * d->KW, st);
+    rc = launch_wgrad_unpack(tab, 1, d->Cin, d->Cout * 8 * d->KH * d->KW, st);
   }
   cudaFreeAsync(buf, st);
   return rc;

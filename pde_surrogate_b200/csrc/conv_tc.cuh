@@ -95,7 +95,8 @@ int launch_act_split(const ActSplitArgs& a, cudaStream_t st);
 size_t act_planes_bytes(int B, int H, int W, int C);
 // max |x| over n floats as float bits, atomicMax-ed into *out (the caller clears it)
 int launch_absmax(const float* x, size_t n, unsigned* out, cudaStream_t st);
-int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_elems, cudaStream_t st);
+// max_cin: largest Cin in the table; max_slab_floats: largest Cout * 8 * KS*KS in the table
+int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_cin, int max_slab_floats, cudaStream_t st);
 
 // ---- TMA-fed bf16x3 convolution (conv_tc2.cu) -----------------------------------------------
 struct Tc2Plan {

@@ -88,7 +88,7 @@ struct pdes_net {
   int n_tc = 0, n_wg = 0, n_tc2 = 0;
   size_t max_tc2_pack = 0;
   size_t max_tc_pack = 0;
-  int max_wg_elems = 0;
+  int max_wg_elems = 0, max_wg_cin = 0;  // largest unpack slab (Cout * 8 * taps) / Cin over the wgrad layers
   int prec = 0;
   // executor-level CUDA graphs: the launch sequence of one forward / backward at a given batch size is
   // captured once (second call) and replayed afterwards; static input/output staging keeps pointers stable
@@ -349,7 +349,8 @@ int build(pdes_net* n) {
       L.dwp = f;
       f += (size_t)L.KS * L.KS * L.ci_pad * L.co_pad;
       n->n_wg++;
-      if (L.Cout * L.Cin * L.KS * L.KS > n->max_wg_elems) n->max_wg_elems = L.Cout * L.Cin * L.KS * L.KS;
+      if (L.Cin > n->max_wg_cin) n->max_wg_cin = L.Cin;
+      if (L.Cout * 8 * L.KS * L.KS > n->max_wg_elems) n->max_wg_elems = L.Cout * 8 * L.KS * L.KS;
     }
   }
   {
@@ -1118,7 +1119,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
     PDES_CUDA(cudaStreamWaitEvent(st, n->ev_join[k], 0));
   }
   if (used_wg) {
-    rc = launch_wgrad_unpack(wg_table(n), n->n_wg_bound, n->max_wg_elems, st);
+    rc = launch_wgrad_unpack(wg_table(n), n->n_wg_bound, n->max_wg_cin, n->max_wg_elems, st);
     if (rc) return rc;
     n->launches++;
     mark(n, st, "wgrad_unpack");

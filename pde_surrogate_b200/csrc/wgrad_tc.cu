@@ -39,9 +39,7 @@ using namespace tc;
 constexpr int kThreads = 192;
 constexpr int kTH = 16, kTW = 8;
 constexpr int kMC = 128;  // input channels per CTA (GEMM M)
-constexpr int kNC = 16;   // output channels per CTA (GEMM N)
 constexpr int kPasses = kPieces;
-constexpr int kStages = 3;
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -308,20 +306,25 @@ __global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int x
 // ---------------------------------------------------------------------------------------
 // the weight-gradient kernel
 // ---------------------------------------------------------------------------------------
-template <int KS>
+// CT = 16-channel output tiles per CTA (GEMM N = pieces * 16 * CT): layers with many output channels
+// amortise the A-operand shared-memory read of an MMA over a 2-4x wider N; their accumulators
+// (TG taps x N columns) then cover one filter row per CTA instead of the whole filter.
+template <int KS, int CT>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 TcWgradArgs t) {
   constexpr int T = KS * KS;
+  constexpr int kNC = 16 * CT;
+  constexpr int kStages = CT == 1 ? 3 : 2;
   constexpr int HWp = kTW + KS - 1;
   constexpr int HH = kTH + KS - 1;
   constexpr int HP = HH * HWp;
   constexpr int QA = kMC / 8;                       // channel octets of the A tile
   constexpr uint32_t A_BYTES = QA * HP * 16u;       // one fp16 plane tile
   constexpr uint32_t B_OCT = 128u * 16u;            // one co-octet: 128 pixels x 16 B
-  constexpr uint32_t B_PIECE = 2u * B_OCT;          // 16 output channels of one piece
+  constexpr uint32_t B_PIECE = 2u * CT * B_OCT;     // 16*CT output channels of one piece
   constexpr uint32_t STAGE = (A_BYTES + (uint32_t)kPieces * B_PIECE + 127u) & ~127u;
-  constexpr int TG = T <= 9 ? T : 10;               // filter taps per CTA (TMEM holds TG accumulators)
+  constexpr int TG = CT == 1 ? (T <= 9 ? T : 10) : (T < 3 ? T : 3);  // filter taps per CTA (TG accumulators in TMEM)
   const int pass = blockIdx.z % kPasses;            // which fp16 piece of `a` this CTA streams
   const int tap0 = (blockIdx.z / kPasses) * TG;     // first tap of this CTA's tap group
   const int ntap = (T - tap0) < TG ? (T - tap0) : TG;
@@ -441,19 +444,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const float osc = t.out_scale * (t.dyn_scale != nullptr ? *t.dyn_scale : 1.f);
     for (int j = 0; j < ntap; ++j) {
       const int tap = tap0 + j;
-      float v[16];
-      tmem_ld16(taddr + (uint32_t)(j * NW + (NP - 1) * kNC), v);  // smallest terms first
-      for (int piece = NP - 2; piece >= 0; --piece) {
-        float x[16];
-        tmem_ld16(taddr + (uint32_t)(j * NW + piece * kNC), x);
+#pragma unroll 1
+      for (int ct = 0; ct < CT; ++ct) {
+        if (n0 + 16 * ct >= t.co_pad) break;  // warp-uniform
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)(j * NW + (NP - 1) * kNC + 16 * ct), v);  // smallest terms first
+        for (int piece = NP - 2; piece >= 0; --piece) {
+          float x[16];
+          tmem_ld16(taddr + (uint32_t)(j * NW + piece * kNC + 16 * ct), x);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += x[i];
-      }
-      if (ci < t.Cin) {
-        float* dst = t.dwp + ((size_t)tap * t.ci_pad + ci) * t.co_pad + n0;
+          for (int i = 0; i < 16; ++i) v[i] += x[i];
+        }
+        if (ci < t.Cin) {
+          float* dst = t.dwp + ((size_t)tap * t.ci_pad + ci) * t.co_pad + n0 + 16 * ct;
 #pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          red_add_v4(dst + i, v[i] * osc, v[i + 1] * osc, v[i + 2] * osc, v[i + 3] * osc);
+          for (int i = 0; i < 16; i += 4)
+            red_add_v4(dst + i, v[i] * osc, v[i + 1] * osc, v[i + 2] * osc, v[i + 3] * osc);
+        }
       }
     }
     tc_fence_before();
@@ -476,21 +483,65 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
   if ((threadIdx.x & 31) == 0 && m != 0u) atomicMax(out, m);
 }
 
-// dW_OIHW[co][ci][tap] += dWp[tap][ci][co]; dWp is cleared for the next step.  One thread per
-// (ci, co): coalesced reads along co, KS*KS contiguous floats written per thread.
+// dW_OIHW[co][ci][tap] += dWp[tap][ci][co]; dWp is cleared for the next step.  One block per
+// (layer, 8 input channels): the [tap][8 ci][co] slab is read with co-contiguous loads, transposed in
+// shared memory to [co][8 ci][tap] — in OIHW that is one contiguous run of 8*T floats per output
+// channel — and accumulated with consecutive threads on consecutive addresses.
+constexpr int kUnpackCi = 8;
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const TcWgradUnpack* tab) {
+  extern __shared__ float tile_u[];  // [Cout][8][T]
   const TcWgradUnpack d = tab[blockIdx.y];
+  const int ci0 = blockIdx.x * kUnpackCi;
+  if (ci0 >= d.Cin) return;
   const int T = d.KS * d.KS;
-  const int total = d.Cout * d.Cin;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int co = i % d.Cout, ci = i / d.Cout;
-    float* dst = d.dw + ((size_t)co * d.Cin + ci) * T;
-    float* src = d.dwp + (size_t)ci * d.co_pad + co;
-    const size_t tap_stride = (size_t)d.ci_pad * d.co_pad;
-    for (int tap = 0; tap < T; ++tap) {
-      dst[tap] += src[tap * tap_stride];
-      src[tap * tap_stride] = 0.f;
+  const int nci = (d.Cin - ci0) < kUnpackCi ? (d.Cin - ci0) : kUnpackCi;
+  const size_t tap_stride = (size_t)d.ci_pad * d.co_pad;
+  const int rows = T * nci;  // (tap, ci) rows of Cout floats
+  constexpr int U = 4;       // independent loads in flight per thread
+  const int n1 = rows * d.Cout;
+  for (int base = threadIdx.x; base < n1; base += U * blockDim.x) {
+    float* src[U];
+    float v[U];
+    int dsti[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      src[u] = nullptr;
+      if (i < n1) {
+        const int co = i % d.Cout, r = i / d.Cout;
+        const int c = r % nci, tap = r / nci;
+        src[u] = d.dwp + (size_t)tap * tap_stride + (size_t)(ci0 + c) * d.co_pad + co;
+        dsti[u] = (co * kUnpackCi + c) * T + tap;
+        v[u] = *src[u];
+      }
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (src[u] != nullptr) {
+        tile_u[dsti[u]] = v[u];
+        *src[u] = 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  const int run = nci * T;  // contiguous floats per output channel
+  const int n2 = d.Cout * run;
+  for (int base = threadIdx.x; base < n2; base += U * blockDim.x) {
+    float* dst[U];
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      dst[u] = nullptr;
+      if (i < n2) {
+        const int co = i / run, k = i - co * run;
+        dst[u] = d.dw + ((size_t)co * d.Cin + ci0) * T + k;
+        v[u] = *dst[u] + tile_u[(size_t)co * kUnpackCi * T + k];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (dst[u] != nullptr) *dst[u] = v[u];
   }
 }
 
@@ -539,11 +590,11 @@ int wg_waves() {
   return w;
 }
 
-template <int KS>
+template <int KS, int CT>
 size_t wg_smem() {
   constexpr int HP = (kTH + KS - 1) * (kTW + KS - 1);
-  const size_t stage = ((size_t)(kMC / 8) * HP * 16 + kPieces * 2 * 128 * 16 + 127) & ~(size_t)127;
-  return 128 + kStages * stage;
+  const size_t stage = ((size_t)(kMC / 8) * HP * 16 + (size_t)kPieces * 2 * CT * 128 * 16 + 127) & ~(size_t)127;
+  return 128 + (CT == 1 ? 3 : 2) * stage;
 }
 
 }  // namespace
@@ -552,7 +603,7 @@ bool wgrad_tc_supported(int KS, int stride) { return (KS == 1 || KS == 3 || KS =
 
 void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad) {
   *ci_pad = (Cin + kMC - 1) / kMC * kMC;
-  *co_pad = (Cout + kNC - 1) / kNC * kNC;
+  *co_pad = (Cout + 15) / 16 * 16;
 }
 
 size_t act_planes_bytes(int B, int H, int W, int C) {
@@ -591,44 +642,57 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
   PDES_REQUIRE(wgrad_tc_supported(t.KS, 1), PDES_ERR_UNSUPPORTED, "wgrad_tc: 1x1 / 3x3 / 5x5 only");
   PDES_REQUIRE(t.planesA && t.planesB && t.dwp, PDES_ERR_INVALID, "wgrad_tc: null operand planes");
   const int CpA = (t.Cin + 7) & ~7, CpB = (t.Cout + 7) & ~7;
+  const int n_ci = (t.Cin + kMC - 1) / kMC, n_co = (t.Cout + 15) / 16;
+  const int CT = n_co >= 3 ? 4 : n_co;  // 16-channel output tiles per CTA: 1, 2 or 4
   CUtensorMap tmA, tmB;
   int rc = make_plane_map(&tmA, t.planesA, t.B, t.Hv, t.Wv, CpA, kTW + t.KS - 1, kTH + t.KS - 1, kMC / 8);
   if (rc) return rc;
-  rc = make_plane_map(&tmB, t.planesB, t.B, t.Ho, t.Wo, CpB, kTW, kTH, kNC / 8);
+  rc = make_plane_map(&tmB, t.planesB, t.B, t.Ho, t.Wo, CpB, kTW, kTH, 2 * CT);
   if (rc) return rc;
   const int tiles = ((t.Wo + kTW - 1) / kTW) * ((t.Ho + kTH - 1) / kTH) * t.B;
-  const int n_ci = (t.Cin + kMC - 1) / kMC, n_co = (t.Cout + kNC - 1) / kNC;
+  const int n_cog = (n_co + CT - 1) / CT;
   const int T = t.KS * t.KS;
-  const int tap_groups = T <= 9 ? 1 : (T + 9) / 10;
-  int P = (wg_waves() * sm_count()) / (n_ci * n_co * kPasses * tap_groups);
+  const int TG = CT == 1 ? (T <= 9 ? T : 10) : (T < 3 ? T : 3);
+  const int tap_groups = (T + TG - 1) / TG;
+  int P = (wg_waves() * sm_count()) / (n_ci * n_cog * kPasses * tap_groups);
   if (P < 1) P = 1;
   if (P > tiles) P = tiles;
-  dim3 grid(P, n_ci * n_co, kPasses * tap_groups);
-#define PDES_WG_LAUNCH(KSV)                                                                                  \
+  dim3 grid(P, n_ci * n_cog, kPasses * tap_groups);
+#define PDES_WG_LAUNCH(KSV, CTV)                                                                             \
   {                                                                                                          \
-    const size_t smem = wg_smem<KSV>();                                                                      \
+    const size_t smem = wg_smem<KSV, CTV>();                                                                 \
     static bool attr = false;                                                                                \
     if (!attr) {                                                                                             \
-      PDES_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KSV>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+      PDES_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KSV, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)smem));                                                            \
       attr = true;                                                                                           \
     }                                                                                                        \
-    PDES_CUDA(launch_pdl(wgrad_tc_kernel<KSV>, grid, dim3(kThreads), smem, st, tmA, tmB, t));                \
+    PDES_CUDA(launch_pdl(wgrad_tc_kernel<KSV, CTV>, grid, dim3(kThreads), smem, st, tmA, tmB, t));           \
   }
-  if (t.KS == 3) PDES_WG_LAUNCH(3)
-  else if (t.KS == 1) PDES_WG_LAUNCH(1)
-  else PDES_WG_LAUNCH(5)
+#define PDES_WG_CT(KSV)                      \
+  {                                          \
+    if (CT == 1) PDES_WG_LAUNCH(KSV, 1)      \
+    else if (CT == 2) PDES_WG_LAUNCH(KSV, 2) \
+    else PDES_WG_LAUNCH(KSV, 4)              \
+  }
+  if (t.KS == 3) PDES_WG_CT(3)
+  else if (t.KS == 1) PDES_WG_CT(1)
+  else PDES_WG_CT(5)
+#undef PDES_WG_CT
 #undef PDES_WG_LAUNCH
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
 
-int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_elems, cudaStream_t st) {
+int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_cin, int max_slab_floats, cudaStream_t st) {
   if (n == 0) return PDES_OK;
-  int bx = (max_elems / 9 + 255) / 256;
-  if (bx > 96) bx = 96;
-  if (bx < 1) bx = 1;
-  wgrad_unpack_kernel<<<dim3(bx, n), 256, 0, st>>>(dev_table);
+  const size_t smem = sizeof(float) * (size_t)max_slab_floats;  // Cout * 8 * T of the largest layer
+  static size_t attr = 48 * 1024;
+  if (smem > attr) {
+    PDES_CUDA(cudaFuncSetAttribute(wgrad_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = smem;
+  }
+  wgrad_unpack_kernel<<<dim3((max_cin + kUnpackCi - 1) / kUnpackCi, n), 256, smem, st>>>(dev_table);
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
