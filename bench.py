@@ -226,7 +226,7 @@ def main():
     launches = ts.kernel_launches * args.steps
     final_loss = float(last["loss"].item())
 
-    # ---- roofline of the conv path (dominant): useful FLOPs of fwd+bwd / device time ---------
+    # ---- roofline of the conv path: useful FLOPs of fwd+bwd / device time (whole executor) ------
     L = _lib.lib()
     ex = model._ex
     flops_step = model.flops(BATCH, True)
@@ -240,12 +240,69 @@ def main():
     ms_conv = timed(conv_only, max(5, args.steps // 4), 3)
     conv_ms_step = ms_conv / max(5, args.steps // 4)
     ach_tf = flops_step / (conv_ms_step * 1e-3) / 1e12
-    roofline = dict(bound="tensor", kernel="DenseED conv path (fwd+dgrad+wgrad, %d launches)" % 0,
-                    achieved=round(ach_tf, 3), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
-                    frac=round(ach_tf / pk["bf16_tflops_sustained"], 5), traffic=None,
-                    note="useful fp32 FLOPs (2*MAC, %.1f GFLOP/step) / CUDA-event time of the executor's "
-                         "forward+backward; peak = %s dense bf16 (sustained) — fp32-accurate convs can "
-                         "reach at most 1/2 (TF32) .. 1/6 (3xTF32) of it" % (flops_step / 1e9, pk["src"]))
+    roofline_step = dict(bound="tensor", kernel="DenseED conv path (all forward / dgrad / wgrad launches of a step)",
+                         achieved=round(ach_tf, 3), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                         frac=round(ach_tf / pk["bf16_tflops_sustained"], 5), traffic=None,
+                         note="useful fp32 FLOPs (2*MAC, %.1f GFLOP/step) / CUDA-event time of the executor's "
+                              "forward+backward" % (flops_step / 1e9))
+
+    # ---- roofline of the dominant kernel: per-launch CUDA events on the launching stream, in situ ----
+    # (a second executor with the wgrad side stream off so that every launch is timed on one stream)
+    roofline, families = None, {}
+    if rank == 0:
+        import ctypes
+        os.environ["PDES_WGRAD_STREAMS"] = "0"
+        model3 = make_model()
+        ts3 = TrainStep(model3, weight_bound=10.0, lr=1e-3)
+        for i in range(3):
+            ts3.step(Kb)
+        h3 = model3._ex.handle.h
+        cap = 512
+        us = (ctypes.c_float * cap)()
+        fl = (ctypes.c_double * cap)()
+        lab = ctypes.create_string_buffer(64 * cap)
+        per = {}
+        reps = 7
+        for r in range(reps):
+            _lib.check(L.pdes_densenet_set_timing(h3, 1))
+            ts3.step(Kb)
+            k = L.pdes_densenet_timing_read(h3, us, fl, cap, lab, len(lab))
+            _lib.check(L.pdes_densenet_set_timing(h3, 0))
+            names = lab.value.decode().split("\n")
+            for i in range(min(k, cap)):
+                per.setdefault(names[i], ([], fl[i]))[0].append(us[i])
+        os.environ.pop("PDES_WGRAD_STREAMS", None)
+        del ts3, model3
+        med = {n: (statistics.median(v), f) for n, (v, f) in per.items()}
+        kname = {"conv.f": "conv_tc2_kernel (forward)", "dgrad": "conv_tc2_kernel (dgrad + BatchNorm-backward epilogue)",
+                 "wgrad": "wgrad_tc_kernel"}
+        for n, (t_us, f) in med.items():
+            fam = n.split()[0]
+            if f > 0:
+                a = families.setdefault(fam, [0.0, 0.0, 0])
+                a[0] += t_us
+                a[1] += f
+                a[2] += 1
+        top = max(((t_us, f, n) for n, (t_us, f) in med.items() if f > 0 and n.split()[0] in kname), default=None)
+        traffic = {}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath))
+        if top is not None:
+            t_us, f, n = top
+            ach = f / (t_us * 1e-6) / 1e12
+            roofline = dict(bound="tensor", kernel="%s, launch '%s'" % (kname[n.split()[0]], n),
+                            achieved=round(ach, 2), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
+                            frac=round(ach / pk["bf16_tflops_sustained"], 4), traffic=traffic.get(n),
+                            us_per_launch=round(t_us, 2), gflop_per_launch=round(f / 1e9, 3),
+                            tensor_issue_frac=round(3 * ach / pk["bf16_tflops_sustained"], 4),
+                            note="dominant launch of the step; achieved = useful fp32 FLOPs (2*MAC) of the launch / "
+                                 "median CUDA-event time between consecutive launches of an eager step (includes "
+                                 "the ~2 us launch gap); peak = %s dense bf16 (sustained); fp32 accuracy costs 3 "
+                                 "fp16 tensor products per useful product, so 1/3 is the ceiling and "
+                                 "tensor_issue_frac = 3*frac is what the tensor pipe executes" % pk["src"])
+        families = {k: dict(us_per_step=round(v[0], 1), launches=v[2], useful_tflops=round(v[1] / (v[0] * 1e-6) / 1e12, 2))
+                    for k, v in families.items()}
 
     # ---- roofline of the fused stencil kernel on a cold, larger-than-L2 batch ----------------
     nb = 8192
@@ -322,7 +379,8 @@ def main():
                              d2h_bytes_per_step=4, ms_per_step=round(ms_e / args.steps, 4),
                              api="models.codec.DenseED + models.darcy.conv_* + torch.optim.Adam, loss.item() per step"),
                     gpu_launches=launches, launches_per_step=ts.kernel_launches, clocks=clocks,
-                    roofline=roofline, roofline_stencil=roofline_stencil, cpu_baseline=cpu,
+                    roofline=roofline, roofline_step=roofline_step, roofline_families=families,
+                    roofline_stencil=roofline_stencil, cpu_baseline=cpu,
                     final_loss=round(final_loss, 5), conv_path_ms_per_step=round(conv_ms_step, 4),
                     useful_gflop_per_step=round(flops_step / 1e9, 2))
         print(json.dumps(line), flush=True)

@@ -143,6 +143,11 @@ int pdes_densenet_set_conv_impl(pdes_net_t* net, int impl);
  * timing_report synchronises the device and prints one "<us> <label>" line per launch to stderr. */
 int pdes_densenet_set_timing(pdes_net_t* net, int on);
 int pdes_densenet_timing_report(pdes_net_t* net);
+/* The same measurements returned to the caller: us[i] / flops[i] (useful 2*MAC of a convolution launch,
+ * 0 otherwise) of launch i and the '\n'-separated labels; returns the number of launches, or a
+ * negative error code.  Clears the recorded marks. */
+int pdes_densenet_timing_read(pdes_net_t* net, float* us, double* flops, int cap, char* labels,
+                              size_t labels_cap);
 
 /* ------------------------------------------------------------------------------------
  * Fused Adam over a flat buffer; replaces torch.optim.Adam.step() as used at

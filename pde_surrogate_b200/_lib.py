@@ -54,6 +54,7 @@ SIGNATURES = {
     "pdes_densenet_set_conv_impl": (c_int, [c_void_p, c_int]),
     "pdes_densenet_set_timing": (c_int, [c_void_p, c_int]),
     "pdes_densenet_timing_report": (c_int, [c_void_p]),
+    "pdes_densenet_timing_read": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t]),
     "pdes_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                c_float, c_float, c_float, c_int64, c_void_p]),
     "pdes_adam_step_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),

@@ -112,21 +112,30 @@ struct pdes_net {
   int conv_impl = 0;
   // PDES_TIMING=1: one CUDA event after every launch of the eager executor (diagnostics)
   bool timing = false;
-  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  struct Mark {
+    std::string first;
+    cudaEvent_t second;
+    double flops;
+  };
+  std::vector<Mark> marks;
 };
 
 namespace {
 
 int64_t pad4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 
-void mark(pdes_net* n, cudaStream_t st, const std::string& label) {
+void mark(pdes_net* n, cudaStream_t st, const std::string& label, double flops = 0.0) {
   if (!n->timing) return;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
   cudaEvent_t e;
   if (cudaEventCreate(&e) != cudaSuccess) return;
   cudaEventRecord(e, st);
-  n->marks.push_back(std::make_pair(label, e));
+  pdes_net::Mark m;
+  m.first = label;
+  m.second = e;
+  m.flops = flops;
+  n->marks.push_back(m);
 }
 int rup(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -690,6 +699,38 @@ extern "C" int pdes_densenet_timing_report(pdes_net_t* n) {
   return PDES_OK;
 }
 
+// Same measurements as pdes_densenet_timing_report, returned to the caller: us[i] / flops[i] of launch i
+// (flops = useful 2*MAC of a convolution launch, 0 otherwise) and the '\n'-separated labels.
+// Returns the number of launches (<= cap filled) or a negative error code; clears the marks.
+extern "C" int pdes_densenet_timing_read(pdes_net_t* n, float* us, double* flops, int cap, char* labels,
+                                         size_t labels_cap) {
+  if (!n || !us || !flops || !labels || labels_cap == 0) return -PDES_ERR_INVALID;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -PDES_ERR_CUDA;
+  int k = 0;
+  size_t pos = 0;
+  labels[0] = 0;
+  for (size_t i = 1; i < n->marks.size(); ++i) {
+    if (n->marks[i].first[0] == '@') continue;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, n->marks[i - 1].second, n->marks[i].second);
+    if (k < cap) {
+      us[k] = ms * 1e3f;
+      flops[k] = n->marks[i].flops;
+      const std::string& lb = n->marks[i].first;
+      if (pos + lb.size() + 2 < labels_cap) {
+        memcpy(labels + pos, lb.c_str(), lb.size());
+        pos += lb.size();
+        labels[pos++] = '\n';
+        labels[pos] = 0;
+      }
+    }
+    ++k;
+  }
+  for (auto& m : n->marks) cudaEventDestroy(m.second);
+  n->marks.clear();
+  return k;
+}
+
 extern "C" int pdes_densenet_last_launches(const pdes_net_t* n) { return n ? n->launches : 0; }
 
 extern "C" double pdes_densenet_flops(const pdes_net_t* n, int B, int training) {
@@ -858,7 +899,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     }
     if (rc) return rc;
     n->launches++;
-    mark(n, st, "conv.f " + L.conv_name);
+    mark(n, st, "conv.f " + L.conv_name, 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B);
   }
   if (tr) {
     rc = launch_bn_running_update(bn_table(n), n->n_bn, n->maxC, 0.1f, B, st);
@@ -1049,7 +1090,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       }
       if (rc) return rc;
       n->launches++;
-      mark(n, st, "wgrad " + L.conv_name);
+      mark(n, st, "wgrad " + L.conv_name, 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B);
     }
     // ---- dgrad (not needed for the first conv: the input does not require grad) ------
     if (L.in_buf >= 0) {
@@ -1110,7 +1151,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       }
       if (rc) return rc;
       n->launches++;
-      mark(n, st, "dgrad " + L.conv_name);
+      mark(n, st, "dgrad " + L.conv_name, 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B);
     }
   }
   for (int k = 0; k < 2; ++k) {
