@@ -401,6 +401,7 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   rc = launch_wgrad_tc(tw, st);
   if (rc == PDES_OK) {
     TcWgradUnpack u;
+    memset(&u, 0, sizeof(u));
     u.dw = dw;
     u.dwp = buf;
     u.Cout = d->Cout;

@@ -86,7 +86,21 @@ struct TcWgradUnpack {
   float* dw;         // OIHW gradient (+=)
   float* dwp;        // staging buffer (read, then cleared)
   int Cout, Cin, KS, ci_pad, co_pad;
+  int taps_in_n;     // > 0: staged as a 1x1 problem with N = (tap, co): dwp[ci][tap * Cout + co], taps_in_n = KS*KS
 };
+
+// Weight gradient of a convolution with very few output channels (the network's last layer): the
+// GEMM N would be Cout padded to 16 per filter tap.  Instead the dY operand is expanded once into
+// KS*KS shifted copies, n = tap * Cout + co:  planes[.][b][y][n/8][x][n%8] = dY[b][co][y-ky+pad][x-kx+pad],
+// and the weight gradient becomes ONE 1x1-convolution GEMM with N = KS*KS*Cout.
+struct DyIm2colArgs {
+  const float* dy;   // planar (B, Cout, H, W) output gradient
+  op16* out;         // [2][B][H][Np/8][W][8], Np = KS*KS*Cout rounded up to 8
+  int B, H, W, Cout, KS, pad, Np;
+  const unsigned* dyn_max;  // dynamic scale as in ActSplitArgs
+  float* dyn_inv;
+};
+int launch_dy_im2col(const DyIm2colArgs& a, cudaStream_t st);
 
 bool wgrad_tc_supported(int KS, int stride);
 void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad);

@@ -53,6 +53,8 @@ struct Layer {
   size_t planesB;    // float offset of this layer's dY piece planes (read by its dgrad and, concurrently, its wgrad)
   bool tc_wg;        // weight gradient on tcgen05
   bool first_k;      // dedicated CUDA-core kernels of the first convolution (first_conv.cu)
+  bool wg_taps_n;    // weight gradient as ONE 1x1 GEMM over an expanded dY (few output channels, DyIm2colArgs)
+  size_t planesI;    // float offset of the expanded dY planes
   int ci_pad, co_pad;
   size_t dwp;        // float offset of the [tap][ci_pad][co_pad] staging gradient
 };
@@ -190,6 +192,8 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   memset(&L.p2b, 0, sizeof(L.p2b));
   L.tc_wg = false;
   L.first_k = false;
+  L.wg_taps_n = false;
+  L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
   memset(&L.pf, 0, sizeof(L.pf));
@@ -372,6 +376,14 @@ int build(pdes_net* n) {
         f += pad4((int64_t)((act_planes_bytes(B, Hv, Wv, L.Cin) + 3) / 4)) + 64;
       }
       const int zi = L.stride == 2 ? 2 : 1;  // dY planes are zero-inserted for stride-2 layers
+      if (L.tc_wg && L.out_buf < 0 && L.stride == 1 && !L.up && L.KS > 1 && L.Cout <= 8 &&
+          L.KS * L.KS * L.Cout <= 128) {
+        // the last convolution: planar dY with a handful of channels
+        L.wg_taps_n = true;
+        const int Np = (L.KS * L.KS * L.Cout + 7) & ~7;
+        L.planesI = f;
+        f += pad4((int64_t)((act_planes_bytes(B, L.Ho, L.Wo, Np) + 3) / 4)) + 64;
+      }
       if (L.in_buf >= 0 && (L.tc_wg || L.tc2_bwd)) {
         L.planesB = f;
         f += pad4((int64_t)((act_planes_bytes(B, zi * L.Ho, zi * L.Wo, L.Cout) + 3) / 4)) + 64;
@@ -648,6 +660,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
   for (const auto& L : n->layers) {
     if (!L.tc_wg || !n->g) continue;
     TcWgradUnpack u;
+    memset(&u, 0, sizeof(u));
     u.dw = n->g + L.w_off;
     u.dwp = wsf(n, L.dwp);
     u.Cout = L.Cout;
@@ -655,6 +668,11 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
     u.KS = L.KS;
     u.ci_pad = L.ci_pad;
     u.co_pad = L.co_pad;
+    u.taps_in_n = 0;
+    if (L.wg_taps_n) {
+      u.taps_in_n = L.KS * L.KS;
+      u.co_pad = (L.KS * L.KS * L.Cout + 15) / 16 * 16;
+    }
     wt.push_back(u);
   }
   n->n_wg_bound = (int)wt.size();
@@ -1036,6 +1054,35 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         n->launches++;
         mark(n, st, "split.b " + L.conv_name);
       }
+      if (use_wg && L.wg_taps_n) {
+        DyIm2colArgs ia;
+        memset(&ia, 0, sizeof(ia));
+        ia.dy = dy;
+        ia.out = reinterpret_cast<op16*>(wsf(n, L.planesI));
+        ia.B = B;
+        ia.H = L.Ho;
+        ia.W = L.Wo;
+        ia.Cout = L.Cout;
+        ia.KS = L.KS;
+        ia.pad = L.pad;
+        ia.Np = (L.KS * L.KS * L.Cout + 7) & ~7;
+        ia.dyn_max = gmax_slot(n, L.out_buf);
+        ia.dyn_inv = wsf(n, n->dyinv) + li;  // the same value the dY split publishes
+        cudaStream_t ist = st;
+        if (n->n_side > 0 && n->side[0]) {
+          // off the critical path: the expansion and the GEMM that reads it both run on the side stream
+          // (wg_rr is advanced by the wgrad launch below, which therefore picks the same stream)
+          const int k = wg_rr % n->n_side;
+          PDES_CUDA(cudaEventRecord(n->ev_fork[k], st));
+          PDES_CUDA(cudaStreamWaitEvent(n->side[k], n->ev_fork[k], 0));
+          ist = n->side[k];
+          side_used |= 1 << k;
+        }
+        rc = launch_dy_im2col(ia, ist);
+        if (rc) return rc;
+        n->launches++;
+        mark(n, st, "im2col.b " + L.conv_name);
+      }
       if (use_wg) {
         const Buf& ib = n->bufs[L.in_buf];
         TcWgradArgs tw;
@@ -1056,6 +1103,13 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         tw.co_pad = L.co_pad;
         tw.out_scale = pow2f(-kActScaleLog2);
         tw.dyn_scale = wsf(n, n->dyinv) + li;
+        if (L.wg_taps_n) {  // one 1x1 GEMM: N = (tap, co) over the expanded dY
+          tw.planesB = reinterpret_cast<const op16*>(wsf(n, L.planesI));
+          tw.Cout = L.KS * L.KS * L.Cout;
+          tw.KS = 1;
+          tw.pad = 0;
+          tw.co_pad = (tw.Cout + 15) / 16 * 16;
+        }
         if (n->n_side > 0 && n->side[0]) {
           // fork: the wgrad kernel only needs the dY planes just written; it runs beside the dgrad chain
           const int k = wg_rr++ % n->n_side;

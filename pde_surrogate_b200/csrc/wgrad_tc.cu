@@ -472,6 +472,47 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// dY expansion for the taps-in-N weight gradient (DyIm2colArgs): one thread per (pixel, n-octet),
+// x-contiguous gathers and 16-byte stores.
+__global__ void __launch_bounds__(256) dy_im2col_kernel(DyIm2colArgs a) {
+  griddep_wait();
+  float mul = 1.f;
+  if (a.dyn_max != nullptr) {
+    const unsigned m = *a.dyn_max;
+    int e = m == 0u ? 0 : kDyTargetLog2 - ((int)((m >> 23) & 0xffu) - 127);
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    mul = __uint_as_float((uint32_t)(e + 127) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.dyn_inv = __uint_as_float((uint32_t)(127 - e) << 23);
+  }
+  const int oct = a.Np >> 3, nreal = a.KS * a.KS * a.Cout;
+  const size_t plane = (size_t)a.B * a.H * a.W * a.Np;
+  const size_t total = (size_t)a.B * a.H * oct * a.W;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % a.W);
+    size_t r = i / a.W;
+    const int q = (int)(r % oct);
+    r /= oct;
+    const int y = (int)(r % a.H), b = (int)(r / a.H);
+    uint32_t h0[8], h1[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int n = 8 * q + k;
+      float v = 0.f;
+      if (n < nreal) {
+        const int tap = n / a.Cout, co = n - tap * a.Cout;
+        const int sy = y - tap / a.KS + a.pad, sx = x - tap % a.KS + a.pad;
+        if (sy >= 0 && sy < a.H && sx >= 0 && sx < a.W) v = __ldg(a.dy + (((size_t)b * a.Cout + co) * a.H + sy) * a.W + sx);
+      }
+      fp16_split2(v * mul, h0[k], h1[k]);
+    }
+    op16* dst = a.out + i * 8;  // (((b*H + y)*oct + q)*W + x)*8
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(h0[0] | (h0[1] << 16), h0[2] | (h0[3] << 16), h0[4] | (h0[5] << 16), h0[6] | (h0[7] << 16));
+    *reinterpret_cast<uint4*>(dst + plane) =
+        make_uint4(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16), h1[4] | (h1[5] << 16), h1[6] | (h1[7] << 16));
+  }
+}
+
 // max |x| as float bits (non-negative floats order like unsigned integers)
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
   unsigned m = 0u;
@@ -493,6 +534,18 @@ __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const TcWgradUnpack* 
   const TcWgradUnpack d = tab[blockIdx.y];
   const int ci0 = blockIdx.x * kUnpackCi;
   if (ci0 >= d.Cin) return;
+  if (d.taps_in_n > 0) {
+    // staged as dwp[ci][tap * Cout + co] (few output channels): a small scattered fold
+    const int Tn = d.taps_in_n, nci = (d.Cin - ci0) < kUnpackCi ? (d.Cin - ci0) : kUnpackCi;
+    for (int i = threadIdx.x; i < nci * Tn * d.Cout; i += blockDim.x) {
+      const int n = i % (Tn * d.Cout), c = i / (Tn * d.Cout);
+      const int tap = n / d.Cout, co = n - tap * d.Cout;
+      float* src = d.dwp + (size_t)(ci0 + c) * d.co_pad + n;
+      d.dw[((size_t)co * d.Cin + ci0 + c) * Tn + tap] += *src;
+      *src = 0.f;
+    }
+    return;
+  }
   const int T = d.KS * d.KS;
   const int nci = (d.Cin - ci0) < kUnpackCi ? (d.Cin - ci0) : kUnpackCi;
   const size_t tap_stride = (size_t)d.ci_pad * d.co_pad;
@@ -609,6 +662,18 @@ void wgrad_tc_dims(int Cin, int Cout, int* ci_pad, int* co_pad) {
 size_t act_planes_bytes(int B, int H, int W, int C) {
   const int Cp = (C + 7) & ~7;
   return (size_t)kPieces * B * H * W * Cp * sizeof(op16);
+}
+
+int launch_dy_im2col(const DyIm2colArgs& a, cudaStream_t st) {
+  PDES_REQUIRE(a.dy && a.out && a.Np % 8 == 0 && a.Np >= a.KS * a.KS * a.Cout, PDES_ERR_INVALID,
+               "dy_im2col: invalid arguments");
+  const size_t total = (size_t)a.B * a.H * (a.Np / 8) * a.W;
+  int blocks = (int)((total + 255) / 256);
+  const int cap = sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  PDES_CUDA(launch_pdl(dy_im2col_kernel, dim3(blocks), dim3(256), 0, st, a));
+  return PDES_OK;
 }
 
 int launch_absmax(const float* x, size_t n, unsigned* out, cudaStream_t st) {
