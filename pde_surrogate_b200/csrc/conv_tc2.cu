@@ -194,7 +194,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
     tmem_relinquish();
   }
   griddep_wait();  // everything below reads what earlier kernels of the step produced
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
   if (warp >= kEpiWarp0) {
+    // epilogue constants (BatchNorm of the consumer: dependent global loads + fp64 math): computed by
+    // the epilogue warps only, behind the CTA barrier, so the producers and the MMA issuer start at once
     const int tt = threadIdx.x - kEpiWarp0 * 32;
     for (int n = tt; n < N; n += kEpiWarps * 32) {
       float s = 0.f, h = 0.f, m = 0.f, is = 0.f;
@@ -205,11 +211,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       ep_s[3 * N + n] = is;
     }
     for (int i = tt; i < kEpiWarps * N * 2; i += kEpiWarps * 32) red_s[i] = 0.f;
+    named_bar_sync(1, kEpiWarps * 32);
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 #define DBG(slot) do { if (t.dbg) t.dbg[(size_t)blockIdx.x * 16 + (slot)] = clock64(); } while (0)
   if (threadIdx.x == 0) DBG(0);
 
