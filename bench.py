@@ -327,9 +327,14 @@ def main():
     msb = timed(sten_b, 10, 3) / 10
     gbs_f = nb * 65536 / (msf * 1e-3) / 1e9
     gbs_b = nb * 114688 / (msb * 1e-3) / 1e9
+    _tr = {}
+    if os.path.exists(os.path.join(ROOT, "profiles", "traffic.json")):
+        _tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
     roofline_stencil = dict(bound="hbm", kernel="darcy_fwd_tile_kernel / darcy_bwd_tile_kernel",
                             achieved=round(gbs_b, 1), peak=pk["hbm_gbs"], unit="GB/s",
-                            frac=round(gbs_b / pk["hbm_gbs"], 4), traffic=None,
+                            frac=round(gbs_b / pk["hbm_gbs"], 4), traffic=_tr.get("darcy_bwd_tile_kernel"),
+                            fwd_traffic=_tr.get("darcy_fwd_tile_kernel"), algorithmic_bytes=nb * 114688,
+                            fwd_algorithmic_bytes=nb * 65536,
                             fwd_achieved=round(gbs_f, 1), fwd_frac=round(gbs_f / pk["hbm_gbs"], 4),
                             note="cold %d-sample batch (%.1f GB, > L2); algorithmic bytes 65536 (fwd) / "
                                  "114688 (bwd) per sample; peak = %s copy bandwidth" % (nb, nb * 114688 / 1e9, pk["src"]))
