@@ -6,7 +6,7 @@ import torch
 from ctypes import byref
 from pde_surrogate_b200 import _lib
 L = _lib.lib()
-for (B, H, Cin, Cout, K, up) in [(32, 64, 49, 3, 5, 0), (32, 32, 128, 16, 3, 0), (32, 16, 184, 16, 3, 0)]:
+for (B, H, Cin, Cout, K, up) in [(32, 32, 196, 98, 3, 0), (32, 32, 98, 49, 3, 1), (32, 32, 100, 100, 3, 0)]:
     d = _lib.ConvDesc()
     Hv = 2 * H if up else H
     d.B, d.Hin, d.Win, d.Cin, d.ld_in = B, H, H, Cin, (Cin + 3) // 4 * 4
