@@ -139,6 +139,7 @@ __device__ __forceinline__ void bn_consts_w(const BnSrc& s, int c, float& scale,
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int xs) {
   griddep_wait();
+  griddep_launch();  // the consumer's CTAs may take their SM slots and run their prologue now
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int Cp = a.Cp;
   float* sc_s = reinterpret_cast<float*>(sm_raw);  // fused dY correction: c1 -> sc_s, c2 -> sh_s
