@@ -196,3 +196,35 @@ def test_engine_graph_replay_matches_eager(golden_dir):
     # the graph path spends two real optimisation steps on warm-up before capture: replay i is step i+2
     for i in range(4):
         assert abs(losses["graph"][i] - losses["eager"][i + 2]) <= 2e-2 * abs(losses["eager"][i + 2]), (i, losses)
+
+
+def test_arbitrary_output_gradient_mse(golden_dir):
+    """SURVEY section 8(f) row 2 (train_codec_max_likelihood.py:201-213): F.mse_loss on labelled data
+    drives the same network; the executor's backward takes any dL/d(output).  Checked against the
+    fp64 oracle evaluated here (small config, seconds on CPU)."""
+    import torch.nn.functional as F
+    from oracle.pdes_oracle import param_names
+    g = np.load(os.path.join(golden_dir, "densenet_fiveblk16.npz"))
+    model, K, cfg = _model(g)
+    plan = orc.densenet_plan(**cfg)
+    tg = torch.Generator().manual_seed(5)
+    target = torch.randn(K.shape[0], cfg["out_channels"], cfg["imsize"], cfg["imsize"], generator=tg)
+    model.train()
+    model.zero_grad()
+    out = model(K)
+    loss = F.mse_loss(out, target.cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    sd64 = orc.to_dtype(orc.make_state(plan, int(g["seed"])), torch.float64)
+    names = param_names(plan)
+    for n in names:
+        sd64[n].requires_grad_(True)
+    o64 = orc.densenet_forward(plan, sd64, K.cpu().double(), training=True)
+    l64 = F.mse_loss(o64, target.double())
+    l64.backward()
+    assert rel(out.detach().cpu().numpy(), o64.detach().numpy()) < 1e-4
+    assert abs(float(loss) - float(l64)) <= 1e-4 * abs(float(l64))
+    params = dict(model.named_parameters())
+    ref = np.concatenate([sd64[n].grad.numpy().ravel() for n in names])
+    got = np.concatenate([params[n].grad.detach().double().cpu().numpy().ravel() for n in names])
+    assert rel(got, ref) < 5e-3, rel(got, ref)   # flip-tolerant aggregate (see test_train_step_matches_reference)

@@ -129,3 +129,35 @@ def test_unmodified_training_script_runs(tmp_path):
     assert (run / "training" / "loss_train.txt").exists() and (run / "training" / "r2_test.txt").exists()
     sd = torch.load(str(run / "checkpoints" / "model_epoch1.pth"))
     assert len(sd) == 163 and "features.LastTransUp.conv3.weight" in sd
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "train_codec_max_likelihood.py")),
+                    reason="reference checkout not present (only in the build container)")
+def test_unmodified_max_likelihood_script_runs(tmp_path):
+    """the data-driven script train_codec_max_likelihood.py (same DenseED,
+    F.mse_loss on labelled data, eval loop) runs byte for byte on this repo's modules — the network's
+    autograd Function takes an arbitrary dL/d(output), not only the Darcy loss gradient."""
+    from pde_surrogate_b200 import data
+    d = tmp_path / "datasets" / "32x32"
+    d.mkdir(parents=True)
+    rs = np.random.RandomState(1)
+    x = data.grf_kle(24, 32, 64, 0.2, seed=2, device="cpu").numpy()
+    data.write_hdf5(str(d / "kle512_lhs10000_train.hdf5"), x[:16], rs.standard_normal((16, 3, 32, 32)))
+    data.write_hdf5(str(d / "kle512_lhs1000_val.hdf5"), x[16:], rs.standard_normal((8, 3, 32, 32)))
+    import run_reference_script
+    argv = ["--script", os.path.join(REF, "train_codec_max_likelihood.py"), "--", "--data-dir",
+            str(tmp_path / "datasets"), "--exp-dir", str(tmp_path / "exp"), "--imsize", "32", "--ntrain", "16",
+            "--ntest", "8", "--batch-size", "8", "--test-batch-size", "8", "--epochs", "2", "--cuda", "0",
+            "--plot-freq", "1", "--ckpt-freq", "1"]
+    old_argv, old_path = list(sys.argv), list(sys.path)
+    try:
+        with cpu_backend():
+            run_reference_script.main(argv)
+    finally:
+        sys.argv, sys.path[:] = old_argv, old_path
+    run_dirs = list((tmp_path / "exp").rglob("args.txt"))
+    assert len(run_dirs) == 1
+    run = run_dirs[0].parent
+    assert (run / "checkpoints" / "model_epoch2.pth").exists()
+    losses = np.loadtxt(str(run / "training" / "loss_train.txt"))
+    assert losses.shape == (2,) and np.all(np.isfinite(losses)) and losses[1] < losses[0]
