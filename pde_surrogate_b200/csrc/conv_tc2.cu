@@ -203,12 +203,11 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
     // the epilogue warps only, behind the CTA barrier, so the producers and the MMA issuer start at once
     const int tt = threadIdx.x - kEpiWarp0 * 32;
     for (int n = tt; n < N; n += kEpiWarps * 32) {
+      // per channel (scale, shift, invstd, -mean*invstd): z = x*scale + shift, xhat = x*invstd + c;
+      // all zero for the padding channels, whose dz is then 0 without a bounds test
       float s = 0.f, h = 0.f, m = 0.f, is = 0.f;
       if (a.epi == EPI_BNBWD && n < a.Cout) bn_consts2(a.fbn, n, s, h, m, is);
-      ep_s[n] = s;
-      ep_s[N + n] = h;
-      ep_s[2 * N + n] = m;
-      ep_s[3 * N + n] = is;
+      *reinterpret_cast<float4*>(ep_s + 4 * n) = make_float4(s, h, is, -m * is);
     }
     for (int i = tt; i < kEpiWarps * N * 2; i += kEpiWarps * 32) red_s[i] = 0.f;
     named_bar_sync(1, kEpiWarps * 32);
@@ -507,13 +506,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
             float o[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const int nl = n0 + i;
-              const float z = fmaf(xv[i], ep_s[nl], ep_s[N + nl]);
-              const float dz = (nl < a.Cout && z > 0.f) ? v[i] : 0.f;
-              const float xh = (xv[i] - ep_s[2 * N + nl]) * ep_s[3 * N + nl];
+              const float4 c = *reinterpret_cast<const float4*>(ep_s + 4 * (n0 + i));
+              const float z = fmaf(xv[i], c.x, c.y);
+              const float dz = z > 0.f ? v[i] : 0.f;
+              const float xh = fmaf(xv[i], c.z, c.w);
               s1[i] = dz;
               s2[i] = dz * xh;
-              o[i] = gv[i] + ep_s[nl] * dz;
+              o[i] = fmaf(c.x, dz, gv[i]);
               gmx = fmaxf(gmx, fabsf(o[i]));
             }
 #pragma unroll
