@@ -136,10 +136,20 @@ def make_state(plan, seed=0, dtype=torch.float32):
     return sd
 
 
-def make_input(B, imsize, seed=0, dtype=torch.float32):
-    """Positive permeability-like field K = exp(0.5 * smooth-ish noise)."""
+def make_input(B, imsize, seed=0, dtype=torch.float32, kind="lognormal"):
+    """Positive permeability-like field.  kind "lognormal": K = exp(0.5 * noise);  kind "channel":
+    a two-valued channelized field K in {1, e^2.5} (thresholded smooth noise) like the reference's
+    `channelized` dataset (train_codec_mixed_residual.py:55, BASELINE config 3)."""
     rs = np.random.RandomState(1000 + seed)
     g = rs.standard_normal((B, 1, imsize, imsize))
+    if kind == "channel":
+        k = max(3, imsize // 8) | 1   # odd box width; anisotropic smoothing gives channel-like bands
+        pad = k // 2
+        gp = np.pad(g, ((0, 0), (0, 0), (0, 0), (pad, pad)), mode="wrap")
+        sm = sum(gp[..., i:i + imsize] for i in range(k)) / k
+        gp = np.pad(sm, ((0, 0), (0, 0), (1, 1), (0, 0)), mode="wrap")
+        sm = (gp[:, :, :-2] + gp[:, :, 1:-1] + gp[:, :, 2:]) / 3.0
+        return torch.tensor(np.where(sm > 0.0, np.exp(2.5), 1.0), dtype=dtype)
     return torch.tensor(np.exp(0.5 * g), dtype=dtype)
 
 

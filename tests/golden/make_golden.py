@@ -46,10 +46,10 @@ def main():
 
     DenseED, darcy, SobelFilter = import_reference()
 
-    def ref_step(cfg, B, seed, dtype):
+    def ref_step(cfg, B, seed, dtype, kind="lognormal"):
         plan = orc.densenet_plan(**cfg)
         sd = orc.to_dtype(orc.make_state(plan, seed), dtype)
-        K = orc.make_input(B, cfg["imsize"], seed).to(dtype)
+        K = orc.make_input(B, cfg["imsize"], seed, kind=kind).to(dtype)
         model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
                         growth_rate=cfg["growth_rate"], init_features=cfg["init_features"])
         model = model.to(dtype)
@@ -82,10 +82,10 @@ def main():
                     l_d_notb=l_d_notb.detach(), names=[n for n, _ in model.named_parameters()],
                     model_size=model.model_size)
 
-    def save_case(fname, cfg, B, seed, full_grads):
-        r32 = ref_step(cfg, B, seed, torch.float32)
-        r64 = ref_step(cfg, B, seed, torch.float64)
-        d = dict(cfg_in_channels=cfg["in_channels"], cfg_out_channels=cfg["out_channels"],
+    def save_case(fname, cfg, B, seed, full_grads, kind="lognormal"):
+        r32 = ref_step(cfg, B, seed, torch.float32, kind)
+        r64 = ref_step(cfg, B, seed, torch.float64, kind)
+        d = dict(input_kind=kind, cfg_in_channels=cfg["in_channels"], cfg_out_channels=cfg["out_channels"],
                  cfg_imsize=cfg["imsize"], cfg_blocks=np.array(cfg["blocks"]),
                  cfg_growth_rate=cfg["growth_rate"], cfg_init_features=cfg["init_features"], B=B,
                  seed=seed, model_size=np.array(r32["model_size"]),
@@ -115,6 +115,16 @@ def main():
         np.savez_compressed(os.path.join(HERE, fname), **d)
         print(fname, "loss", float(r32["loss"]), "l4", r32["l4"].tolist(), "model_size", r32["model_size"])
 
+    full = dict(in_channels=1, out_channels=3, blocks=[6, 8, 6], growth_rate=16, init_features=48)
+
+    def channel_case():
+        # BASELINE config 3's data: two-valued channelized permeability, 64x64, a batch of 4
+        save_case("densenet_full64_channel.npz", dict(full, imsize=64), B=4, seed=13, full_grads=False,
+                  kind="channel")
+
+    if "--only-channel" in sys.argv:
+        channel_case()
+        return
     small = dict(in_channels=1, out_channels=3, imsize=16, blocks=[1, 2, 1], growth_rate=4,
                  init_features=8)
     save_case("densenet_small16.npz", small, B=3, seed=3, full_grads=True)
@@ -124,6 +134,7 @@ def main():
     full = dict(in_channels=1, out_channels=3, blocks=[6, 8, 6], growth_rate=16, init_features=48)
     save_case("densenet_full32.npz", dict(full, imsize=32), B=2, seed=7, full_grads=False)
     save_case("densenet_full64.npz", dict(full, imsize=64), B=2, seed=11, full_grads=False)
+    channel_case()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----
     rs = np.random.RandomState(42)

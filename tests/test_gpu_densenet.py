@@ -13,7 +13,7 @@ import torch
 from oracle import pdes_oracle as orc
 
 pytestmark = pytest.mark.gpu
-CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64"]
+CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64", "densenet_full64_channel"]
 
 
 def rel(a, b):
@@ -37,7 +37,7 @@ def _model(g):
     assert list(model.state_dict().keys()) == list(sd.keys())
     model.load_state_dict(sd)
     model = model.to("cuda")
-    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"])).to("cuda")
+    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]), kind=str(g["input_kind"]) if "input_kind" in g.files else "lognormal").to("cuda")
     return model, K, cfg
 
 

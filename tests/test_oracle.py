@@ -8,7 +8,7 @@ import torch
 
 from oracle import pdes_oracle as orc
 
-CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64"]
+CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64", "densenet_full64_channel"]
 
 
 def _load(golden_dir, name):
@@ -44,7 +44,7 @@ def test_train_step_fp64_matches_reference(golden_dir, name):
     cfg = _cfg(g)
     plan = orc.densenet_plan(**cfg)
     sd = orc.to_dtype(orc.make_state(plan, int(g["seed"])), torch.float64)
-    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"])).double()
+    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]), kind=str(g["input_kind"]) if "input_kind" in g.files else "lognormal").double()
     sd_eval = orc.to_dtype(sd, torch.float64)
     with torch.no_grad():
         out_eval = orc.densenet_forward(plan, sd_eval, K, training=False)
@@ -76,7 +76,7 @@ def test_train_step_fp32_within_noise_floor(golden_dir, name):
     cfg = _cfg(g)
     plan = orc.densenet_plan(**cfg)
     sd = orc.make_state(plan, int(g["seed"]))
-    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]))
+    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]), kind=str(g["input_kind"]) if "input_kind" in g.files else "lognormal")
     out, l4, loss, dout, grads = orc.train_step(plan, sd, K)
     assert rel(out.numpy(), g["out"]) < 2e-5
     assert rel(l4.numpy(), g["l4"]) < 1e-5
