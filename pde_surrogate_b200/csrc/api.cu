@@ -90,6 +90,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void __launch_bounds__(256)
 adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                 float* __restrict__ v, int64_t n, const float* __restrict__ hyper) {
+  griddep_wait();
   const float step_size = hyper[0], inv_sqrt_bc2 = hyper[1], b1 = hyper[2], b2 = hyper[3], eps = hyper[4],
               wd = hyper[5], gscale = hyper[6];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -167,7 +168,7 @@ extern "C" int pdes_adam_step_dev(float* p, const float* g, float* m, float* v, 
   int blocks = (int)((n + 255) / 256);
   const int cap = sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  adam_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper);
+  PDES_CUDA(launch_pdl(adam_dev_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, hyper));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(kConvThreads) wgrad_simt_kernel(WgradArgs a) {
 // helper kernels
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) fix_dy_kernel(FixDyArgs a) {
+  griddep_wait();
   __shared__ float c1_s[256], c2_s[256], mean_s[256], is_s[256];
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
     const double m = a.sum[c] * a.inv_count;
@@ -504,6 +505,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* tab) 
 
 // running_mean = (1-m) rm + m mean ; running_var = (1-m) rv + m var*N/(N-1)
 __global__ void bn_running_update_kernel(const BnLayerDesc* tab, float momentum, int B) {
+  griddep_wait();
   BnLayerDesc d = tab[blockIdx.y];
   d.count *= (double)B;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -517,6 +519,7 @@ __global__ void bn_running_update_kernel(const BnLayerDesc* tab, float momentum,
 }
 
 __global__ void bn_param_grad_kernel(const BnLayerDesc* tab) {
+  griddep_wait();
   const BnLayerDesc d = tab[blockIdx.y];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d.C) return;
@@ -616,7 +619,7 @@ int launch_fix_dy(const FixDyArgs& a, cudaStream_t st) {
   const int cap = sm_count() * 4;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  fix_dy_kernel<<<blocks, 256, 0, st>>>(a);
+  PDES_CUDA(launch_pdl(fix_dy_kernel, dim3(blocks), dim3(256), 0, st, a));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
@@ -633,14 +636,14 @@ int launch_pack_weights(const PackDesc* dev_table, int n_layers, int max_elems, 
 int launch_bn_running_update(const BnLayerDesc* dev_table, int n, int maxC, float momentum,
                              int B, cudaStream_t st) {
   if (n == 0) return PDES_OK;
-  bn_running_update_kernel<<<dim3((maxC + 127) / 128, n), 128, 0, st>>>(dev_table, momentum, B);
+  PDES_CUDA(launch_pdl(bn_running_update_kernel, dim3((maxC + 127) / 128, n), dim3(128), 0, st, dev_table, momentum, B));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
 
 int launch_bn_param_grad(const BnLayerDesc* dev_table, int n, int maxC, cudaStream_t st) {
   if (n == 0) return PDES_OK;
-  bn_param_grad_kernel<<<dim3((maxC + 127) / 128, n), 128, 0, st>>>(dev_table);
+  PDES_CUDA(launch_pdl(bn_param_grad_kernel, dim3((maxC + 127) / 128, n), dim3(128), 0, st, dev_table));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

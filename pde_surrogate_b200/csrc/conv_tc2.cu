@@ -579,6 +579,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
 // filter packing: OIHW fp32 -> [chunk][tap][k-octet][piece][n][8] fp16 pieces of w * 2^kWScaleLog2
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
+  griddep_wait();
   const Tc2PackDesc d = tab[blockIdx.y];
   const int T = d.KS * d.KS;
   const int koct = d.KC >> 3;
@@ -748,7 +749,7 @@ int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaS
   int bx = (int)((max_elems / kPieces + 255) / 256);
   if (bx > 128) bx = 128;
   if (bx < 1) bx = 1;
-  pack_tc2_kernel<<<dim3(bx, n), 256, 0, st>>>(dev_table);
+  PDES_CUDA(launch_pdl(pack_tc2_kernel, dim3(bx, n), dim3(256), 0, st, dev_table));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

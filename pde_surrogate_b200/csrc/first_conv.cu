@@ -35,6 +35,7 @@ __device__ __forceinline__ void stage_input(const FirstConvArgs& a, float* xs, i
 }
 
 __global__ void __launch_bounds__(kFwdThreads) first_conv_fwd_kernel(FirstConvArgs a) {
+  griddep_wait();
   extern __shared__ __align__(16) float sm[];
   const int CoP = (a.Cout + 15) & ~15;
   float* ws = sm;                                      // [Cin*49][CoP]
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(kFwdThreads) first_conv_fwd_kernel(FirstConvAr
 // input channel in registers.  blockDim / n_items pixel subsets share a tile; a CTA walks several
 // tiles before it reduces the subsets through shared memory and issues one atomic per weight.
 __global__ void __launch_bounds__(kWgThreads) first_conv_wgrad_kernel(FirstConvArgs a, int n_tiles) {
+  griddep_wait();
   extern __shared__ __align__(16) float sm[];
   const int Co4 = (a.Cout + 3) >> 2, CoP = Co4 * 4;
   const int n_items = Co4 * kKS;
@@ -237,7 +239,7 @@ int launch_first_conv_fwd(const FirstConvArgs& a0, cudaStream_t st) {
     attr = smem;
   }
   const dim3 grid(((a.Wo + kTOW - 1) / kTOW) * ((a.Ho + kTOH - 1) / kTOH), a.B);
-  first_conv_fwd_kernel<<<grid, kFwdThreads, smem, st>>>(a);
+  PDES_CUDA(launch_pdl(first_conv_fwd_kernel, grid, dim3(kFwdThreads), smem, st, a));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
@@ -255,7 +257,7 @@ int launch_first_conv_wgrad(const FirstConvArgs& a, cudaStream_t st) {
   const int n_tiles = ((a.Wo + kTOW - 1) / kTOW) * ((a.Ho + kTOH - 1) / kTOH) * a.B;
   int grid = sm_count();
   if (grid > n_tiles) grid = n_tiles;
-  first_conv_wgrad_kernel<<<grid, kWgThreads, smem, st>>>(a, n_tiles);
+  PDES_CUDA(launch_pdl(first_conv_wgrad_kernel, dim3(grid), dim3(kWgThreads), smem, st, a, n_tiles));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

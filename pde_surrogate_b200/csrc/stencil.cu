@@ -296,6 +296,7 @@ darcy_fwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
   const uint32_t plane_bytes = (uint32_t)HW * 4u;
   const bool hasK = (K != nullptr);
   const uint32_t tx_bytes = plane_bytes * (hasK ? 4u : 3u);
+  griddep_wait();
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[0], 1);
@@ -357,6 +358,7 @@ darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
   const uint32_t plane_bytes = (uint32_t)HW * 4u;
   const bool hasK = (K != nullptr);
   const uint32_t tx_bytes = plane_bytes * (hasK ? 4u : 3u);
+  griddep_wait();
   const float a = hasK ? gw4[0] * cf.n_c : 0.f;
   const float bb = gw4[1] * cf.n_d;
   const float cdir = gw4[2] * cf.n_dir, cneu = gw4[3] * cf.n_neu;
@@ -524,7 +526,7 @@ extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int 
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
       attr_smem = smem;                                                                                   \
     }                                                                                                     \
-    darcy_fwd_tile_kernel<NT, R><<<grid, NT, smem, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm); \
+    PDES_CUDA(launch_pdl(darcy_fwd_tile_kernel<NT, R>, dim3(grid), dim3(NT), smem, st, K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm)); \
   } while (0)
     if (tv.nt == 512 && tv.R == 2) PDES_FWD_TILE(512, 2);
     else if (tv.nt == 256 && tv.R == 4) PDES_FWD_TILE(256, 4);
@@ -571,7 +573,7 @@ extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
       attr_smem = smem;                                                                                   \
     }                                                                                                     \
-    darcy_bwd_tile_kernel<NT, R><<<grid, NT, smem, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);           \
+    PDES_CUDA(launch_pdl(darcy_bwd_tile_kernel<NT, R>, dim3(grid), dim3(NT), smem, st, K, out, gw4, B, H, W, use_tb, dout, cf)); \
   } while (0)
     if (tv.nt == 512 && tv.R == 2) PDES_BWD_TILE(512, 2);
     else if (tv.nt == 256 && tv.R == 4) PDES_BWD_TILE(256, 4);

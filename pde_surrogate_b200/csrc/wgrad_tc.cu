@@ -516,6 +516,7 @@ __global__ void __launch_bounds__(256) dy_im2col_kernel(DyIm2colArgs a) {
 
 // max |x| as float bits (non-negative floats order like unsigned integers)
 __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, size_t n, unsigned* out) {
+  griddep_wait();
   unsigned m = 0u;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const unsigned u = __float_as_uint(x[i]) & 0x7fffffffu;
@@ -531,6 +532,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 // channel — and accumulated with consecutive threads on consecutive addresses.
 constexpr int kUnpackCi = 8;
 __global__ void __launch_bounds__(256) wgrad_unpack_kernel(const TcWgradUnpack* tab) {
+  griddep_wait();
   extern __shared__ float tile_u[];  // [Cout][8][T]
   const TcWgradUnpack d = tab[blockIdx.y];
   const int ci0 = blockIdx.x * kUnpackCi;
@@ -681,7 +683,7 @@ int launch_absmax(const float* x, size_t n, unsigned* out, cudaStream_t st) {
   int blocks = (int)((n / 4 + 255) / 256);
   if (blocks > 2 * sm_count()) blocks = 2 * sm_count();
   if (blocks < 1) blocks = 1;
-  absmax_kernel<<<blocks, 256, 0, st>>>(x, n, out);
+  PDES_CUDA(launch_pdl(absmax_kernel, dim3(blocks), dim3(256), 0, st, x, n, out));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
@@ -758,7 +760,7 @@ int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_cin, int 
     PDES_CUDA(cudaFuncSetAttribute(wgrad_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }
-  wgrad_unpack_kernel<<<dim3((max_cin + kUnpackCi - 1) / kUnpackCi, n), 256, smem, st>>>(dev_table);
+  PDES_CUDA(launch_pdl(wgrad_unpack_kernel, dim3((max_cin + kUnpackCi - 1) / kUnpackCi, n), dim3(256), smem, st, dev_table));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
