@@ -282,8 +282,8 @@ class DenseED(nn.Module):
             parent.add_module(path[-1], leaf)
             leaves[key] = leaf
         self._flat = self._flat_grad = self._flat_running = self._flat_nbt = None
-        # convolution implementation: 0 = tcgen05 3xTF32 where supported (default), 1 = SIMT fp32
-        # everywhere, 2 = tcgen05 single-pass TF32 (fails the 1e-4 parity bar; benchmarking only)
+        # convolution implementation: 0 = tcgen05 on two-piece fp16 operands where supported (default),
+        # 1 = CUDA-core fp32 everywhere, 3 / 4 / 5 = tensor cores for the forward / dgrad / wgrad only
         self.conv_impl = int(os.environ.get("PDES_CONV_IMPL", "0"))
         self._ex = _executor_factory(self)
         self._flatten()

@@ -61,7 +61,7 @@ int pack(const pdes_conv_desc* d, const float* w, cudaStream_t st, Packed& pk) {
   PDES_CUDA(cudaStreamSynchronize(st));  // h is a stack variable
   return launch_pack_weights(pk.tab, 1, (int)(nf + nb), st);
 }
-// tcgen05 path for the unit-test entry points: split the GEMM-K operand into bf16 piece planes,
+// tcgen05 path for the unit-test entry points: split the GEMM-K operand into fp16 piece planes,
 // pack the filter pieces into scratch, then launch the TMA-fed kernel.
 int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int transpose, cudaStream_t st) {
   const int Cin_k = transpose ? d->Cout : d->Cin;

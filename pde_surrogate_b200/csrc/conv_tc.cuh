@@ -26,29 +26,6 @@ inline float pow2f(int e) {
   return v.f;
 }
 
-struct TcConvArgs {
-  ConvArgs c;        // geometry, prologue, epilogue (weights pointer `w` unused)
-  const float* wtc;  // filter tiles packed by pack_tc_kernel
-  int N;             // GEMM N = output channels padded to a multiple of 16 (<= 256)
-  int KC;            // input channels per pipeline chunk (8, 16 or 32)
-  int NB;            // filter-tile ring depth
-  int TPB;           // filter taps per ring stage (one TMA bulk copy)
-  int nchunks;
-  int S;             // accumulator sets in TMEM (K range spread over S accumulators)
-  int prec;          // 0 = 3xTF32 (fp32 parity), 1 = single-pass TF32
-};
-
-struct TcPlan {
-  int KC, nchunks, NB, S, TPB;
-  size_t smem, pack_floats;
-};
-
-struct TcPackDesc {
-  const float* w;  // OIHW
-  float* dst;
-  int Cout, Cin, KS, N, KC, nchunks, transpose;
-};
-
 // elementwise pre-pass of the tensor-core wgrad: two fp16 piece planes of the operand
 struct ActSplitArgs {
   const float* x;        // NHWC, ldx floats per pixel (channel offset already applied)
@@ -112,10 +89,10 @@ int launch_absmax(const float* x, size_t n, unsigned* out, cudaStream_t st);
 // max_cin: largest Cin in the table; max_slab_floats: largest Cout * 8 * KS*KS in the table
 int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_cin, int max_slab_floats, cudaStream_t st);
 
-// ---- TMA-fed bf16x3 convolution (conv_tc2.cu) -----------------------------------------------
+// ---- TMA-fed two-piece fp16 convolution (conv_tc2.cu) -----------------------------------------------
 struct Tc2Plan {
   int KC, nchunks, ngroups, S, TS, AST, NB, TPB;
-  size_t smem, pack_elems;  // pack_elems: bf16 elements of the packed filter
+  size_t smem, pack_elems;  // pack_elems: 16-bit elements of the packed filter
 };
 struct Tc2Args {
   ConvArgs c;                  // geometry (B, Ho, Wo, KS, pad, Cout) and epilogue; x/w/prologue unused
@@ -134,14 +111,8 @@ struct Tc2PackDesc {
 };
 void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p);
 bool tc2_supported(int KS, int stride, int Cin_k, int N);
-// planes: [2][B][Hv][round8(Cin_k)/8][Wv][8] bf16 pieces of the GEMM-K operand (act_split_kernel)
+// planes: [2][B][Hv][round8(Cin_k)/8][Wv][8] fp16 pieces of the GEMM-K operand (act_split_kernel)
 int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Cin_k, cudaStream_t st);
 int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st);
-
-// tiling for a convolution whose GEMM-K operand has Cin_k channels and GEMM-N is N
-void tc_plan(int KS, int Cin_k, int N, TcPlan* p);
-bool tc_supported(int KS, int stride, int Cin_k, int N);
-int launch_conv_tc(const TcConvArgs& t, cudaStream_t st);
-int launch_pack_tc(const TcPackDesc* dev_table, int n, size_t max_elems, cudaStream_t st);
 
 }  // namespace pdes

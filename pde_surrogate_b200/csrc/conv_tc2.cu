@@ -1,9 +1,9 @@
 // conv_tc2.cu — TMA-fed, persistent, warp-specialised tcgen05 implicit-GEMM convolution
-// (forward and dgrad) on exact three-way bf16 operand splits.
+// (forward and dgrad) on two-piece fp16 operand splits.
 //
 // Operands never pass through registers: the activation side (BN+ReLU'd, optionally nearest-
-// upsampled input — or the corrected dY slice for dgrad) is pre-split once per layer into three
-// bf16 planes by act_split_kernel; 4-D TMA boxes (cp.async.bulk.tensor, zero fill outside the
+// upsampled input — or the corrected dY slice for dgrad) is pre-split once per layer into two
+// fp16 planes by act_split_kernel; 4-D TMA boxes (cp.async.bulk.tensor, zero fill outside the
 // image = convolution padding) drop a (TH+2)x(TW+2) halo tile of one channel chunk into shared
 // memory as [channel octet][halo pixel][16 B] — the canonical no-swizzle K-major UMMA layout —
 // and the KSxKS filter taps are shifted descriptors into that one tile (im2col-free).  Filter
@@ -41,7 +41,7 @@ constexpr int kEpiWarp0 = 4, kEpiWarps = 8;
 __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {  // D fp32, A/B fp16 (format 0), K-major
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -65,7 +65,7 @@ __device__ __forceinline__ bool elect_one() {
 }
 // same instruction with the 64-bit descriptors given as (lo, hi) words: all per-MMA address
 // arithmetic happens on the 32-bit low words (start address / LBO fields)
-__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -317,7 +317,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
 #pragma unroll
                     for (int i = 0; i < OP::n; ++i) {
                       const bool first = fresh && tap == 0 && k16 == 0 && ((FirstW<MODE>::mask >> i) & 1u);
-                      umma_bf16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
+                      umma_f16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
                                   idesc[i], first ? 0u : 1u);
                     }
                   }
@@ -354,7 +354,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
 #pragma unroll
                       for (int i = 0; i < OP::n; ++i) {
                         const bool first = fresh && tap == 0 && k16 == 0 && ((FirstW<MODE>::mask >> i) & 1u);
-                        umma_bf16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
+                        umma_f16_w(dcol[i], a_k + (uint32_t)OPF(OP::A, i) * a_piece_u, a_hi, b_k + boff[i], b_hi,
                                     idesc[i], first ? 0u : 1u);
                       }
                     }

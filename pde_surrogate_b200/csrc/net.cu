@@ -42,11 +42,8 @@ struct Layer {
   int CinP, CoP, CoutPb, CiPb;
   bool last_consumer;
   // tcgen05 path
-  bool tc_fwd, tc_bwd;
-  TcPlan pf, pb;     // tiling of the forward / dgrad GEMM
   int Nf, Nb;        // padded GEMM-N (Cout / Cin rounded up to 16)
-  size_t wtf, wtb;   // float offsets of the packed filter tiles
-  bool tc2_fwd, tc2_bwd;  // TMA-fed bf16x3 tcgen05 path (conv_tc2.cu)
+  bool tc2_fwd, tc2_bwd;  // TMA-fed two-piece fp16 tcgen05 path (conv_tc2.cu)
   Tc2Plan p2f, p2b;
   size_t w2f, w2b;   // float offsets of the packed fp16 filter pieces
   size_t planes;     // float offset of this layer's activation piece planes [2][B][Hv][Wv][Cp] fp16
@@ -87,11 +84,9 @@ struct pdes_net {
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   int n_side = 1;
   int n_bn = 0, maxC = 0, max_pack = 0;
-  int n_tc = 0, n_wg = 0, n_tc2 = 0;
+  int n_wg = 0, n_tc2 = 0;
   size_t max_tc2_pack = 0;
-  size_t max_tc_pack = 0;
   int max_wg_elems = 0, max_wg_cin = 0;  // largest unpack slab (Cout * 8 * taps) / Cin over the wgrad layers
-  int prec = 0;
   // executor-level CUDA graphs: the launch sequence of one forward / backward at a given batch size is
   // captured once (second call) and replayed afterwards; static input/output staging keeps pointers stable
   struct GraphSlot {
@@ -182,10 +177,8 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.CoutPb = rup(Cout, 4);
   L.CiPb = rup(Cin, 16);
   L.last_consumer = false;
-  L.tc_fwd = L.tc_bwd = false;
   L.Nf = rup(Cout, 16);
   L.Nb = rup(Cin, 16);
-  L.wtf = L.wtb = 0;
   L.tc2_fwd = L.tc2_bwd = false;
   L.w2f = L.w2b = L.planes = L.planesB = 0;
   memset(&L.p2f, 0, sizeof(L.p2f));
@@ -196,8 +189,6 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
-  memset(&L.pf, 0, sizeof(L.pf));
-  memset(&L.pb, 0, sizeof(L.pb));
   n->layers.push_back(L);
 }
 
@@ -416,7 +407,7 @@ int build(pdes_net* n) {
   n->off_doubles = (n->ws_floats * sizeof(float) + 255) & ~(size_t)255;
   n->off_tables = (n->off_doubles + n->ws_doubles * sizeof(double) + 255) & ~(size_t)255;
   n->ws_bytes = n->off_tables + sizeof(PackDesc) * n->layers.size() +
-                sizeof(BnLayerDesc) * (size_t)n->n_bn + sizeof(TcPackDesc) * (size_t)n->n_tc +
+                sizeof(BnLayerDesc) * (size_t)n->n_bn +
                 sizeof(TcWgradUnpack) * (size_t)n->n_wg + sizeof(Tc2PackDesc) * (size_t)n->n_tc2 + 256;
   return PDES_OK;
 }
@@ -433,14 +424,9 @@ inline BnLayerDesc* bn_table(const pdes_net* n) {
   return reinterpret_cast<BnLayerDesc*>(n->ws + n->off_tables + sizeof(PackDesc) * n->layers.size());
 }
 
-inline TcPackDesc* tc_table(const pdes_net* n) {
-  return reinterpret_cast<TcPackDesc*>(n->ws + n->off_tables + sizeof(PackDesc) * n->layers.size() +
-                                       sizeof(BnLayerDesc) * (size_t)n->n_bn);
-}
-
 inline TcWgradUnpack* wg_table(const pdes_net* n) {
-  return reinterpret_cast<TcWgradUnpack*>(reinterpret_cast<unsigned char*>(tc_table(n)) +
-                                          sizeof(TcPackDesc) * (size_t)n->n_tc);
+  return reinterpret_cast<TcWgradUnpack*>(n->ws + n->off_tables + sizeof(PackDesc) * n->layers.size() +
+                                          sizeof(BnLayerDesc) * (size_t)n->n_bn);
 }
 
 inline Tc2PackDesc* tc2_table(const pdes_net* n) {
@@ -618,25 +604,6 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       bt.push_back(b);
     }
   }
-  std::vector<TcPackDesc> tt;
-  for (const auto& L : n->layers) {
-    for (int dir = 0; dir < 2; ++dir) {
-      if (!(dir == 0 ? L.tc_fwd : L.tc_bwd)) continue;
-      TcPackDesc d;
-      d.w = n->p + L.w_off;
-      d.dst = wsf(n, dir == 0 ? L.wtf : L.wtb);
-      d.Cout = L.Cout;
-      d.Cin = L.Cin;
-      d.KS = L.KS;
-      d.N = dir == 0 ? L.Nf : L.Nb;
-      d.KC = dir == 0 ? L.pf.KC : L.pb.KC;
-      d.nchunks = dir == 0 ? L.pf.nchunks : L.pb.nchunks;
-      d.transpose = dir;
-      tt.push_back(d);
-    }
-  }
-  if (!tt.empty())
-    PDES_CUDA(cudaMemcpy(tc_table(n), tt.data(), sizeof(TcPackDesc) * tt.size(), cudaMemcpyHostToDevice));
   std::vector<Tc2PackDesc> t2;
   for (const auto& L : n->layers) {
     for (int dir = 0; dir < 2; ++dir) {
@@ -685,11 +652,10 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
 }
 
 extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
-  // 0 = tcgen05 (3xTF32) where supported, 1 = SIMT fp32 everywhere, 2 = tcgen05 single-pass TF32
+  // 0 = tcgen05 (two-piece fp16) where supported, 1 = CUDA-core fp32 everywhere, 2 = same as 0,
   // 3 / 4 / 5 = tcgen05 for the forward only / the dgrad only / the wgrad only (diagnostics)
   PDES_REQUIRE(n && impl >= 0 && impl <= 5, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..5");
   n->conv_impl = impl == 1 ? 1 : 0;
-  n->prec = impl == 2 ? 1 : 0;
   n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : (impl == 5 ? 4 : 7));
   return PDES_OK;
 }

@@ -25,17 +25,6 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    smem_u32(bar))
@@ -59,7 +48,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // UMMA shared-memory descriptor, SWIZZLE_NONE, K-major canonical layout
-//   ((8,m),(4,2)) : ((16 B, SBO), (4 B, LBO))   [tf32: 4 elements per 16-byte core-matrix row]
+//   8 rows x 16 B core matrices (8 fp16 elements per row); SBO = next 8-row group, LBO = next k octet
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
@@ -67,17 +56,6 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
   return d;
 }
-// instruction descriptor: D fp32, A/B tf32, both K-major, M x N
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-  lo = v - hi;
-}
-
 __device__ __forceinline__ void bn_consts_tc(const BnSrc& s, int c, float& scale, float& shift,
                                              float& mean, float& invstd) {
   if (s.scale != nullptr) {

@@ -61,7 +61,7 @@ __device__ __forceinline__ void fp16_split2(float x, uint32_t& p0, uint32_t& p1)
 __device__ __forceinline__ uint32_t make_idesc_f16_mn(int M, int N) {
   return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -83,7 +83,7 @@ __device__ __forceinline__ bool elect_one_w() {
       : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void umma_bf16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+__device__ __forceinline__ void umma_f16_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                             uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
@@ -420,7 +420,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const int tap = tap0 + j;
               if (j < ntap) {
                 const uint32_t a_lo = a_lo0 + (uint32_t)((r + tap / KS) * HWp + (tap % KS));
-                umma_bf16_w(tmem_base + (uint32_t)(j * NW), a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                umma_f16_w(tmem_base + (uint32_t)(j * NW), a_lo, a_hi, b_lo, b_hi, idesc, acc);
               }
             }
           }

@@ -64,7 +64,7 @@ def test_conv_fwd_dgrad_wgrad(case):
 
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tensor_core(case):
-    """tcgen05 3xTF32 kernels (forward and dgrad) against the same fp64 reference."""
+    """tcgen05 kernels on two-piece fp16 operands (forward, dgrad, wgrad) against the same fp64 reference."""
     _run_case(case, 2)
 
 

@@ -48,7 +48,7 @@ def test_train_step_matches_reference(golden_dir, name, impl):
     from utils.image_gradient import SobelFilter
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     model, K, cfg = _model(g)
-    model.conv_impl = impl  # 0: tcgen05 3xTF32 where supported, 1: SIMT fp32 everywhere
+    model.conv_impl = impl  # 0: tcgen05 (two-piece fp16 operands) where supported, 1: CUDA-core fp32 everywhere
     assert tuple(model.model_size) == tuple(int(v) for v in g["model_size"])
     sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
     # eval forward with the given running statistics
