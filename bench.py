@@ -98,11 +98,36 @@ class ClockSampler(object):
                     samples=len(sm), reasons=sorted(reasons))
 
 
+def host_threads():
+    """All host threads the CPU arm can use: the physical cores visible to this process (what torch picks
+    by default) — set explicitly because torchrun exports OMP_NUM_THREADS=1 to every rank."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = set()
+    try:
+        phys = core = None
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("physical id"):
+                phys = ln.split(":")[1].strip()
+            elif ln.startswith("core id"):
+                core = ln.split(":")[1].strip()
+            elif not ln.strip():
+                if phys is not None and core is not None:
+                    cores.add((phys, core))
+                phys = core = None
+    except OSError:
+        pass
+    n = len(cores) if cores else avail
+    return max(1, min(n, avail))
+
+
 def cpu_baseline(steps, threads=None):
     """Oracle port (same PyTorch CPU kernels as the reference) on the host cores, bounded sample."""
     import torch
     from oracle.cpu_train import CpuTrainer
-    tr = CpuTrainer(IMSIZE, threads=threads)
+    tr = CpuTrainer(IMSIZE, threads=threads or host_threads())
     g = torch.Generator().manual_seed(1)
     batches = [torch.exp(0.5 * torch.randn(BATCH, 1, IMSIZE, IMSIZE, generator=g)) for _ in range(steps)]
     sps, dt = tr.timed(batches, warmup=1)
@@ -118,7 +143,7 @@ def run_reference(args, rank):
         return
     import torch
     from oracle.cpu_train import CpuTrainer
-    tr = CpuTrainer(IMSIZE)
+    tr = CpuTrainer(IMSIZE, threads=host_threads())
     g = torch.Generator().manual_seed(1)
     n = max(1, min(args.steps, 40))
     batches = [torch.exp(0.5 * torch.randn(BATCH, 1, IMSIZE, IMSIZE, generator=g)) for _ in range(min(n, 8))]
