@@ -422,34 +422,53 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
         Wd = (Wd + 1) >> 1;
       }
       const size_t pix = ((size_t)b * Hd + oy) * Wd + ox;
+      // The BatchNorm-backward operands do not depend on the accumulator.  x of the consumer's input is
+      // needed first (ReLU mask): it is software-pipelined one column chunk ahead — chunk 0 is fetched
+      // while this tile's MMAs are still running — so its L2 round trip never sits on the chunk's path.
+      const bool bnb = a.epi == EPI_BNBWD && valid;
+      float xn[16];
+      auto load_x = [&](int n0) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xn[i] = 0.f;
+        if (bnb && n0 < N) {
+          const float* xs = a.fx + pix * a.ldfx + n0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            if (n0 + i + 3 < a.Cout) {
+              const float4 f = __ldg(reinterpret_cast<const float4*>(xs + i));
+              xn[i] = f.x; xn[i + 1] = f.y; xn[i + 2] = f.z; xn[i + 3] = f.w;
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (n0 + i + k < a.Cout) xn[i + k] = xs[i + k];
+            }
+          }
+        }
+      };
+      load_x(half * 16);
       mbar_wait(&acc_full[ts], (uint32_t)((tile_it / TS) & 1));
       tc_fence_after();
       if (ew == 0 && lane == 0 && tile_it == 0) DBG(6);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ts * ts_cols;
       for (int n0 = half * 16; n0 < N; n0 += 32) {
-        // operands of the BatchNorm-backward epilogue do not depend on the accumulator: fetch first
         float xv[16], gv[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) xv[i] = gv[i] = 0.f;
-        if (a.epi == EPI_BNBWD && valid) {
-          const float* xs = a.fx + pix * a.ldfx + n0;
+        for (int i = 0; i < 16; ++i) {
+          xv[i] = xn[i];
+          gv[i] = 0.f;
+        }
+        load_x(n0 + 32);  // next chunk of this warp
+        if (bnb && a.g_accum) {
           const float* gp = a.G + pix * a.ldG + n0;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) {
             if (n0 + i + 3 < a.Cout) {
-              const float4 f = __ldg(reinterpret_cast<const float4*>(xs + i));
-              xv[i] = f.x; xv[i + 1] = f.y; xv[i + 2] = f.z; xv[i + 3] = f.w;
-              if (a.g_accum) {
-                const float4 g4 = *reinterpret_cast<const float4*>(gp + i);
-                gv[i] = g4.x; gv[i + 1] = g4.y; gv[i + 2] = g4.z; gv[i + 3] = g4.w;
-              }
+              const float4 g4 = *reinterpret_cast<const float4*>(gp + i);
+              gv[i] = g4.x; gv[i + 1] = g4.y; gv[i + 2] = g4.z; gv[i + 3] = g4.w;
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                if (n0 + i + k < a.Cout) {
-                  xv[i + k] = xs[i + k];
-                  if (a.g_accum) gv[i + k] = gp[i + k];
-                }
+                if (n0 + i + k < a.Cout) gv[i + k] = gp[i + k];
             }
           }
         }
