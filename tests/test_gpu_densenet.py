@@ -228,3 +228,33 @@ def test_arbitrary_output_gradient_mse(golden_dir):
     ref = np.concatenate([sd64[n].grad.numpy().ravel() for n in names])
     got = np.concatenate([params[n].grad.detach().double().cpu().numpy().ravel() for n in names])
     assert rel(got, ref) < 5e-3, rel(got, ref)   # flip-tolerant aggregate (see test_train_step_matches_reference)
+
+
+def test_batch_size_changes_rebind_executor(golden_dir):
+    """The script alternates training batches (32) with larger evaluation batches (64,
+    train_codec_mixed_residual.py:166-206): a larger batch re-creates the executor (workspace, side
+    stream, tables) and the smaller one must keep working on it afterwards."""
+    from models.darcy import conv_boundary_condition
+    g = np.load(os.path.join(golden_dir, "densenet_small16.npz"))
+    model, K, cfg = _model(g)
+    B = K.shape[0]
+
+    def train_out():
+        model.train()
+        model.zero_grad()
+        out = model(K)
+        d, n = conv_boundary_condition(out)
+        (d + n).backward()
+        return out.detach().clone(), model.flat_parameters()[1].clone()
+
+    o1, g1 = train_out()
+    model.eval()
+    with torch.no_grad():
+        big = model(torch.cat([K, K, K], 0))           # 3x the batch: new executor
+        small = model(K[:1])                           # and a smaller one on the same executor
+    assert big.shape[0] == 3 * B and small.shape[0] == 1
+    assert rel(big[:B].cpu().numpy(), big[B:2 * B].cpu().numpy()) < 1e-6
+    assert rel(small.cpu().numpy(), big[:1].cpu().numpy()) < 1e-6
+    o2, g2 = train_out()
+    assert rel(o2.cpu().numpy(), o1.cpu().numpy()) < 1e-6
+    assert rel(g2.cpu().numpy(), g1.cpu().numpy()) < 1e-5
