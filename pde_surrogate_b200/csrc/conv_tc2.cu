@@ -52,6 +52,10 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -451,27 +455,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       if (ew == 0 && lane == 0 && tile_it == 0) DBG(6);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ts * ts_cols;
       for (int n0 = half * 16; n0 < N; n0 += 32) {
-        float xv[16], gv[16];
+        float xv[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          xv[i] = xn[i];
-          gv[i] = 0.f;
-        }
+        for (int i = 0; i < 16; ++i) xv[i] = xn[i];
         load_x(n0 + 32);  // next chunk of this warp
-        if (bnb && a.g_accum) {
-          const float* gp = a.G + pix * a.ldG + n0;
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            if (n0 + i + 3 < a.Cout) {
-              const float4 g4 = *reinterpret_cast<const float4*>(gp + i);
-              gv[i] = g4.x; gv[i + 1] = g4.y; gv[i + 2] = g4.z; gv[i + 3] = g4.w;
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (n0 + i + k < a.Cout) gv[i + k] = gp[i + k];
-            }
-          }
-        }
         // accumulator: small groups first, then the big one, over all sets
         float v[16];
 #pragma unroll
@@ -531,17 +518,21 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
               const float xh = fmaf(xv[i], c.z, c.w);
               s1[i] = dz;
               s2[i] = dz * xh;
-              o[i] = fmaf(c.x, dz, gv[i]);
+              o[i] = c.x * dz;  // this consumer's contribution to dL/dx
               gmx = fmaxf(gmx, fabsf(o[i]));
             }
+            // the first consumer to run stores, the others add with fire-and-forget vector reductions:
+            // no read of the gradient row, nothing to wait for (one add per element and kernel, kernels
+            // are stream-ordered: the sum is as deterministic as a read-modify-write)
 #pragma unroll
             for (int i = 0; i < 16; i += 4) {
               if (n0 + i + 3 < a.Cout) {
-                *reinterpret_cast<float4*>(gp + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                if (a.g_accum) red_add_v4(gp + i, o[i], o[i + 1], o[i + 2], o[i + 3]);
+                else *reinterpret_cast<float4*>(gp + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
               } else {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  if (n0 + i + k < a.Cout) gp[i + k] = o[i + k];
+                  if (n0 + i + k < a.Cout) gp[i + k] = a.g_accum ? gp[i + k] + o[i + k] : o[i + k];
               }
             }
           }

@@ -183,8 +183,12 @@ __global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int x
   float mul = a.scale;
   if (a.dyn_max != nullptr) {
     // power of two that brings the buffer's running |gradient| maximum to 2^kDyTargetLog2
+    // *dyn_max = largest single contribution any dgrad epilogue added to this gradient buffer; a slice
+    // with n_cons consumers is bounded by n_cons times that (the contributions are summed)
     const unsigned m = *a.dyn_max;
     int e = m == 0u ? 0 : kDyTargetLog2 - ((int)((m >> 23) & 0xffu) - 127);
+    if (a.fix)
+      for (int c = 1; c < a.fx.n_cons; c <<= 1) --e;
     e = e < -100 ? -100 : (e > 100 ? 100 : e);
     mul = __uint_as_float((uint32_t)(e + 127) << 23);
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.dyn_inv = __uint_as_float((uint32_t)(127 - e) << 23);
