@@ -201,6 +201,12 @@ int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const float* scal
                       const float* shift, const float* dy, float* dw, int impl,
                       void* stream);
 
+/* Diagnostics, host only: the tiling of the tensor-core convolution kernel for a GEMM-K operand of Cin_k
+ * channels and N (multiple of 16, <= 256) output channels: out[0..10] = supported, channels per chunk,
+ * chunks, accumulator groups, accumulator sets, accumulator stages, activation ring depth, filter ring
+ * depth, taps per filter stage, dynamic shared memory bytes, TMEM columns. */
+int pdes_conv_tc_plan(int KS, int Cin_k, int N, int64_t out[11]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -417,3 +417,26 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   cudaFreeAsync(buf, st);
   return rc;
 }
+
+// Diagnostics (host only): the tiling the tensor-core convolution kernel would use for a GEMM-K operand of
+// Cin_k channels and N (padded) output channels.  out[0..10] = supported, KC, nchunks, ngroups, S, TS, AST,
+// NB, TPB, shared-memory bytes, TMEM columns.
+extern "C" int pdes_conv_tc_plan(int KS, int Cin_k, int N, int64_t out[11]) {
+  PDES_REQUIRE(out != nullptr, PDES_ERR_INVALID, "pdes_conv_tc_plan: null output");
+  PDES_REQUIRE((KS == 1 || KS == 3 || KS == 5 || KS == 7) && Cin_k >= 1 && N >= 16 && N <= 256 && (N & 15) == 0,
+               PDES_ERR_INVALID, "pdes_conv_tc_plan: KS in {1,3,5,7}, N a multiple of 16 in 16..256");
+  Tc2Plan p;
+  tc2_plan(KS, Cin_k, N, &p);
+  out[0] = tc2_supported(KS, 1, Cin_k, N) ? 1 : 0;
+  out[1] = p.KC;
+  out[2] = p.nchunks;
+  out[3] = p.ngroups;
+  out[4] = p.S;
+  out[5] = p.TS;
+  out[6] = p.AST;
+  out[7] = p.NB;
+  out[8] = p.TPB;
+  out[9] = (int64_t)p.smem;
+  out[10] = (int64_t)p.S * p.ngroups * N * p.TS;
+  return PDES_OK;
+}

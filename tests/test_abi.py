@@ -46,3 +46,32 @@ def test_host_only_calls(built_lib):
     cfg.n_blocks = 2  # even number of blocks is rejected like the reference (codec.py:231-233)
     assert built_lib.pdes_densenet_create(byref(cfg), byref(h)) != 0
     assert b"odd" in built_lib.pdes_last_error()
+
+
+def test_every_densenet_layer_has_a_tensor_core_plan_within_the_sm_limits(built_lib):
+    """Host-only check of the tiling logic: for every convolution of DenseED (blocks [6,8,6] and a few other
+    layouts) but the first, forward (K = Cin, N = Cout) and dgrad (K = Cout, N = Cin) get a plan that fits an
+    sm_100a SM: <= 227 KB of dynamic shared memory, <= 512 TMEM columns, rings at least 2 deep."""
+    from ctypes import c_int64
+    from oracle import pdes_oracle as orc
+
+    def rup(v, m):
+        return (v + m - 1) // m * m
+
+    n_checked = 0
+    for blocks, growth, init in (([6, 8, 6], 16, 48), ([3, 4, 3], 16, 48), ([2, 2, 2], 8, 16), ([4, 4, 4, 4, 4], 24, 64)):
+        plan = orc.densenet_plan(1, 3, 64, blocks, growth_rate=growth, init_features=init)
+        convs = [(L["cin"], L["cout"], L["k"]) for L in plan]  # every stage holds exactly one convolution
+        for cin, cout, k in convs[1:]:
+            for ck, n in ((cin, rup(cout, 16)), (cout, rup(cin, 16))):
+                if n > 256:
+                    continue  # served by the CUDA-core kernels
+                out = (c_int64 * 11)()
+                assert built_lib.pdes_conv_tc_plan(k, ck, n, out) == 0
+                sup, KC, nchunks, ngroups, S, TS, AST, NB, TPB, smem, tmem = [int(v) for v in out]
+                assert sup == 1, (blocks, cin, cout, k, ck, n, list(out))
+                assert KC in (16, 32) and nchunks * KC >= ck and ngroups == 2
+                assert smem <= 227 * 1024 and tmem <= 512 and AST >= 2 and NB >= 2
+                assert (k * k) % TPB == 0 and 1 <= S <= 4 and TS in (1, 2)
+                n_checked += 1
+    assert n_checked > 100
