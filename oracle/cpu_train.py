@@ -15,12 +15,19 @@ from . import pdes_oracle as orc
 
 class CpuTrainer(object):
     def __init__(self, imsize=64, blocks=(6, 8, 6), growth_rate=16, init_features=48, lr=1e-3, seed=1,
-                 threads=None):
+                 threads=None, device="cpu"):
+        """device="cpu": the reference's CPU path.  device="cuda": the SAME program on PyTorch's eager CUDA
+        kernels (cuDNN convolutions, native batch norm) - the library baseline of bench.py, i.e. what the
+        unmodified reference would run on the same GPU."""
         if threads:
             torch.set_num_threads(int(threads))
         self.threads = torch.get_num_threads()
+        self.device = torch.device(device)
         self.plan = orc.densenet_plan(1, 3, imsize, blocks, growth_rate, init_features)
         self.sd = orc.make_state(self.plan, seed)
+        if self.device.type != "cpu":
+            for k in self.sd:
+                self.sd[k] = self.sd[k].to(self.device)
         self.names = orc.param_names(self.plan)
         for n in self.names:
             self.sd[n].requires_grad_(True)

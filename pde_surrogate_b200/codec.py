@@ -134,6 +134,7 @@ class CudaExecutor(object):
         self.ws = None
         self.bound = None
         self.applied_impl = None
+        self.fwd_gen = 0
 
     def _ensure(self, x):
         m = self.m
@@ -151,7 +152,8 @@ class CudaExecutor(object):
                              % (c["in_channels"], c["imsize"], c["imsize"], tuple(x.shape)))
         B = x.shape[0]
         if self.handle is None or B > self.handle.max_batch:
-            self.handle = _NetHandle(c, max(B, 1))
+            with torch.cuda.device(x.device):
+                self.handle = _NetHandle(c, max(B, 1))
             self.ws, self.bound = None, None
             self.applied_impl = None
         if self.applied_impl != m.conv_impl:
@@ -172,6 +174,7 @@ class CudaExecutor(object):
 
     def forward(self, x, training):
         self._ensure(x)
+        self.fwd_gen += 1   # the executor keeps ONE set of saved activations: see _DenseEDTrainFn.backward
         x = x.contiguous()
         c = self.m._cfg
         out = torch.empty(x.shape[0], c["out_channels"], c["imsize"], c["imsize"], dtype=torch.float32,
@@ -206,7 +209,9 @@ class _DenseEDTrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, module):
         ctx.module = module
-        return module._ex.forward(x, True)
+        out = module._ex.forward(x, True)
+        ctx.fwd_gen = getattr(module._ex, "fwd_gen", None)
+        return out
 
     @staticmethod
     def backward(ctx, dout):
@@ -214,6 +219,10 @@ class _DenseEDTrainFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             raise NotImplementedError("pde_surrogate_b200.DenseED: gradient w.r.t. the network input is "
                                       "not implemented (the training path never needs it)")
+        if ctx.fwd_gen != getattr(m._ex, "fwd_gen", None):
+            raise RuntimeError("pde_surrogate_b200.DenseED: another forward pass (training or evaluation) ran "
+                               "between this output's forward and its backward; the executor keeps the saved "
+                               "activations of the LAST forward only - call backward() before the next forward")
         m._prepare_grads()
         m._ex.backward(dout)
         return None, None, None

@@ -33,14 +33,23 @@ bool pdl_enabled() {
   return v != 0;
 }
 
+int cur_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return dev < 0 ? 0 : (dev >= kMaxDevices ? kMaxDevices - 1 : dev);
+}
+
 int sm_count() {
-  static int cached = -1;
-  if (cached > 0) return cached;
-  int dev = 0, n = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  static int cached[kMaxDevices];  // zero-initialised
+  const int dev = cur_device();
+  if (cached[dev] > 0) return cached[dev];
+  int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
     return 148;
-  cached = n;
+  cached[dev] = n;
   return n;
 }
 

@@ -33,7 +33,24 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define PDES_LAUNCH_CHECK() PDES_CUDA(cudaGetLastError())
 
-int sm_count();
+int sm_count();      // of the CURRENT device (cached per device)
+int cur_device();    // cudaGetDevice(), clamped to [0, kMaxDevices)
+constexpr int kMaxDevices = 64;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device (per-context) attribute: the high-water
+// mark already applied is tracked per device, so that a process driving several GPUs raises it on each
+struct SmemAttr {
+  size_t v[kMaxDevices];
+  SmemAttr() { for (int i = 0; i < kMaxDevices; ++i) v[i] = 0; }
+};
+#define PDES_ENSURE_SMEM(kernel, bytes)                                                                   \
+  do {                                                                                                    \
+    static ::pdes::SmemAttr _pdes_attr;                                                                   \
+    size_t& _cur = _pdes_attr.v[::pdes::cur_device()];                                                    \
+    if ((size_t)(bytes) > _cur) {                                                                         \
+      PDES_CUDA(cudaFuncSetAttribute((kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes))); \
+      _cur = (size_t)(bytes);                                                                             \
+    }                                                                                                     \
+  } while (0)
 bool pdl_enabled();  // programmatic dependent launch of the kernel chain (opt-in: env PDES_PDL=1)
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may start (and run its

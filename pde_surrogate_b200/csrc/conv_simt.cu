@@ -548,12 +548,7 @@ int launch_conv_t(const ConvArgs& a, cudaStream_t st) {
   const size_t smem = conv_smem_bytes(a.Cin, KS, a.stride, TN);
   PDES_REQUIRE(smem <= 227 * 1024, PDES_ERR_UNSUPPORTED,
                "conv_simt: tile needs %zu bytes of shared memory", smem);
-  static size_t attr = 0;
-  if (smem > attr) {
-    PDES_CUDA(cudaFuncSetAttribute(conv_simt_kernel<TN, KS>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  PDES_ENSURE_SMEM((conv_simt_kernel<TN, KS>), smem);
   const int tiles = ((a.Wo + kTile - 1) / kTile) * ((a.Ho + kTile - 1) / kTile) * a.B;
   dim3 grid(tiles, (a.Cout + TN - 1) / TN);
   conv_simt_kernel<TN, KS><<<grid, kConvThreads, smem, st>>>(a);
@@ -566,12 +561,7 @@ int launch_wgrad_t(const WgradArgs& a, cudaStream_t st) {
   const size_t smem = wgrad_smem_bytes(a.Cin, KS, a.stride, TN);
   PDES_REQUIRE(smem <= 227 * 1024, PDES_ERR_UNSUPPORTED,
                "wgrad_simt: tile needs %zu bytes of shared memory", smem);
-  static size_t attr = 0;
-  if (smem > attr) {
-    PDES_CUDA(cudaFuncSetAttribute(wgrad_simt_kernel<TN, KS, TR>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  PDES_ENSURE_SMEM((wgrad_simt_kernel<TN, KS, TR>), smem);
   const int CinP4 = (a.Cin + 3) & ~3;
   const int KC = CinP4 < 16 ? CinP4 : 16;
   dim3 grid(a.B, (CinP4 + KC - 1) / KC, ((a.Cout + TN - 1) / TN) * (KS / TR));

@@ -731,12 +731,7 @@ int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Ci
   const int mode = 2 * t.N <= 256 ? 0 : 1;
 #define PDES_TC2_LAUNCH(KSV, MODEV)                                                                          \
   {                                                                                                          \
-    static size_t attr = 0;                                                                                  \
-    if (smem > attr) {                                                                                       \
-      PDES_CUDA(cudaFuncSetAttribute(conv_tc2_kernel<KSV, MODEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)smem));                                                            \
-      attr = smem;                                                                                           \
-    }                                                                                                        \
+    PDES_ENSURE_SMEM((conv_tc2_kernel<KSV, MODEV>), smem);                                                   \
     PDES_CUDA(launch_pdl(conv_tc2_kernel<KSV, MODEV>, dim3(grid), dim3(kThreads), smem, st, tm, t));         \
   }
 #define PDES_TC2_MODES(KSV)                        \

@@ -233,11 +233,7 @@ int launch_first_conv_fwd(const FirstConvArgs& a0, cudaStream_t st) {
                "first_conv: unsupported shape (Cin %d, Cout %d, k%d s%d)", a.Cin, a.Cout, a.KS, a.stride);
   a.vec_ok = (((a.ldy | a.coff) & 3) == 0 && ((uintptr_t)a.y & 15u) == 0) ? 1 : 0;
   const size_t smem = fwd_smem(a.Cin, a.Cout);
-  static size_t attr = 0;
-  if (smem > attr) {
-    PDES_CUDA(cudaFuncSetAttribute(first_conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  PDES_ENSURE_SMEM(first_conv_fwd_kernel, smem);
   const dim3 grid(((a.Wo + kTOW - 1) / kTOW) * ((a.Ho + kTOH - 1) / kTOH), a.B);
   PDES_CUDA(launch_pdl(first_conv_fwd_kernel, grid, dim3(kFwdThreads), smem, st, a));
   PDES_LAUNCH_CHECK();
@@ -249,11 +245,7 @@ int launch_first_conv_wgrad(const FirstConvArgs& a, cudaStream_t st) {
                "first_conv wgrad: unsupported shape (Cin %d, Cout %d, k%d s%d)", a.Cin, a.Cout, a.KS, a.stride);
   PDES_REQUIRE(a.dy && a.dw, PDES_ERR_INVALID, "first_conv wgrad: null pointer");
   const size_t smem = wg_smem(a.Cin, a.Cout);
-  static size_t attr = 0;
-  if (smem > attr) {
-    PDES_CUDA(cudaFuncSetAttribute(first_conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  PDES_ENSURE_SMEM(first_conv_wgrad_kernel, smem);
   const int n_tiles = ((a.Wo + kTOW - 1) / kTOW) * ((a.Ho + kTOH - 1) / kTOH) * a.B;
   int grid = sm_count();
   if (grid > n_tiles) grid = n_tiles;

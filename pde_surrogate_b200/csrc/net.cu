@@ -82,7 +82,7 @@ struct pdes_net {
   // pass (nothing but the final unpack reads them), so they overlap with the dgrad chain
   cudaStream_t side[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
-  int n_side = 1;
+  int n_side = 0, n_side_req = 1, side_dev = -1;
   int n_bn = 0, maxC = 0, max_pack = 0;
   int n_wg = 0, n_tc2 = 0;
   size_t max_tc2_pack = 0;
@@ -466,27 +466,52 @@ extern "C" int pdes_densenet_create(const pdes_densenet_config* cfg, pdes_net_t*
   }
   {
     // PDES_WGRAD_STREAMS = 0 | 1 | 2 side streams for the weight-gradient kernels (default 1;
-    // measured on B200: eager step 4.36 -> 3.97 ms with one, 4.07 ms with two)
+    // measured on B200: eager step 4.36 -> 3.97 ms with one, 4.07 ms with two).  The streams and
+    // events themselves are created by bind(), on the device that owns the workspace: this
+    // constructor touches no device (it also serves as a pure layout query).
     const char* e = getenv("PDES_WGRAD_STREAMS");
-    n->n_side = e ? atoi(e) : 1;
-    if (n->n_side < 0) n->n_side = 0;
-    if (n->n_side > 2) n->n_side = 2;
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least priority
-    for (int k = 0; k < n->n_side; ++k) {
-      if (cudaStreamCreateWithPriority(&n->side[k], cudaStreamNonBlocking, lo) != cudaSuccess ||
-          cudaEventCreateWithFlags(&n->ev_fork[k], cudaEventDisableTiming) != cudaSuccess ||
-          cudaEventCreateWithFlags(&n->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
-        cudaGetLastError();
-        n->n_side = 0;
-        n->side[0] = nullptr;
-        break;
-      }
-    }
+    n->n_side_req = e ? atoi(e) : 1;
+    if (n->n_side_req < 0) n->n_side_req = 0;
+    if (n->n_side_req > 2) n->n_side_req = 2;
+    n->n_side = 0;
   }
   *out = n;
   return PDES_OK;
 }
+
+namespace {
+void drop_side_streams(pdes_net* n) {
+  for (int k = 0; k < 2; ++k) {
+    if (n->side[k]) cudaStreamDestroy(n->side[k]);
+    if (n->ev_fork[k]) cudaEventDestroy(n->ev_fork[k]);
+    if (n->ev_join[k]) cudaEventDestroy(n->ev_join[k]);
+    n->side[k] = nullptr;
+    n->ev_fork[k] = n->ev_join[k] = nullptr;
+  }
+  n->n_side = 0;
+  n->side_dev = -1;
+}
+// side streams / fork-join events live on the device current at bind() time
+void ensure_side_streams(pdes_net* n) {
+  const int dev = cur_device();
+  if (n->side_dev == dev) return;
+  drop_side_streams(n);
+  n->side_dev = dev;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least priority
+  for (int k = 0; k < n->n_side_req; ++k) {
+    if (cudaStreamCreateWithPriority(&n->side[k], cudaStreamNonBlocking, lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n->ev_fork[k], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&n->ev_join[k], cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      drop_side_streams(n);
+      n->side_dev = dev;
+      return;
+    }
+    n->n_side = k + 1;
+  }
+}
+}  // namespace
 
 extern "C" void pdes_densenet_destroy(pdes_net_t* net) {
   if (!net) return;
@@ -494,11 +519,7 @@ extern "C" void pdes_densenet_destroy(pdes_net_t* net) {
     if (gs.exec) cudaGraphExecDestroy(gs.exec);
   for (auto& gs : net->gbwd)
     if (gs.exec) cudaGraphExecDestroy(gs.exec);
-  for (int k = 0; k < 2; ++k) {
-    if (net->side[k]) cudaStreamDestroy(net->side[k]);
-    if (net->ev_fork[k]) cudaEventDestroy(net->ev_fork[k]);
-    if (net->ev_join[k]) cudaEventDestroy(net->ev_join[k]);
-  }
+  drop_side_streams(net);
   delete net;
 }
 
@@ -556,6 +577,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
   // The caller zero-fills the workspace on ITS stream (possibly a non-blocking one that the
   // synchronous table uploads below do not order against): wait for everything first.
   PDES_CUDA(cudaDeviceSynchronize());
+  ensure_side_streams(n);
   for (auto& gs : n->gfwd) {
     if (gs.exec) cudaGraphExecDestroy(gs.exec);
     gs = pdes_net::GraphSlot();
@@ -892,6 +914,8 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     mark(n, st, "bn_running_update");
     n->last_B = B;
     n->fwd_train_done = true;
+  } else {
+    n->fwd_train_done = false;  // the evaluation pass overwrote the activations a backward would need
   }
   return PDES_OK;
 }
@@ -1273,10 +1297,8 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   PDES_CUDA(cudaGraphLaunch(gs->exec, st));
   PDES_CUDA(cudaMemcpyAsync(out, wsf(n, n->outs), obytes, cudaMemcpyDeviceToDevice, st));
   n->launches = gs->launches + 2;
-  if (tr) {
-    n->last_B = B;
-    n->fwd_train_done = true;
-  }
+  n->fwd_train_done = tr != 0;
+  if (tr) n->last_B = B;
   return PDES_OK;
 }
 

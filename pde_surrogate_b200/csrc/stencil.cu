@@ -520,12 +520,7 @@ extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int 
     const TileVariant tv = pick_variant(g_loss_impl, H, W / 4, false);
 #define PDES_FWD_TILE(NT, R)                                                                              \
   do {                                                                                                    \
-    static size_t attr_smem = 0; /* one per variant; not re-set while a graph is being captured */        \
-    if (smem > attr_smem) {                                                                               \
-      PDES_CUDA(cudaFuncSetAttribute(darcy_fwd_tile_kernel<NT, R>,                                        \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-      attr_smem = smem;                                                                                   \
-    }                                                                                                     \
+    PDES_ENSURE_SMEM((darcy_fwd_tile_kernel<NT, R>), smem); /* one mark per variant and device */         \
     PDES_CUDA(launch_pdl(darcy_fwd_tile_kernel<NT, R>, dim3(grid), dim3(NT), smem, st, K, out, B, H, W, use_tb, loss4, (LossWs*)ws, nrm)); \
   } while (0)
     if (tv.nt == 512 && tv.R == 2) PDES_FWD_TILE(512, 2);
@@ -567,12 +562,7 @@ extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float
     const TileVariant tv = pick_variant(g_loss_impl, H, W / 4, true);
 #define PDES_BWD_TILE(NT, R)                                                                              \
   do {                                                                                                    \
-    static size_t attr_smem = 0; /* one per variant; not re-set while a graph is being captured */        \
-    if (smem > attr_smem) {                                                                               \
-      PDES_CUDA(cudaFuncSetAttribute(darcy_bwd_tile_kernel<NT, R>,                                        \
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));            \
-      attr_smem = smem;                                                                                   \
-    }                                                                                                     \
+    PDES_ENSURE_SMEM((darcy_bwd_tile_kernel<NT, R>), smem); /* one mark per variant and device */         \
     PDES_CUDA(launch_pdl(darcy_bwd_tile_kernel<NT, R>, dim3(grid), dim3(NT), smem, st, K, out, gw4, B, H, W, use_tb, dout, cf)); \
   } while (0)
     if (tv.nt == 512 && tv.R == 2) PDES_BWD_TILE(512, 2);

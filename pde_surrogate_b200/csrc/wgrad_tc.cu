@@ -733,12 +733,7 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
 #define PDES_WG_LAUNCH(KSV, CTV)                                                                             \
   {                                                                                                          \
     const size_t smem = wg_smem<KSV, CTV>();                                                                 \
-    static bool attr = false;                                                                                \
-    if (!attr) {                                                                                             \
-      PDES_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KSV, CTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                     (int)smem));                                                            \
-      attr = true;                                                                                           \
-    }                                                                                                        \
+    PDES_ENSURE_SMEM((wgrad_tc_kernel<KSV, CTV>), smem);                                                     \
     PDES_CUDA(launch_pdl(wgrad_tc_kernel<KSV, CTV>, grid, dim3(kThreads), smem, st, tmA, tmB, t));           \
   }
 #define PDES_WG_CT(KSV)                      \
@@ -759,11 +754,7 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
 int launch_wgrad_unpack(const TcWgradUnpack* dev_table, int n, int max_cin, int max_slab_floats, cudaStream_t st) {
   if (n == 0) return PDES_OK;
   const size_t smem = sizeof(float) * (size_t)max_slab_floats;  // Cout * 8 * T of the largest layer
-  static size_t attr = 48 * 1024;
-  if (smem > attr) {
-    PDES_CUDA(cudaFuncSetAttribute(wgrad_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  if (smem > 48 * 1024) PDES_ENSURE_SMEM(wgrad_unpack_kernel, smem);
   PDES_CUDA(launch_pdl(wgrad_unpack_kernel, dim3((max_cin + kUnpackCi - 1) / kUnpackCi, n), dim3(256), smem, st, dev_table));
   PDES_LAUNCH_CHECK();
   return PDES_OK;

@@ -25,7 +25,13 @@ class TrainStep(object):
         self.steps = 0
         self.kernel_launches = 0
         self.l4 = torch.zeros(4, device=self.flat.device)
-        self.hyper_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        # Adam scalars of step t travel host -> device through a RING of pinned slots, each guarded by a
+        # CUDA event: the host may run many graph replays ahead of the device, so a single pinned
+        # buffer would be overwritten before its asynchronous copy has executed
+        self._hyper_slots = 32
+        self.hyper_host = torch.zeros(self._hyper_slots, 8, dtype=torch.float32).pin_memory()
+        self._hyper_ev = [None] * self._hyper_slots
+        self._hyper_i = 0
         self.hyper_dev = torch.zeros(8, dtype=torch.float32, device=self.flat.device)
         self.graph = None
         self.static_K = None
@@ -72,15 +78,20 @@ class TrainStep(object):
         the gradient bucket, the NCCL all-reduce and Adam follow eagerly)."""
         self.static_K = torch.empty_like(K_example)
         self.static_K.copy_(K_example)
+        # The warm-up (lazily-set kernel attributes, workspaces, tensor maps) runs the real device work,
+        # Adam and BatchNorm running-statistics updates included: snapshot everything a step mutates and
+        # restore it afterwards, so that replay i IS optimisation step i of the eager / reference trajectory.
+        m = self.model
+        snap = [t.clone() for t in (self.flat, self.m, self.v, m._flat_running, m._flat_nbt)]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            for _ in range(2):  # warm-up: lazily-set kernel attributes, workspaces, tensor maps
-                self._set_hyper(self.lr)
+            for _ in range(2):
+                self._set_hyper(0.0)
                 self._device_work(self.static_K)
-                if self.world == 1:  # these are real optimisation steps (Adam is part of the device work)
-                    self.steps += 1
         torch.cuda.current_stream().wait_stream(side)
+        for t, s0 in zip((self.flat, self.m, self.v, m._flat_running, m._flat_nbt), snap):
+            t.copy_(s0)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
@@ -88,9 +99,17 @@ class TrainStep(object):
 
     def _set_hyper(self, lr):
         L = _lib.lib()
-        _lib.check(L.pdes_adam_hyper(self.hyper_host.data_ptr(), float(lr), self.betas[0], self.betas[1], self.eps,
+        i = self._hyper_i % self._hyper_slots
+        self._hyper_i += 1
+        if self._hyper_ev[i] is not None:
+            self._hyper_ev[i].synchronize()   # the copy that last read this slot has executed
+        slot = self.hyper_host[i]
+        _lib.check(L.pdes_adam_hyper(slot.data_ptr(), float(lr), self.betas[0], self.betas[1], self.eps,
                                      self.wd, 1.0 / self.world, self.steps + 1), "pdes_adam_hyper")
-        self.hyper_dev.copy_(self.hyper_host, non_blocking=True)
+        self.hyper_dev.copy_(slot, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_ev[i] = ev
 
     def step_graph(self, K, lr=None):
         """Replay the captured step on batch K (copied into the graph's static input)."""

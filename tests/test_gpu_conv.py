@@ -54,6 +54,16 @@ TC_CASES = [
     (2, 16, 49, 3, 5, 1, 2, 0, 1),     # last conv (5x5, 3 output channels)
     (1, 32, 52, 16, 5, 1, 2, 0, 1),
     (2, 16, 4, 48, 7, 1, 3, 0, 0),     # 7x7 taps
+    # the shapes bench.py times (batch 32): 256-1024 pixel tiles over <= 148 persistent CTAs, i.e. every CTA
+    # walks several tiles (accumulator-stage ring and its phases, operand-ring wrap across tiles, multi-tile
+    # split-K of the weight gradient)
+    (32, 32, 128, 16, 3, 1, 1, 0, 1),  # EncBlock1.denselayer6
+    (32, 16, 184, 16, 3, 1, 1, 0, 1),  # DecBlock1.denselayer8
+    (32, 32, 196, 98, 3, 1, 1, 0, 1),  # LastTransUp.conv1
+    (32, 32, 98, 49, 3, 1, 1, 1, 1),   # LastTransUp.conv2 (nearest x2 -> 64x64, 1024 tiles)
+    (32, 64, 49, 3, 5, 1, 2, 0, 1),    # LastTransUp.conv3
+    (32, 32, 144, 72, 1, 1, 0, 0, 1),  # TransDown1.conv1
+    (5, 24, 36, 16, 3, 1, 1, 0, 1),    # ragged: 5 x 2 x 3 = 30 partial tiles
 ]
 
 
@@ -73,6 +83,8 @@ def _run_case(case, impl):
     L = _lib.lib()
     B, H, Cin, Cout, K, s, p, up, bn = case
     g = torch.Generator().manual_seed(hash(case) % 1000)
+    if B * H * H * Cin * Cout * K * K > 4e9:
+        torch.set_num_threads(max(1, min(16, (torch.get_num_threads() or 1))))
     ld_in = (Cin + 3) // 4 * 4 + 4
     tol = 2e-6 if impl == 1 else 1e-5
     coff = 8

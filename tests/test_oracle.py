@@ -8,7 +8,8 @@ import torch
 
 from oracle import pdes_oracle as orc
 
-CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64", "densenet_full64_channel"]
+CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64", "densenet_full64_channel",
+         "densenet_full32_b32", "densenet_full64_b32"]   # *_b32: the batch bench.py times (fields stored as fp32)
 
 
 def _load(golden_dir, name):
@@ -48,12 +49,13 @@ def test_train_step_fp64_matches_reference(golden_dir, name):
     sd_eval = orc.to_dtype(sd, torch.float64)
     with torch.no_grad():
         out_eval = orc.densenet_forward(plan, sd_eval, K, training=False)
-    assert rel(out_eval.numpy(), g["out_eval64"]) < 1e-12
+    ftol = 1e-7 if "compact" in g.files else 1.0   # compact fixtures hold the fp64 fields rounded to fp32
+    assert rel(out_eval.numpy(), g["out_eval64"]) < (ftol if ftol < 1.0 else 1e-12)
     out, l4, loss, dout, grads = orc.train_step(plan, sd, K)
-    assert rel(out.numpy(), g["out64"]) < 1e-11
+    assert rel(out.numpy(), g["out64"]) < (ftol if ftol < 1.0 else 1e-11)
     assert rel(l4.numpy(), g["l4_64"]) < 1e-11
     assert abs(float(loss) - float(g["loss64"])) / float(g["loss64"]) < 1e-11
-    assert rel(dout.numpy(), g["dout64"]) < 1e-10
+    assert rel(dout.numpy(), g["dout64"]) < (ftol if ftol < 1.0 else 1e-10)
     names = [str(s) for s in g["param_names"]]
     norms = np.array([float(grads[n].norm()) for n in names])
     assert np.allclose(norms, g["grad_norm64"], rtol=1e-8, atol=1e-300)
@@ -105,3 +107,43 @@ def test_sobel_and_losses_match_reference(golden_dir):
             assert rel(l4.detach().numpy(), g[f"{tag}{tb}_l4"]) < 1e-13
             d, = torch.autograd.grad((gw * l4).sum(), out)
             assert rel(d.numpy(), g[f"{tag}{tb}_dout"]) < 1e-12
+
+
+def test_adam_reference_matches_torch_optim():
+    """oracle.adam_reference (the checker of the fused Adam kernel) against torch.optim.Adam, with and
+    without weight decay (train_codec_mixed_residual.py:151, 239)."""
+    gen = torch.Generator().manual_seed(0)
+    for wd in (0.0, 1e-2):
+        p = torch.randn(257, generator=gen, dtype=torch.float64).requires_grad_(True)
+        opt = torch.optim.Adam([p], lr=1e-3, weight_decay=wd)
+        q, m, v = p.detach().clone(), torch.zeros(257, dtype=torch.float64), torch.zeros(257, dtype=torch.float64)
+        for step in (1, 2, 3, 4, 5):
+            g = torch.randn(257, generator=gen, dtype=torch.float64)
+            lr = 1e-3 * step
+            for grp in opt.param_groups:
+                grp["lr"] = lr
+            p.grad = g.clone()
+            opt.step()
+            q, m, v = orc.adam_reference(q, g, m, v, lr, step, wd=wd)
+            assert rel(q.numpy(), p.detach().numpy()) < 1e-13
+
+
+def test_finite_volume_reference_solver():
+    """pde_surrogate_b200.data.darcy_fv_solve (stand-in for the FEniCS labels, utils/fenics.py upstream):
+    exact for constant permeability, discretely conservative, satisfies the boundary conditions, and its
+    fields make the reference's mixed-residual loss small compared with a perturbed field."""
+    from pde_surrogate_b200 import data
+    u, s1, s2 = data.darcy_fv_solve(np.full((16, 16), 2.5))
+    assert np.allclose(u[3], np.linspace(1.0, 0.0, 16)) and np.allclose(s2, 0.0)
+    assert np.allclose(s1, 2.5 * 16.0 / 15.0)
+    rs = np.random.RandomState(0)
+    K = np.exp(0.5 * rs.standard_normal((32, 32)))
+    o = data.darcy_fv_solve(K)
+    assert np.allclose(o[0][:, 0], 1.0) and np.allclose(o[0][:, -1], 0.0)
+    assert o[0].min() >= -1e-12 and o[0].max() <= 1.0 + 1e-12      # discrete maximum principle
+    col_flux = o[1].sum(0)[1:-1]
+    assert np.ptp(col_flux) < 1e-10 * abs(col_flux.mean())          # the same total flux crosses every column
+    Kt = torch.tensor(K[None, None])
+    good = orc.total_loss(Kt, torch.tensor(o[None]))[0]
+    bad = orc.total_loss(Kt, torch.tensor(o[None] + 0.05 * rs.standard_normal(o[None].shape)))[0]
+    assert float(good) < 0.2 * float(bad)
