@@ -187,7 +187,9 @@ typedef struct pdes_conv_desc {
 /* w: OIHW fp32 (Cout,Cin,KH,KW); scale/shift: Cin floats or NULL; y as described.
  * ch_sum/ch_sumsq: Cout doubles accumulated (+=) with the per-channel sum and sum of
  * squares of the outputs, or NULL.  impl: 0/1 CUDA-core fp32, 2 tensor-core (two-piece fp16), 3 the dedicated
- * first-convolution kernels (x is then the PLANAR (B, Cin, H, W) network input; fwd and wgrad only). */
+ * first-convolution kernels (x is then the PLANAR (B, Cin, H, W) network input; fwd and wgrad only),
+ * 4 (fwd only) the fused thin-layer kernel: BatchNorm+ReLU+operand split inside the convolution
+ * (3x3, stride 1, pad 1, Cout <= 16, Win in {8, 16, 32}). */
 int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const float* w,
                     const float* scale, const float* shift, float* y, double* ch_sum,
                     double* ch_sumsq, int impl, void* stream);

@@ -292,7 +292,7 @@ class DenseED(nn.Module):
             leaves[key] = leaf
         self._flat = self._flat_grad = self._flat_running = self._flat_nbt = None
         # convolution implementation: 0 = tcgen05 on two-piece fp16 operands where supported (default),
-        # 1 = CUDA-core fp32 everywhere, 3 / 4 / 5 = tensor cores for the forward / dgrad / wgrad only
+        # 1 = CUDA-core fp32 everywhere, 3 / 4 / 5 = tensor cores for the forward / dgrad / wgrad only, 6 = none
         self.conv_impl = int(os.environ.get("PDES_CONV_IMPL", "0"))
         self._ex = _executor_factory(self)
         self._flatten()

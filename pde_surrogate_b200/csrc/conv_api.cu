@@ -115,6 +115,8 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
   h.KC = p.KC;
   h.nchunks = p.nchunks;
   h.transpose = transpose;
+  h.dxn = 0;
+  h.CoP = 0;
   if (rc == PDES_OK) {
     PDES_CUDA(cudaMemcpyAsync(tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     PDES_CUDA(cudaStreamSynchronize(st));
@@ -168,6 +170,59 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
 }  // namespace
 
 namespace {
+// impl 4: the fused thin-layer forward (conv_dense.cu): pack the filter into scratch, one launch
+int run_dense(const ConvArgs& a, const pdes_conv_desc* d, const float* w, cudaStream_t st) {
+  PDES_REQUIRE(dense_fwd_supported(d->KH, d->stride, d->pad, d->upsample, d->Cin, d->Cout, d->Hin, d->Win) &&
+                   !d->out_nchw,
+               PDES_ERR_UNSUPPORTED, "fused thin-layer path does not support this convolution");
+  const size_t pe = dense_pack_elems(d->Cin, 16);
+  const size_t pack_bytes = (pe * 2 + 255) & ~(size_t)255;
+  unsigned char* buf = nullptr;
+  PDES_CUDA(cudaMallocAsync((void**)&buf, pack_bytes + 256, st));
+  Tc2PackDesc* tab = reinterpret_cast<Tc2PackDesc*>(buf + pack_bytes);
+  Tc2PackDesc h;
+  memset(&h, 0, sizeof(h));
+  h.w = w;
+  h.dst = reinterpret_cast<op16*>(buf);
+  h.Cout = d->Cout;
+  h.Cin = d->Cin;
+  h.KS = 3;
+  h.N = 48;
+  h.KC = 32;
+  h.nchunks = (d->Cin + 31) / 32;
+  h.dxn = 1;
+  h.CoP = 16;
+  PDES_CUDA(cudaMemcpyAsync(tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  PDES_CUDA(cudaStreamSynchronize(st));
+  int rc = launch_pack_tc2(tab, 1, pe, st);
+  if (rc == PDES_OK) {
+    DenseFwdArgs da;
+    memset(&da, 0, sizeof(da));
+    da.x = a.x;
+    da.ldx = a.ldx;
+    da.Cin = d->Cin;
+    da.H = d->Hin;
+    da.W = d->Win;
+    da.B = d->B;
+    da.pro = a.pro;
+    da.bn = a.bn;
+    da.wpk = h.dst;
+    da.CoP = 16;
+    da.Cout = d->Cout;
+    da.y = a.y;
+    da.ldy = a.ldy;
+    da.coff = a.coff;
+    da.o_sum = a.o_sum;
+    da.o_sumsq = a.o_sumsq;
+    da.out_scale = pow2f(-(kActScaleLog2 + kWScaleLog2));
+    rc = launch_conv_dense_fwd(da, st);
+  }
+  cudaFreeAsync(buf, st);
+  return rc;
+}
+}  // namespace
+
+namespace {
 // impl 3: the dedicated first-convolution kernels; x is the PLANAR (B, Cin, H, W) network input
 int first_args(const pdes_conv_desc* d, FirstConvArgs& fa, const char* fn) {
   PDES_REQUIRE(!d->bn_relu && !d->upsample && !d->out_nchw, PDES_ERR_UNSUPPORTED,
@@ -196,7 +251,7 @@ extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const fl
   if (rc) return rc;
   PDES_REQUIRE(x && w && y, PDES_ERR_INVALID, "pdes_conv2d_fwd: null pointer");
   PDES_REQUIRE(!d->bn_relu || (scale && shift), PDES_ERR_INVALID, "pdes_conv2d_fwd: bn_relu needs scale/shift");
-  PDES_REQUIRE(impl >= 0 && impl <= 3, PDES_ERR_UNSUPPORTED, "pdes_conv2d_fwd: impl %d not available", impl);
+  PDES_REQUIRE(impl >= 0 && impl <= 4, PDES_ERR_UNSUPPORTED, "pdes_conv2d_fwd: impl %d not available", impl);
   cudaStream_t st = (cudaStream_t)stream;
   if (impl == 3) {
     FirstConvArgs fa;
@@ -243,6 +298,8 @@ extern "C" int pdes_conv2d_fwd(const pdes_conv_desc* d, const float* x, const fl
   a.o_sumsq = ch_sumsq;
   if (impl == 2)
     rc = run_tc(a, d, w, 0, st);
+  else if (impl == 4)
+    rc = run_dense(a, d, w, st);
   else
     rc = launch_conv_simt(a, st);
   cudaFreeAsync(pk.buf, st);

@@ -108,11 +108,32 @@ struct Tc2PackDesc {
   const float* w;  // OIHW
   op16* dst;
   int Cout, Cin, KS, N, KC, nchunks, transpose;
+  int dxn, CoP;    // dxn = 1: "dx in N" layout of conv_dense.cu, [chunk][ky][k-octet][piece][n = kx*CoP + co][8]
 };
 void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p);
 bool tc2_supported(int KS, int stride, int Cin_k, int N);
 // planes: [2][B][Hv][round8(Cin_k)/8][Wv][8] fp16 pieces of the GEMM-K operand (act_split_kernel)
 int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Cin_k, cudaStream_t st);
 int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st);
+
+// ---- fused thin-layer forward (conv_dense.cu): BatchNorm + ReLU + fp16 split inside the convolution ----
+struct DenseFwdArgs {
+  const float* x;      // NHWC fp32 input (the dense block's buffer), ldx floats per pixel
+  int ldx, Cin, H, W, B;
+  int pro;             // 1: a = max(0, x*scale+shift) first
+  BnSrc bn;
+  const op16* wpk;     // packed filter, Tc2PackDesc::dxn layout
+  int CoP, Cout;       // CoP = 16
+  float* y;            // NHWC output slice: y[pixel*ldy + coff + co]
+  int ldy, coff;
+  double* o_sum;       // per-channel sum / sum of squares of what was stored (+=), offset to the slice; or null
+  double* o_sumsq;
+  op16* planes;        // optional [2][B][H][Cp/8][W][8]: the operand pieces, written once for the weight gradient
+  int Cp;
+  float out_scale;     // exact inverse of the static operand scales
+};
+bool dense_fwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout, int H, int W);
+size_t dense_pack_elems(int Cin, int CoP);   // 16-bit elements of the packed filter (both pieces)
+int launch_conv_dense_fwd(const DenseFwdArgs& a, cudaStream_t st);
 
 }  // namespace pdes

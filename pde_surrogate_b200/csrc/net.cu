@@ -50,6 +50,8 @@ struct Layer {
   size_t planesB;    // float offset of this layer's dY piece planes (read by its dgrad and, concurrently, its wgrad)
   bool tc_wg;        // weight gradient on tcgen05
   bool first_k;      // dedicated CUDA-core kernels of the first convolution (first_conv.cu)
+  bool dense_fwd;    // fused BatchNorm+ReLU+split+conv forward of a thin 3x3 layer (conv_dense.cu)
+  size_t wdn;        // float offset of its packed filter ("dx in N" layout)
   bool wg_taps_n;    // weight gradient as ONE 1x1 GEMM over an expanded dY (few output channels, DyIm2colArgs)
   size_t planesI;    // float offset of the expanded dY planes
   int ci_pad, co_pad;
@@ -98,6 +100,7 @@ struct pdes_net {
   size_t xs = 0, outs = 0, douts = 0;  // float offsets of the static x / out / dout buffers
   int n_wg_bound = 0;
   int tc_mask = 7;  // bit 0: forward, bit 1: dgrad, bit 2: wgrad on tcgen05
+  int dense_on = 1; // PDES_DENSE_FWD=0: thin layers go through operand split + conv_tc2 (round-1 path)
   // bound
   float* p = nullptr;
   float* g = nullptr;
@@ -186,6 +189,8 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.tc_wg = false;
   L.first_k = false;
   L.wg_taps_n = false;
+  L.dense_fwd = false;
+  L.wdn = 0;
   L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
@@ -338,6 +343,16 @@ int build(pdes_net* n) {
       n->n_tc2++;
       if (L.p2f.pack_elems > n->max_tc2_pack) n->max_tc2_pack = L.p2f.pack_elems;
     }
+    if (aligned && L.tc2_fwd && L.in_buf >= 0 && L.out_buf >= 0 && n->dense_on &&
+        dense_fwd_supported(L.KS, L.stride, L.pad, L.up, L.Cin, L.Cout, n->bufs[L.in_buf].H, n->bufs[L.in_buf].W)) {
+      L.dense_fwd = true;
+      n->n_tc2--;  // its conv_tc2 forward filter is never used: not packed (bind() skips the entry)
+      const size_t pe = dense_pack_elems(L.Cin, 16);
+      L.wdn = f;
+      f += pad4((int64_t)((pe + 1) / 2));
+      n->n_tc2++;
+      if (pe > n->max_tc2_pack) n->max_tc2_pack = pe;
+    }
     if (L.in_buf < 0) continue;  // the first convolution needs no dgrad; its wgrad stays SIMT
     if (aligned && tc2_supported(L.KS, 1, L.Cout, L.Nb)) {
       L.tc2_bwd = true;
@@ -459,6 +474,10 @@ extern "C" int pdes_densenet_create(const pdes_densenet_config* cfg, pdes_net_t*
   PDES_REQUIRE(cfg && out, PDES_ERR_INVALID, "pdes_densenet_create: null argument");
   pdes_net* n = new pdes_net();
   n->cfg = *cfg;
+  {
+    const char* e = getenv("PDES_DENSE_FWD");
+    n->dense_on = (e && e[0] == '0') ? 0 : 1;
+  }
   const int rc = build(n);
   if (rc != PDES_OK) {
     delete n;
@@ -630,6 +649,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
   for (const auto& L : n->layers) {
     for (int dir = 0; dir < 2; ++dir) {
       if (!(dir == 0 ? L.tc2_fwd : L.tc2_bwd)) continue;
+      if (dir == 0 && L.dense_fwd) continue;
       Tc2PackDesc d;
       d.w = n->p + L.w_off;
       d.dst = reinterpret_cast<op16*>(wsf(n, dir == 0 ? L.w2f : L.w2b));
@@ -640,6 +660,23 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       d.KC = dir == 0 ? L.p2f.KC : L.p2b.KC;
       d.nchunks = dir == 0 ? L.p2f.nchunks : L.p2b.nchunks;
       d.transpose = dir;
+      d.dxn = 0;
+      d.CoP = 0;
+      t2.push_back(d);
+    }
+    if (L.dense_fwd) {
+      Tc2PackDesc d;
+      d.w = n->p + L.w_off;
+      d.dst = reinterpret_cast<op16*>(wsf(n, L.wdn));
+      d.Cout = L.Cout;
+      d.Cin = L.Cin;
+      d.KS = L.KS;
+      d.N = 3 * 16;
+      d.KC = 32;
+      d.nchunks = (L.Cin + 31) / 32;
+      d.transpose = 0;
+      d.dxn = 1;
+      d.CoP = 16;
       t2.push_back(d);
     }
   }
@@ -675,10 +712,12 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
 
 extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
   // 0 = tcgen05 (two-piece fp16) where supported, 1 = CUDA-core fp32 everywhere, 2 = same as 0,
-  // 3 / 4 / 5 = tcgen05 for the forward only / the dgrad only / the wgrad only (diagnostics)
-  PDES_REQUIRE(n && impl >= 0 && impl <= 5, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..5");
+  // 3 / 4 / 5 = tcgen05 for the forward only / the dgrad only / the wgrad only (diagnostics),
+  // 6 = the launch structure of 3..5 (dedicated first-convolution kernels) with NO tensor-core kernel:
+  // the exact-fp32 baseline whose forward is bitwise the forward of 4 and 5
+  PDES_REQUIRE(n && impl >= 0 && impl <= 6, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..6");
   n->conv_impl = impl == 1 ? 1 : 0;
-  n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : (impl == 5 ? 4 : 7));
+  n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : (impl == 5 ? 4 : (impl == 6 ? 0 : 7)));
   return PDES_OK;
 }
 
@@ -831,7 +870,8 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
         a.o_sumsq = wsd(n, ob.stat) + ob.C + L.coff;
       }
     }
-    const bool want_planes = n->conv_impl == 0 && (L.tc2_fwd || (tr && L.tc_wg));
+    const bool use_dense = n->conv_impl == 0 && L.dense_fwd && (n->tc_mask & 1);
+    const bool want_planes = n->conv_impl == 0 && (L.tc2_fwd || (tr && L.tc_wg)) && !use_dense;
     const int Hs_l = L.in_buf >= 0 ? n->bufs[L.in_buf].H : L.Hs, Ws_l = L.in_buf >= 0 ? n->bufs[L.in_buf].W : L.Ws;
     if (want_planes) {
       // fp16 pieces of relu(bn(x)) (nearest-upsampled if needed): read by the forward conv and,
@@ -877,6 +917,31 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       fa.Ho = L.Ho;
       fa.Wo = L.Wo;
       rc = launch_first_conv_fwd(fa, st);
+    } else if (use_dense) {
+      // thin layer: BatchNorm + ReLU + fp16 split happen inside the convolution kernel, which also emits
+      // the operand planes of the weight gradient (training)
+      DenseFwdArgs da;
+      memset(&da, 0, sizeof(da));
+      da.x = a.x;
+      da.ldx = a.ldx;
+      da.Cin = L.Cin;
+      da.H = Hs_l;
+      da.W = Ws_l;
+      da.B = B;
+      da.pro = a.pro;
+      da.bn = a.bn;
+      da.wpk = reinterpret_cast<const op16*>(wsf(n, L.wdn));
+      da.CoP = 16;
+      da.Cout = L.Cout;
+      da.y = a.y;
+      da.ldy = a.ldy;
+      da.coff = a.coff;
+      da.o_sum = a.o_sum;
+      da.o_sumsq = a.o_sumsq;
+      da.planes = (tr && L.tc_wg) ? reinterpret_cast<op16*>(wsf(n, L.planes)) : nullptr;
+      da.Cp = (L.Cin + 7) & ~7;
+      da.out_scale = pow2f(-(kActScaleLog2 + kWScaleLog2));
+      rc = launch_conv_dense_fwd(da, st);
     } else if (n->conv_impl == 0 && L.tc2_fwd && (n->tc_mask & 1)) {
       const int Hv = L.up ? 2 * Hs_l : Hs_l, Wv = L.up ? 2 * Ws_l : Ws_l;
       Tc2Args t;

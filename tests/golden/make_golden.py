@@ -138,8 +138,55 @@ def main():
         save_case("densenet_full64_b32.npz", dict(full, imsize=64), B=32, seed=17, full_grads=False, compact=True)
         save_case("densenet_full32_b32.npz", dict(full, imsize=32), B=32, seed=19, full_grads=False, compact=True)
 
+    def trajectory_case():
+        # Three optimisation steps of the reference itself (its DenseED + losses + torch.optim.Adam, the
+        # loop body of train_codec_mixed_residual.py:226-240 with a per-step learning rate) at batch 32, in
+        # fp32 and in fp64: the losses, and a strided sample of the final parameters.  The fp32-vs-fp64
+        # gap IS the reference's own trajectory noise (chaotic: ReLU flips + sign-like first Adam steps).
+        d = {}
+        lrs = [5e-4, 7e-4, 1e-3]
+        for imsize in (32, 64):
+            cfg = dict(full, imsize=imsize)
+            plan = orc.densenet_plan(**cfg)
+            res = {}
+            for dtype in (torch.float32, torch.float64):
+                sd = orc.to_dtype(orc.make_state(plan, 1), dtype)
+                model = DenseED(1, 3, imsize, cfg["blocks"]).to(dtype)
+                model.load_state_dict(sd, strict=True)
+                sob = SobelFilter(imsize, correct=True, device="cpu")
+                if dtype == torch.float64:
+                    for a in ("HSOBEL_WEIGHTS_3x3", "VSOBEL_WEIGHTS_3x3", "modifier"):
+                        setattr(sob, a, getattr(sob, a).double())
+                opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0.0)
+                model.train()
+                losses = []
+                for i, lr in enumerate(lrs):
+                    K = orc.make_input(32, imsize, 100 + i).to(dtype)
+                    model.zero_grad()
+                    out = model(K)
+                    loss = (darcy.conv_constitutive_constraint(K, out, sob) + darcy.conv_continuity_constraint(out, sob))
+                    l_dir, l_neu = darcy.conv_boundary_condition(out)
+                    loss = loss + (l_dir + l_neu) * 10.0
+                    loss.backward()
+                    for grp in opt.param_groups:
+                        grp["lr"] = lr
+                    opt.step()
+                    losses.append(float(loss))
+                flat = np.concatenate([p.detach().double().numpy().ravel() for p in model.parameters()])
+                res[dtype] = (np.array(losses), flat)
+            d["loss32_%d" % imsize], d["loss64_%d" % imsize] = res[torch.float32][0], res[torch.float64][0]
+            d["params32_%d" % imsize] = res[torch.float32][1][::97].copy()
+            d["params64_%d" % imsize] = res[torch.float64][1][::97].copy()
+            print("trajectory", imsize, res[torch.float32][0], res[torch.float64][0])
+        d["lrs"] = np.array(lrs)
+        d["stride"] = 97
+        np.savez_compressed(os.path.join(HERE, "trajectory_b32.npz"), **d)
+
     if "--only-channel" in sys.argv:
         channel_case()
+        return
+    if "--only-trajectory" in sys.argv:
+        trajectory_case()
         return
     if "--only-b32" in sys.argv:
         timed_shape_cases()
@@ -155,6 +202,7 @@ def main():
     save_case("densenet_full64.npz", dict(full, imsize=64), B=2, seed=11, full_grads=False)
     channel_case()
     timed_shape_cases()
+    trajectory_case()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----
     rs = np.random.RandomState(42)

@@ -188,3 +188,54 @@ def test_first_conv_kernels(case):
     dw = torch.ones(Cout, Cin, 7, 7, device="cuda")
     _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), None, None, _lib.ptr(dyd), _lib.ptr(dw), 3, st))
     assert rel(dw - 1.0, wr.grad) < 1e-5, rel(dw - 1.0, wr.grad)
+
+
+DENSE_CASES = [
+    # B, H(=W), Cin, Cout  — 3x3, stride 1, pad 1, BatchNorm+ReLU prologue
+    (2, 16, 48, 16),
+    (1, 8, 184, 16),      # 8x8 image: one 16-row tile, half of it outside the image
+    (3, 8, 8, 16),
+    (2, 32, 100, 16),     # Cin not a multiple of 8: partial channel octet
+    (1, 32, 52, 4),       # few output channels
+    (2, 16, 20, 8),
+    (5, 32, 36, 16),      # 40 tiles
+    (32, 32, 128, 16),    # EncBlock1.denselayer6 at the timed batch: 256 tiles over 148 CTAs
+    (32, 16, 184, 16),    # DecBlock1.denselayer8
+    (32, 32, 180, 16),    # DecBlock2.denselayer6: 6 channel chunks, resident filter 108 KB
+    (2, 32, 224, 16),     # largest supported Cin (7 chunks)
+]
+
+
+@pytest.mark.parametrize("bn", [1, 0])
+@pytest.mark.parametrize("case", DENSE_CASES)
+def test_conv_dense_fused_forward(case, bn):
+    """The fused thin-layer forward (impl 4: BatchNorm + ReLU + two-piece fp16 split inside the tcgen05
+    convolution, three horizontal taps folded into GEMM-N) against torch fp64."""
+    from pde_surrogate_b200 import _lib
+    L = _lib.lib()
+    B, H, Cin, Cout = case
+    g = torch.Generator().manual_seed(sum(case) + bn)
+    ld_in = (Cin + 3) // 4 * 4 + 4
+    coff = 8
+    ld_out = coff + (Cout + 3) // 4 * 4 + 4
+    x = torch.randn(B, H, H, ld_in, generator=g)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (Cin * 9) ** 0.5
+    scale = torch.rand(Cin, generator=g) + 0.5
+    shift = torch.randn(Cin, generator=g) * 0.3
+    d, Ho = _desc(B, H, Cin, Cout, 3, 1, 1, 0, bn, ld_in, ld_out, coff)
+    a = x[..., :Cin].permute(0, 3, 1, 2).double()
+    if bn:
+        a = F.relu(a * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1))
+    yr = F.conv2d(a, w.double(), None, 1, 1).permute(0, 2, 3, 1)
+    xd, wd, sd, hd = x.cuda(), w.cuda(), scale.cuda(), shift.cuda()
+    y = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
+    csum = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    csq = torch.zeros(Cout, dtype=torch.float64, device="cuda")
+    _lib.check(L.pdes_conv2d_fwd(byref(d), _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(sd) if bn else None,
+                                 _lib.ptr(hd) if bn else None, _lib.ptr(y), _lib.ptr(csum), _lib.ptr(csq), 4,
+                                 _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert rel(y[..., coff:coff + Cout], yr) < 1e-5, rel(y[..., coff:coff + Cout], yr)
+    assert float(y[..., :coff].abs().max()) == 0.0 and float(y[..., coff + Cout:].abs().max()) == 0.0
+    assert rel(csum, yr.sum((0, 1, 2))) < 5e-5 or float(yr.sum((0, 1, 2)).norm()) < 1e-3
+    assert rel(csq, (yr ** 2).sum((0, 1, 2))) < 5e-5
