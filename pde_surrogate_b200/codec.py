@@ -292,7 +292,7 @@ class DenseED(nn.Module):
             leaves[key] = leaf
         self._flat = self._flat_grad = self._flat_running = self._flat_nbt = None
         # convolution implementation: 0 = tcgen05 on two-piece fp16 operands where supported (default),
-        # 1 = CUDA-core fp32 everywhere, 3 / 4 / 5 = tensor cores for the forward / dgrad / wgrad only, 6 = none
+        # 1 = CUDA-core fp32 everywhere, 3 / 4 / 5 = tensor cores for the forward / dgrad / wgrad only, 6 = none, 7 = dgrad + wgrad
         self.conv_impl = int(os.environ.get("PDES_CONV_IMPL", "0"))
         self._ex = _executor_factory(self)
         self._flatten()
@@ -362,6 +362,21 @@ class DenseED(nn.Module):
                 p.grad = v
 
     # ------------------------------------------------------------------ nn.Module surface
+    def zero_grad(self, set_to_none=True):
+        """nn.Module.zero_grad semantics (train_codec_mixed_residual.py:226) without the walk over the
+        module tree: the script calls it once per step right after a host synchronisation, i.e. with the
+        GPU idle, so its host time (126 us for 82 parameters through named_parameters) is on the
+        critical path of every step."""
+        if set_to_none:
+            for p in self._params:
+                p.grad = None
+        else:
+            self._flat_grad.zero_()
+            for p, v in zip(self._params, self._grad_views):
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    p.grad.detach_()
+                    p.grad.zero_()
+
     def forward(self, x):
         anchor = self._params[0]
         grad_on = torch.is_grad_enabled() and anchor.requires_grad

@@ -2,11 +2,13 @@
 // handful of output channels; reference models/codec.py:65-69), ONE kernel instead of operand-split +
 // convolution:
 //
-//   * the operand never makes a round trip through global memory: producer warps read the fp32 NHWC rows
-//     of the block buffer, apply BatchNorm + ReLU, split every value into two fp16 pieces (conv_tc.cuh)
-//     and store them straight into the shared-memory image the tensor core reads
-//     ([channel octet][pixel][16 B] = canonical K-major, no swizzle).  In training they also emit the
-//     pieces once to global memory for the weight-gradient kernel (planes [piece][b][y][octet][x][8]).
+//   * the operand never makes a round trip through global memory: 3-D TMA boxes (32 channels x tile pixels,
+//     128-byte swizzle, zero fill outside the image / beyond Cin) bring the raw fp32 NHWC rows of the block
+//     buffer into a shared-memory ring two to three stages ahead; converter warps apply BatchNorm + ReLU,
+//     split every value into two fp16 pieces (conv_tc.cuh) and store them straight into the shared-memory
+//     image the tensor core reads ([channel octet][pixel][16 B] = canonical K-major, no swizzle).  In
+//     training they also emit the pieces once to global memory for the weight-gradient kernel (planes
+//     [piece][b][y][octet][x][8]).
 //   * "dx in N": a pixel tile is 128/W full image rows.  An M=128, N<=48 tcgen05.mma is paced by the
 //     shared-memory fetch of its A operand (~51 clk whatever N), so reading A once per tap is what made
 //     thin layers slow.  Here the three horizontal taps are folded into GEMM-N,
@@ -34,12 +36,15 @@ using namespace tc;
 
 constexpr int kEpiWarps = 4;                 // warps 0..3: TMEM lane quarter = warp index
 constexpr int kMmaWarp = 4;                  // filter loads, TMEM allocation, MMA issue
-constexpr int kProdWarp0 = 5, kProdWarps = 8;
-constexpr int kThreads = 32 * (kProdWarp0 + kProdWarps);   // 416
-constexpr int kKC = 32;                      // channels per activation stage
-constexpr int kStages = 3;
+constexpr int kTmaWarp = 5;                  // raw fp32 tile loads (one lane)
+constexpr int kProdWarp0 = 6, kProdWarps = 12; // converters: 384 threads = exactly 2 items each for a 6 x 32 tile
+constexpr int kThreads = 32 * (kProdWarp0 + kProdWarps);   // 576
+constexpr int kKC = 32;                      // channels per activation stage (32 fp32 = one 128-byte swizzle row)
+constexpr int kStages = 2;                   // fp16 operand stages
+constexpr int kMaxRaw = 3;                   // raw fp32 stages (2 when the resident filter leaves no room for 3)
 constexpr int kMaxChunks = 8;
 constexpr int kTS = 2;                       // accumulator stages in TMEM
+constexpr int kHdrBytes = 3072;              // barriers + BatchNorm constants + reduction scratch (1024-aligned)
 
 __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {  // D fp32, A/B fp16, K-major
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -78,12 +83,21 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 
 struct Geo {
   int W, H, TR, HP, tiles_per_img, n_tiles;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) conv_dense_fwd_kernel(DenseFwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 1)
+conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, int RST) {
   const int W = a.W, H = a.H;
   const int TR = 128 / W;                 // output rows per tile (GEMM-M = 128 pixels)
   const int HP = (TR + 2) * W;            // pixels of the staged tile (one halo row above and below)
@@ -97,17 +111,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dense_fwd_kernel(DenseFwdArg
   const uint32_t b_ky_bytes = (uint32_t)(kKC / 8) * 2u * NQ * 16u;   // [k-octet][piece][n][16 B]
   const uint32_t b_chunk_bytes = 3u * b_ky_bytes;
 
-  extern __shared__ __align__(128) unsigned char smem[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // the 128-byte swizzle pattern of the raw stages is a function of the shared-memory address: 1024-byte base
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);   // [kStages]
   uint64_t* a_empty = a_full + kStages;                   // [kStages]
   uint64_t* b_full = a_empty + kStages;                   // [kMaxChunks]
   uint64_t* acc_full = b_full + kMaxChunks;               // [kTS]
   uint64_t* acc_empty = acc_full + kTS;                   // [kTS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + kTS);
+  uint64_t* raw_full = acc_empty + kTS;                   // [kMaxRaw]
+  uint64_t* raw_empty = raw_full + kMaxRaw;               // [kMaxRaw]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kMaxRaw);
   float* sc_s = reinterpret_cast<float*>(smem + 256);     // [nchunks * 32] scale (x 2^kActScaleLog2)
   float* sh_s = sc_s + kMaxChunks * kKC;                  // shift
   float* red_s = sh_s + kMaxChunks * kKC;                 // [kEpiWarps][16][2]
-  unsigned char* A_s = smem + 256 + sizeof(float) * (2 * kMaxChunks * kKC + kEpiWarps * 32);
+  // raw stages first: the 128-byte swizzle pattern needs 1024-byte aligned stage bases
+  const uint32_t raw_stage_bytes = (uint32_t)HP * 128u;   // [pixel][32 fp32], a multiple of 1024 (HP % 8 == 0)
+  unsigned char* R_s = smem + kHdrBytes;
+  unsigned char* A_s = R_s + (size_t)RST * raw_stage_bytes;
   unsigned char* B_s = A_s + (size_t)kStages * a_stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,11 +142,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dense_fwd_kernel(DenseFwdArg
       mbar_init(&a_empty[i], 1);
     }
     for (int i = 0; i < kMaxChunks; ++i) mbar_init(&b_full[i], 1);
+    for (int i = 0; i < kMaxRaw; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kProdWarps);
+    }
     for (int i = 0; i < kTS; ++i) {
       mbar_init(&acc_full[i], 1);
       mbar_init(&acc_empty[i], kEpiWarps);
     }
     fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
   }
   if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, tmem_cols);
@@ -157,126 +183,94 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dense_fwd_kernel(DenseFwdArg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= kProdWarp0) {
-    // ===== producers: fp32 rows -> BN + ReLU -> two fp16 pieces -> UMMA shared-memory image =====
-    // item = (8-pixel group g, channel octet q, pixel e): consecutive lanes walk e, then q: a warp reads
-    // eight full 128-byte lines (8 pixels x 32 channels) and a quarter-warp stores 128 contiguous bytes.
+  if (warp == kTmaWarp) {
+    // ===== raw tile loads: box (32 channels, HP pixels, 1 image) -> [pixel][128 B], 128-byte swizzle =====
+    if (lane == 0) {
+      int q_it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
+        for (int ch = 0; ch < nchunks; ++ch, ++q_it) {
+          const int s = q_it % RST;
+          mbar_wait(&raw_empty[s], (uint32_t)(((q_it / RST) & 1) ^ 1));
+          mbar_arrive_expect_tx(&raw_full[s], raw_stage_bytes);
+          tma_load_3d(R_s + (size_t)s * raw_stage_bytes, &tmX, ch * kKC, (r0 - 1) * W, b, &raw_full[s]);
+        }
+      }
+    }
+  } else if (warp >= kProdWarp0) {
+    // ===== converters: raw fp32 -> BN + ReLU -> two fp16 pieces -> UMMA shared-memory image =====
+    // item = (8-pixel group g, channel octet q, pixel e): consecutive lanes walk e, then q.  A quarter-warp
+    // reads one 16-byte chunk column of eight consecutive swizzled rows (conflict-free) and stores 128
+    // contiguous bytes.
     const int pt = threadIdx.x - kProdWarp0 * 32;
-    const int n_items = HP * (kKC / 8);
-    constexpr int kMaxIt = 3;                  // HP*4 <= 768 = 3 * 256 (W = 32: 6 rows x 32)
+    const int e = pt & 7, q = (pt >> 3) & 3, g0 = pt >> 5;   // a warp = one 8-pixel group x 4 channel octets
+    const int n_groups = HP >> 3;
+    const int wsh = W == 32 ? 5 : (W == 16 ? 4 : 3);
     const bool relu = a.pro != 0;
     const size_t plane_elems = (size_t)a.B * H * W * a.Cp;
     const int oct_total = a.Cp >> 3;
-    const bool vec_ok = (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0;
-    float4 v0[kMaxIt], v1[kMaxIt];
-    auto issue_loads = [&](int tile, int ch) {
-      const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
-#pragma unroll
-      for (int j = 0; j < kMaxIt; ++j) {
-        const int it = pt + j * (kProdWarps * 32);
-        v0[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        v1[j] = v0[j];
-        if (it < n_items) {
-          const int e = it & 7, q = (it >> 3) & 3, g = it >> 5;
-          const int p = g * 8 + e;
-          const int row = r0 - 1 + p / W, col = p % W;
-          const int c = ch * kKC + q * 8;
-          if (row >= 0 && row < H && c < a.Cin) {
-            const float* src = a.x + ((size_t)(b * H + row) * W + col) * a.ldx + c;
-            if (vec_ok && c + 7 < a.Cin) {
-              v0[j] = __ldg(reinterpret_cast<const float4*>(src));
-              v1[j] = __ldg(reinterpret_cast<const float4*>(src + 4));
-            } else {
-              float t[8];
-#pragma unroll
-              for (int k = 0; k < 8; ++k) t[k] = (c + k < a.Cin) ? __ldg(src + k) : 0.f;
-              v0[j] = make_float4(t[0], t[1], t[2], t[3]);
-              v1[j] = make_float4(t[4], t[5], t[6], t[7]);
-            }
-          }
-        }
-      }
-    };
     int q_it = 0;  // global (tile, chunk) counter of this CTA
-    int tile = blockIdx.x, ch = 0;
-    if (tile < n_tiles) issue_loads(tile, 0);
-    while (tile < n_tiles) {
-      const int s = q_it % kStages;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
-      if (lane == 0) mbar_wait(&a_empty[s], (uint32_t)(((q_it / kStages) & 1) ^ 1));
-      __syncwarp();
-      unsigned char* st = A_s + (size_t)s * a_stage_bytes;
-      // convert what is in registers
-      uint4 h1[kMaxIt], h2[kMaxIt];
-#pragma unroll
-      for (int j = 0; j < kMaxIt; ++j) {
-        const int it = pt + j * (kProdWarps * 32);
-        if (it < n_items) {
-          const int q = (it >> 3) & 3;
-          // rows outside the image are the convolution's zero padding of the ACTIVATION (after BN + ReLU)
-          const int prow_i = ((it >> 5) * 8 + (it & 7)) / W;
-          const bool inside = (r0 - 1 + prow_i) >= 0 && (r0 - 1 + prow_i) < H;
-          const float4 s0 = *reinterpret_cast<const float4*>(sc_s + ch * kKC + q * 8);
-          const float4 s1 = *reinterpret_cast<const float4*>(sc_s + ch * kKC + q * 8 + 4);
-          const float4 o0 = *reinterpret_cast<const float4*>(sh_s + ch * kKC + q * 8);
-          const float4 o1 = *reinterpret_cast<const float4*>(sh_s + ch * kKC + q * 8 + 4);
-          float t[8] = {fmaf(v0[j].x, s0.x, o0.x), fmaf(v0[j].y, s0.y, o0.y), fmaf(v0[j].z, s0.z, o0.z),
-                        fmaf(v0[j].w, s0.w, o0.w), fmaf(v1[j].x, s1.x, o1.x), fmaf(v1[j].y, s1.y, o1.y),
-                        fmaf(v1[j].z, s1.z, o1.z), fmaf(v1[j].w, s1.w, o1.w)};
-          if (relu) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t[k] = fmaxf(t[k], 0.f);
-          }
-          if (!inside) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) t[k] = 0.f;
-          }
-          uint32_t p1[4], p2[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            p1[k] = pack_h2(t[2 * k], t[2 * k + 1]);
-            const float2 f = unpack_h2(p1[k]);
-            p2[k] = pack_h2(t[2 * k] - f.x, t[2 * k + 1] - f.y);
-          }
-          h1[j] = make_uint4(p1[0], p1[1], p1[2], p1[3]);
-          h2[j] = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+      for (int ch = 0; ch < nchunks; ++ch, ++q_it) {
+        const int rs = q_it % RST, s = q_it % kStages;
+        if (lane == 0) {
+          mbar_wait(&raw_full[rs], (uint32_t)((q_it / RST) & 1));
+          mbar_wait(&a_empty[s], (uint32_t)(((q_it / kStages) & 1) ^ 1));
         }
-      }
-      // next (tile, chunk): its loads fly while this chunk is stored and the MMAs of earlier stages run
-      int ntile = tile, nch = ch + 1;
-      if (nch == nchunks) {
-        nch = 0;
-        ntile = tile + gridDim.x;
-      }
-      const int cur_ch = ch;
-      if (ntile < n_tiles) issue_loads(ntile, nch);
-#pragma unroll
-      for (int j = 0; j < kMaxIt; ++j) {
-        const int it = pt + j * (kProdWarps * 32);
-        if (it < n_items) {
-          const int e = it & 7, q = (it >> 3) & 3, g = it >> 5;
+        __syncwarp();
+        const unsigned char* raw = R_s + (size_t)rs * raw_stage_bytes;
+        unsigned char* st = A_s + (size_t)s * a_stage_bytes + (size_t)q * HP * 16;
+        const float4 s0 = *reinterpret_cast<const float4*>(sc_s + ch * kKC + q * 8);
+        const float4 s1 = *reinterpret_cast<const float4*>(sc_s + ch * kKC + q * 8 + 4);
+        const float4 o0 = *reinterpret_cast<const float4*>(sh_s + ch * kKC + q * 8);
+        const float4 o1 = *reinterpret_cast<const float4*>(sh_s + ch * kKC + q * 8 + 4);
+        const int oq = ch * (kKC / 8) + q;
+        const bool want_plane = a.planes != nullptr && oq < oct_total;
+#pragma unroll 2
+        for (int g = g0; g < n_groups; g += kProdWarps) {
           const int p = g * 8 + e;
-          unsigned char* dst = st + (size_t)q * HP * 16 + (size_t)p * 16;
-          *reinterpret_cast<uint4*>(dst) = h1[j];
-          *reinterpret_cast<uint4*>(dst + a_piece_bytes) = h2[j];
-          if (a.planes != nullptr) {
-            const int prow = p / W, col = p - prow * W;
-            const int row = r0 - 1 + prow;
-            const int oq = cur_ch * (kKC / 8) + q;
-            if (prow >= 1 && prow <= TR && row < H && oq < oct_total) {
+          const int prow = p >> wsh, row = r0 - 1 + prow;   // warp-uniform (8 divides W)
+          uint4 h1 = make_uint4(0u, 0u, 0u, 0u), h2 = h1;
+          // rows outside the image are the convolution's zero padding of the ACTIVATION (after BN + ReLU)
+          if (row >= 0 && row < H) {
+            // swizzled row p: logical 16-byte chunk c sits at chunk c ^ (p & 7)
+            const unsigned char* rrow = raw + (size_t)p * 128;
+            const float4 x0 = *reinterpret_cast<const float4*>(rrow + (((2 * q) ^ e) << 4));
+            const float4 x1 = *reinterpret_cast<const float4*>(rrow + (((2 * q + 1) ^ e) << 4));
+            float t[8] = {fmaf(x0.x, s0.x, o0.x), fmaf(x0.y, s0.y, o0.y), fmaf(x0.z, s0.z, o0.z),
+                          fmaf(x0.w, s0.w, o0.w), fmaf(x1.x, s1.x, o1.x), fmaf(x1.y, s1.y, o1.y),
+                          fmaf(x1.z, s1.z, o1.z), fmaf(x1.w, s1.w, o1.w)};
+            if (relu) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) t[k] = fmaxf(t[k], 0.f);
+            }
+            uint32_t p1[4], p2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              p1[k] = pack_h2(t[2 * k], t[2 * k + 1]);
+              const float2 f = unpack_h2(p1[k]);
+              p2[k] = pack_h2(t[2 * k] - f.x, t[2 * k + 1] - f.y);
+            }
+            h1 = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+            h2 = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+            if (want_plane && prow >= 1 && prow <= TR) {
+              const int col = p & (W - 1);
               op16* pd = a.planes + ((((size_t)b * H + row) * oct_total + oq) * W + col) * 8;
-              *reinterpret_cast<uint4*>(pd) = h1[j];
-              *reinterpret_cast<uint4*>(pd + plane_elems) = h2[j];
+              *reinterpret_cast<uint4*>(pd) = h1;
+              *reinterpret_cast<uint4*>(pd + plane_elems) = h2;
             }
           }
+          *reinterpret_cast<uint4*>(st + (size_t)p * 16) = h1;
+          *reinterpret_cast<uint4*>(st + (size_t)p * 16 + a_piece_bytes) = h2;
+        }
+        fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&raw_empty[rs]);
+          mbar_arrive(&a_full[s]);
         }
       }
-      fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_full[s]);
-      ++q_it;
-      tile = ntile;
-      ch = nch;
     }
   } else if (warp == kMmaWarp) {
     // ===== resident filter (bulk TMA, once per CTA) + MMA issue =====
@@ -434,11 +428,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dense_fwd_kernel(DenseFwdArg
   }
 }
 
-size_t dense_smem(int W, int Cin, int CoP) {
+static_assert(256 + sizeof(float) * (2 * kMaxChunks * kKC + kEpiWarps * 32) <= kHdrBytes, "header overflow");
+
+size_t dense_smem(int W, int Cin, int CoP, int RST) {
   const int TR = 128 / W, HP = (TR + 2) * W;
   const int nchunks = (Cin + kKC - 1) / kKC;
-  return 256 + sizeof(float) * (2 * kMaxChunks * kKC + kEpiWarps * 32) +
+  return 1024 /* alignment slack of the dynamic window */ + kHdrBytes + (size_t)RST * HP * 128 +
          (size_t)kStages * 2 * (kKC / 8) * HP * 16 + (size_t)nchunks * 3 * (kKC / 8) * 2 * (3 * CoP) * 16;
+}
+int dense_raw_stages(int W, int Cin) {
+  for (int r = kMaxRaw; r >= 2; --r)
+    if (dense_smem(W, Cin, 16, r) <= 227 * 1024) return r;
+  return 0;
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                             CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode_d() {
+  static EncodeFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeFn>(p);
+  return fn;
 }
 
 }  // namespace
@@ -448,7 +464,7 @@ bool dense_fwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout,
   if (!(W == 8 || W == 16 || W == 32) || H < 1) return false;
   if (Cout < 1 || Cout > 16) return false;
   if (Cin < 1 || (Cin + kKC - 1) / kKC > kMaxChunks) return false;
-  return dense_smem(W, Cin, 16) <= 227 * 1024;
+  return dense_raw_stages(W, Cin) >= 2;
 }
 
 size_t dense_pack_elems(int Cin, int CoP) {
@@ -464,13 +480,30 @@ int launch_conv_dense_fwd(const DenseFwdArgs& a, cudaStream_t st) {
                "conv_dense: output slice must be 16-byte aligned");
   PDES_REQUIRE(a.planes == nullptr || (a.Cp % 8 == 0 && a.Cp >= a.Cin), PDES_ERR_INVALID,
                "conv_dense: padded plane channels %d invalid", a.Cp);
-  const size_t smem = dense_smem(a.W, a.Cin, a.CoP);
+  PDES_REQUIRE((a.ldx & 3) == 0 && ((uintptr_t)a.x & 15u) == 0, PDES_ERR_INVALID,
+               "conv_dense: input rows must be 16-byte aligned (ldx %d)", a.ldx);
+  const int RST = dense_raw_stages(a.W, a.Cin);
+  const size_t smem = dense_smem(a.W, a.Cin, a.CoP, RST);
   PDES_ENSURE_SMEM(conv_dense_fwd_kernel, smem);
-  const int TR = 128 / a.W;
+  const int TR = 128 / a.W, HP = (TR + 2) * a.W;
   const int tiles = ((a.H + TR - 1) / TR) * a.B;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  PDES_CUDA(launch_pdl(conv_dense_fwd_kernel, dim3(grid), dim3(kThreads), smem, st, a));
+  EncodeFn enc = get_encode_d();
+  PDES_REQUIRE(enc != nullptr, PDES_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  CUtensorMap tm;
+  {
+    // x viewed as (channel, pixel of one image, image): reads beyond Cin and outside the image are zero-filled
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.Cin, (cuuint64_t)a.H * a.W, (cuuint64_t)a.B};
+    const cuuint64_t gstr[2] = {(cuuint64_t)a.ldx * 4, (cuuint64_t)a.H * a.W * a.ldx * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kKC, (cuuint32_t)HP, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.x), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled (conv_dense) failed with code %d", (int)r);
+  }
+  PDES_CUDA(launch_pdl(conv_dense_fwd_kernel, dim3(grid), dim3(kThreads), smem, st, tm, a, RST));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

@@ -109,6 +109,7 @@ struct Tc2PackDesc {
   op16* dst;
   int Cout, Cin, KS, N, KC, nchunks, transpose;
   int dxn, CoP;    // dxn = 1: "dx in N" layout of conv_dense.cu, [chunk][ky][k-octet][piece][n = kx*CoP + co][8]
+                   // dxn = 2: "dx in K" layout of conv_dense_bwd.cu, [jy][k-octet (jx, co octet)][piece][n = ci][8]
 };
 void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p);
 bool tc2_supported(int KS, int stride, int Cin_k, int N);
@@ -132,6 +133,28 @@ struct DenseFwdArgs {
   int Cp;
   float out_scale;     // exact inverse of the static operand scales
 };
+// ---- fused thin-layer data gradient (conv_dense_bwd.cu) ----
+struct DenseBwdArgs {
+  FixDyArgs fx;          // gradient slice G / activation slice X of the layer's OUTPUT + the consumers' lazy
+                         // BatchNorm-backward corrections (n_cons == 0: dY = G as it is)
+  int H, W, B, Cout;
+  const unsigned* dyn_max;   // running |G| maximum of the buffer (float bits) -> dynamic power-of-two scale
+  float* dyn_inv;            // its exact inverse, published for the weight-gradient epilogue
+  op16* planesB;             // optional: dY pieces [2][B][H][round8(Cout)/8][W][8] for the weight gradient
+  const op16* wpk;           // packed filter, Tc2PackDesc::dxn == 2 layout: [jy][k-octet (jx, co octet)][piece][n = ci][8]
+  int N, Cin;                // N = Cin rounded up to 16
+  const float* x;            // the layer's INPUT activations (block buffer), ldx floats per pixel
+  int ldx;
+  BnSrc fbn;                 // the layer's BatchNorm
+  float* G;                  // gradient buffer of the same tensor
+  int ldG, g_accum;
+  double* bsum;              // [0,Cin): sum dZ ; [Cin,2Cin): sum dZ*xhat
+  unsigned* gmax;
+  float out_scale;
+};
+bool dense_bwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout, int H, int W);
+size_t dense_bwd_pack_elems(int N);
+int launch_conv_dense_bwd(const DenseBwdArgs& a, cudaStream_t st);
 bool dense_fwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout, int H, int W);
 size_t dense_pack_elems(int Cin, int CoP);   // 16-bit elements of the packed filter (both pieces)
 int launch_conv_dense_fwd(const DenseFwdArgs& a, cudaStream_t st);

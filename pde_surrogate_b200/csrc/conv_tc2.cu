@@ -591,7 +591,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
 __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
   griddep_wait();
   const Tc2PackDesc d = tab[blockIdx.y];
-  const int T = d.dxn ? d.KS : d.KS * d.KS;   // dxn: one "tap" per filter ROW, the columns live in n
+  const int T = d.dxn ? d.KS : d.KS * d.KS;   // dxn: one "tap" per filter ROW, the columns live in n (1) / in k (2)
   const int koct = d.KC >> 3;
   const size_t per_tap = (size_t)koct * d.N * 8;  // elements of ONE piece of one (chunk, tap)
   const size_t total = (size_t)d.nchunks * T * per_tap;
@@ -605,7 +605,12 @@ __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
     const int chunk = (int)(step / T), tap = (int)(step % T);
     const int k = chunk * d.KC + ko * 8 + k8;
     float v = 0.f;
-    if (d.dxn) {
+    if (d.dxn == 2) {
+      // data gradient: k = (jx, co), n = ci, tap = jy; flipped filter W[co, ci, 2-jy, 2-jx]
+      const int jx = k >> 4, co = k & 15;
+      if (n < d.Cin && co < d.Cout)
+        v = d.w[((size_t)co * d.Cin + n) * (d.KS * d.KS) + (d.KS - 1 - tap) * d.KS + (d.KS - 1 - jx)];
+    } else if (d.dxn) {
       const int kx = n / d.CoP, co = n - kx * d.CoP;
       if (co < d.Cout && k < d.Cin) v = d.w[((size_t)co * d.Cin + k) * (d.KS * d.KS) + tap * d.KS + kx];
     } else if (!d.transpose) {

@@ -52,6 +52,8 @@ struct Layer {
   bool first_k;      // dedicated CUDA-core kernels of the first convolution (first_conv.cu)
   bool dense_fwd;    // fused BatchNorm+ReLU+split+conv forward of a thin 3x3 layer (conv_dense.cu)
   size_t wdn;        // float offset of its packed filter ("dx in N" layout)
+  bool dense_bwd;    // fused dY-correction+split+dgrad of a thin 3x3 layer (conv_dense_bwd.cu)
+  size_t wdb;        // float offset of its packed filter ("dx in K" layout)
   bool wg_taps_n;    // weight gradient as ONE 1x1 GEMM over an expanded dY (few output channels, DyIm2colArgs)
   size_t planesI;    // float offset of the expanded dY planes
   int ci_pad, co_pad;
@@ -101,6 +103,7 @@ struct pdes_net {
   int n_wg_bound = 0;
   int tc_mask = 7;  // bit 0: forward, bit 1: dgrad, bit 2: wgrad on tcgen05
   int dense_on = 1; // PDES_DENSE_FWD=0: thin layers go through operand split + conv_tc2 (round-1 path)
+  int dense_bwd_on = 1;  // PDES_DENSE_BWD=0: thin-layer dgrad through dY split + conv_tc2
   // bound
   float* p = nullptr;
   float* g = nullptr;
@@ -191,6 +194,8 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.wg_taps_n = false;
   L.dense_fwd = false;
   L.wdn = 0;
+  L.dense_bwd = false;
+  L.wdb = 0;
   L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
@@ -362,6 +367,16 @@ int build(pdes_net* n) {
       n->n_tc2++;
       if (L.p2b.pack_elems > n->max_tc2_pack) n->max_tc2_pack = L.p2b.pack_elems;
     }
+    if (aligned && L.tc2_bwd && L.out_buf >= 0 && n->dense_bwd_on && wgrad_tc_supported(L.KS, 1) &&
+        dense_bwd_supported(L.KS, L.stride, L.pad, L.up, L.Cin, L.Cout, n->bufs[L.in_buf].H, n->bufs[L.in_buf].W)) {
+      L.dense_bwd = true;
+      n->n_tc2--;  // the conv_tc2 dgrad filter is not packed (bind() skips the entry)
+      const size_t pe = dense_bwd_pack_elems(L.Nb);
+      L.wdb = f;
+      f += pad4((int64_t)((pe + 1) / 2));
+      n->n_tc2++;
+      if (pe > n->max_tc2_pack) n->max_tc2_pack = pe;
+    }
     if (aligned && wgrad_tc_supported(L.KS, 1)) {
       L.tc_wg = true;
       wgrad_tc_dims(L.Cin, L.Cout, &L.ci_pad, &L.co_pad);
@@ -477,6 +492,8 @@ extern "C" int pdes_densenet_create(const pdes_densenet_config* cfg, pdes_net_t*
   {
     const char* e = getenv("PDES_DENSE_FWD");
     n->dense_on = (e && e[0] == '0') ? 0 : 1;
+    const char* e2 = getenv("PDES_DENSE_BWD");
+    n->dense_bwd_on = (e2 && e2[0] == '0') ? 0 : 1;
   }
   const int rc = build(n);
   if (rc != PDES_OK) {
@@ -650,6 +667,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
     for (int dir = 0; dir < 2; ++dir) {
       if (!(dir == 0 ? L.tc2_fwd : L.tc2_bwd)) continue;
       if (dir == 0 && L.dense_fwd) continue;
+      if (dir == 1 && L.dense_bwd) continue;
       Tc2PackDesc d;
       d.w = n->p + L.w_off;
       d.dst = reinterpret_cast<op16*>(wsf(n, dir == 0 ? L.w2f : L.w2b));
@@ -676,6 +694,21 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       d.nchunks = (L.Cin + 31) / 32;
       d.transpose = 0;
       d.dxn = 1;
+      d.CoP = 16;
+      t2.push_back(d);
+    }
+    if (L.dense_bwd) {
+      Tc2PackDesc d;
+      d.w = n->p + L.w_off;
+      d.dst = reinterpret_cast<op16*>(wsf(n, L.wdb));
+      d.Cout = L.Cout;
+      d.Cin = L.Cin;
+      d.KS = L.KS;
+      d.N = L.Nb;
+      d.KC = 48;
+      d.nchunks = 1;
+      d.transpose = 0;
+      d.dxn = 2;
       d.CoP = 16;
       t2.push_back(d);
     }
@@ -715,9 +748,10 @@ extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
   // 3 / 4 / 5 = tcgen05 for the forward only / the dgrad only / the wgrad only (diagnostics),
   // 6 = the launch structure of 3..5 (dedicated first-convolution kernels) with NO tensor-core kernel:
   // the exact-fp32 baseline whose forward is bitwise the forward of 4 and 5
-  PDES_REQUIRE(n && impl >= 0 && impl <= 6, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..6");
+  // 7 = exact-fp32 forward of 6 with BOTH backward kernels on tcgen05 (the fused thin-layer dgrad needs both)
+  PDES_REQUIRE(n && impl >= 0 && impl <= 7, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..7");
   n->conv_impl = impl == 1 ? 1 : 0;
-  n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : (impl == 5 ? 4 : (impl == 6 ? 0 : 7)));
+  n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : (impl == 5 ? 4 : (impl == 6 ? 0 : (impl == 7 ? 6 : 7))));
   return PDES_OK;
 }
 
@@ -1008,6 +1042,8 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
   }
   for (int li = (int)n->layers.size() - 1; li >= 0; --li) {
     const Layer& L = n->layers[li];
+    const bool use_dense_bwd = n->conv_impl == 0 && L.dense_bwd && (n->tc_mask & 2) && (n->tc_mask & 4) &&
+                               L.in_buf >= 0 && L.out_buf >= 0;
     const float* dy;
     int lddy = 0, dy_nchw = 0;
     FixDyArgs fixargs;
@@ -1036,7 +1072,8 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         f.cons_C[f.n_cons] = M.Cin;
         f.n_cons++;
       }
-      const bool fuse_fix = n->conv_impl == 0 && ((L.tc_wg && (n->tc_mask & 4)) || (L.tc2_bwd && (n->tc_mask & 2)));
+      const bool fuse_fix = n->conv_impl == 0 && (use_dense_bwd || (L.tc_wg && (n->tc_mask & 4)) ||
+                                                  (L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2)));
       if (!fuse_fix) {
         rc = launch_fix_dy(f, st);
         if (rc) return rc;
@@ -1050,7 +1087,8 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       lddy = ob.ld;
     }
     // ---- wgrad ---------------------------------------------------------------------
-    {
+    auto run_wgrad = [&]() -> int {
+      int rc = PDES_OK;
       WgradArgs w;
       memset(&w, 0, sizeof(w));
       w.B = B;
@@ -1082,8 +1120,10 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         w.Ws = L.Ws;
       }
       const bool use_wg = n->conv_impl == 0 && L.tc_wg && (n->tc_mask & 4);
-      const bool use_dg = n->conv_impl == 0 && L.tc2_bwd && (n->tc_mask & 2) && L.in_buf >= 0;
-      if (use_wg || use_dg) {
+      // (a layer with the fused dgrad has no conv_tc2 dgrad filter packed: without both backward bits it
+      // falls back to the CUDA-core kernels)
+      const bool use_dg = n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2) && L.in_buf >= 0;
+      if ((use_wg || use_dg) && !use_dense_bwd) {
         // fp16 pieces of the corrected dY slice: GEMM-K operand of dgrad, GEMM-N operand of wgrad
         ActSplitArgs sb;
         memset(&sb, 0, sizeof(sb));
@@ -1200,9 +1240,12 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       if (rc) return rc;
       n->launches++;
       mark(n, st, "wgrad " + L.conv_name, 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B);
-    }
+      return PDES_OK;
+    };
     // ---- dgrad (not needed for the first conv: the input does not require grad) ------
-    if (L.in_buf >= 0) {
+    auto run_dgrad = [&]() -> int {
+      int rc = PDES_OK;
+      if (L.in_buf < 0) return PDES_OK;
       const Buf& ib = n->bufs[L.in_buf];
       ConvArgs a;
       memset(&a, 0, sizeof(a));
@@ -1235,7 +1278,33 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       a.g_accum = L.last_consumer ? 0 : 1;
       a.bsum = wsd(n, L.bsum);
       a.gmax = gmax_slot(n, L.in_buf);
-      if (n->conv_impl == 0 && L.tc2_bwd && (n->tc_mask & 2)) {
+      if (use_dense_bwd) {
+        // thin layer: lazy dY correction + dynamic scale + split happen inside the dgrad kernel, which also
+        // emits the dY planes of the weight gradient (launched right behind it)
+        DenseBwdArgs db;
+        memset(&db, 0, sizeof(db));
+        db.fx = fixargs;
+        db.H = ib.H;
+        db.W = ib.W;
+        db.B = B;
+        db.Cout = L.Cout;
+        db.dyn_max = gmax_slot(n, L.out_buf);
+        db.dyn_inv = wsf(n, n->dyinv) + li;
+        db.planesB = reinterpret_cast<op16*>(wsf(n, L.planesB));
+        db.wpk = reinterpret_cast<const op16*>(wsf(n, L.wdb));
+        db.N = L.Nb;
+        db.Cin = L.Cin;
+        db.x = a.fx;
+        db.ldx = a.ldfx;
+        db.fbn = a.fbn;
+        db.G = a.G;
+        db.ldG = a.ldG;
+        db.g_accum = a.g_accum;
+        db.bsum = a.bsum;
+        db.gmax = a.gmax;
+        db.out_scale = pow2f(-kWScaleLog2);
+        rc = launch_conv_dense_bwd(db, st);
+      } else if (n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2)) {
         Tc2Args t;
         memset(&t, 0, sizeof(t));
         t.c = a;
@@ -1261,6 +1330,19 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       if (rc) return rc;
       n->launches++;
       mark(n, st, "dgrad " + L.conv_name, 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B);
+      return PDES_OK;
+    };
+    // the fused dgrad produces the dY planes its layer's weight gradient reads: it goes first
+    if (use_dense_bwd) {
+      rc = run_dgrad();
+      if (rc) return rc;
+      rc = run_wgrad();
+      if (rc) return rc;
+    } else {
+      rc = run_wgrad();
+      if (rc) return rc;
+      rc = run_dgrad();
+      if (rc) return rc;
     }
   }
   for (int k = 0; k < 2; ++k) {

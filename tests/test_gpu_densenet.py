@@ -118,6 +118,15 @@ def test_train_step_matches_reference(golden_dir, name, impl):
     assert nbt == [int(v) for v in g["num_batches_tracked"]]
 
 
+@pytest.mark.parametrize("name", ["densenet_fiveblk16", "densenet_full32_b32"])
+def test_train_step_legacy_thin_layer_path(golden_dir, name, monkeypatch):
+    """The round-1 launch structure of the thin layers (operand split + conv_tc2 forward, dY split + conv_tc2
+    dgrad) stays selectable (PDES_DENSE_FWD=0 / PDES_DENSE_BWD=0) and stays correct."""
+    monkeypatch.setenv("PDES_DENSE_FWD", "0")
+    monkeypatch.setenv("PDES_DENSE_BWD", "0")
+    test_train_step_matches_reference(golden_dir, name, 0)
+
+
 def test_grad_accumulation_and_zero_grad(golden_dir):
     from models.darcy import conv_boundary_condition
     g = np.load(os.path.join(golden_dir, "densenet_small16.npz"))
@@ -382,7 +391,7 @@ def test_tensor_core_backward_strict_per_tensor(golden_dir, name):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     grads = {}
     outs = {}
-    for impl in (6, 4, 5):
+    for impl in (6, 4, 5, 7):
         model, K, cfg = _model(g)
         model.conv_impl = impl
         sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
@@ -396,8 +405,9 @@ def test_tensor_core_backward_strict_per_tensor(golden_dir, name):
         grads[impl] = {k: p.grad.detach().double().cpu().numpy().copy() for k, p in model.named_parameters()}
         outs[impl] = out.detach().cpu().numpy().copy()
     assert np.array_equal(outs[4], outs[6]) and np.array_equal(outs[5], outs[6])   # the same forward, bit for bit
+    assert np.array_equal(outs[7], outs[6])
     worst = {}
-    for impl in (4, 5):
+    for impl in (4, 5, 7):   # 7: dgrad AND wgrad on tensor cores = the fused thin-layer dgrad (conv_dense_bwd.cu)
         errs = {k: rel(grads[impl][k], grads[6][k]) for k in grads[6]}
         worst[impl] = max(errs.items(), key=lambda kv: kv[1])
         assert worst[impl][1] < 2e-4, (impl, worst[impl])
