@@ -40,7 +40,7 @@ constexpr int kTmaWarp = 5;                  // raw fp32 tile loads (one lane)
 constexpr int kProdWarp0 = 6, kProdWarps = 12; // converters: 384 threads = exactly 2 items each for a 6 x 32 tile
 constexpr int kThreads = 32 * (kProdWarp0 + kProdWarps);   // 576
 constexpr int kKC = 32;                      // channels per activation stage (32 fp32 = one 128-byte swizzle row)
-constexpr int kStages = 2;                   // fp16 operand stages
+constexpr int kMaxStages = 4;                // fp16 operand stages (as many as fit: hides the MMA -> converter handshake)
 constexpr int kMaxRaw = 3;                   // raw fp32 stages (2 when the resident filter leaves no room for 3)
 constexpr int kMaxChunks = 8;
 constexpr int kTS = 2;                       // accumulator stages in TMEM
@@ -97,7 +97,7 @@ struct Geo {
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, int RST) {
+conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, int RST, int AST) {
   const int W = a.W, H = a.H;
   const int TR = 128 / W;                 // output rows per tile (GEMM-M = 128 pixels)
   const int HP = (TR + 2) * W;            // pixels of the staged tile (one halo row above and below)
@@ -114,9 +114,9 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // the 128-byte swizzle pattern of the raw stages is a function of the shared-memory address: 1024-byte base
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);   // [kStages]
-  uint64_t* a_empty = a_full + kStages;                   // [kStages]
-  uint64_t* b_full = a_empty + kStages;                   // [kMaxChunks]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);   // [kMaxStages]
+  uint64_t* a_empty = a_full + kMaxStages;                // [kMaxStages]
+  uint64_t* b_full = a_empty + kMaxStages;                // [kMaxChunks]
   uint64_t* acc_full = b_full + kMaxChunks;               // [kTS]
   uint64_t* acc_empty = acc_full + kTS;                   // [kTS]
   uint64_t* raw_full = acc_empty + kTS;                   // [kMaxRaw]
@@ -129,15 +129,17 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
   const uint32_t raw_stage_bytes = (uint32_t)HP * 128u;   // [pixel][32 fp32], a multiple of 1024 (HP % 8 == 0)
   unsigned char* R_s = smem + kHdrBytes;
   unsigned char* A_s = R_s + (size_t)RST * raw_stage_bytes;
-  unsigned char* B_s = A_s + (size_t)kStages * a_stage_bytes;
+  unsigned char* B_s = A_s + (size_t)AST * a_stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#define DBG(slot) do { if (a.dbg != nullptr && blockIdx.x < 4 && (slot) < 64) a.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+  if (threadIdx.x == 0) DBG(0);
   const uint32_t ts_cols = 2u * NQ;       // G0 = a1*w1 | G1 = a1*w2 + a2*w1
   uint32_t tmem_cols = 32;
   while (tmem_cols < ts_cols * kTS) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) {
+    for (int i = 0; i < kMaxStages; ++i) {
       mbar_init(&a_full[i], kProdWarps);
       mbar_init(&a_empty[i], 1);
     }
@@ -152,12 +154,23 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
     }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    // resident filter, fetched before griddepcontrol.wait when it was packed >= 2 launches ago (see
+    // conv_dense_bwd.cu); the unit-test entry point (b_early = 0) loads it behind the wait
+    if (a.b_early && (int)blockIdx.x < n_tiles) {
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_arrive_expect_tx(&b_full[c], b_chunk_bytes);
+        tma_load_1d(B_s + (size_t)c * b_chunk_bytes,
+                    reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)c * b_chunk_bytes, b_chunk_bytes,
+                    &b_full[c]);
+      }
+    }
   }
   if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
   griddep_wait();  // x, the batch statistics and the packed filter come from earlier kernels of the step
+  if (threadIdx.x == 0) DBG(1);
   if (warp >= kProdWarp0) {
     // BatchNorm constants of this layer, the activation scale folded in: relu(s*x+h)*2^k = relu(2^k s x + 2^k h)
     const float mul = (float)(1 << kActScaleLog2);
@@ -182,6 +195,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG(2);
 
   if (warp == kTmaWarp) {
     // ===== raw tile loads: box (32 channels, HP pixels, 1 image) -> [pixel][128 B], 128-byte swizzle =====
@@ -192,6 +206,10 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
         for (int ch = 0; ch < nchunks; ++ch, ++q_it) {
           const int s = q_it % RST;
           mbar_wait(&raw_empty[s], (uint32_t)(((q_it / RST) & 1) ^ 1));
+          if (a.exp & 4) {
+            mbar_arrive(&raw_full[s]);
+            continue;
+          }
           mbar_arrive_expect_tx(&raw_full[s], raw_stage_bytes);
           tma_load_3d(R_s + (size_t)s * raw_stage_bytes, &tmX, ch * kKC, (r0 - 1) * W, b, &raw_full[s]);
         }
@@ -213,10 +231,11 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
       for (int ch = 0; ch < nchunks; ++ch, ++q_it) {
-        const int rs = q_it % RST, s = q_it % kStages;
+        const int rs = q_it % RST, s = q_it % AST;
         if (lane == 0) {
           mbar_wait(&raw_full[rs], (uint32_t)((q_it / RST) & 1));
-          mbar_wait(&a_empty[s], (uint32_t)(((q_it / kStages) & 1) ^ 1));
+          if (warp == kProdWarp0) DBG(32 + q_it);
+          mbar_wait(&a_empty[s], (uint32_t)(((q_it / AST) & 1) ^ 1));
         }
         __syncwarp();
         const unsigned char* raw = R_s + (size_t)rs * raw_stage_bytes;
@@ -228,7 +247,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
         const int oq = ch * (kKC / 8) + q;
         const bool want_plane = a.planes != nullptr && oq < oct_total;
 #pragma unroll 2
-        for (int g = g0; g < n_groups; g += kProdWarps) {
+        for (int g = g0; g < ((a.exp & 1) ? 0 : n_groups); g += kProdWarps) {
           const int p = g * 8 + e;
           const int prow = p >> wsh, row = r0 - 1 + prow;   // warp-uniform (8 divides W)
           uint4 h1 = make_uint4(0u, 0u, 0u, 0u), h2 = h1;
@@ -269,12 +288,13 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
         if (lane == 0) {
           mbar_arrive(&raw_empty[rs]);
           mbar_arrive(&a_full[s]);
+          if (warp == kProdWarp0) DBG(48 + q_it);
         }
       }
     }
   } else if (warp == kMmaWarp) {
     // ===== resident filter (bulk TMA, once per CTA) + MMA issue =====
-    if (lane == 0 && blockIdx.x < n_tiles) {
+    if (!a.b_early && lane == 0 && (int)blockIdx.x < n_tiles) {
       for (int c = 0; c < nchunks; ++c) {
         mbar_arrive_expect_tx(&b_full[c], b_chunk_bytes);
         tma_load_1d(B_s + (size_t)c * b_chunk_bytes,
@@ -298,6 +318,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
         if (tile_it == 0) mbar_wait(&b_full[ch], 0);
         mbar_wait(&a_full[sa], pa);
         tc_fence_after();
+        if (lane == 0) DBG(3 + tile_it * nchunks + ch);
         const uint64_t ad0 = make_desc(smem_u32(A_s + (size_t)sa * a_stage_bytes), lbo_a, sbo_a);
         const uint64_t bd0 = make_desc(smem_u32(B_s + (size_t)ch * b_chunk_bytes), lbo_b, sbo_b);
         const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32);
@@ -313,7 +334,8 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
                 const uint32_t b_k = b_lo0 + (uint32_t)ky * b_ky_u + (uint32_t)k16 * kstep_b;
                 const bool first = ch == 0 && ky == 0 && k16 == 0;
                 umma_f16_w(d0, a_k, a_hi, b_k, b_hi, idesc2, first ? 0u : 1u);                       // a1 x [w1|w2]
-                umma_f16_w(d0 + (uint32_t)NQ, a_k + a_piece_u, a_hi, b_k, b_hi, idesc1, 1u);          // a2 x w1 -> G1
+                if (!(a.exp & 2))
+                  umma_f16_w(d0 + (uint32_t)NQ, a_k + a_piece_u, a_hi, b_k, b_hi, idesc1, 1u);        // a2 x w1 -> G1
               }
             }
           }
@@ -321,7 +343,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
           if (ch == nchunks - 1) umma_commit(&acc_full[ts]);
         }
         __syncwarp();
-        if (++sa == kStages) {
+        if (++sa == AST) {
           sa = 0;
           pa ^= 1u;
         }
@@ -331,6 +353,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
         pt ^= 1u;
       }
     }
+    if (lane == 0) DBG(20);
     griddep_launch();
   } else {
     // ===== epilogue: finish the convolution along x with shuffles, store the slice, batch statistics =====
@@ -350,6 +373,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
       const bool valid = row < H;
       mbar_wait(&acc_full[ts], (uint32_t)((tile_it / kTS) & 1));
       tc_fence_after();
+      if (threadIdx.x == 0) DBG(24 + 2 * tile_it);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ts * ts_cols;
       for (int c0 = 0; c0 < CoP; c0 += 16) {
         float o[16];
@@ -405,6 +429,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ts]);
+      if (threadIdx.x == 0) DBG(25 + 2 * tile_it);
     }
     if (want_red) {
       named_bar_sync(1, kEpiWarps * 32);
@@ -422,6 +447,8 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG(30);
+#undef DBG
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -430,16 +457,22 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
 
 static_assert(256 + sizeof(float) * (2 * kMaxChunks * kKC + kEpiWarps * 32) <= kHdrBytes, "header overflow");
 
-size_t dense_smem(int W, int Cin, int CoP, int RST) {
+size_t dense_smem(int W, int Cin, int CoP, int RST, int AST) {
   const int TR = 128 / W, HP = (TR + 2) * W;
   const int nchunks = (Cin + kKC - 1) / kKC;
   return 1024 /* alignment slack of the dynamic window */ + kHdrBytes + (size_t)RST * HP * 128 +
-         (size_t)kStages * 2 * (kKC / 8) * HP * 16 + (size_t)nchunks * 3 * (kKC / 8) * 2 * (3 * CoP) * 16;
+         (size_t)AST * 2 * (kKC / 8) * HP * 16 + (size_t)nchunks * 3 * (kKC / 8) * 2 * (3 * CoP) * 16;
 }
-int dense_raw_stages(int W, int Cin) {
-  for (int r = kMaxRaw; r >= 2; --r)
-    if (dense_smem(W, Cin, 16, r) <= 227 * 1024) return r;
-  return 0;
+// stage counts that fit: operand stages first (they hide the MMA -> converter handshake), then raw stages
+bool dense_stages(int W, int Cin, int* RST, int* AST) {
+  for (int a = kMaxStages; a >= 2; --a)
+    for (int r = (a > 2 ? 2 : kMaxRaw); r >= 2; --r)
+      if (dense_smem(W, Cin, 16, r, a) <= 227 * 1024) {
+        *RST = r;
+        *AST = a;
+        return true;
+      }
+  return false;
 }
 
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -464,7 +497,8 @@ bool dense_fwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout,
   if (!(W == 8 || W == 16 || W == 32) || H < 1) return false;
   if (Cout < 1 || Cout > 16) return false;
   if (Cin < 1 || (Cin + kKC - 1) / kKC > kMaxChunks) return false;
-  return dense_raw_stages(W, Cin) >= 2;
+  int r, a;
+  return dense_stages(W, Cin, &r, &a);
 }
 
 size_t dense_pack_elems(int Cin, int CoP) {
@@ -482,8 +516,9 @@ int launch_conv_dense_fwd(const DenseFwdArgs& a, cudaStream_t st) {
                "conv_dense: padded plane channels %d invalid", a.Cp);
   PDES_REQUIRE((a.ldx & 3) == 0 && ((uintptr_t)a.x & 15u) == 0, PDES_ERR_INVALID,
                "conv_dense: input rows must be 16-byte aligned (ldx %d)", a.ldx);
-  const int RST = dense_raw_stages(a.W, a.Cin);
-  const size_t smem = dense_smem(a.W, a.Cin, a.CoP, RST);
+  int RST = 2, AST = 2;
+  dense_stages(a.W, a.Cin, &RST, &AST);
+  const size_t smem = dense_smem(a.W, a.Cin, a.CoP, RST, AST);
   PDES_ENSURE_SMEM(conv_dense_fwd_kernel, smem);
   const int TR = 128 / a.W, HP = (TR + 2) * a.W;
   const int tiles = ((a.H + TR - 1) / TR) * a.B;
@@ -503,7 +538,7 @@ int launch_conv_dense_fwd(const DenseFwdArgs& a, cudaStream_t st) {
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled (conv_dense) failed with code %d", (int)r);
   }
-  PDES_CUDA(launch_pdl(conv_dense_fwd_kernel, dim3(grid), dim3(kThreads), smem, st, tm, a, RST));
+  PDES_CUDA(launch_pdl(conv_dense_fwd_kernel, dim3(grid), dim3(kThreads), smem, st, tm, a, RST, AST));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

@@ -90,8 +90,8 @@ struct BwdPlan {
 };
 
 __host__ __device__ inline size_t bwd_hdr_bytes(int N) {
-  // barriers (256) | ep_s 4*N | red_s 4 quarters * N * 2 | fix_s 4*16   (floats), rounded to 1024
-  const size_t b = 256 + sizeof(float) * ((size_t)4 * N + (size_t)8 * N + 64);
+  // barriers (256) | ep_s 4*N | red_s 4 quarters * N * 2 | fix_s 4*16 | fixd 32 doubles  (floats), rounded to 1024
+  const size_t b = 256 + sizeof(float) * ((size_t)4 * N + (size_t)8 * N + 64 + 64);
   return (b + 1023) & ~(size_t)1023;
 }
 
@@ -122,6 +122,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
   float* ep_s = reinterpret_cast<float*>(smem + 256);     // [N][4]: scale, shift, invstd, -mean*invstd
   float* red_s = ep_s + 4 * N;                            // [4 quarters][N][2]
   float* fix_s = red_s + 8 * N;                           // [4][16]: c1, c2, mean, invstd of the dY channels
+  double* fixd = reinterpret_cast<double*>(fix_s + 64);   // [2][16]: sum over consumers of scale*bsum (N % 2 == 0: aligned)
   const size_t hdr = bwd_hdr_bytes(N);
   unsigned char* X_s = smem + hdr;
   unsigned char* A_s = X_s + (size_t)XST * x_stage_bytes;
@@ -148,6 +149,18 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
     }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    // The packed filter was written by the pack kernel at the head of the step, several launches ago.  Under
+    // programmatic dependent launch this kernel starts once the PREVIOUS kernel has passed its own
+    // griddepcontrol.wait, i.e. once everything before the previous kernel has completed: the resident
+    // filter can be fetched while the previous kernel drains.  (b_early = 0: the unit-test entry point,
+    // whose pack kernel is the immediately preceding launch.)
+    if (a.b_early && (int)blockIdx.x < n_tiles) {
+      for (int jy = 0; jy < 3; ++jy) {
+        mbar_arrive_expect_tx(&b_full[jy], b_jy_bytes);
+        tma_load_1d(B_s + (size_t)jy * b_jy_bytes,
+                    reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)jy * b_jy_bytes, b_jy_bytes, &b_full[jy]);
+      }
+    }
   }
   if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, tmem_cols);
@@ -174,30 +187,33 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
       *reinterpret_cast<float4*>(ep_s + 4 * n) = make_float4(s, h, is, -m * is);
     }
     for (int i = tt; i < 8 * N; i += kEpiWarps * 32) red_s[i] = 0.f;
-  } else if (warp >= kProdWarp0) {
+  } else if (warp == kMmaWarp) {
+    fixd[lane] = 0.0;
+  }
+  __syncthreads();
+  if (warp >= kMmaWarp) {
+    // lazy BatchNorm-backward corrections of the dY channels: c1 = sum_l scale_l * sum dZ_l / count,
+    // c2 = sum_l scale_l * sum dZ_l xhat / count over the consumers l.  One thread per (consumer, channel):
+    // every global load of the prologue is in flight at once (one memory latency instead of n_cons)
     const FixDyArgs& f = a.fx;
-    for (int c = threadIdx.x - kProdWarp0 * 32; c < 16; c += kProdWarps * 32) {
-      float c1 = 0.f, c2 = 0.f, mean = 0.f, is = 0.f;
-      if (c < a.Cout && f.n_cons > 0) {
+    const int t0 = threadIdx.x - kMmaWarp * 32, nt = kThreads - kMmaWarp * 32;
+    for (int idx = t0; idx < f.n_cons * 16; idx += nt) {
+      const int l = idx >> 4, c = idx & 15;
+      if (c < a.Cout) {
         const double m = f.sum[c] * f.inv_count;
         double var = f.sumsq[c] * f.inv_count - m * m;
+        const float gam = f.cons_gamma[l][c];
+        const double b1 = f.cons_bsum[l][c], b2 = f.cons_bsum[l][f.cons_C[l] + c];
         if (var < 0.0) var = 0.0;
         const double isd = 1.0 / sqrt(var + (double)f.eps);
-        double d1 = 0.0, d2 = 0.0;
-        for (int l = 0; l < f.n_cons; ++l) {
-          const double sc = (double)f.cons_gamma[l][c] * (double)(float)isd;
-          d1 += sc * f.cons_bsum[l][c];
-          d2 += sc * f.cons_bsum[l][f.cons_C[l] + c];
+        const double sc = (double)gam * (double)(float)isd;
+        atomicAdd(&fixd[c], sc * b1);
+        atomicAdd(&fixd[16 + c], sc * b2);
+        if (l == 0) {
+          fix_s[32 + c] = (float)m;
+          fix_s[48 + c] = (float)isd;
         }
-        c1 = (float)(d1 * f.inv_count);
-        c2 = (float)(d2 * f.inv_count);
-        mean = (float)m;
-        is = (float)isd;
       }
-      fix_s[c] = c1;
-      fix_s[16 + c] = c2;
-      fix_s[32 + c] = mean;
-      fix_s[48 + c] = is;
     }
   }
   tc_fence_before();
@@ -213,13 +229,14 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
     const bool fix = f.n_cons > 0;
     const int CpB = (a.Cout + 7) & ~7, octB = CpB >> 3;
     const size_t planeB_elems = (size_t)a.B * H * W * CpB;
-    float c1[8], c2[8], mn[8], isd[8];
+    float c1[8], c2[8], mn[8], isd[8];  // (filled below)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      c1[k] = fix_s[oct * 8 + k];
-      c2[k] = fix_s[16 + oct * 8 + k];
-      mn[k] = fix_s[32 + oct * 8 + k];
-      isd[k] = fix_s[48 + oct * 8 + k];
+      const bool on = fix && (oct * 8 + k < a.Cout);
+      c1[k] = on ? (float)(fixd[oct * 8 + k] * f.inv_count) : 0.f;
+      c2[k] = on ? (float)(fixd[16 + oct * 8 + k] * f.inv_count) : 0.f;
+      mn[k] = on ? fix_s[32 + oct * 8 + k] : 0.f;
+      isd[k] = on ? fix_s[48 + oct * 8 + k] : 0.f;
     }
     const bool vec = (f.ldG & 3) == 0 && (f.ldX & 3) == 0 && (reinterpret_cast<uintptr_t>(f.G) & 15u) == 0 &&
                      (reinterpret_cast<uintptr_t>(f.X) & 15u) == 0 && oct * 8 + 7 < a.Cout;
@@ -314,7 +331,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0 && blockIdx.x < n_tiles) {
+    if (!a.b_early && lane == 0 && (int)blockIdx.x < n_tiles) {
       for (int jy = 0; jy < 3; ++jy) {
         mbar_arrive_expect_tx(&b_full[jy], b_jy_bytes);
         tma_load_1d(B_s + (size_t)jy * b_jy_bytes,

@@ -132,6 +132,10 @@ struct DenseFwdArgs {
   op16* planes;        // optional [2][B][H][Cp/8][W][8]: the operand pieces, written once for the weight gradient
   int Cp;
   float out_scale;     // exact inverse of the static operand scales
+  int b_early;         // 1: the filter may be fetched before griddepcontrol.wait (packed >= 2 launches ago)
+  long long* dbg;      // optional phase timestamps (clock64), 64 slots per CTA for the first 4 CTAs (diagnostics)
+  int exp;             // timing experiments (PDES_DENSE_EXP; results are wrong): 1 converters skip their shared-memory
+                       // traffic, 2 no a2 x w1 MMAs, 4 no raw TMA loads
 };
 // ---- fused thin-layer data gradient (conv_dense_bwd.cu) ----
 struct DenseBwdArgs {
@@ -151,6 +155,7 @@ struct DenseBwdArgs {
   double* bsum;              // [0,Cin): sum dZ ; [Cin,2Cin): sum dZ*xhat
   unsigned* gmax;
   float out_scale;
+  int b_early;               // 1: the filter may be fetched before griddepcontrol.wait (packed >= 2 launches ago)
 };
 bool dense_bwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout, int H, int W);
 size_t dense_bwd_pack_elems(int N);

@@ -127,6 +127,15 @@ namespace {
 
 int64_t pad4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 
+bool stream_capturing(cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return cs != cudaStreamCaptureStatusNone;
+}
+
 void mark(pdes_net* n, cudaStream_t st, const std::string& label, double flops = 0.0) {
   if (!n->timing) return;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -975,7 +984,42 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       da.planes = (tr && L.tc_wg) ? reinterpret_cast<op16*>(wsf(n, L.planes)) : nullptr;
       da.Cp = (L.Cin + 7) & ~7;
       da.out_scale = pow2f(-(kActScaleLog2 + kWScaleLog2));
-      rc = launch_conv_dense_fwd(da, st);
+      da.b_early = 1;  // packed by pack_tc2 at the head of the forward pass, >= 2 launches ago
+      {
+        // PDES_DENSE_DBG=<layer index>: phase timestamps of that layer's kernel, printed after the launch
+        static int dbg_layer = -2;
+        static long long* dbg_buf = nullptr;
+        if (dbg_layer == -2) {
+          const char* e = getenv("PDES_DENSE_DBG");
+          dbg_layer = e ? atoi(e) : -1;
+          if (dbg_layer >= 0 && cudaMalloc((void**)&dbg_buf, sizeof(long long) * 256) != cudaSuccess) dbg_layer = -1;
+        }
+        {
+          static int exp_v = -1;
+          if (exp_v < 0) {
+            const char* e = getenv("PDES_DENSE_EXP");
+            exp_v = e ? atoi(e) : 0;
+          }
+          da.exp = exp_v;
+        }
+        const int my_index = (int)(&L - &n->layers[0]);
+        if (dbg_layer == my_index && dbg_buf != nullptr && !stream_capturing(st)) {
+          cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 256, st);
+          da.dbg = dbg_buf;
+          rc = launch_conv_dense_fwd(da, st);
+          long long h[256];
+          cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st);
+          cudaStreamSynchronize(st);
+          for (int c = 0; c < 2; ++c) {
+            fprintf(stderr, "[dense dbg] %s CTA %d:", L.conv_name.c_str(), c);
+            for (int i = 1; i < 64; ++i)
+              if (h[c * 64 + i]) fprintf(stderr, " s%d=+%lld", i, h[c * 64 + i] - h[c * 64]);
+            fprintf(stderr, "\n");
+          }
+        } else {
+          rc = launch_conv_dense_fwd(da, st);
+        }
+      }
     } else if (n->conv_impl == 0 && L.tc2_fwd && (n->tc_mask & 1)) {
       const int Hv = L.up ? 2 * Hs_l : Hs_l, Wv = L.up ? 2 * Ws_l : Ws_l;
       Tc2Args t;
@@ -1303,6 +1347,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         db.bsum = a.bsum;
         db.gmax = a.gmax;
         db.out_scale = pow2f(-kWScaleLog2);
+        db.b_early = 1;  // packed during the forward pass
         rc = launch_conv_dense_bwd(db, st);
       } else if (n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2)) {
         Tc2Args t;
