@@ -18,6 +18,13 @@ def shard_permutation(n, world_size, rank, seed, epoch, batch_per_rank):
     return perm[:, rank, :]  # (n_batches, batch_per_rank) indices for this rank
 
 
+def allreduce_sum_(flat, group=None):
+    """In-place SUM all-reduce of the flat gradient bucket (the 1/world of the mean is folded into the
+    consumer: the fused Adam's grad_scale).  Capturable into a CUDA graph on NCCL."""
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
 def allreduce_mean_(flat, group=None, world_size=None):
     """In-place average of a flat gradient bucket over the group (sum all-reduce, then scale)."""
     ws = world_size if world_size is not None else dist.get_world_size(group)

@@ -8,6 +8,7 @@ import torch
 
 from . import _lib
 from . import darcy as _darcy
+from . import ddp
 
 
 class TrainStep(object):
@@ -22,6 +23,9 @@ class TrainStep(object):
         self.gw = torch.tensor([1.0, 1.0, weight_bound, weight_bound], device=self.flat.device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.pg, self.world = process_group, world_size
+        # data parallel: the gradient all-reduce and Adam are captured INSIDE the step graph (falls back to
+        # eager launches behind the replay if the collective cannot be captured)
+        self.collective_in_graph = world_size > 1
         self.steps = 0
         self.kernel_launches = 0
         self.l4 = torch.zeros(4, device=self.flat.device)
@@ -40,11 +44,19 @@ class TrainStep(object):
         for p, v in zip(model._params, model._grad_views):
             p.grad = v
 
+    def release(self):
+        """Drop the captured step graph (it holds the NCCL all-reduce when data parallel): call before
+        torch.distributed.destroy_process_group(), which otherwise waits on a communicator that a live
+        graph still references."""
+        import gc
+        self.graph = None
+        self.static_loss = None
+        gc.collect()
+        torch.cuda.synchronize()
+
     def broadcast_parameters(self):
         """Rank 0's parameters and BatchNorm buffers to every rank (start of DDP training)."""
-        import torch.distributed as dist
-        dist.broadcast(self.flat, 0, group=self.pg)
-        dist.broadcast(self.model._flat_running, 0, group=self.pg)
+        ddp.broadcast_state_([self.flat, self.model._flat_running], 0, group=self.pg)
 
     # ------------------------------------------------------------------ CUDA-graph replay
     def _device_work(self, K):
@@ -64,7 +76,12 @@ class TrainStep(object):
                                          _lib.ptr(dout), st), "pdes_darcy_loss_bwd")
         ex.backward(dout)
         n += L.pdes_densenet_last_launches(ex.handle.h) + 2
-        if self.world == 1:
+        if self.world == 1 or self.collective_in_graph:
+            if self.world > 1:
+                # ONE sum all-reduce of the flat gradient bucket (wgrad wrote straight into it); the 1/world
+                # of the mean is folded into the fused Adam (grad_scale).  NCCL collectives are capturable:
+                # inside the step graph the all-reduce and Adam follow the backward without host launches.
+                ddp.allreduce_sum_(self.gflat, group=self.pg)
             _lib.check(L.pdes_adam_step_dev(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m),
                                             _lib.ptr(self.v), self.flat.numel(), _lib.ptr(self.hyper_dev), st),
                        "pdes_adam_step_dev")
@@ -93,9 +110,21 @@ class TrainStep(object):
         for t, s0 in zip((self.flat, self.m, self.v, m._flat_running, m._flat_nbt), snap):
             t.copy_(s0)
         torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._device_work(self.static_K)
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._device_work(self.static_K)
+        except Exception:
+            if not (self.world > 1 and self.collective_in_graph):
+                raise
+            # the collective refused capture: keep it (and Adam) eager behind the replayed backward
+            self.collective_in_graph = False
+            torch.cuda.synchronize()
+            for t, s0 in zip((self.flat, self.m, self.v, m._flat_running, m._flat_nbt), snap):
+                t.copy_(s0)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._device_work(self.static_K)
 
     def _set_hyper(self, lr):
         L = _lib.lib()
@@ -119,10 +148,9 @@ class TrainStep(object):
         self._set_hyper(self.lr if lr is None else lr)
         self.graph.replay()
         self.steps += 1
-        if self.world > 1:
-            import torch.distributed as dist
+        if self.world > 1 and not self.collective_in_graph:
             L = _lib.lib()
-            dist.all_reduce(self.gflat, group=self.pg)
+            ddp.allreduce_sum_(self.gflat, group=self.pg)
             _lib.check(L.pdes_adam_step_dev(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m),
                                             _lib.ptr(self.v), self.flat.numel(), _lib.ptr(self.hyper_dev),
                                             _lib.stream_ptr()), "pdes_adam_step_dev")
@@ -145,8 +173,7 @@ class TrainStep(object):
         ex.backward(dout)
         n += L.pdes_densenet_last_launches(ex.handle.h) + 2
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.gflat, group=self.pg)
+            ddp.allreduce_sum_(self.gflat, group=self.pg)
         self.steps += 1
         _lib.check(L.pdes_adam_step(_lib.ptr(self.flat), _lib.ptr(self.gflat), _lib.ptr(self.m),
                                     _lib.ptr(self.v), self.flat.numel(), float(self.lr if lr is None else lr),
