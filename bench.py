@@ -26,6 +26,7 @@ if ROOT not in sys.path:
 METRIC = "training-samples/sec GRF-KLE512 64x64 codec mixed-residual"
 IMSIZE, BATCH, NTRAIN = 64, 32, 4096
 WORKLOAD = "DenseED[6,8,6] codec mixed-residual, GRF KLE512 64x64, ntrain=4096, batch 32/GPU, fp32"
+WORKLOAD_LOWP = "DenseED[6,8,6] codec mixed-residual, Channelized 64x64, ntrain=4096, batch 32/GPU, %s tensor-core conv path"
 
 
 def parse():
@@ -37,6 +38,9 @@ def parse():
     ap.add_argument("--ntrain", type=int, default=NTRAIN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=6, help="bounded CPU-baseline sample (steps of 32)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "fp16"],
+                    help="f32: fp32-accurate tensor-core path (headline, BASELINE config 2); bf16 / fp16: one-piece "
+                         "tensor-core conv path on channelized 64x64 data (BASELINE config 3)")
     return ap.parse_args()
 
 
@@ -245,6 +249,8 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if args.dtype != "f32":
+        os.environ["PDES_CONV_DTYPE"] = args.dtype   # read by the executor when a network is created
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -266,7 +272,11 @@ def main():
     pk = peaks()
     # ---- data: synthetic GRF KLE512 64x64, rank-sharded ------------------------------------
     n_local = args.ntrain // world
-    host = data.grf_kle(n_local, IMSIZE, 512, 0.1, seed=1 + rank, device=dev).pin_memory()
+    lowp = args.dtype != "f32"
+    if lowp:   # BASELINE config 3: two-valued channelized permeability fields
+        host = data.channelized(n_local, IMSIZE, seed=1 + rank).pin_memory()
+    else:
+        host = data.grf_kle(n_local, IMSIZE, 512, 0.1, seed=1 + rank, device=dev).pin_memory()
     dset = host.to(dev)
     n_batches = n_local // BATCH
 
@@ -324,11 +334,12 @@ def main():
         Kp = torch.exp(0.5 * torch.randn(BATCH, 1, IMSIZE, IMSIZE))
         pts = TrainStep(pm.to(dev), weight_bound=10.0, lr=1e-3)
         lp = float((pts.step_graph(Kp.to(dev), lr=1e-3) if use_graph else pts.step(Kp.to(dev), lr=1e-3)).item())
+        pbar = {"f32": 1e-4, "fp16": 2e-2, "bf16": 1e-1}[args.dtype]   # one-piece modes: the format's own error
         parity = dict(loss=round(lp, 5), expected=PINNED_LOSS, rel_err=abs(lp - PINNED_LOSS) / PINNED_LOSS,
-                      bar=1e-4, what="first training-mode loss, seed-1 default init, K = exp(0.5 randn) "
+                      bar=pbar, what="first training-mode loss, seed-1 default init, K = exp(0.5 randn) "
                                      "(reference-probed scalar, SURVEY.md section 8c), through the timed "
                                      "engine path")
-        if not parity["rel_err"] <= 1e-4:
+        if not parity["rel_err"] <= pbar:
             raise SystemExit("bench.py: parity preflight failed: loss %.6f vs pinned %.6f" % (lp, PINNED_LOSS))
         del pts, pm
     sampler = ClockSampler(local_rank)
@@ -409,12 +420,13 @@ def main():
                             achieved=round(ach, 2), peak=pk["bf16_tflops_sustained"], unit="TFLOP/s",
                             frac=round(ach / pk["bf16_tflops_sustained"], 4), traffic=traffic.get(n),
                             us_per_launch=round(t_us, 2), gflop_per_launch=round(f / 1e9, 3),
-                            tensor_issue_frac=round(3 * ach / pk["bf16_tflops_sustained"], 4),
+                            tensor_issue_frac=round((1 if lowp else 3) * ach / pk["bf16_tflops_sustained"], 4),
                             note="dominant launch of the step; achieved = useful fp32 FLOPs (2*MAC) of the launch / "
                                  "median CUDA-event time between consecutive launches of an eager step (includes "
-                                 "the ~2 us launch gap); peak = %s dense bf16 (sustained); fp32 accuracy costs 3 "
-                                 "fp16 tensor products per useful product, so 1/3 is the ceiling and "
-                                 "tensor_issue_frac = 3*frac is what the tensor pipe executes" % pk["src"])
+                                 "the ~2 us launch gap); peak = %s dense bf16 (sustained); %s" % (pk["src"],
+                                 "one tensor product per useful product (one-piece operands)" if lowp else
+                                 "fp32 accuracy costs 3 fp16 tensor products per useful product, so 1/3 is the "
+                                 "ceiling and tensor_issue_frac = 3*frac is what the tensor pipe executes"))
         families = {k: dict(us_per_step=round(v[0], 1), launches=v[2], useful_tflops=round(v[1] / (v[0] * 1e-6) / 1e12, 2))
                     for k, v in families.items()}
 
@@ -481,20 +493,23 @@ def main():
 
     cpu = None
     lib_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not lowp:
         lib_base = gpu_library_baseline(dev, host, n_batches)
         cpu = cpu_baseline(args.cpu_steps)
 
     if rank == 0:
         line = dict(metric=METRIC, value=round(value, 1), unit="samples/s", n_gpus=world, steps=args.steps,
                     warmup=max(args.warmup, 3), ms_per_step=round(ms / args.steps, 4), higher_is_better=True,
-                    scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=WORKLOAD, global_batch=BATCH * world,
+                    scaling="weak", vs_baseline=None, dtype=args.dtype, data="synthetic",
+                    config=dict(workload=WORKLOAD if not lowp else WORKLOAD_LOWP % args.dtype, global_batch=BATCH * world,
                                 parallelism="dp%d" % world if world > 1 else "single",
                                 cuda_graph=bool(use_graph),
                                 l2="each step streams ~210 MB of activations+gradients (> 126 MB L2) and a "
                                    "different batch of the HBM-resident dataset; no explicit flush",
-                                grf="exp covariance, l=0.1, 512 KLE modes, seed 1"),
+                                grf=("exp covariance, l=0.1, 512 KLE modes, seed 1" if not lowp else
+                                     "channelized: two-valued fields {1, e^2.5} from thresholded low-pass noise"),
+                                conv_dtype=("two fp16 pieces per operand, 3 tensor-core products (fp32-accurate)"
+                                            if not lowp else "one %s piece per operand, 1 tensor-core product" % args.dtype)),
                     e2e=dict(value=round(e2e_val, 1), unit="samples/s", h2d_bytes_per_step=BATCH * IMSIZE * IMSIZE * 4,
                              d2h_bytes_per_step=4, ms_per_step=round(ms_e / args.steps, 4),
                              api="models.codec.DenseED + models.darcy.conv_* + torch.optim.Adam, loss.item() per step"),

@@ -184,6 +184,12 @@ typedef struct pdes_conv_desc {
   int32_t out_nchw;          /* 1: output written planar (B,Cout,Hout,Wout)          */
 } pdes_conv_desc;
 
+/* Precision of the tensor-core paths of the three entry points below (impl 2 / 4): 0 = fp32-accurate (every
+ * operand as two fp16 pieces, three tensor-core products per useful product; default), 1 = one fp16 piece,
+ * 2 = one bf16 piece (one product; the "bf16 tensor-core conv path" of the reference's benchmark configs).
+ * The DenseED executor takes the same choice from the environment: PDES_CONV_DTYPE = fp32 | fp16 | bf16. */
+int pdes_conv2d_set_precision(int mode);
+
 /* w: OIHW fp32 (Cout,Cin,KH,KW); scale/shift: Cin floats or NULL; y as described.
  * ch_sum/ch_sumsq: Cout doubles accumulated (+=) with the per-channel sum and sum of
  * squares of the outputs, or NULL.  impl: 0/1 CUDA-core fp32, 2 tensor-core (two-piece fp16), 3 the dedicated

@@ -153,8 +153,25 @@ def make_input(B, imsize, seed=0, dtype=torch.float32, kind="lognormal"):
     return torch.tensor(np.exp(0.5 * g), dtype=dtype)
 
 
-def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_running=True):
+def round_operand(t, mode, scale_log2=0):
+    """Value of a convolution operand as the reduced-precision tensor-core modes see it (BASELINE config 3,
+    SURVEY.md section 8d "CPU emulation with bf16-rounded conv operands"): one bf16 piece, or one fp16 piece of
+    the power-of-two scaled value.  Products of the rounded operands are exact in fp32; accumulation is fp32."""
+    if mode is None:
+        return t
+    if mode == "bf16":
+        return t.detach().to(torch.bfloat16).to(t.dtype) + (t - t.detach())   # straight-through for autograd
+    if mode == "fp16":
+        s = 2.0 ** scale_log2
+        return ((t.detach() * s).to(torch.float16).to(t.dtype) / s) + (t - t.detach())
+    raise ValueError(mode)
+
+
+def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_running=True, operand_round=None):
     """DenseED.forward (codec.py:295-296) as a flat functional program.
+
+    operand_round = "bf16" | "fp16": emulate the one-piece tensor-core modes - every convolution but the first
+    (which runs on exact-fp32 CUDA-core kernels) sees rounded activations and filters.
 
     sd maps reference state_dict keys to tensors (parameters may require grad).  In training
     mode running_mean / running_var / num_batches_tracked entries of `sd` are updated in place
@@ -178,7 +195,10 @@ def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_
         a = F.relu(a)
         if s["up"]:
             a = F.interpolate(a, scale_factor=2.0, mode="nearest")  # codec.py:24-30
-        y = F.conv2d(a, sd[_conv_name(s) + ".weight"], None, s["stride"], s["pad"])
+        w = sd[_conv_name(s) + ".weight"]
+        if operand_round is not None:
+            a, w = round_operand(a, operand_round, 4), round_operand(w, operand_round, 8)
+        y = F.conv2d(a, w, None, s["stride"], s["pad"])
         h = torch.cat([h, y], 1) if s["kind"] == "dense" else y  # codec.py:73-75
     return h
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "pdes_conv2d_fwd": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p]),
     "pdes_conv2d_dgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pdes_conv2d_set_precision": (c_int, [c_int]),
     "pdes_conv_tc_plan": (c_int, [c_int, c_int, c_int, POINTER(c_int64)]),
     "pdes_conv2d_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                   c_void_p]),

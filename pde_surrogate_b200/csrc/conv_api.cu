@@ -12,6 +12,7 @@ using namespace pdes;
 
 namespace {
 int rup(int v, int m) { return (v + m - 1) / m * m; }
+int g_unit_lowp = 0;  // precision mode of the tensor-core unit entry points (pdes_conv2d_set_precision)
 
 int check_desc(const pdes_conv_desc* d, const char* fn) {
   PDES_REQUIRE(d != nullptr, PDES_ERR_INVALID, "%s: null descriptor", fn);
@@ -70,7 +71,7 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
                "tensor-core path does not support this convolution (K=%d stride=%d N=%d)", d->KH,
                d->stride, N);
   Tc2Plan p;
-  tc2_plan(d->KH, Cin_k, N, &p);
+  tc2_plan(d->KH, Cin_k, N, &p, g_unit_lowp);
   // operand planes
   ActSplitArgs sa;
   memset(&sa, 0, sizeof(sa));
@@ -96,6 +97,7 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
   float* dinv = reinterpret_cast<float*>(dmax + 1);
   sa.out = planes;
   sa.scale = pow2f(kActScaleLog2);
+  sa.lowp = g_unit_lowp;
   int rc = PDES_OK;
   if (transpose) {
     PDES_CUDA(cudaMemsetAsync(dmax, 0, 8, st));
@@ -117,6 +119,7 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
   h.transpose = transpose;
   h.dxn = 0;
   h.CoP = 0;
+  h.lowp = g_unit_lowp;
   if (rc == PDES_OK) {
     PDES_CUDA(cudaMemcpyAsync(tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     PDES_CUDA(cudaStreamSynchronize(st));
@@ -127,6 +130,7 @@ int run_tc(const ConvArgs& a, const pdes_conv_desc* d, const float* w, int trans
     memset(&t, 0, sizeof(t));
     t.c = a;
     t.wpk = wpk;
+    t.lowp = g_unit_lowp;
     t.out_scale = transpose ? pow2f(-kWScaleLog2) : pow2f(-(kActScaleLog2 + kWScaleLog2));
     t.dyn_scale = transpose ? dinv : nullptr;
     t.N = N;
@@ -192,6 +196,7 @@ int run_dense(const ConvArgs& a, const pdes_conv_desc* d, const float* w, cudaSt
   h.nchunks = (d->Cin + 31) / 32;
   h.dxn = 1;
   h.CoP = 16;
+  h.lowp = g_unit_lowp;
   PDES_CUDA(cudaMemcpyAsync(tab, &h, sizeof(h), cudaMemcpyHostToDevice, st));
   PDES_CUDA(cudaStreamSynchronize(st));
   int rc = launch_pack_tc2(tab, 1, pe, st);
@@ -215,6 +220,7 @@ int run_dense(const ConvArgs& a, const pdes_conv_desc* d, const float* w, cudaSt
     da.o_sum = a.o_sum;
     da.o_sumsq = a.o_sumsq;
     da.out_scale = pow2f(-(kActScaleLog2 + kWScaleLog2));
+    da.lowp = g_unit_lowp;
     rc = launch_conv_dense_fwd(da, st);
   }
   cudaFreeAsync(buf, st);
@@ -419,6 +425,7 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   sa.out = pa;
   sa.Cp = (d->Cin + 7) & ~7;
   sa.scale = pow2f(kActScaleLog2);
+  sa.lowp = g_unit_lowp;
   rc = launch_act_split(sa, st);
   if (rc) return rc;
   unsigned* dmax = reinterpret_cast<unsigned*>(buf + nf) + 64;  // behind the unpack table slot
@@ -439,6 +446,7 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   sb.scale = 1.f;
   sb.dyn_max = dmax;
   sb.dyn_inv = dinv;
+  sb.lowp = g_unit_lowp;
   rc = launch_act_split(sb, st);
   if (rc) return rc;
   tw.planesA = pa;
@@ -455,6 +463,7 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   tw.pad = d->pad;
   tw.out_scale = pow2f(-kActScaleLog2);
   tw.dyn_scale = dinv;
+  tw.lowp = g_unit_lowp;
   rc = launch_wgrad_tc(tw, st);
   if (rc == PDES_OK) {
     TcWgradUnpack u;
@@ -473,6 +482,14 @@ extern "C" int pdes_conv2d_wgrad(const pdes_conv_desc* d, const float* x, const 
   }
   cudaFreeAsync(buf, st);
   return rc;
+}
+
+// Precision mode of the tensor-core unit entry points above (impl 2 / 4): 0 = fp32-accurate (two fp16 pieces,
+// three products; default), 1 = one fp16 piece, 2 = one bf16 piece (BASELINE config 3).
+extern "C" int pdes_conv2d_set_precision(int lowp) {
+  PDES_REQUIRE(lowp >= 0 && lowp <= 2, PDES_ERR_INVALID, "pdes_conv2d_set_precision: mode in 0..2");
+  g_unit_lowp = lowp;
+  return PDES_OK;
 }
 
 // Diagnostics (host only): the tiling the tensor-core convolution kernel would use for a GEMM-K operand of

@@ -24,6 +24,7 @@
 // separate TMEM column groups) + a2 x w1.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
@@ -82,6 +83,11 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
                                             uint64_t* bar) {
@@ -265,11 +271,19 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
               for (int k = 0; k < 8; ++k) t[k] = fmaxf(t[k], 0.f);
             }
             uint32_t p1[4], p2[4];
+            if (a.lowp == LOWP_BF16) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              p1[k] = pack_h2(t[2 * k], t[2 * k + 1]);
-              const float2 f = unpack_h2(p1[k]);
-              p2[k] = pack_h2(t[2 * k] - f.x, t[2 * k + 1] - f.y);
+              for (int k = 0; k < 4; ++k) {
+                p1[k] = pack_bf2(t[2 * k], t[2 * k + 1]);
+                p2[k] = 0u;
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                p1[k] = pack_h2(t[2 * k], t[2 * k + 1]);
+                const float2 f = unpack_h2(p1[k]);
+                p2[k] = a.lowp ? 0u : pack_h2(t[2 * k] - f.x, t[2 * k + 1] - f.y);
+              }
             }
             h1 = make_uint4(p1[0], p1[1], p1[2], p1[3]);
             h2 = make_uint4(p2[0], p2[1], p2[2], p2[3]);
@@ -277,11 +291,11 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
               const int col = p & (W - 1);
               op16* pd = a.planes + ((((size_t)b * H + row) * oct_total + oq) * W + col) * 8;
               *reinterpret_cast<uint4*>(pd) = h1;
-              *reinterpret_cast<uint4*>(pd + plane_elems) = h2;
+              if (!a.lowp) *reinterpret_cast<uint4*>(pd + plane_elems) = h2;
             }
           }
           *reinterpret_cast<uint4*>(st + (size_t)p * 16) = h1;
-          *reinterpret_cast<uint4*>(st + (size_t)p * 16 + a_piece_bytes) = h2;
+          if (!a.lowp) *reinterpret_cast<uint4*>(st + (size_t)p * 16 + a_piece_bytes) = h2;
         }
         fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
         __syncwarp();
@@ -302,7 +316,8 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
                     &b_full[c]);
       }
     }
-    const uint32_t idesc2 = make_idesc_f16(128, 2 * NQ), idesc1 = make_idesc_f16(128, NQ);
+    const uint32_t idesc2 = make_idesc_f16(128, 2 * NQ) | idesc_fmt_bits(a.lowp);
+    const uint32_t idesc1 = make_idesc_f16(128, NQ) | idesc_fmt_bits(a.lowp);
     const uint32_t lbo_a = (uint32_t)HP * 16u, sbo_a = 128u;
     const uint32_t lbo_b = 2u * NQ * 16u, sbo_b = 128u;
     const uint32_t kstep_a = (2u * lbo_a) >> 4, kstep_b = (2u * lbo_b) >> 4;
@@ -333,9 +348,13 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
                 const uint32_t a_k = a_lo0 + (uint32_t)ky * ky_a + (uint32_t)k16 * kstep_a;
                 const uint32_t b_k = b_lo0 + (uint32_t)ky * b_ky_u + (uint32_t)k16 * kstep_b;
                 const bool first = ch == 0 && ky == 0 && k16 == 0;
-                umma_f16_w(d0, a_k, a_hi, b_k, b_hi, idesc2, first ? 0u : 1u);                       // a1 x [w1|w2]
-                if (!(a.exp & 2))
-                  umma_f16_w(d0 + (uint32_t)NQ, a_k + a_piece_u, a_hi, b_k, b_hi, idesc1, 1u);        // a2 x w1 -> G1
+                if (a.lowp) {
+                  umma_f16_w(d0, a_k, a_hi, b_k, b_hi, idesc1, first ? 0u : 1u);                     // one piece: a1 x w1
+                } else {
+                  umma_f16_w(d0, a_k, a_hi, b_k, b_hi, idesc2, first ? 0u : 1u);                     // a1 x [w1|w2]
+                  if (!(a.exp & 2))
+                    umma_f16_w(d0 + (uint32_t)NQ, a_k + a_piece_u, a_hi, b_k, b_hi, idesc1, 1u);      // a2 x w1 -> G1
+                }
               }
             }
           }
@@ -380,7 +399,12 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           float g1[16], g0[16];
-          tmem_ld16(taddr + (uint32_t)(NQ + kx * CoP + c0), g1);   // cross terms first (small), then the leading ones
+          if (a.lowp) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g1[i] = 0.f;
+          } else {
+            tmem_ld16(taddr + (uint32_t)(NQ + kx * CoP + c0), g1);   // cross terms first (small), then the leading ones
+          }
           tmem_ld16(taddr + (uint32_t)(kx * CoP + c0), g0);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {

@@ -16,6 +16,7 @@
 //     TMA ring (32-channel boxes, 128-byte swizzle) issued far ahead of the MMAs.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
@@ -70,6 +71,11 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_h2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ uint32_t pack_bf2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2,
                                             uint64_t* bar) {
@@ -282,9 +288,14 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const float t0 = v[2 * k] * dmul, t1 = v[2 * k + 1] * dmul;
-            p1[k] = pack_h2(t0, t1);
-            const float2 fl = unpack_h2(p1[k]);
-            p2[k] = pack_h2(t0 - fl.x, t1 - fl.y);
+            if (a.lowp == LOWP_BF16) {
+              p1[k] = pack_bf2(t0, t1);
+              p2[k] = 0u;
+            } else {
+              p1[k] = pack_h2(t0, t1);
+              const float2 fl = unpack_h2(p1[k]);
+              p2[k] = a.lowp ? 0u : pack_h2(t0 - fl.x, t1 - fl.y);
+            }
           }
           h1 = make_uint4(p1[0], p1[1], p1[2], p1[3]);
           h2 = make_uint4(p2[0], p2[1], p2[2], p2[3]);
@@ -338,7 +349,8 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
                     reinterpret_cast<const unsigned char*>(a.wpk) + (size_t)jy * b_jy_bytes, b_jy_bytes, &b_full[jy]);
       }
     }
-    const uint32_t idesc2 = make_idesc_f16(128, 2 * N), idesc1 = make_idesc_f16(128, N);
+    const uint32_t idesc2 = make_idesc_f16(128, 2 * N) | idesc_fmt_bits(a.lowp);
+    const uint32_t idesc1 = make_idesc_f16(128, N) | idesc_fmt_bits(a.lowp);
     const uint32_t lbo_a = (uint32_t)HP * 16u, sbo_a = 128u;
     const uint32_t lbo_b = 2u * N * 16u, sbo_b = 128u;
     const uint32_t kstep_a = (2u * lbo_a) >> 4, kstep_b = (2u * lbo_b) >> 4;
@@ -366,7 +378,9 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
             const uint32_t a_k = a_lo0 + (uint32_t)(jy * W) + (uint32_t)k16 * kstep_a;
             const uint32_t b_k = b_lo0 + (uint32_t)jy * b_jy_u + (uint32_t)k16 * kstep_b;
             const uint32_t first = (jy == 0 && k16 == 0) ? 0u : 1u;
-            if (ngroups == 2) {
+            if (a.lowp) {
+              umma_f16_w(d0, a_k, a_hi, b_k, b_hi, idesc1, first);                           // one piece: a1 x w1
+            } else if (ngroups == 2) {
               umma_f16_w(d0, a_k, a_hi, b_k, b_hi, idesc2, first);                           // a1 x [w1|w2] -> G0 | G1
               umma_f16_w(d0 + (uint32_t)N, a_k + a_piece_u, a_hi, b_k, b_hi, idesc1, 1u);    // a2 x w1 -> G1
             } else {
@@ -418,7 +432,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
             xv[4 * c4] = t.x; xv[4 * c4 + 1] = t.y; xv[4 * c4 + 2] = t.z; xv[4 * c4 + 3] = t.w;
           }
           float v[16];
-          if (ngroups == 2) {
+          if (ngroups == 2 && !a.lowp) {
             float w1[16];
             tmem_ld16(taddr + (uint32_t)(N + n0), v);     // cross terms first (small), then the leading ones
             tmem_ld16(taddr + (uint32_t)n0, w1);

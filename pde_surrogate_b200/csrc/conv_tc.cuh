@@ -15,8 +15,14 @@ namespace pdes {
 // from the running maximum of the gradient buffer the slice lives in); the epilogues multiply by
 // the exact inverse.  Below 2^-2 (scaled) the second piece is subnormal: the absolute error of an
 // element is max(2^-23 |x|, 2^-25 / 2^s).
-using op16 = __half;
+using op16 = __half;   // 16-bit storage of a piece (fp16, or bf16 bits in the bf16 one-piece mode)
 constexpr int kPieces = 2;
+// Reduced-precision modes (BASELINE config 3, "bf16 tensor-core conv path"): ONE piece per operand and one
+// tensor-core product per useful product instead of three.  The memory layouts stay those of the two-piece
+// mode (the second piece is simply never written, loaded or multiplied).
+enum { LOWP_NONE = 0, LOWP_FP16 = 1, LOWP_BF16 = 2 };
+// instruction-descriptor bits selecting bf16 A/B operands (kind::f16: format 0 = fp16, 1 = bf16)
+__host__ __device__ inline uint32_t idesc_fmt_bits(int lowp) { return lowp == LOWP_BF16 ? ((1u << 7) | (1u << 10)) : 0u; }
 constexpr int kActScaleLog2 = 4;    // activations (post BatchNorm+ReLU, O(1)):   x * 16
 constexpr int kWScaleLog2 = 8;      // filters (|w| << 256):                      w * 256
 constexpr int kDyTargetLog2 = 10;   // gradients: buffer maximum scaled into [2^10, 2^11)
@@ -47,6 +53,7 @@ struct ActSplitArgs {
   float scale;
   const unsigned* dyn_max;
   float* dyn_inv;
+  int lowp;              // LOWP_*: one piece (fp16 / bf16) instead of two fp16 pieces
 };
 
 struct TcWgradArgs {
@@ -57,6 +64,7 @@ struct TcWgradArgs {
   int ci_pad, co_pad;
   float out_scale;               // exact inverse of the static operand scales
   const float* dyn_scale;        // optional device scalar multiplied in as well (dynamic dY scale)
+  int lowp;                      // LOWP_*: a1 x d1 only (one pass)
 };
 
 struct TcWgradUnpack {
@@ -76,6 +84,7 @@ struct DyIm2colArgs {
   int B, H, W, Cout, KS, pad, Np;
   const unsigned* dyn_max;  // dynamic scale as in ActSplitArgs
   float* dyn_inv;
+  int lowp;
 };
 int launch_dy_im2col(const DyIm2colArgs& a, cudaStream_t st);
 
@@ -103,15 +112,17 @@ struct Tc2Args {
   float out_scale;             // exact inverse of the static operand scales, applied to the accumulator
   const float* dyn_scale;      // optional device scalar multiplied in as well (dynamic dY scale)
   int exp;                     // timing experiments (PDES_TC2_EXP): 1 = skip activation loads, 2 = skip filter loads
+  int lowp;                    // LOWP_*: single product a1 x w1 (one accumulator group)
 };
 struct Tc2PackDesc {
   const float* w;  // OIHW
   op16* dst;
   int Cout, Cin, KS, N, KC, nchunks, transpose;
+  int lowp;        // LOWP_*: only the first piece is written, in fp16 or bf16
   int dxn, CoP;    // dxn = 1: "dx in N" layout of conv_dense.cu, [chunk][ky][k-octet][piece][n = kx*CoP + co][8]
                    // dxn = 2: "dx in K" layout of conv_dense_bwd.cu, [jy][k-octet (jx, co octet)][piece][n = ci][8]
 };
-void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p);
+void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p, int lowp = 0);
 bool tc2_supported(int KS, int stride, int Cin_k, int N);
 // planes: [2][B][Hv][round8(Cin_k)/8][Wv][8] fp16 pieces of the GEMM-K operand (act_split_kernel)
 int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Cin_k, cudaStream_t st);
@@ -133,6 +144,7 @@ struct DenseFwdArgs {
   int Cp;
   float out_scale;     // exact inverse of the static operand scales
   int b_early;         // 1: the filter may be fetched before griddepcontrol.wait (packed >= 2 launches ago)
+  int lowp;            // LOWP_*
   long long* dbg;      // optional phase timestamps (clock64), 64 slots per CTA for the first 4 CTAs (diagnostics)
   int exp;             // timing experiments (PDES_DENSE_EXP; results are wrong): 1 converters skip their shared-memory
                        // traffic, 2 no a2 x w1 MMAs, 4 no raw TMA loads
@@ -156,6 +168,7 @@ struct DenseBwdArgs {
   unsigned* gmax;
   float out_scale;
   int b_early;               // 1: the filter may be fetched before griddepcontrol.wait (packed >= 2 launches ago)
+  int lowp;                  // LOWP_*
 };
 bool dense_bwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout, int H, int W);
 size_t dense_bwd_pack_elems(int N);

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
@@ -133,9 +134,14 @@ template <> struct Ops<1> {
   static constexpr int n = 3;
   static constexpr uint32_t A = 0x100u, Bp = 0x010u, NP = 0x111u, G = 0x110u;
 };
+//  MODE 2: one-piece (fp16 / bf16) operands: the single product a1xw1 -> G0
+template <> struct Ops<2> {
+  static constexpr int n = 1;
+  static constexpr uint32_t A = 0x0u, Bp = 0x0u, NP = 0x1u, G = 0x0u;
+};
 #define OPF(tab, i) ((int)(((tab) >> (4 * (i))) & 0xFu))
 // ops that are the first writer of (all of) their column groups within one k16 step
-template <int MODE> struct FirstW { static constexpr uint32_t mask = MODE == 0 ? 0x1u : 0x3u; };
+template <int MODE> struct FirstW { static constexpr uint32_t mask = MODE == 1 ? 0x3u : 0x1u; };
 
 template <int KS, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -238,9 +244,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
             mbar_arrive(&a_full[s]);
             continue;
           }
-          mbar_arrive_expect_tx(&a_full[s], a_stage_bytes);
+          const int npl = MODE == 2 ? 1 : kPieces;   // one-piece modes never touch the second plane
+          mbar_arrive_expect_tx(&a_full[s], (uint32_t)npl * a_piece_bytes);
 #pragma unroll
-          for (int p = 0; p < kPieces; ++p)
+          for (int p = 0; p < npl; ++p)
             tma_load_4d(st + (size_t)p * a_piece_bytes, &tmA, ix0 * 8, iy0, ch * koct, p * a.B + b, &a_full[s]);
         }
       }
@@ -271,7 +278,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
       using OP = Ops<MODE>;
       uint32_t idesc[OP::n];
 #pragma unroll
-      for (int i = 0; i < OP::n; ++i) idesc[i] = make_idesc_f16(128, OPF(OP::NP, i) * N);
+      for (int i = 0; i < OP::n; ++i) idesc[i] = make_idesc_f16(128, OPF(OP::NP, i) * N) | idesc_fmt_bits(t.lowp);
       const uint32_t lbo_a = HP * 16u, sbo_a = HWp * 16u;            // K-major: LBO = next channel octet
       const uint32_t lbo_b = (uint32_t)kPieces * (uint32_t)N * 16u, sbo_b = 128u;   // [koct][piece][n][16 B]
       // per-op loop invariants: filter-piece offset (16-byte units) inside a k-octet block
@@ -620,8 +627,13 @@ __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
     }
     uint32_t p[kPieces];
     v *= (float)(1 << kWScaleLog2);
-    p[0] = f2h_sat(v);
-    p[1] = f2h_sat(v - __half2float(__ushort_as_half((unsigned short)p[0])));
+    if (d.lowp == LOWP_BF16) {
+      p[0] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+      p[1] = 0u;
+    } else {
+      p[0] = f2h_sat(v);
+      p[1] = d.lowp ? 0u : f2h_sat(v - __half2float(__ushort_as_half((unsigned short)p[0])));
+    }
     op16* base = d.dst + step * per_tap * kPieces + (size_t)ko * kPieces * d.N * 8 + (size_t)n * 8 + k8;
 #pragma unroll
     for (int pc = 0; pc < kPieces; ++pc) base[(size_t)pc * d.N * 8] = __ushort_as_half((unsigned short)p[pc]);
@@ -651,12 +663,12 @@ size_t tc2_smem(int KS, int N, int KC, int AST, int NB, int TPB) {
 
 }  // namespace
 
-void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p) {
+void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p, int lowp) {
   const int T = KS * KS;
   int KC = Cin_k >= 32 ? 32 : 16;
   p->KC = KC;
   p->nchunks = (Cin_k + KC - 1) / KC;
-  p->ngroups = 2;  // G0 = a1*w1, G1 = a1*w2 + a2*w1
+  p->ngroups = lowp ? 1 : 2;  // G0 = a1*w1, G1 = a1*w2 + a2*w1
   int S = 256 / (p->ngroups * N), TS = 2;
   if (S < 1) {
     S = 512 / (p->ngroups * N);
@@ -736,7 +748,8 @@ int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Ci
   const int tiles = ((a.Wo + kTW - 1) / kTW) * ((a.Ho + kTH - 1) / kTH) * a.B;
   int grid = sm_count();
   if (grid > tiles) grid = tiles;
-  const int mode = 2 * t.N <= 256 ? 0 : 1;
+  const int mode = t.lowp ? 2 : (2 * t.N <= 256 ? 0 : 1);
+  PDES_REQUIRE(!t.lowp || t.ngroups == 1, PDES_ERR_INVALID, "conv_tc2: one-piece modes use one accumulator group");
 #define PDES_TC2_LAUNCH(KSV, MODEV)                                                                          \
   {                                                                                                          \
     PDES_ENSURE_SMEM((conv_tc2_kernel<KSV, MODEV>), smem);                                                   \
@@ -745,7 +758,8 @@ int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Ci
 #define PDES_TC2_MODES(KSV)                        \
   {                                                \
     if (mode == 0) PDES_TC2_LAUNCH(KSV, 0)         \
-    else PDES_TC2_LAUNCH(KSV, 1)                   \
+    else if (mode == 1) PDES_TC2_LAUNCH(KSV, 1)    \
+    else PDES_TC2_LAUNCH(KSV, 2)                   \
   }
   if (a.KS == 3) PDES_TC2_MODES(3)
   else if (a.KS == 1) PDES_TC2_MODES(1)

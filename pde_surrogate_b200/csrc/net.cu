@@ -104,6 +104,7 @@ struct pdes_net {
   int tc_mask = 7;  // bit 0: forward, bit 1: dgrad, bit 2: wgrad on tcgen05
   int dense_on = 1; // PDES_DENSE_FWD=0: thin layers go through operand split + conv_tc2 (round-1 path)
   int dense_bwd_on = 1;  // PDES_DENSE_BWD=0: thin-layer dgrad through dY split + conv_tc2
+  int lowp = 0;     // PDES_CONV_DTYPE = fp32 (default: two fp16 pieces, three products) | fp16 | bf16 (one piece)
   // bound
   float* p = nullptr;
   float* g = nullptr;
@@ -351,7 +352,7 @@ int build(pdes_net* n) {
     }
     if (aligned && tc2_supported(L.KS, 1, L.Cin, L.Nf)) {
       L.tc2_fwd = true;
-      tc2_plan(L.KS, L.Cin, L.Nf, &L.p2f);
+      tc2_plan(L.KS, L.Cin, L.Nf, &L.p2f, n->lowp);
       L.w2f = f;
       f += pad4((int64_t)((L.p2f.pack_elems + 1) / 2));
       n->n_tc2++;
@@ -370,7 +371,7 @@ int build(pdes_net* n) {
     if (L.in_buf < 0) continue;  // the first convolution needs no dgrad; its wgrad stays SIMT
     if (aligned && tc2_supported(L.KS, 1, L.Cout, L.Nb)) {
       L.tc2_bwd = true;
-      tc2_plan(L.KS, L.Cout, L.Nb, &L.p2b);
+      tc2_plan(L.KS, L.Cout, L.Nb, &L.p2b, n->lowp);
       L.w2b = f;
       f += pad4((int64_t)((L.p2b.pack_elems + 1) / 2));
       n->n_tc2++;
@@ -503,6 +504,8 @@ extern "C" int pdes_densenet_create(const pdes_densenet_config* cfg, pdes_net_t*
     n->dense_on = (e && e[0] == '0') ? 0 : 1;
     const char* e2 = getenv("PDES_DENSE_BWD");
     n->dense_bwd_on = (e2 && e2[0] == '0') ? 0 : 1;
+    const char* e3 = getenv("PDES_CONV_DTYPE");
+    n->lowp = (e3 && !strcmp(e3, "bf16")) ? LOWP_BF16 : ((e3 && !strcmp(e3, "fp16")) ? LOWP_FP16 : LOWP_NONE);
   }
   const int rc = build(n);
   if (rc != PDES_OK) {
@@ -689,6 +692,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       d.transpose = dir;
       d.dxn = 0;
       d.CoP = 0;
+      d.lowp = n->lowp;
       t2.push_back(d);
     }
     if (L.dense_fwd) {
@@ -704,6 +708,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       d.transpose = 0;
       d.dxn = 1;
       d.CoP = 16;
+      d.lowp = n->lowp;
       t2.push_back(d);
     }
     if (L.dense_bwd) {
@@ -719,6 +724,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       d.transpose = 0;
       d.dxn = 2;
       d.CoP = 16;
+      d.lowp = n->lowp;
       t2.push_back(d);
     }
   }
@@ -934,6 +940,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       sa.out = reinterpret_cast<op16*>(wsf(n, L.planes));
       sa.Cp = (L.Cin + 7) & ~7;
       sa.scale = pow2f(kActScaleLog2);
+      sa.lowp = n->lowp;
       rc = launch_act_split(sa, st);
       if (rc) return rc;
       n->launches++;
@@ -984,6 +991,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       da.planes = (tr && L.tc_wg) ? reinterpret_cast<op16*>(wsf(n, L.planes)) : nullptr;
       da.Cp = (L.Cin + 7) & ~7;
       da.out_scale = pow2f(-(kActScaleLog2 + kWScaleLog2));
+      da.lowp = n->lowp;
       da.b_early = 1;  // packed by pack_tc2 at the head of the forward pass, >= 2 launches ago
       {
         // PDES_DENSE_DBG=<layer index>: phase timestamps of that layer's kernel, printed after the launch
@@ -1032,6 +1040,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
         t.osub = 1;
       }
       t.wpk = reinterpret_cast<const op16*>(wsf(n, L.w2f));
+      t.lowp = n->lowp;
       t.out_scale = pow2f(-(kActScaleLog2 + kWScaleLog2));
       t.N = L.Nf;
       t.KC = L.p2f.KC;
@@ -1184,6 +1193,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         sb.scale = 1.f;
         sb.dyn_max = gmax_slot(n, L.out_buf);
         sb.dyn_inv = wsf(n, n->dyinv) + li;
+        sb.lowp = n->lowp;
         if (have_fix) {
           sb.fix = 1;
           sb.fx = fixargs;
@@ -1207,6 +1217,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         ia.Np = (L.KS * L.KS * L.Cout + 7) & ~7;
         ia.dyn_max = gmax_slot(n, L.out_buf);
         ia.dyn_inv = wsf(n, n->dyinv) + li;  // the same value the dY split publishes
+        ia.lowp = n->lowp;
         cudaStream_t ist = st;
         if (n->n_side > 0 && n->side[0]) {
           // off the critical path: the expansion and the GEMM that reads it both run on the side stream
@@ -1242,6 +1253,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         tw.co_pad = L.co_pad;
         tw.out_scale = pow2f(-kActScaleLog2);
         tw.dyn_scale = wsf(n, n->dyinv) + li;
+        tw.lowp = n->lowp;
         if (L.wg_taps_n) {  // one 1x1 GEMM: N = (tap, co) over the expanded dY
           tw.planesB = reinterpret_cast<const op16*>(wsf(n, L.planesI));
           tw.Cout = L.KS * L.KS * L.Cout;
@@ -1347,6 +1359,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         db.bsum = a.bsum;
         db.gmax = a.gmax;
         db.out_scale = pow2f(-kWScaleLog2);
+        db.lowp = n->lowp;
         db.b_early = 1;  // packed during the forward pass
         rc = launch_conv_dense_bwd(db, st);
       } else if (n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2)) {
@@ -1354,6 +1367,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         memset(&t, 0, sizeof(t));
         t.c = a;
         t.wpk = reinterpret_cast<const op16*>(wsf(n, L.w2b));
+        t.lowp = n->lowp;
         t.out_scale = pow2f(-kWScaleLog2);
         t.dyn_scale = wsf(n, n->dyinv) + li;
         t.N = L.Nb;

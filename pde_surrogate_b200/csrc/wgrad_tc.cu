@@ -26,6 +26,7 @@
 // [tap][ci][co] staging buffer that a small kernel folds into the OIHW gradient.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdlib.h>
 #include "conv.cuh"
 #include "conv_tc.cuh"
@@ -55,6 +56,18 @@ __device__ __forceinline__ uint32_t f2h_sat(float x) {
 __device__ __forceinline__ void fp16_split2(float x, uint32_t& p0, uint32_t& p1) {
   p0 = f2h_sat(x);
   p1 = f2h_sat(x - __half2float(__ushort_as_half((unsigned short)p0)));
+}
+// the pieces of a value in the given precision mode (conv_tc.cuh): two fp16 pieces, or one fp16 / bf16 piece
+__device__ __forceinline__ void split_mode(float x, int lowp, uint32_t& p0, uint32_t& p1) {
+  if (lowp == LOWP_BF16) {
+    p0 = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+    p1 = 0u;
+  } else if (lowp == LOWP_FP16) {
+    p0 = f2h_sat(x);
+    p1 = 0u;
+  } else {
+    fp16_split2(x, p0, p1);
+  }
 }
 
 // instruction descriptor: D fp32, A/B fp16 (format 0), both MN-major
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int x
         }
         uint32_t h0[8], h1[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) fp16_split2(v[k] * mul, h0[k], h1[k]);
+        for (int k = 0; k < 8; ++k) split_mode(v[k] * mul, a.lowp, h0[k], h1[k]);
         const uint4 w0 = make_uint4(h0[0] | (h0[1] << 16), h0[2] | (h0[3] << 16), h0[4] | (h0[5] << 16), h0[6] | (h0[7] << 16));
         const uint4 w1 = make_uint4(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16), h1[4] | (h1[5] << 16), h1[6] | (h1[7] << 16));
         const int ox = up ? 2 * px : px;
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int x
     while ((1 << xsh) < nxo) ++xsh;
     const int ox = threadIdx.x & ((1 << xsh) - 1);
     if (ox < nxo) {
-      for (int r = threadIdx.x >> xsh; r < kPieces * oct; r += 256 >> xsh) {  // r = piece * oct + q
+      for (int r = threadIdx.x >> xsh; r < (a.lowp ? 1 : kPieces) * oct; r += 256 >> xsh) {  // r = piece * oct + q
         const int piece = r >= oct ? 1 : 0, q = r - piece * oct;
         const uint4 val = *reinterpret_cast<const uint4*>(tile + (size_t)r * rstride + ox * 16);
         op16* dst = a.out + (size_t)piece * plane + ((((size_t)b * Hv + (up ? 2 * sy : sy)) * oct + q) * Wv + xo0 + ox) * 8;
@@ -330,10 +343,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   constexpr uint32_t B_PIECE = 2u * CT * B_OCT;     // 16*CT output channels of one piece
   constexpr uint32_t STAGE = (A_BYTES + (uint32_t)kPieces * B_PIECE + 127u) & ~127u;
   constexpr int TG = CT == 1 ? (T <= 9 ? T : 10) : (T < 3 ? T : 3);  // filter taps per CTA (TG accumulators in TMEM)
-  const int pass = blockIdx.z % kPasses;            // which fp16 piece of `a` this CTA streams
-  const int tap0 = (blockIdx.z / kPasses) * TG;     // first tap of this CTA's tap group
+  const int passes = t.lowp ? 1 : kPasses;          // one-piece modes: the single product a1 x d1
+  const int pass = blockIdx.z % passes;             // which fp16 piece of `a` this CTA streams
+  const int tap0 = (blockIdx.z / passes) * TG;      // first tap of this CTA's tap group
   const int ntap = (T - tap0) < TG ? (T - tap0) : TG;
-  const int NP = kPasses - pass;                    // dY pieces multiplied: 2, 1
+  const int NP = t.lowp ? 1 : kPasses - pass;       // dY pieces multiplied: 2, 1
   const int NW = NP * kNC;                          // accumulator columns per tap
 
   extern __shared__ __align__(128) unsigned char smem[];
@@ -399,7 +413,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 1) {
     // ===== MMA issuer: whole warp walks the uniform loop, one elected lane issues =====
     if (my_tiles > 0) {
-      const uint32_t idesc = make_idesc_f16_mn(128, NW);
+      const uint32_t idesc = make_idesc_f16_mn(128, NW) | idesc_fmt_bits(t.lowp);
       // MN-major canonical layout ((8,1,m),(8,k)) : ((1,8,SBO),(8,LBO)): SBO strides along the
       // channels (next octet), LBO along the pixels (next 8-pixel tile row)
       const uint32_t sbo_a = HP * 16u, lbo_a = HWp * 16u;
@@ -508,7 +522,7 @@ __global__ void __launch_bounds__(256) dy_im2col_kernel(DyIm2colArgs a) {
         const int sy = y - tap / a.KS + a.pad, sx = x - tap % a.KS + a.pad;
         if (sy >= 0 && sy < a.H && sx >= 0 && sx < a.W) v = __ldg(a.dy + (((size_t)b * a.Cout + co) * a.H + sy) * a.W + sx);
       }
-      fp16_split2(v * mul, h0[k], h1[k]);
+      split_mode(v * mul, a.lowp, h0[k], h1[k]);
     }
     op16* dst = a.out + i * 8;  // (((b*H + y)*oct + q)*W + x)*8
     *reinterpret_cast<uint4*>(dst) =
@@ -726,10 +740,11 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
   const int T = t.KS * t.KS;
   const int TG = CT == 1 ? (T <= 9 ? T : 10) : (T < 3 ? T : 3);
   const int tap_groups = (T + TG - 1) / TG;
-  int P = (wg_waves() * sm_count()) / (n_ci * n_cog * kPasses * tap_groups);
+  const int passes = t.lowp ? 1 : kPasses;
+  int P = (wg_waves() * sm_count()) / (n_ci * n_cog * passes * tap_groups);
   if (P < 1) P = 1;
   if (P > tiles) P = tiles;
-  dim3 grid(P, n_ci * n_cog, kPasses * tap_groups);
+  dim3 grid(P, n_ci * n_cog, passes * tap_groups);
 #define PDES_WG_LAUNCH(KSV, CTV)                                                                             \
   {                                                                                                          \
     const size_t smem = wg_smem<KSV, CTV>();                                                                 \

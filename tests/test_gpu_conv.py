@@ -239,3 +239,81 @@ def test_conv_dense_fused_forward(case, bn):
     assert float(y[..., :coff].abs().max()) == 0.0 and float(y[..., coff + Cout:].abs().max()) == 0.0
     assert rel(csum, yr.sum((0, 1, 2))) < 5e-5 or float(yr.sum((0, 1, 2)).norm()) < 1e-3
     assert rel(csq, (yr ** 2).sum((0, 1, 2))) < 5e-5
+
+
+LOWP_CASES = [
+    (2, 16, 48, 16, 3, 1, 1, 0, 1),
+    (2, 16, 144, 72, 1, 1, 0, 0, 1),
+    (2, 8, 100, 100, 3, 1, 1, 1, 1),
+    (4, 32, 196, 98, 3, 1, 1, 0, 1),   # 2N > 256 in the three-product mode: N = 112 single product here
+    (2, 16, 49, 3, 5, 1, 2, 0, 1),
+    (8, 32, 128, 16, 3, 1, 1, 0, 1),
+]
+
+
+def _round(t, mode, log2):
+    if mode == 2:
+        return t.float().to(torch.bfloat16).double()
+    s = 2.0 ** log2
+    return (t.float() * s).to(torch.float16).double() / s
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("case", LOWP_CASES)
+def test_conv_one_piece_modes(case, mode):
+    """Reduced-precision tensor-core modes (1 = one fp16 piece, 2 = one bf16 piece = BASELINE config 3): ONE
+    product per useful product.  The kernels must reproduce an fp64 convolution of the ROUNDED operands to
+    fp32-accumulation accuracy (forward and the fused thin-layer forward), and stay within the format's
+    rounding error of the exact result in dgrad / wgrad (dynamic gradient scale)."""
+    from pde_surrogate_b200 import _lib
+    L = _lib.lib()
+    B, H, Cin, Cout, K, s, p, up, bn = case
+    g = torch.Generator().manual_seed(sum(case) + mode)
+    ld_in = (Cin + 3) // 4 * 4 + 4
+    coff = 8
+    ld_out = coff + (Cout + 3) // 4 * 4 + 4
+    x = torch.randn(B, H, H, ld_in, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
+    scale = torch.rand(Cin, generator=g) + 0.5
+    shift = torch.randn(Cin, generator=g) * 0.3
+    d, Ho = _desc(B, H, Cin, Cout, K, s, p, up, bn, ld_in, ld_out, coff)
+    a32 = F.relu(x[..., :Cin].permute(0, 3, 1, 2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))  # fp32 like the kernel
+    ar = _round(a32, mode, 4)
+    wr = _round(w, mode, 8)
+    au = F.interpolate(ar, scale_factor=2.0, mode="nearest") if up else ar
+    yr = F.conv2d(au, wr, None, s, p).permute(0, 2, 3, 1)
+    y_exact = F.conv2d(F.interpolate(a32.double(), scale_factor=2.0, mode="nearest") if up else a32.double(), w.double(), None, s, p).permute(0, 2, 3, 1)
+    st = _lib.stream_ptr()
+    xd, wd, sd, hd = x.cuda(), w.cuda(), scale.cuda(), shift.cuda()
+    fmt_err = 2.0 ** -8 if mode == 2 else 2.0 ** -11
+    try:
+        _lib.check(L.pdes_conv2d_set_precision(mode))
+        impls = [2] + ([4] if (K == 3 and s == 1 and not up and Cout <= 16 and H in (8, 16, 32)) else [])
+        for impl in impls:
+            y = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
+            _lib.check(L.pdes_conv2d_fwd(byref(d), _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(sd), _lib.ptr(hd), _lib.ptr(y),
+                                         None, None, impl, st))
+            # a value within an fp32 ulp of a rounding boundary may round the other way on the GPU (fmaf vs the
+            # two-step CPU expression): a handful of elements differ by one format ulp
+            assert rel(y[..., coff:coff + Cout], yr) < 3e-4, (impl, rel(y[..., coff:coff + Cout], yr))
+            assert rel(y[..., coff:coff + Cout], y_exact) < 3 * fmt_err
+        if Cin % 4 == 0:
+            dy = torch.randn(B, Ho, Ho, Cout, generator=g, dtype=torch.float64)
+            dyd = torch.zeros(B, Ho, Ho, ld_out, device="cuda")
+            dyd[..., coff:coff + Cout] = dy.float().cuda()
+            da = torch.zeros(B, H, H, Cin, device="cuda")
+            _lib.check(L.pdes_conv2d_dgrad(byref(d), _lib.ptr(dyd), _lib.ptr(wd), _lib.ptr(da), 2, st))
+            au_ = (F.interpolate(a32.double(), scale_factor=2.0, mode="nearest") if up else a32.double()).requires_grad_(True)
+            F.conv2d(au_, w.double(), None, s, p).backward(dy.permute(0, 3, 1, 2))
+            da_ref = au_.grad
+            if up:
+                da_ref = da_ref.view(B, Cin, H, 2, H, 2).sum((3, 5))
+            assert rel(da, da_ref.permute(0, 2, 3, 1)) < 3 * fmt_err, rel(da, da_ref.permute(0, 2, 3, 1))
+            dw = torch.zeros(Cout, Cin, K, K, device="cuda")
+            _lib.check(L.pdes_conv2d_wgrad(byref(d), _lib.ptr(xd), _lib.ptr(sd), _lib.ptr(hd), _lib.ptr(dyd), _lib.ptr(dw), 2, st))
+            wq = w.double().requires_grad_(True)
+            F.conv2d(F.interpolate(a32.double(), scale_factor=2.0, mode="nearest") if up else a32.double(), wq, None, s, p).backward(dy.permute(0, 3, 1, 2))
+            assert rel(dw, wq.grad) < 3 * fmt_err, rel(dw, wq.grad)
+        torch.cuda.synchronize()
+    finally:
+        _lib.check(L.pdes_conv2d_set_precision(0))

@@ -411,3 +411,52 @@ def test_tensor_core_backward_strict_per_tensor(golden_dir, name):
         errs = {k: rel(grads[impl][k], grads[6][k]) for k in grads[6]}
         worst[impl] = max(errs.items(), key=lambda kv: kv[1])
         assert worst[impl][1] < 2e-4, (impl, worst[impl])
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("name", ["densenet_fiveblk16", "densenet_full64_channel"])
+def test_one_piece_precision_modes(golden_dir, name, dtype, monkeypatch):
+    """BASELINE config 3 ("bf16 tensor-core conv path"; PDES_CONV_DTYPE = bf16 | fp16): every convolution but the
+    first runs ONE tensor-core product on one-piece operands.  Parity gate of SURVEY.md section 8d: the training
+    forward must match a CPU emulation with rounded conv operands (oracle.densenet_forward(operand_round=...))
+    far more closely than either matches fp32, the loss likewise, and the gradients must stay within the
+    format's error of the fp32 reference."""
+    from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
+    from utils.image_gradient import SobelFilter
+    monkeypatch.setenv("PDES_CONV_DTYPE", dtype)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    model, K, cfg = _model(g)
+    plan = orc.densenet_plan(**cfg)
+    sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
+    model.train()
+    model.zero_grad()
+    out = model(K)
+    loss = conv_constitutive_constraint(K, out, sob) + conv_continuity_constraint(out, sob)
+    d, n = conv_boundary_condition(out)
+    loss = loss + 10.0 * (d + n)
+    loss.backward()
+    torch.cuda.synchronize()
+    sd = orc.make_state(plan, int(g["seed"]))
+    with torch.no_grad():
+        emu = orc.densenet_forward(plan, sd, K.cpu(), training=True, operand_round=dtype)
+    e_emu = rel(out.detach().cpu().numpy(), emu.numpy())
+    e_f32 = rel(out.detach().cpu().numpy(), g["out64"])
+    # the format's own error against fp32: 3e-2 (bf16) on the full network (SURVEY.md headline facts), up to
+    # 9e-2 / 1.1e-2 (bf16 / fp16) on the small five-block test network (CPU emulation)
+    bar = 0.2 if dtype == "bf16" else 0.03
+    assert e_f32 < bar, e_f32
+    # and it IS the rounded-operand computation: far closer to the emulation than to fp32 on the small network;
+    # on the 28-convolution network values that straddle a rounding boundary (GPU fmaf vs the CPU's two-step
+    # BatchNorm) decorrelate the two bf16 computations to about half the format error
+    assert e_emu < max(0.25 * e_f32 + 2e-3, 0.6 * e_f32), (e_emu, e_f32)
+    loss_emu = float(orc.total_loss(K.cpu(), emu)[0])
+    assert abs(float(loss) - loss_emu) <= 2e-2 * abs(loss_emu), (float(loss), loss_emu)
+    names = [str(s) for s in g["param_names"]]
+    params = dict(model.named_parameters())
+    num = den = 0.0
+    for i, nme in enumerate(names):
+        gn = float(params[nme].grad.double().norm())
+        num += (gn - float(g["grad_norm64"][i])) ** 2
+        den += float(g["grad_norm64"][i]) ** 2
+    assert np.sqrt(num / den) < (0.5 if dtype == "bf16" else 0.1), np.sqrt(num / den)
+    assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters())
