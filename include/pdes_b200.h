@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PDES_ABI_VERSION 1
+#define PDES_ABI_VERSION 2
 
 #define PDES_OK 0
 #define PDES_ERR_INVALID 1     /* bad argument (shape, null pointer, alignment)        */
@@ -71,6 +71,13 @@ int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int H, int W, i
  *   dout : (B,3,H,W) fp32, overwritten. */
 int pdes_darcy_loss_bwd(const float* K, const float* out, const float* gw4, int B, int H,
                         int W, int use_tb, float* dout, void* stream);
+/* The same two calls for the NONLINEAR constitutive law of conv_constitutive_constraint_nonlinear
+ * (models/darcy.py:179-191):  -K grad(u) = sigma + beta1 sqrt(K) sigma^2 + beta2 K sigma^3  (loss4[0]; the other
+ * three terms are unchanged).  K is required.  Used by solve_conv_mixed_residual.py --nonlinear (lines 73-77, 134-137). */
+int pdes_darcy_loss_nl_fwd(const float* K, const float* out, int B, int H, int W, int use_tb,
+                           float beta1, float beta2, float* loss4, void* ws, void* stream);
+int pdes_darcy_loss_nl_bwd(const float* K, const float* out, const float* gw4, int B, int H, int W,
+                           int use_tb, float beta1, float beta2, float* dout, void* stream);
 /* Selects the implementation of the two calls above: 0 = auto, 1 = force the generic
  * (any H,W) kernels, 2 / 3 = force the whole-image-in-shared-memory TMA kernels with 256 / 512
  * threads per CTA (unrolled 4- / 2-row strips when they tile the image exactly, else rolling
@@ -95,6 +102,9 @@ typedef struct pdes_densenet_config {
   int32_t growth_rate;   /* default 16                         */
   int32_t init_features; /* default 48                         */
   int32_t max_batch;     /* capacity the workspace is sized for */
+  int32_t arch;          /* 0: DenseED (models/codec.py:210-318).  1: Decoder (models/codec.py:321-370): a plain 3x3
+                          * conv0 on a planar (B, in_channels, imsize, imsize) latent, then decoding blocks only;
+                          * the output is imsize * 2^n_blocks wide.  (ABI version 2) */
 } pdes_densenet_config;
 
 /* Host-side object (no device memory). */
@@ -114,6 +124,9 @@ int pdes_densenet_num_bn(const pdes_net_t* net);
 int64_t pdes_densenet_running_floats(const pdes_net_t* net);
 int pdes_densenet_bn_info(const pdes_net_t* net, int idx, char* name, size_t name_cap,
                           int64_t* mean_offset, int64_t* var_offset, int32_t* channels);
+
+/* Spatial size (H = W) of the network output: imsize for DenseED, imsize * 2^n_blocks for Decoder. */
+int pdes_densenet_output_size(const pdes_net_t* net);
 
 size_t pdes_densenet_workspace_bytes(const pdes_net_t* net);
 /* Bind device buffers.  params/grads: pdes_densenet_param_floats() floats each;

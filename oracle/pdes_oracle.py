@@ -31,8 +31,38 @@ import torch.nn.functional as F
 # ---------------------------------------------------------------------------------------
 
 
+def decoder_plan(dim_latent, out_channels, blocks, growth_rate=16, init_features=48):
+    """Stage list of `Decoder` (models/codec.py:321-370): conv0 = Conv2d(dim_latent, init_features, 3, 1, 1)
+    (line 331), dense decoding blocks (333-338), nearest-upsampling transitions between them (341-348),
+    last decoding (351-353).  Same stage kinds as densenet_plan."""
+    st = [dict(kind="conv", name="features.conv0", cin=dim_latent, cout=init_features, k=3, stride=1, pad=1,
+               up=False)]
+    c = init_features
+    blocks = list(blocks)
+    for i, n in enumerate(blocks):
+        for j in range(n):
+            st.append(dict(kind="dense", name=f"features.DecBlock{i + 1}.denselayer{j + 1}",
+                           cin=c + j * growth_rate, cout=growth_rate, k=3, stride=1, pad=1, up=False))
+        c += n * growth_rate
+        if i < len(blocks) - 1:
+            t = f"features.TransUp{i + 1}"
+            st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=1,
+                           stride=1, pad=0, up=False))
+            st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 2,
+                           k=3, stride=1, pad=1, up=True))
+            c //= 2
+    t = "features.LastTransUp"
+    st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=3, stride=1,
+                   pad=1, up=False))
+    st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 4, k=3,
+                   stride=1, pad=1, up=True))
+    st.append(dict(kind="bnconv", name=t, bn="norm3", conv="conv3", cin=c // 4, cout=out_channels, k=5,
+                   stride=1, pad=2, up=False))
+    return st
+
+
 def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), growth_rate=16,
-                  init_features=48):
+                  init_features=48, arch=0):
     """Ordered list of stages describing DenseED with the defaults the training script uses
     (bottleneck=False in dense layers, bottleneck=True transitions, upsample='nearest',
     drop_rate=0, out_activation=None).
@@ -42,6 +72,8 @@ def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), gr
       'dense'  : BN -> ReLU -> conv3x3(cin->growth) -> cat([x, y])   codec.py:65-69, 73-75
       'bnconv' : BN -> ReLU -> [nearest x2] -> conv                  codec.py:103-150, 163-188
     """
+    if arch == 1:
+        return decoder_plan(in_channels, out_channels, blocks, growth_rate, init_features)
     blocks = list(blocks)
     if len(blocks) > 1 and len(blocks) % 2 == 0:
         raise ValueError("length of blocks must be odd")  # codec.py:231-233
@@ -252,6 +284,16 @@ def constitutive(K, out):
     r1 = out[:, 1:2] + K * sobel_grad_h(u)
     r2 = out[:, 2:3] + K * sobel_grad_v(u)
     return (r1 ** 2 + r2 ** 2).mean()
+
+
+def constitutive_nonlinear(K, out, beta1, beta2):
+    """conv_constitutive_constraint_nonlinear (darcy.py:179-191):
+    -K grad(u) = sigma + beta1 sqrt(K) sigma^2 + beta2 K sigma^3, squared residual mean."""
+    ku_h = -K * sobel_grad_h(out[:, 0:1])
+    ku_v = -K * sobel_grad_v(out[:, 0:1])
+    sigma = out[:, 1:3]
+    rhs = sigma + beta1 * torch.sqrt(K) * sigma ** 2 + beta2 * K * sigma ** 3
+    return ((ku_h - rhs[:, 0:1]) ** 2 + (ku_v - rhs[:, 1:2]) ** 2).mean()
 
 
 def continuity(out, use_tb=True):

@@ -16,7 +16,7 @@ _lib = None
 class DensenetConfig(Structure):
     _fields_ = [("in_channels", c_int32), ("out_channels", c_int32), ("imsize", c_int32),
                 ("n_blocks", c_int32), ("blocks", c_int32 * 15), ("growth_rate", c_int32),
-                ("init_features", c_int32), ("max_batch", c_int32)]
+                ("init_features", c_int32), ("max_batch", c_int32), ("arch", c_int32)]
 
 
 class ConvDesc(Structure):
@@ -34,6 +34,10 @@ SIGNATURES = {
     "pdes_darcy_loss_workspace_bytes": (c_size_t, []),
     "pdes_darcy_loss_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "pdes_darcy_loss_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "pdes_darcy_loss_nl_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p,
+                                       c_void_p, c_void_p]),
+    "pdes_darcy_loss_nl_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float,
+                                       c_void_p, c_void_p]),
     "pdes_darcy_loss_set_impl": (c_int, [c_int]),
     "pdes_densenet_create": (c_int, [POINTER(DensenetConfig), POINTER(c_void_p)]),
     "pdes_densenet_destroy": (None, [c_void_p]),
@@ -45,6 +49,7 @@ SIGNATURES = {
     "pdes_densenet_running_floats": (c_int64, [c_void_p]),
     "pdes_densenet_bn_info": (c_int, [c_void_p, c_int, c_char_p, c_size_t, POINTER(c_int64), POINTER(c_int64),
                                       POINTER(c_int32)]),
+    "pdes_densenet_output_size": (c_int, [c_void_p]),
     "pdes_densenet_workspace_bytes": (c_size_t, [c_void_p]),
     "pdes_densenet_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "pdes_densenet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -82,10 +82,12 @@ class _BNParams(nn.Module):
 class _NetHandle(object):
     """Owns a pdes_net_t* (host-side object of the C library)."""
 
-    def __init__(self, cfg, max_batch):
+    def __init__(self, cfg, max_batch, imsize=None):
         L = _lib.lib()
         c = _lib.DensenetConfig()
-        c.in_channels, c.out_channels, c.imsize = cfg["in_channels"], cfg["out_channels"], cfg["imsize"]
+        self.imsize = int(cfg["imsize"] if imsize is None else imsize)
+        c.in_channels, c.out_channels, c.imsize = cfg["in_channels"], cfg["out_channels"], self.imsize
+        c.arch = int(cfg.get("arch", 0))
         c.n_blocks = len(cfg["blocks"])
         for i, b in enumerate(cfg["blocks"]):
             c.blocks[i] = int(b)
@@ -93,6 +95,7 @@ class _NetHandle(object):
         h = c_void_p()
         _lib.check(L.pdes_densenet_create(byref(c), byref(h)), "pdes_densenet_create")
         self.h, self.max_batch = h, max_batch
+        self.out_size = int(L.pdes_densenet_output_size(h))
 
     def __del__(self):
         try:
@@ -147,13 +150,20 @@ class CudaExecutor(object):
         if m._flat.device != x.device:
             raise RuntimeError("DenseED parameters are on %s but the input is on %s" % (m._flat.device, x.device))
         c = m._cfg
-        if x.dim() != 4 or tuple(x.shape[1:]) != (c["in_channels"], c["imsize"], c["imsize"]):
-            raise ValueError("DenseED expects input (B, %d, %d, %d), got %s"
-                             % (c["in_channels"], c["imsize"], c["imsize"], tuple(x.shape)))
+        if c.get("arch", 0) == 1:
+            # Decoder: the latent's spatial size is free (models/codec.py:321-370 upstream has no imsize argument)
+            if x.dim() != 4 or x.shape[1] != c["in_channels"] or x.shape[2] != x.shape[3]:
+                raise ValueError("Decoder expects a square latent (B, %d, h, h), got %s" % (c["in_channels"], tuple(x.shape)))
+            imsize = int(x.shape[2])
+        else:
+            if x.dim() != 4 or tuple(x.shape[1:]) != (c["in_channels"], c["imsize"], c["imsize"]):
+                raise ValueError("DenseED expects input (B, %d, %d, %d), got %s"
+                                 % (c["in_channels"], c["imsize"], c["imsize"], tuple(x.shape)))
+            imsize = c["imsize"]
         B = x.shape[0]
-        if self.handle is None or B > self.handle.max_batch:
+        if self.handle is None or B > self.handle.max_batch or self.handle.imsize != imsize:
             with torch.cuda.device(x.device):
-                self.handle = _NetHandle(c, max(B, 1))
+                self.handle = _NetHandle(c, max(B, 1), imsize)
             self.ws, self.bound = None, None
             self.applied_impl = None
         if self.applied_impl != m.conv_impl:
@@ -177,8 +187,8 @@ class CudaExecutor(object):
         self.fwd_gen += 1   # the executor keeps ONE set of saved activations: see _DenseEDTrainFn.backward
         x = x.contiguous()
         c = self.m._cfg
-        out = torch.empty(x.shape[0], c["out_channels"], c["imsize"], c["imsize"], dtype=torch.float32,
-                          device=x.device)
+        hw = self.handle.out_size
+        out = torch.empty(x.shape[0], c["out_channels"], hw, hw, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             rc = _lib.lib().pdes_densenet_forward(self.handle.h, _lib.ptr(x), _lib.ptr(out), x.shape[0],
                                                   int(bool(training)), _lib.stream_ptr())
@@ -239,33 +249,26 @@ class _EvalGuardFn(torch.autograd.Function):
                                   "implemented; call model.train() or use torch.no_grad()")
 
 
-class DenseED(nn.Module):
-    """Dense convolutional encoder-decoder (reference models/codec.py:210-318).
+def _reject_options(cls, drop_rate=0, bottleneck=False, upsample='nearest', out_activation=None):
+    unsupported = []
+    if drop_rate and drop_rate > 0:
+        unsupported.append("drop_rate=%r" % drop_rate)
+    if bottleneck:
+        unsupported.append("bottleneck=True")
+    if upsample != 'nearest':
+        unsupported.append("upsample=%r" % (upsample,))
+    if out_activation is not None:
+        unsupported.append("out_activation=%r" % (out_activation,))
+    if unsupported:
+        raise NotImplementedError("pde_surrogate_b200.%s does not implement: %s" % (cls, ", ".join(unsupported)))
 
-    Args as in the reference.  Options the training script never uses raise a clear error
-    instead of silently differing: drop_rate > 0, bottleneck dense layers, upsample other than
-    'nearest', out_activation.
-    """
 
-    def __init__(self, in_channels, out_channels, imsize, blocks, growth_rate=16, init_features=48,
-                 drop_rate=0, bn_size=8, bottleneck=False, out_activation=None, upsample='nearest'):
-        super(DenseED, self).__init__()
-        blocks = [int(b) for b in blocks]
-        if len(blocks) > 1 and len(blocks) % 2 == 0:
-            raise ValueError('length of blocks must be an odd number, but got {}'.format(len(blocks)))
-        unsupported = []
-        if drop_rate and drop_rate > 0:
-            unsupported.append("drop_rate=%r" % drop_rate)
-        if bottleneck:
-            unsupported.append("bottleneck=True")
-        if upsample != 'nearest':
-            unsupported.append("upsample=%r" % (upsample,))
-        if out_activation is not None:
-            unsupported.append("out_activation=%r" % (out_activation,))
-        if unsupported:
-            raise NotImplementedError("pde_surrogate_b200.DenseED does not implement: " + ", ".join(unsupported))
-        self._cfg = dict(in_channels=int(in_channels), out_channels=int(out_channels), imsize=int(imsize),
-                         blocks=blocks, growth_rate=int(growth_rate), init_features=int(init_features))
+class _ExecutorNet(nn.Module):
+    """Parameter holder + autograd wiring shared by DenseED and Decoder: the module tree with the
+    reference's names, ONE flat parameter / gradient / running-statistics buffer, the executor."""
+
+    def _build(self, cfg):
+        self._cfg = cfg
         layout = _NetHandle(self._cfg, 1)
         self._param_table, self._n_flat = layout.params()
         self._bn_table, self._n_running = layout.bns()
@@ -296,7 +299,6 @@ class DenseED(nn.Module):
         self.conv_impl = int(os.environ.get("PDES_CONV_IMPL", "0"))
         self._ex = _executor_factory(self)
         self._flatten()
-        print('# params {}, # conv layers {}'.format(*self.model_size))
 
     # ------------------------------------------------------------------ flat storage
     def _named_param_list(self):
@@ -334,7 +336,7 @@ class DenseED(nn.Module):
         self._flat, self._flat_grad, self._flat_running, self._flat_nbt = flat, gflat, run, nbt
 
     def _apply(self, fn, recurse=True):
-        r = super(DenseED, self)._apply(fn, recurse)
+        r = super(_ExecutorNet, self)._apply(fn, recurse)
         if self._flat is not None:
             self._flatten()
         return r
@@ -410,3 +412,38 @@ class DenseED(nn.Module):
     def flops(self, batch, training=True):
         """Useful 2*MAC FLOPs of one forward (or forward+backward) at this batch size."""
         return self._ex.flops(batch, training)
+
+
+class DenseED(_ExecutorNet):
+    """Dense convolutional encoder-decoder (reference models/codec.py:210-318).
+
+    Args as in the reference.  Options the training script never uses raise a clear error
+    instead of silently differing: drop_rate > 0, bottleneck dense layers, upsample other than
+    'nearest', out_activation.
+    """
+
+    def __init__(self, in_channels, out_channels, imsize, blocks, growth_rate=16, init_features=48,
+                 drop_rate=0, bn_size=8, bottleneck=False, out_activation=None, upsample='nearest'):
+        super(DenseED, self).__init__()
+        blocks = [int(b) for b in blocks]
+        if len(blocks) > 1 and len(blocks) % 2 == 0:
+            raise ValueError('length of blocks must be an odd number, but got {}'.format(len(blocks)))
+        _reject_options("DenseED", drop_rate, bottleneck, upsample, out_activation)
+        self._build(dict(in_channels=int(in_channels), out_channels=int(out_channels), imsize=int(imsize),
+                         blocks=blocks, growth_rate=int(growth_rate), init_features=int(init_features), arch=0))
+        print('# params {}, # conv layers {}'.format(*self.model_size))
+
+
+class Decoder(_ExecutorNet):
+    """Decoder to solve one PDE (reference models/codec.py:321-370): conv0 (3x3) on a latent
+    (B, dim_latent, h, h), dense decoding blocks with nearest-upsampling transitions, last decoding;
+    the output is h * 2^len(blocks) wide.  Same kernels as DenseED (solve_conv_mixed_residual.py:122)."""
+
+    def __init__(self, dim_latent, out_channels, blocks, growth_rate=16, init_features=48, drop_rate=0.,
+                 upsample='nearest', out_activation=None):
+        super(Decoder, self).__init__()
+        blocks = [int(b) for b in blocks]
+        _reject_options("Decoder", drop_rate, False, upsample, out_activation)
+        # imsize here only sizes the layout query: the latent's spatial size is taken from the input
+        self._build(dict(in_channels=int(dim_latent), out_channels=int(out_channels), imsize=16, blocks=blocks,
+                         growth_rate=int(growth_rate), init_features=int(init_features), arch=1))

@@ -80,6 +80,7 @@ struct pdes_net {
   int64_t param_floats = 0, running_floats = 0;
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
   size_t xin = 0;
+  int in_hw = 0, out_hw = 0;  // spatial size of the network input / output (DenseED: both imsize)
   size_t gmax_off = 0;  // double offset: running |G| maxima (unsigned float bits), one per buffer + one for dout
   size_t dyinv = 0;     // float offset: per-layer inverse of the dynamic dY scale (written by the dY split)
   // side streams for the weight-gradient kernels: they are off the critical path of the backward
@@ -216,24 +217,28 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
 // uses: dense layers without bottleneck, bottleneck transitions, nearest upsampling.
 int build(pdes_net* n) {
   const pdes_densenet_config& c = n->cfg;
-  PDES_REQUIRE(c.n_blocks >= 1 && c.n_blocks <= 15 && (c.n_blocks == 1 || c.n_blocks % 2 == 1),
+  PDES_REQUIRE(c.arch == 0 || c.arch == 1, PDES_ERR_INVALID, "pdes_densenet_create: arch %d (0 DenseED, 1 Decoder)", c.arch);
+  PDES_REQUIRE(c.n_blocks >= 1 && c.n_blocks <= 15 && (c.arch == 1 || c.n_blocks == 1 || c.n_blocks % 2 == 1),
                PDES_ERR_INVALID, "length of blocks must be an odd number, but got %d", c.n_blocks);
-  PDES_REQUIRE(c.in_channels >= 1 && c.out_channels >= 1 && c.imsize >= 8 && c.growth_rate >= 1 &&
+  PDES_REQUIRE(c.in_channels >= 1 && c.out_channels >= 1 && c.imsize >= (c.arch == 1 ? 2 : 8) && c.growth_rate >= 1 &&
                    c.init_features >= 1 && c.max_batch >= 1,
                PDES_ERR_INVALID, "pdes_densenet_create: invalid configuration");
   for (int i = 0; i < c.n_blocks; ++i)
     PDES_REQUIRE(c.blocks[i] >= 1 && c.blocks[i] < kMaxConsumers - 1, PDES_ERR_UNSUPPORTED,
                  "dense block of %d layers (supported: 1..%d)", c.blocks[i], kMaxConsumers - 2);
-  const int n_enc = c.n_blocks / 2;
+  const bool decoder = c.arch == 1;
+  const int n_enc = decoder ? 0 : c.n_blocks / 2;
   const int pad0 = (c.imsize % 2 == 0) ? 3 : 2;  // codec.py:238
-  int H = conv_out(c.imsize, 7, 2, pad0);
+  int H = decoder ? c.imsize : conv_out(c.imsize, 7, 2, pad0);
   int C = c.init_features;
+  n->in_hw = c.imsize;
   // every dense block (or single-consumer tensor) is one buffer
   auto block_channels = [&](int C0, int nl) { return C0 + nl * c.growth_rate; };
   int cur = add_buf(n, H, H, block_channels(C, c.blocks[0]));
-  if (n_enc == 0 && c.n_blocks == 1) { /* single decoding block */ }
-  add_layer(n, 0, "features.In_conv", "", -1, cur, 0, c.in_channels, C, 7, 2, pad0, 0, c.imsize,
-            c.imsize);
+  if (decoder)  // Decoder.conv0: Conv2d(dim_latent, init_features, 3, 1, 1, bias=False)  (codec.py:331)
+    add_layer(n, 0, "features.conv0", "", -1, cur, 0, c.in_channels, C, 3, 1, 1, 0, c.imsize, c.imsize);
+  else
+    add_layer(n, 0, "features.In_conv", "", -1, cur, 0, c.in_channels, C, 7, 2, pad0, 0, c.imsize, c.imsize);
   char nm[128];
   for (int bi = 0; bi < c.n_blocks; ++bi) {
     const bool enc = bi < n_enc;
@@ -265,7 +270,8 @@ int build(pdes_net* n) {
       add_layer(n, 2, t + ".conv2", t + ".norm2", b1, b2, 0, C / 2, C / 4, 3, 1, 1, 1, H, H);
       add_layer(n, 2, t + ".conv3", t + ".norm3", b2, -1, 0, C / 4, c.out_channels, 5, 1, 2, 0, 2 * H,
                 2 * H);
-      PDES_REQUIRE(2 * H == c.imsize, PDES_ERR_UNSUPPORTED,
+      n->out_hw = 2 * H;
+      PDES_REQUIRE(decoder || 2 * H == c.imsize, PDES_ERR_UNSUPPORTED,
                    "imsize %d does not map back to itself through the encoder-decoder (got %d)",
                    c.imsize, 2 * H);
     }
@@ -424,13 +430,13 @@ int build(pdes_net* n) {
   n->dyinv = f;
   f += pad4((int64_t)n->layers.size());
   n->xin = f;
-  f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
+  f += pad4((int64_t)B * c.in_channels * n->in_hw * n->in_hw);
   n->xs = f;
-  f += pad4((int64_t)B * c.in_channels * c.imsize * c.imsize);
+  f += pad4((int64_t)B * c.in_channels * n->in_hw * n->in_hw);
   n->outs = f;
-  f += pad4((int64_t)B * c.out_channels * c.imsize * c.imsize);
+  f += pad4((int64_t)B * c.out_channels * n->out_hw * n->out_hw);
   n->douts = f;
-  f += pad4((int64_t)B * c.out_channels * c.imsize * c.imsize);
+  f += pad4((int64_t)B * c.out_channels * n->out_hw * n->out_hw);
   n->ws_floats = f;
   size_t d = 0;
   for (auto& b : n->bufs) {
@@ -612,6 +618,8 @@ extern "C" int pdes_densenet_bn_info(const pdes_net_t* n, int idx, char* name, s
   }
   return PDES_ERR_INVALID;
 }
+
+extern "C" int pdes_densenet_output_size(const pdes_net_t* n) { return n ? n->out_hw : 0; }
 
 extern "C" size_t pdes_densenet_workspace_bytes(const pdes_net_t* n) { return n ? n->ws_bytes : 0; }
 
@@ -870,7 +878,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
   }
   if (tr) {
     PDES_CUDA(cudaMemcpyAsync(wsf(n, n->xin), x,
-                              sizeof(float) * (size_t)B * n->cfg.in_channels * n->cfg.imsize * n->cfg.imsize,
+                              sizeof(float) * (size_t)B * n->cfg.in_channels * n->in_hw * n->in_hw,
                               cudaMemcpyDeviceToDevice, st));
     n->launches++;
     mark(n, st, "copy xin");
@@ -1088,7 +1096,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
   if (n->conv_impl == 0) {
     // dynamic fp16 scale of the last layer's dY pieces: |dout| maximum (the other layers' slices take
     // the running maximum their gradient buffer collected from the dgrad epilogues)
-    rc = launch_absmax(dout, (size_t)B * n->cfg.out_channels * n->cfg.imsize * n->cfg.imsize, gmax_slot(n, -1), st);
+    rc = launch_absmax(dout, (size_t)B * n->cfg.out_channels * n->out_hw * n->out_hw, gmax_slot(n, -1), st);
     if (rc) return rc;
     n->launches++;
     mark(n, st, "absmax dout");
@@ -1487,8 +1495,8 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   }
   gs->calls++;
   if (gs->calls == 1) return forward_impl(n, x, out, B, training, stream);  // warm-up (lazy attributes)
-  const size_t xbytes = sizeof(float) * (size_t)B * n->cfg.in_channels * n->cfg.imsize * n->cfg.imsize;
-  const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->cfg.imsize * n->cfg.imsize;
+  const size_t xbytes = sizeof(float) * (size_t)B * n->cfg.in_channels * n->in_hw * n->in_hw;
+  const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->out_hw * n->out_hw;
   if (!gs->exec) {
     pdes_net* nn = n;
     const int rc = capture_into(*gs, n, st, [&]() {
@@ -1530,7 +1538,7 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
   }
   gs->calls++;
   if (gs->calls == 1) return backward_impl(n, dout, stream);
-  const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->cfg.imsize * n->cfg.imsize;
+  const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->out_hw * n->out_hw;
   if (!gs->exec) {
     pdes_net* nn = n;
     const int rc = capture_into(*gs, n, st, [&]() { return backward_impl(nn, wsf(nn, nn->douts), stream); });

@@ -208,7 +208,7 @@ __device__ __forceinline__ void loss_block_reduce_and_finish(FwdPartial part, Lo
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 darcy_fwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ out, int B, int H,
-                         int W, int use_tb, float* loss4, LossWs* ws, LossNorm nrm) {
+                         int W, int use_tb, float* loss4, LossWs* ws, LossNorm nrm, float beta1, float beta2) {
   FwdPartial part;
   part.c = part.d = part.dir = part.neu = 0.f;
   const int64_t total = (int64_t)B * H * W;
@@ -221,9 +221,13 @@ darcy_fwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ 
     const float* s1 = u + H * W;
     const float* s2 = s1 + H * W;
     if (K != nullptr) {
+      // nonlinear Darcy law (models/darcy.py:179-191 upstream): sigma -> f(sigma) = sigma + beta1 sqrt(K) sigma^2
+      // + beta2 K sigma^3; beta1 = beta2 = 0 is the linear law
       const float k = K[i];
-      const float r1 = s1[p] + k * sobel_dx(u, y, x, H, W, true);
-      const float r2 = s2[p] + k * sobel_dy(u, y, x, H, W, true);
+      const float b1 = beta1 * sqrtf(k), b2 = beta2 * k;
+      const float f1 = s1[p] * (1.f + s1[p] * (b1 + b2 * s1[p])), f2 = s2[p] * (1.f + s2[p] * (b1 + b2 * s2[p]));
+      const float r1 = f1 + k * sobel_dx(u, y, x, H, W, true);
+      const float r2 = f2 + k * sobel_dy(u, y, x, H, W, true);
       part.c += r1 * r1 + r2 * r2;
     }
     if (use_tb || (y >= 1 && y <= H - 2)) {
@@ -244,7 +248,7 @@ struct BwdCoef {
 __global__ void __launch_bounds__(256)
 darcy_bwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ out,
                          const float* __restrict__ gw4, int B, int H, int W, int use_tb,
-                         float* dout, BwdCoef cf) {
+                         float* dout, BwdCoef cf, float beta1, float beta2) {
   const float a = K != nullptr ? gw4[0] * cf.n_c : 0.f;
   const float bb = gw4[1] * cf.n_d;
   const float cdir = gw4[2] * cf.n_dir, cneu = gw4[3] * cf.n_neu;
@@ -262,10 +266,13 @@ darcy_bwd_generic_kernel(const float* __restrict__ K, const float* __restrict__ 
     float* g2 = g1 + H * W;
     if (K != nullptr) {
       const float k = K[i];
-      const float r1 = s1[p] + k * sobel_dx(u, y, x, H, W, true);
-      const float r2 = s2[p] + k * sobel_dy(u, y, x, H, W, true);
-      atomicAdd(g1 + p, a * r1);
-      atomicAdd(g2 + p, a * r2);
+      const float b1 = beta1 * sqrtf(k), b2 = beta2 * k;
+      const float f1 = s1[p] * (1.f + s1[p] * (b1 + b2 * s1[p])), f2 = s2[p] * (1.f + s2[p] * (b1 + b2 * s2[p]));
+      const float d1 = 1.f + s1[p] * (2.f * b1 + 3.f * b2 * s1[p]), d2 = 1.f + s2[p] * (2.f * b1 + 3.f * b2 * s2[p]);
+      const float r1 = f1 + k * sobel_dx(u, y, x, H, W, true);
+      const float r2 = f2 + k * sobel_dy(u, y, x, H, W, true);
+      atomicAdd(g1 + p, a * r1 * d1);   // d r1 / d sigma1 = f'(sigma1)
+      atomicAdd(g2 + p, a * r2 * d2);
       scat_dx(gu, y, x, H, W, true, a * k * r1);
       scat_dy(gu, y, x, H, W, true, a * k * r2);
     }
@@ -498,8 +505,9 @@ static int check_loss_args(const float* out, int B, int H, int W, const char* fn
   return PDES_OK;
 }
 
-extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int H, int W,
-                                   int use_tb, float* loss4, void* ws, void* stream) {
+static int darcy_loss_fwd_impl(const float* K, const float* out, int B, int H, int W, int use_tb, float* loss4,
+                               void* ws, void* stream, float beta1, float beta2) {
+  const bool nonlinear = beta1 != 0.f || beta2 != 0.f;
   int rc = check_loss_args(out, B, H, W, "pdes_darcy_loss_fwd");
   if (rc) return rc;
   PDES_REQUIRE(loss4 && ws, PDES_ERR_INVALID, "pdes_darcy_loss_fwd: null loss4/workspace");
@@ -511,9 +519,9 @@ extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int 
   nrm.inv_dir = 1.0 / ((double)B * H);
   nrm.inv_neu = 1.0 / ((double)B * 2 * W);
   const bool can_tile = tile_ok(H, W, K ? (const void*)K : (const void*)out, out, false);
-  PDES_REQUIRE(g_loss_impl < 2 || can_tile, PDES_ERR_UNSUPPORTED,
+  PDES_REQUIRE(g_loss_impl < 2 || nonlinear || can_tile, PDES_ERR_UNSUPPORTED,
                "pdes_darcy_loss_fwd: tile kernel forced but %dx%d does not qualify", H, W);
-  if (g_loss_impl != 1 && can_tile) {
+  if (g_loss_impl != 1 && can_tile && !nonlinear) {   // (the nonlinear law lives in the generic kernels)
     const size_t smem = 128 + (size_t)H * W * 4 * 8;
     int grid = sm_count();
     if (grid > B) grid = B;
@@ -534,14 +542,25 @@ extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int 
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
     darcy_fwd_generic_kernel<<<blocks, 256, 0, st>>>(K, out, B, H, W, use_tb, loss4, (LossWs*)ws,
-                                                     nrm);
+                                                     nrm, beta1, beta2);
   }
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }
 
-extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float* gw4, int B,
-                                   int H, int W, int use_tb, float* dout, void* stream) {
+extern "C" int pdes_darcy_loss_fwd(const float* K, const float* out, int B, int H, int W,
+                                   int use_tb, float* loss4, void* ws, void* stream) {
+  return darcy_loss_fwd_impl(K, out, B, H, W, use_tb, loss4, ws, stream, 0.f, 0.f);
+}
+extern "C" int pdes_darcy_loss_nl_fwd(const float* K, const float* out, int B, int H, int W, int use_tb,
+                                      float beta1, float beta2, float* loss4, void* ws, void* stream) {
+  PDES_REQUIRE(K != nullptr, PDES_ERR_INVALID, "pdes_darcy_loss_nl_fwd: the nonlinear law needs the permeability field");
+  return darcy_loss_fwd_impl(K, out, B, H, W, use_tb, loss4, ws, stream, beta1, beta2);
+}
+
+static int darcy_loss_bwd_impl(const float* K, const float* out, const float* gw4, int B, int H, int W,
+                               int use_tb, float* dout, void* stream, float beta1, float beta2) {
+  const bool nonlinear = beta1 != 0.f || beta2 != 0.f;
   int rc = check_loss_args(out, B, H, W, "pdes_darcy_loss_bwd");
   if (rc) return rc;
   PDES_REQUIRE(gw4 && dout, PDES_ERR_INVALID, "pdes_darcy_loss_bwd: null gw4/dout");
@@ -553,9 +572,9 @@ extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float
   cf.n_neu = (float)(2.0 / ((double)B * 2 * W));
   const bool can_tile = tile_ok(H, W, K ? (const void*)K : (const void*)out, out, true) &&
                         (((uintptr_t)dout & 15u) == 0);
-  PDES_REQUIRE(g_loss_impl < 2 || can_tile, PDES_ERR_UNSUPPORTED,
+  PDES_REQUIRE(g_loss_impl < 2 || nonlinear || can_tile, PDES_ERR_UNSUPPORTED,
                "pdes_darcy_loss_bwd: tile kernel forced but %dx%d does not qualify", H, W);
-  if (g_loss_impl != 1 && can_tile) {
+  if (g_loss_impl != 1 && can_tile && !nonlinear) {
     const size_t smem = 128 + (size_t)H * W * 4 * 13;
     int grid = sm_count();
     if (grid > B) grid = B;
@@ -576,10 +595,20 @@ extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float
     int blocks = (int)((total + 255) / 256);
     const int cap = sm_count() * 8;
     if (blocks > cap) blocks = cap;
-    darcy_bwd_generic_kernel<<<blocks, 256, 0, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf);
+    darcy_bwd_generic_kernel<<<blocks, 256, 0, st>>>(K, out, gw4, B, H, W, use_tb, dout, cf, beta1, beta2);
   }
   PDES_LAUNCH_CHECK();
   return PDES_OK;
+}
+
+extern "C" int pdes_darcy_loss_bwd(const float* K, const float* out, const float* gw4, int B,
+                                   int H, int W, int use_tb, float* dout, void* stream) {
+  return darcy_loss_bwd_impl(K, out, gw4, B, H, W, use_tb, dout, stream, 0.f, 0.f);
+}
+extern "C" int pdes_darcy_loss_nl_bwd(const float* K, const float* out, const float* gw4, int B, int H, int W,
+                                      int use_tb, float beta1, float beta2, float* dout, void* stream) {
+  PDES_REQUIRE(K != nullptr, PDES_ERR_INVALID, "pdes_darcy_loss_nl_bwd: the nonlinear law needs the permeability field");
+  return darcy_loss_bwd_impl(K, out, gw4, B, H, W, use_tb, dout, stream, beta1, beta2);
 }
 
 }  // namespace pdes

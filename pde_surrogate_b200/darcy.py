@@ -43,15 +43,21 @@ class _DarcyLossFn(torch.autograd.Function):
     """(K, out) -> tensor[4] = [constitutive, continuity, dirichlet, neumann]."""
 
     @staticmethod
-    def forward(ctx, K, out, use_tb):
+    def forward(ctx, K, out, use_tb, beta1=0.0, beta2=0.0):
         outc = out.contiguous()
         Kc = K.contiguous() if K is not None else None
         B, _, H, W = outc.shape
         l4 = torch.empty(4, dtype=torch.float32, device=outc.device)
+        ctx.betas = (float(beta1), float(beta2))
         with torch.cuda.device(outc.device):
-            rc = _lib.lib().pdes_darcy_loss_fwd(_lib.ptr(Kc), _lib.ptr(outc), B, H, W, int(use_tb),
-                                                _lib.ptr(l4), _lib.ptr(_workspace(outc.device)),
-                                                _lib.stream_ptr())
+            if ctx.betas != (0.0, 0.0):
+                rc = _lib.lib().pdes_darcy_loss_nl_fwd(_lib.ptr(Kc), _lib.ptr(outc), B, H, W, int(use_tb),
+                                                       ctx.betas[0], ctx.betas[1], _lib.ptr(l4),
+                                                       _lib.ptr(_workspace(outc.device)), _lib.stream_ptr())
+            else:
+                rc = _lib.lib().pdes_darcy_loss_fwd(_lib.ptr(Kc), _lib.ptr(outc), B, H, W, int(use_tb),
+                                                    _lib.ptr(l4), _lib.ptr(_workspace(outc.device)),
+                                                    _lib.stream_ptr())
         _lib.check(rc, "pdes_darcy_loss_fwd")
         ctx.use_tb = use_tb
         ctx.has_K = Kc is not None
@@ -74,23 +80,30 @@ class _DarcyLossFn(torch.autograd.Function):
         g4 = g4.contiguous().float()
         dout = torch.empty_like(outc)
         with torch.cuda.device(outc.device):
-            rc = _lib.lib().pdes_darcy_loss_bwd(_lib.ptr(Kc), _lib.ptr(outc), _lib.ptr(g4), B, H, W,
-                                                int(ctx.use_tb), _lib.ptr(dout), _lib.stream_ptr())
+            if ctx.betas != (0.0, 0.0):
+                rc = _lib.lib().pdes_darcy_loss_nl_bwd(_lib.ptr(Kc), _lib.ptr(outc), _lib.ptr(g4), B, H, W,
+                                                       int(ctx.use_tb), ctx.betas[0], ctx.betas[1],
+                                                       _lib.ptr(dout), _lib.stream_ptr())
+            else:
+                rc = _lib.lib().pdes_darcy_loss_bwd(_lib.ptr(Kc), _lib.ptr(outc), _lib.ptr(g4), B, H, W,
+                                                    int(ctx.use_tb), _lib.ptr(dout), _lib.stream_ptr())
         _lib.check(rc, "pdes_darcy_loss_bwd")
-        return None, dout, None
+        return None, dout, None, None, None
 
 
 def _alive(ref, t, ver):
     return ref is not None and ref() is t and t._version == ver
 
 
-def _fused_parts(input, output, use_tb=True):
-    """The four partial losses of (input, output) as 0-d tensors, computed once per distinct pair."""
+def _fused_parts(input, output, use_tb=True, betas=None):
+    """The four partial losses of (input, output) as 0-d tensors, computed once per distinct pair.
+    betas = (beta1, beta2) selects the nonlinear constitutive law for parts[0]; calls that do not name a
+    law (continuity / boundary terms: betas None) are served from whatever evaluation is memoised."""
     idx = output.device.index
     grad_mode = torch.is_grad_enabled() and output.requires_grad
     m = _memo.get(idx)
     if m is not None and _alive(m["out_ref"], output, m["out_ver"]) and m["grad"] == grad_mode \
-            and m["use_tb"] == use_tb:
+            and m["use_tb"] == use_tb and (betas is None or m.get("betas", (0.0, 0.0)) == betas):
         if input is None or (m["K_ref"] is not None and _alive(m["K_ref"], input, m["K_ver"])):
             return m["parts"]
     _check(output, "output", 3)
@@ -98,9 +111,13 @@ def _fused_parts(input, output, use_tb=True):
         _check(input, "input", 1)
         if input.shape[0] != output.shape[0] or input.shape[2:] != output.shape[2:]:
             raise ValueError("input %s and output %s do not match" % (tuple(input.shape), tuple(output.shape)))
-    l4 = _DarcyLossFn.apply(input, output, bool(use_tb))
+    b = betas if betas is not None else (0.0, 0.0)
+    if b != (0.0, 0.0):
+        l4 = _DarcyLossFn.apply(input, output, bool(use_tb), b[0], b[1])
+    else:
+        l4 = _DarcyLossFn.apply(input, output, bool(use_tb))
     parts = l4.unbind(0)
-    _memo[idx] = dict(out_ref=weakref.ref(output), out_ver=output._version,
+    _memo[idx] = dict(betas=b, out_ref=weakref.ref(output), out_ver=output._version,
                       K_ref=weakref.ref(input) if input is not None else None,
                       K_ver=input._version if input is not None else None, grad=grad_mode,
                       use_tb=use_tb, parts=parts)
@@ -117,7 +134,19 @@ def conv_constitutive_constraint(input, output, sobel_filter):
         gh = sobel_filter.grad_h(output[:, [0]])
         gv = sobel_filter.grad_v(output[:, [0]])
         return ((output[:, [1]] + input * gh) ** 2 + (output[:, [2]] + input * gv) ** 2).mean()
-    return _fused_parts(input, output)[0]
+    return _fused_parts(input, output, betas=(0.0, 0.0))[0]
+
+
+def conv_constitutive_constraint_nonlinear(input, output, sobel_filter, beta1, beta2):
+    """Nonlinear extension of Darcy's law, -K grad(u) = sigma + beta1 sqrt(K) sigma^2 + beta2 K sigma^3
+    (darcy.py:179-191; solve_conv_mixed_residual.py --nonlinear).  Same fused kernel pair as the linear law."""
+    if _needs_composite(sobel_filter):
+        ku_h = -input * sobel_filter.grad_h(output[:, [0]])
+        ku_v = -input * sobel_filter.grad_v(output[:, [0]])
+        sigma = output[:, [1, 2]]
+        rhs = sigma + beta1 * torch.sqrt(input) * sigma ** 2 + beta2 * input * sigma ** 3
+        return ((ku_h - rhs[:, [0]]) ** 2 + (ku_v - rhs[:, [1]]) ** 2).mean()
+    return _fused_parts(input, output, betas=(float(beta1), float(beta2)))[0]
 
 
 def conv_continuity_constraint(output, sobel_filter, use_tb=True):

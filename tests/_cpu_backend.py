@@ -47,8 +47,13 @@ class OracleExecutor(object):
 
 class _OracleDarcyFn(object):
     @staticmethod
-    def apply(K, out, use_tb):
-        c = orc.constitutive(K, out) if K is not None else out.new_zeros(())
+    def apply(K, out, use_tb, beta1=0.0, beta2=0.0):
+        if K is None:
+            c = out.new_zeros(())
+        elif beta1 != 0.0 or beta2 != 0.0:
+            c = orc.constitutive_nonlinear(K, out, beta1, beta2)
+        else:
+            c = orc.constitutive(K, out)
         d, n = orc.boundary(out)
         return torch.stack([c, orc.continuity(out, use_tb), d, n])
 

@@ -35,7 +35,9 @@ def import_reference():
     from models.codec import DenseED
     from models import darcy
     from utils.image_gradient import SobelFilter
+    import models.codec as _codec
     sys.path.remove(REF)
+    import_reference.Decoder = _codec.Decoder
     return DenseED, darcy, SobelFilter
 
 
@@ -182,8 +184,67 @@ def main():
         d["stride"] = 97
         np.savez_compressed(os.path.join(HERE, "trajectory_b32.npz"), **d)
 
+    def decoder_cases():
+        # `Decoder` (models/codec.py:321-370) driven by the solver's closure
+        # (solve_conv_mixed_residual.py:131-145) with the linear and the nonlinear constitutive law
+        # (models/darcy.py:179-191), batch 1, in fp64 and fp32.
+        Decoder = import_reference.Decoder
+        d = {}
+        for tag, (nz, hz, blocks, gr, feat, seed) in dict(a=(2, 8, [3, 2], 8, 16, 23), b=(1, 16, [8, 6], 16, 48, 29)).items():
+            plan = orc.decoder_plan(nz, 3, blocks, gr, feat)
+            imsize = hz * 2 ** len(blocks)
+            rs = np.random.RandomState(500 + seed)
+            z = torch.tensor(0.5 * rs.standard_normal((1, nz, hz, hz)))
+            K = orc.make_input(1, imsize, seed).double()
+            for dtype, sfx in ((torch.float64, "64"), (torch.float32, "32")):
+                sd = orc.to_dtype(orc.make_state(plan, seed), dtype)
+                model = Decoder(nz, 3, blocks, growth_rate=gr, init_features=feat).to(dtype)
+                res = model.load_state_dict(sd, strict=True)
+                assert not res.missing_keys and not res.unexpected_keys
+                assert list(model.state_dict().keys()) == list(sd.keys())
+                sob = SobelFilter(imsize, correct=True, device="cpu")
+                if dtype == torch.float64:
+                    for a in ("HSOBEL_WEIGHTS_3x3", "VSOBEL_WEIGHTS_3x3", "modifier"):
+                        setattr(sob, a, getattr(sob, a).double())
+                model.train()
+                for law, (a1, a2) in dict(lin=(0.0, 0.0), nl=(1.0, 0.7)).items():
+                    model.zero_grad()
+                    for m_ in model.modules():   # same BatchNorm running statistics before every pass
+                        if isinstance(m_, torch.nn.BatchNorm2d):
+                            m_.reset_running_stats()
+                    out = model(z.to(dtype))
+                    out.retain_grad()
+                    Kd = K.to(dtype)
+                    if law == "nl":
+                        e = darcy.conv_constitutive_constraint_nonlinear(Kd, out, sob, a1, a2)
+                    else:
+                        e = darcy.conv_constitutive_constraint(Kd, out, sob)
+                    c = darcy.conv_continuity_constraint(out, sob)
+                    l_dir, l_neu = darcy.conv_boundary_condition(out)
+                    loss = e + c + (l_dir + l_neu) * 10.0
+                    loss.backward()
+                    names = [n for n, _ in model.named_parameters()]
+                    d[f"{tag}_{law}_l4_{sfx}"] = torch.stack([e, c, l_dir, l_neu]).detach().numpy()
+                    d[f"{tag}_{law}_loss_{sfx}"] = loss.detach().numpy()
+                    if sfx == "64":
+                        d[f"{tag}_{law}_out64"] = out.detach().numpy()
+                        d[f"{tag}_{law}_dout64"] = out.grad.detach().numpy()
+                        d[f"{tag}_{law}_grad_norm64"] = np.array([float(p.grad.norm()) for _, p in model.named_parameters()])
+                        d[f"{tag}_{law}_grads64_head"] = np.concatenate([p.grad.numpy().ravel()[:16] for _, p in model.named_parameters()])
+                d[f"{tag}_param_names"] = np.array(names)
+                d[f"{tag}_model_size"] = np.array(model.model_size)
+            d[f"{tag}_cfg"] = np.array([nz, hz, gr, feat, seed, imsize])
+            d[f"{tag}_blocks"] = np.array(blocks)
+            d[f"{tag}_z"] = z.numpy()
+            d[f"{tag}_alphas"] = np.array([1.0, 0.7])
+            print("decoder", tag, "loss lin/nl", float(d[f"{tag}_lin_loss_64"]), float(d[f"{tag}_nl_loss_64"]))
+        np.savez_compressed(os.path.join(HERE, "decoder_solver.npz"), **d)
+
     if "--only-channel" in sys.argv:
         channel_case()
+        return
+    if "--only-decoder" in sys.argv:
+        decoder_cases()
         return
     if "--only-trajectory" in sys.argv:
         trajectory_case()
@@ -203,6 +264,7 @@ def main():
     channel_case()
     timed_shape_cases()
     trajectory_case()
+    decoder_cases()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----
     rs = np.random.RandomState(42)

@@ -460,3 +460,68 @@ def test_one_piece_precision_modes(golden_dir, name, dtype, monkeypatch):
         den += float(g["grad_norm64"][i]) ** 2
     assert np.sqrt(num / den) < (0.5 if dtype == "bf16" else 0.1), np.sqrt(num / den)
     assert all(bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_decoder_solver_step_matches_reference(golden_dir, tag):
+    """`Decoder` (models/codec.py:321-370) at batch 1 driven by the solver's
+    closure (solve_conv_mixed_residual.py:131-145) with the linear and the NONLINEAR constitutive law
+    (models/darcy.py:179-191) against the reference's fp64 run; then torch.optim.LBFGS (the solver's
+    optimiser, line 124) over the executor's parameters."""
+    from models.codec import Decoder
+    from models.darcy import (conv_boundary_condition, conv_constitutive_constraint,
+                              conv_constitutive_constraint_nonlinear, conv_continuity_constraint)
+    from utils.image_gradient import SobelFilter
+    g = np.load(os.path.join(golden_dir, "decoder_solver.npz"))
+    nz, hz, gr, feat, seed, imsize = [int(v) for v in g[f"{tag}_cfg"]]
+    blocks = [int(b) for b in g[f"{tag}_blocks"]]
+    plan = orc.decoder_plan(nz, 3, blocks, gr, feat)
+    a1, a2 = [float(v) for v in g[f"{tag}_alphas"]]
+    z = torch.tensor(g[f"{tag}_z"]).float().cuda()
+    K = orc.make_input(1, imsize, seed).cuda()
+    sob = SobelFilter(imsize, correct=True, device="cuda")
+    for law in ("lin", "nl"):
+        model = Decoder(nz, 3, blocks, growth_rate=gr, init_features=feat)
+        sd = orc.make_state(plan, seed)
+        assert list(model.state_dict().keys()) == list(sd.keys())
+        assert tuple(model.model_size) == tuple(int(v) for v in g[f"{tag}_model_size"])
+        model.load_state_dict(sd)
+        model = model.cuda()
+        model.train()
+        model.zero_grad()
+        out = model(z)
+        assert tuple(out.shape) == (1, 3, imsize, imsize)
+        out.retain_grad()
+        if law == "nl":
+            e = conv_constitutive_constraint_nonlinear(K, out, sob, a1, a2)
+        else:
+            e = conv_constitutive_constraint(K, out, sob)
+        c = conv_continuity_constraint(out, sob)
+        l_dir, l_neu = conv_boundary_condition(out)
+        loss = e + c + (l_dir + l_neu) * 10.0
+        loss.backward()
+        torch.cuda.synchronize()
+        assert rel(out.detach().cpu().numpy(), g[f"{tag}_{law}_out64"]) < 1e-4
+        l4 = torch.stack([e, c, l_dir, l_neu]).detach().cpu().numpy()
+        assert np.all(np.abs(l4 - g[f"{tag}_{law}_l4_64"]) <= 1e-4 * np.abs(g[f"{tag}_{law}_l4_64"])), (l4, g[f"{tag}_{law}_l4_64"])
+        assert rel(out.grad.cpu().numpy(), g[f"{tag}_{law}_dout64"]) < 1e-4
+        norms = np.array([float(p.grad.double().norm()) for p in model.parameters()])
+        ref = g[f"{tag}_{law}_grad_norm64"]
+        assert np.sqrt(((norms - ref) ** 2).sum() / (ref ** 2).sum()) < 2e-2
+    # L-BFGS over the executor (closure = several forward/backward pairs per step)
+    opt = torch.optim.LBFGS(model.parameters(), lr=0.5, max_iter=5, history_size=50)
+    hist = []
+
+    def closure():
+        opt.zero_grad()
+        o = model(z)
+        en = conv_constitutive_constraint_nonlinear(K, o, sob, a1, a2) + conv_continuity_constraint(o, sob)
+        d_, n_ = conv_boundary_condition(o)
+        ls = en + (d_ + n_) * 10.0
+        ls.backward()
+        hist.append(float(ls))
+        return ls
+
+    for _ in range(3):
+        opt.step(closure)
+    assert np.all(np.isfinite(hist)) and hist[-1] < 0.5 * hist[0], hist

@@ -161,3 +161,67 @@ def test_unmodified_max_likelihood_script_runs(tmp_path):
     assert (run / "checkpoints" / "model_epoch2.pth").exists()
     losses = np.loadtxt(str(run / "training" / "loss_train.txt"))
     assert losses.shape == (2,) and np.all(np.isfinite(losses)) and losses[1] < losses[0]
+
+
+def test_decoder_module_surface_and_lbfgs_cpu():
+    """`Decoder` (models/codec.py:321-370 upstream) on the repo's modules: reference state_dict layout, any
+    latent size, and torch.optim.LBFGS closures (several forward/backward pairs per step) drive it."""
+    from models.codec import Decoder
+    from models.darcy import (conv_boundary_condition, conv_constitutive_constraint_nonlinear,
+                              conv_continuity_constraint)
+    from utils.image_gradient import SobelFilter
+    with cpu_backend():
+        model = Decoder(2, 3, [3, 2], growth_rate=8, init_features=16)
+        plan = orc.decoder_plan(2, 3, [3, 2], 8, 16)
+        assert list(model.state_dict().keys()) == [n for n, _ in orc.state_layout(plan)]
+        model.load_state_dict(orc.make_state(plan, 23))
+        z = 0.5 * torch.randn(1, 2, 8, 8, generator=torch.Generator().manual_seed(0))
+        K = orc.make_input(1, 32, 23)
+        sob = SobelFilter(32, correct=True, device="cpu")
+        model.train()
+        opt = torch.optim.LBFGS(model.parameters(), lr=0.5, max_iter=4, history_size=50)
+        hist = []
+
+        def closure():
+            opt.zero_grad()
+            out = model(z)
+            assert tuple(out.shape) == (1, 3, 32, 32)
+            e = conv_constitutive_constraint_nonlinear(K, out, sob, 1.0, 0.7) + conv_continuity_constraint(out, sob)
+            d, n = conv_boundary_condition(out)
+            loss = e + (d + n) * 10.0
+            loss.backward()
+            hist.append(float(loss))
+            return loss
+
+        for _ in range(2):
+            opt.step(closure)
+        assert np.all(np.isfinite(hist)) and hist[-1] < hist[0]
+        out4 = model(0.5 * torch.randn(1, 2, 4, 4))      # another latent size: 4 -> 16
+        assert tuple(out4.shape) == (1, 3, 16, 16)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "solve_conv_mixed_residual.py")),
+                    reason="reference checkout not present (only in the build container)")
+def test_unmodified_solver_script_runs(tmp_path):
+    """solve_conv_mixed_residual.py (Decoder + L-BFGS on the conv losses), byte for
+    byte, against this repo's modules (oracle-backed executor on CPU), linear law."""
+    from pde_surrogate_b200 import data
+    d = tmp_path / "datasets" / "64x64"
+    d.mkdir(parents=True)
+    x = data.grf_kle(10, 64, 64, 0.2, seed=3, device="cpu").numpy()
+    data.write_hdf5(str(d / "kle512_lhs1000_test.hdf5"), x, data.darcy_fv_dataset(x))
+    import run_reference_script
+    argv = ["--script", os.path.join(REF, "solve_conv_mixed_residual.py"), "--", "--data-dir", str(tmp_path / "datasets"),
+            "--exp-dir", str(tmp_path / "exp"), "--idx", "3", "--epochs", "2", "--test-freq", "1", "--ckpt-freq", "2",
+            "--cuda", "0"]
+    old_argv, old_path = list(sys.argv), list(sys.path)
+    try:
+        with cpu_backend():
+            run_reference_script.main(argv)
+    finally:
+        sys.argv, sys.path[:] = old_argv, old_path
+    losses = list((tmp_path / "exp").rglob("loss.txt"))
+    assert len(losses) == 1
+    vals = np.loadtxt(str(losses[0]))
+    assert vals.shape == (2,) and np.all(np.isfinite(vals)) and vals[1] < vals[0]
+    assert list((tmp_path / "exp").rglob("model_epoch2.pth"))

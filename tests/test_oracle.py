@@ -147,3 +147,37 @@ def test_finite_volume_reference_solver():
     good = orc.total_loss(Kt, torch.tensor(o[None]))[0]
     bad = orc.total_loss(Kt, torch.tensor(o[None] + 0.05 * rs.standard_normal(o[None].shape)))[0]
     assert float(good) < 0.2 * float(bad)
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_decoder_and_nonlinear_law_match_reference(golden_dir, tag):
+    """the oracle's `Decoder` plan (models/codec.py:321-370) and nonlinear
+    constitutive law (models/darcy.py:179-191) against the reference's own outputs (decoder_solver.npz)."""
+    torch.set_num_threads(4)
+    g = _load(golden_dir, "decoder_solver")
+    nz, hz, gr, feat, seed, imsize = [int(v) for v in g[f"{tag}_cfg"]]
+    blocks = [int(b) for b in g[f"{tag}_blocks"]]
+    plan = orc.decoder_plan(nz, 3, blocks, gr, feat)
+    assert orc.param_names(plan) == [str(s) for s in g[f"{tag}_param_names"]]
+    z = torch.tensor(g[f"{tag}_z"])
+    K = orc.make_input(1, imsize, seed).double()
+    a1, a2 = [float(v) for v in g[f"{tag}_alphas"]]
+    for law in ("lin", "nl"):
+        sd = orc.to_dtype(orc.make_state(plan, seed), torch.float64)
+        names = orc.param_names(plan)
+        for n in names:
+            sd[n].requires_grad_(True)
+        out = orc.densenet_forward(plan, sd, z, training=True)
+        out.retain_grad()
+        e = orc.constitutive_nonlinear(K, out, a1, a2) if law == "nl" else orc.constitutive(K, out)
+        d_, n_ = orc.boundary(out)
+        l4 = torch.stack([e, orc.continuity(out), d_, n_])
+        loss = (l4[0] + l4[1]) + (l4[2] + l4[3]) * 10.0
+        loss.backward()
+        assert rel(out.detach().numpy(), g[f"{tag}_{law}_out64"]) < 1e-11
+        assert rel(l4.detach().numpy(), g[f"{tag}_{law}_l4_64"]) < 1e-11
+        assert rel(out.grad.numpy(), g[f"{tag}_{law}_dout64"]) < 1e-10
+        norms = np.array([float(sd[n].grad.norm()) for n in names])
+        assert np.allclose(norms, g[f"{tag}_{law}_grad_norm64"], rtol=1e-8, atol=1e-300)
+        head = np.concatenate([sd[n].grad.numpy().ravel()[:16] for n in names])
+        assert rel(head, g[f"{tag}_{law}_grads64_head"]) < 1e-8

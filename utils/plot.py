@@ -42,6 +42,15 @@ def plot_prediction_det(save_dir, target, prediction, epoch, index, plot_fn='con
     plt.close(fig)
 
 
+def plot_prediction_det_animate2(save_dir, target, prediction, epoch, index, i_plot, plot_fn='imshow',
+                                 cmap='jet', same_scale=False):
+    """Frame writer of the solver's --animate option (utils/plot.py upstream; imported unconditionally by
+    solve_conv_mixed_residual.py:23): the numeric frame is always saved, the figure when matplotlib exists."""
+    target, prediction = to_numpy(target), to_numpy(prediction)
+    np.save(save_dir + '/frame{:04d}_epoch{}_{}.npy'.format(int(i_plot), epoch, index), np.stack([target, prediction]))
+    plot_prediction_det(save_dir, target, prediction, epoch, index, plot_fn=plot_fn, cmap=cmap, same_scale=same_scale)
+
+
 def save_stats(save_dir, logger, *metrics):
     plt = _pyplot()
     for metric in metrics:
