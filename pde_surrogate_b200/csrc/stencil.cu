@@ -401,9 +401,10 @@ darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
     float* Q2 = scratch + 4 * HW;
     const int W4 = W >> 2;
     const int cs = threadIdx.x % W4, y0 = (threadIdx.x / W4) * R;
+    float qreg[2 * (R > 0 ? R : 2) * 4];   // a*r1, a*r2 of the thread's own pixels: registers, not shared memory
     if (R > 0)
       (void)fwd_strip_r<(R > 0 ? R : 2), true, false>(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW,
-                                                      H, W, cs, y0, use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
+                                                      H, W, cs, y0, use_tb != 0, a, bb, P1, P2, P3, Q1, Q2, qreg);
     else
       (void)fwd_strip(hasK ? st : nullptr, st + HW, st + 2 * HW, st + 3 * HW, H, W, threadIdx.x, NT, true,
                       use_tb != 0, a, bb, P1, P2, P3, Q1, Q2);
@@ -411,7 +412,7 @@ darcy_bwd_tile_kernel(const float* __restrict__ K, const float* __restrict__ out
     // gradient planes overwrite u, s1, s2 in place (own-position reads only)
     if (R > 0)
       bwd_strip_pass2_r<(R > 0 ? R : 2)>(P1, P2, P3, Q1, Q2, st + HW, st + 3 * HW, st + HW, st + 2 * HW,
-                                         st + 3 * HW, H, W, cs, y0, cdir, cneu);
+                                         st + 3 * HW, H, W, cs, y0, cdir, cneu, qreg);
     else
       bwd_strip_pass2(P1, P2, P3, Q1, Q2, st + HW, st + 3 * HW, st + HW, st + 2 * HW, st + 3 * HW, H, W,
                       threadIdx.x, NT, true, cdir, cneu);

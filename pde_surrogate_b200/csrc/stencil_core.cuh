@@ -426,7 +426,9 @@ PDES_HD void hdiff_Tc(const float e[6], bool first, bool last, float t[4]) {
 template <int R, bool WRITE, bool SUMS>
 PDES_HD FwdPartial fwd_strip_r(const float* Kp, const float* up, const float* s1p, const float* s2p,
                                int H, int W, int cs, int y0, bool use_tb, float a, float b,
-                               float* P1, float* P2, float* P3, float* Q1, float* Q2) {
+                               float* P1, float* P2, float* P3, float* Q1, float* Q2, float* qreg = nullptr) {
+  // qreg != nullptr: Q1 / Q2 (only ever read back at the thread's OWN pixels by the adjoint pass) stay in the
+  // caller's thread-private array qreg[2][R][4] (registers) instead of making a shared-memory round trip
   static_assert(R >= 2, "the one-sided boundary rows must lie inside the window");
   FwdPartial acc;
   acc.c = acc.d = acc.dir = acc.neu = 0.f;
@@ -567,8 +569,16 @@ PDES_HD FwdPartial fwd_strip_r(const float* Kp, const float* up, const float* s1
       *reinterpret_cast<float4*>(P1 + o) = make_float4(p1[0], p1[1], p1[2], p1[3]);
       *reinterpret_cast<float4*>(P2 + o) = make_float4(p2[0], p2[1], p2[2], p2[3]);
       *reinterpret_cast<float4*>(P3 + o) = make_float4(p3[0], p3[1], p3[2], p3[3]);
-      *reinterpret_cast<float4*>(Q1 + o) = make_float4(q1[0], q1[1], q1[2], q1[3]);
-      *reinterpret_cast<float4*>(Q2 + o) = make_float4(q2[0], q2[1], q2[2], q2[3]);
+      if (qreg != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          qreg[i * 4 + k] = q1[k];
+          qreg[(R + i) * 4 + k] = q2[k];
+        }
+      } else {
+        *reinterpret_cast<float4*>(Q1 + o) = make_float4(q1[0], q1[1], q1[2], q1[3]);
+        *reinterpret_cast<float4*>(Q2 + o) = make_float4(q2[0], q2[1], q2[2], q2[3]);
+      }
     }
   }
   return acc;
@@ -578,7 +588,8 @@ PDES_HD FwdPartial fwd_strip_r(const float* Kp, const float* up, const float* s1
 template <int R>
 PDES_HD void bwd_strip_pass2_r(const float* P1, const float* P2, const float* P3, const float* Q1,
                                const float* Q2, const float* up, const float* s2p, float* du, float* ds1,
-                               float* ds2, int H, int W, int cs, int y0, float cdir, float cneu) {
+                               float* ds2, int H, int W, int cs, int y0, float cdir, float cneu,
+                               const float* qreg = nullptr) {
   static_assert(R >= 2, "R >= 2");
   const int W4 = W >> 2;
   const bool first = (cs == 0), last = (cs == W4 - 1);
@@ -654,10 +665,19 @@ PDES_HD void bwd_strip_pass2_r(const float* P1, const float* P2, const float* P3
     const bool yedge = (i == 0 && top) || (i == R - 1 && bot);
     const float wy = yedge ? 3.f : 2.f;
     const size_t o = (size_t)y * W + x0;
-    const float4 q1 = *reinterpret_cast<const float4*>(Q1 + o);
-    const float4 q2 = *reinterpret_cast<const float4*>(Q2 + o);
-    const float q1a[4] = {q1.x, q1.y, q1.z, q1.w};
-    const float q2a[4] = {q2.x, q2.y, q2.z, q2.w};
+    float q1a[4], q2a[4];
+    if (qreg != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        q1a[k] = qreg[i * 4 + k];
+        q2a[k] = qreg[(R + i) * 4 + k];
+      }
+    } else {
+      const float4 q1 = *reinterpret_cast<const float4*>(Q1 + o);
+      const float4 q2 = *reinterpret_cast<const float4*>(Q2 + o);
+      q1a[0] = q1.x; q1a[1] = q1.y; q1a[2] = q1.z; q1a[3] = q1.w;
+      q2a[0] = q2.x; q2a[1] = q2.y; q2a[2] = q2.z; q2a[3] = q2.w;
+    }
     float gu[4], g1[4], g2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

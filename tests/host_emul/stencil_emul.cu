@@ -25,12 +25,15 @@ static void fast_sample(const float* st, int hasK, int H, int W, int use_tb, flo
     acc[0] += p.c; acc[1] += p.d; acc[2] += p.dir; acc[3] += p.neu;
   }
   float *P1 = scratch, *P2 = P1 + HW, *P3 = P2 + HW, *Q1 = P3 + HW, *Q2 = Q1 + HW;
+  // the kernel keeps Q1 / Q2 in per-thread registers (qreg): emulated with one private array per thread
+  std::vector<float> qreg((size_t)nthreads * 2 * R * 4);
   for (int t = 0; t < nthreads; ++t)
     (void)fwd_strip_r<R, true, false>(hasK ? s : nullptr, s + HW, s + 2 * HW, s + 3 * HW, H, W, t % W4,
-                                      (t / W4) * R, use_tb != 0, a, b, P1, P2, P3, Q1, Q2);
+                                      (t / W4) * R, use_tb != 0, a, b, P1, P2, P3, Q1, Q2,
+                                      qreg.data() + (size_t)t * 2 * R * 4);
   for (int t = 0; t < nthreads; ++t)
     bwd_strip_pass2_r<R>(P1, P2, P3, Q1, Q2, s + HW, s + 3 * HW, s + HW, s + 2 * HW, s + 3 * HW, H, W, t % W4,
-                         (t / W4) * R, cdir, cneu);
+                         (t / W4) * R, cdir, cneu, qreg.data() + (size_t)t * 2 * R * 4);
 }
 
 static int run_case(int B, int H, int W, int use_tb, int hasK, int nthreads, int fitR = 0) {
