@@ -105,6 +105,10 @@ typedef struct pdes_densenet_config {
   int32_t arch;          /* 0: DenseED (models/codec.py:210-318).  1: Decoder (models/codec.py:321-370): a plain 3x3
                           * conv0 on a planar (B, in_channels, imsize, imsize) latent, then decoding blocks only;
                           * the output is imsize * 2^n_blocks wide.  (ABI version 2) */
+  int32_t dropout;       /* 1: the network was built with drop_rate > 0 (nn.Dropout2d behind its convolutions,
+                          * models/codec.py:70-71, 110-149, 171-172): pdes_densenet_set_dropout may be used */
+  int32_t upsample;      /* x2 upsampling of the decoding transitions (models/codec.py:139-150, 175-178):
+                          * 0 'nearest' (default), 1 'bilinear' (align_corners=True) */
 } pdes_densenet_config;
 
 /* Host-side object (no device memory). */
@@ -124,6 +128,13 @@ int pdes_densenet_num_bn(const pdes_net_t* net);
 int64_t pdes_densenet_running_floats(const pdes_net_t* net);
 int pdes_densenet_bn_info(const pdes_net_t* net, int idx, char* name, size_t name_cap,
                           int64_t* mean_offset, int64_t* var_offset, int32_t* channels);
+
+/* nn.Dropout2d sites in execution order: fills channels[i] (the convolution's Cout) for up to `cap` sites and
+ * returns their number.  Before a TRAINING forward the caller passes the masks of that pass, one contiguous
+ * (B, channels[i]) fp32 block per site in the same order (values 0 or 1/(1-p); device memory that stays valid
+ * until the matching backward has run); NULL switches dropout off (evaluation). */
+int pdes_densenet_dropout_sites(const pdes_net_t* net, int32_t* channels, int cap);
+int pdes_densenet_set_dropout(pdes_net_t* net, const float* masks);
 
 /* Spatial size (H = W) of the network output: imsize for DenseED, imsize * 2^n_blocks for Decoder. */
 int pdes_densenet_output_size(const pdes_net_t* net);

@@ -199,7 +199,14 @@ def round_operand(t, mode, scale_log2=0):
     raise ValueError(mode)
 
 
-def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_running=True, operand_round=None):
+def _drop_site(s):
+    """nn.Dropout2d follows every convolution but In_conv / conv0 and the last two of the last decoding
+    (codec.py:70-71, 110-149, 171-172)."""
+    return s["kind"] != "conv" and not (s["name"] == "features.LastTransUp" and s.get("conv") in ("conv2", "conv3"))
+
+
+def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_running=True, operand_round=None,
+                     drop_rate=0.0, upsample="nearest"):
     """DenseED.forward (codec.py:295-296) as a flat functional program.
 
     operand_round = "bf16" | "fp16": emulate the one-piece tensor-core modes - every convolution but the first
@@ -225,12 +232,16 @@ def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_
         else:
             a = F.batch_norm(h, rm, rv, sd[b + ".weight"], sd[b + ".bias"], False, momentum, eps)
         a = F.relu(a)
-        if s["up"]:
+        if s["up"] and upsample == "bilinear":
+            a = F.interpolate(a, scale_factor=2.0, mode="bilinear", align_corners=True)  # codec.py:33-40
+        elif s["up"]:
             a = F.interpolate(a, scale_factor=2.0, mode="nearest")  # codec.py:24-30
         w = sd[_conv_name(s) + ".weight"]
         if operand_round is not None:
             a, w = round_operand(a, operand_round, 4), round_operand(w, operand_round, 8)
         y = F.conv2d(a, w, None, s["stride"], s["pad"])
+        if drop_rate > 0 and _drop_site(s):
+            y = F.dropout2d(y, drop_rate, training)   # nn.Dropout2d: whole channels, scaled by 1/(1-p)
         h = torch.cat([h, y], 1) if s["kind"] == "dense" else y  # codec.py:73-75
     return h
 
@@ -322,14 +333,14 @@ def total_loss(K, out, weight_bound=10.0):
     return (l4[0] + l4[1]) + (l4[2] + l4[3]) * weight_bound, l4
 
 
-def train_step(plan, sd, K, weight_bound=10.0):
+def train_step(plan, sd, K, weight_bound=10.0, upsample="nearest"):
     """One step body of train_codec_mixed_residual.py:226-233 (zero_grad, forward, loss,
     backward).  Returns output, 4 partial losses, loss, dL/d(output), {param name: grad}."""
     names = param_names(plan)
     for n in names:
         sd[n].requires_grad_(True)
         sd[n].grad = None
-    out = densenet_forward(plan, sd, K, training=True)
+    out = densenet_forward(plan, sd, K, training=True, upsample=upsample)
     out.retain_grad()
     loss, l4 = total_loss(K, out, weight_bound)
     loss.backward()

@@ -16,7 +16,7 @@ _lib = None
 class DensenetConfig(Structure):
     _fields_ = [("in_channels", c_int32), ("out_channels", c_int32), ("imsize", c_int32),
                 ("n_blocks", c_int32), ("blocks", c_int32 * 15), ("growth_rate", c_int32),
-                ("init_features", c_int32), ("max_batch", c_int32), ("arch", c_int32)]
+                ("init_features", c_int32), ("max_batch", c_int32), ("arch", c_int32), ("dropout", c_int32), ("upsample", c_int32)]
 
 
 class ConvDesc(Structure):
@@ -50,6 +50,8 @@ SIGNATURES = {
     "pdes_densenet_bn_info": (c_int, [c_void_p, c_int, c_char_p, c_size_t, POINTER(c_int64), POINTER(c_int64),
                                       POINTER(c_int32)]),
     "pdes_densenet_output_size": (c_int, [c_void_p]),
+    "pdes_densenet_dropout_sites": (c_int, [c_void_p, POINTER(c_int32), c_int]),
+    "pdes_densenet_set_dropout": (c_int, [c_void_p, c_void_p]),
     "pdes_densenet_workspace_bytes": (c_size_t, [c_void_p]),
     "pdes_densenet_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "pdes_densenet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -88,6 +88,8 @@ class _NetHandle(object):
         self.imsize = int(cfg["imsize"] if imsize is None else imsize)
         c.in_channels, c.out_channels, c.imsize = cfg["in_channels"], cfg["out_channels"], self.imsize
         c.arch = int(cfg.get("arch", 0))
+        c.dropout = 1 if cfg.get("drop_rate", 0.0) > 0 else 0
+        c.upsample = {"nearest": 0, "bilinear": 1}[cfg.get("upsample", "nearest")]
         c.n_blocks = len(cfg["blocks"])
         for i, b in enumerate(cfg["blocks"]):
             c.blocks[i] = int(b)
@@ -96,6 +98,10 @@ class _NetHandle(object):
         _lib.check(L.pdes_densenet_create(byref(c), byref(h)), "pdes_densenet_create")
         self.h, self.max_batch = h, max_batch
         self.out_size = int(L.pdes_densenet_output_size(h))
+        ns = int(L.pdes_densenet_dropout_sites(h, None, 0))
+        ch = (c_int32 * max(ns, 1))()
+        L.pdes_densenet_dropout_sites(h, ch, ns)
+        self.drop_channels = [int(ch[i]) for i in range(ns)]
 
     def __del__(self):
         try:
@@ -138,6 +144,7 @@ class CudaExecutor(object):
         self.bound = None
         self.applied_impl = None
         self.fwd_gen = 0
+        self.masks = None
 
     def _ensure(self, x):
         m = self.m
@@ -182,9 +189,31 @@ class CudaExecutor(object):
                            "pdes_densenet_bind")
             self.bound = key
 
+    def _dropout_masks(self, x, training):
+        """nn.Dropout2d masks of this pass (models/codec.py:70-71, 110-149, 171-172): one (B, C, 1, 1) block per
+        site, drawn exactly like torch.feature_dropout draws them (empty(B,C,1,1).bernoulli_(1-p).div_(1-p), in
+        module order) so that a seeded run consumes the generator like the reference does."""
+        p = float(self.m._cfg.get("drop_rate", 0.0))
+        L = _lib.lib()
+        if not (training and p > 0 and self.handle.drop_channels):
+            if self.handle.drop_channels:
+                _lib.check(L.pdes_densenet_set_dropout(self.handle.h, None), "pdes_densenet_set_dropout")
+            self.masks = None
+            return
+        B = x.shape[0]
+        dev = getattr(self.m, "_mask_device", None) or x.device   # test hook: draw on the CPU generator
+        flat = torch.empty(B * sum(self.handle.drop_channels), dtype=torch.float32, device=dev)
+        o = 0
+        for C in self.handle.drop_channels:
+            flat[o:o + B * C].view(B, C, 1, 1).bernoulli_(1.0 - p).div_(1.0 - p)
+            o += B * C
+        self.masks = flat.to(x.device)
+        _lib.check(L.pdes_densenet_set_dropout(self.handle.h, _lib.ptr(self.masks)), "pdes_densenet_set_dropout")
+
     def forward(self, x, training):
         self._ensure(x)
         self.fwd_gen += 1   # the executor keeps ONE set of saved activations: see _DenseEDTrainFn.backward
+        self._dropout_masks(x, training)
         x = x.contiguous()
         c = self.m._cfg
         hw = self.handle.out_size
@@ -251,11 +280,11 @@ class _EvalGuardFn(torch.autograd.Function):
 
 def _reject_options(cls, drop_rate=0, bottleneck=False, upsample='nearest', out_activation=None):
     unsupported = []
-    if drop_rate and drop_rate > 0:
-        unsupported.append("drop_rate=%r" % drop_rate)
+    if drop_rate and not (0.0 <= drop_rate < 1.0):
+        raise ValueError("dropout probability has to be between 0 and 1, but got {}".format(drop_rate))
     if bottleneck:
         unsupported.append("bottleneck=True")
-    if upsample != 'nearest':
+    if upsample not in ('nearest', 'bilinear'):
         unsupported.append("upsample=%r" % (upsample,))
     if out_activation is not None:
         unsupported.append("out_activation=%r" % (out_activation,))
@@ -430,7 +459,8 @@ class DenseED(_ExecutorNet):
             raise ValueError('length of blocks must be an odd number, but got {}'.format(len(blocks)))
         _reject_options("DenseED", drop_rate, bottleneck, upsample, out_activation)
         self._build(dict(in_channels=int(in_channels), out_channels=int(out_channels), imsize=int(imsize),
-                         blocks=blocks, growth_rate=int(growth_rate), init_features=int(init_features), arch=0))
+                         blocks=blocks, growth_rate=int(growth_rate), init_features=int(init_features), arch=0,
+                         drop_rate=float(drop_rate or 0.0), upsample=upsample))
         print('# params {}, # conv layers {}'.format(*self.model_size))
 
 
@@ -446,4 +476,5 @@ class Decoder(_ExecutorNet):
         _reject_options("Decoder", drop_rate, False, upsample, out_activation)
         # imsize here only sizes the layout query: the latent's spatial size is taken from the input
         self._build(dict(in_channels=int(dim_latent), out_channels=int(out_channels), imsize=16, blocks=blocks,
-                         growth_rate=int(growth_rate), init_features=int(init_features), arch=1))
+                         growth_rate=int(growth_rate), init_features=int(init_features), arch=1,
+                         drop_rate=float(drop_rate or 0.0), upsample=upsample))

@@ -79,7 +79,32 @@ struct FixDyArgs {
   const float* cons_gamma[kMaxConsumers];  // consumer BN weight, offset to this slice
   const double* cons_bsum[kMaxConsumers];  // consumer bsum base, offset to this slice
   int cons_C[kMaxConsumers];               // consumer channel count (stride to the 2nd half)
+  // nn.Dropout2d behind the producing convolution (models/codec.py:70-71, 110-149, 171-172): the slice holds
+  // y * mask; its gradient is multiplied by the same per-(sample, channel) mask.  null: no dropout
+  const float* drop_mask;                  // [B][C], values 0 or 1/(1-p)
+  int64_t pix_per_img;
 };
+// y[:, c] *= mask[b][c] in place on an NHWC slice, and per-channel sum / sum of squares of the result (+=)
+int launch_dropout_fwd(float* y, int ld, int C, int64_t npix, int64_t pix_per_img, const float* mask,
+                       double* o_sum, double* o_sumsq, cudaStream_t st);
+
+// upsample='bilinear' (bilinear.cu): x = the layer's input (NHWC, H x W, ldx), up = the fp32 NHWC scratch at
+// 2H x 2W (ldu): the upsampled activation in the forward pass, the convolution's data gradient in the backward
+struct BilinearArgs {
+  const float* x;
+  int ldx, C, H, W, B;
+  int pro;          // forward: apply BatchNorm + ReLU before interpolating
+  BnSrc bn;
+  float* up;
+  int ldu;
+  // backward only
+  float* G;
+  int ldG, g_accum;
+  double* bsum;     // [0,C): sum dZ ; [C,2C): sum dZ*xhat
+  unsigned* gmax;
+};
+int launch_bilinear_up(const BilinearArgs& a, cudaStream_t st);
+int launch_bilinear_bwd(const BilinearArgs& a, cudaStream_t st);
 
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad_simt(const WgradArgs& a, cudaStream_t st);

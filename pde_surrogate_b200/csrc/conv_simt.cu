@@ -474,8 +474,38 @@ __global__ void __launch_bounds__(256) fix_dy_kernel(FixDyArgs a) {
     const int c = (int)(i - p * a.C);
     const float xh = (a.X[p * a.ldX + c] - mean_s[c]) * is_s[c];
     float* g = a.G + p * a.ldG + c;
-    *g = *g - c1_s[c] - xh * c2_s[c];
+    float v = *g - c1_s[c] - xh * c2_s[c];
+    if (a.drop_mask != nullptr) v *= a.drop_mask[(p / a.pix_per_img) * a.C + c];   // d(y*mask)/dy
+    *g = v;
   }
+}
+
+// nn.Dropout2d forward on a freshly written NHWC slice + the batch statistics the next BatchNorm needs
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(float* y, int ld, int C, int64_t npix, int64_t pix_per_img,
+                                                          const float* __restrict__ mask, double* o_sum,
+                                                          double* o_sumsq) {
+  griddep_wait();
+  __shared__ float s1[256], s2[256];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s1[c] = s2[c] = 0.f;
+  __syncthreads();
+  const int64_t total = npix * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / C;
+    const int c = (int)(i - p * C);
+    float* q = y + p * ld + c;
+    const float v = *q * mask[(p / pix_per_img) * C + c];
+    *q = v;
+    if (o_sum != nullptr && v != 0.f) {
+      atomicAdd(&s1[c], v);
+      atomicAdd(&s2[c], v * v);
+    }
+  }
+  __syncthreads();
+  if (o_sum != nullptr)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      atomicAdd(o_sum + c, (double)s1[c]);
+      atomicAdd(o_sumsq + c, (double)s2[c]);
+    }
 }
 
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackDesc* tab) {
@@ -610,6 +640,18 @@ int launch_fix_dy(const FixDyArgs& a, cudaStream_t st) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   PDES_CUDA(launch_pdl(fix_dy_kernel, dim3(blocks), dim3(256), 0, st, a));
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+int launch_dropout_fwd(float* y, int ld, int C, int64_t npix, int64_t pix_per_img, const float* mask,
+                       double* o_sum, double* o_sumsq, cudaStream_t st) {
+  PDES_REQUIRE(y && mask && C >= 1 && C <= 256, PDES_ERR_INVALID, "dropout_fwd: invalid arguments (C %d)", C);
+  int blocks = (int)((npix * C + 255) / 256);
+  const int cap = sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  PDES_CUDA(launch_pdl(dropout_fwd_kernel, dim3(blocks), dim3(256), 0, st, y, ld, C, npix, pix_per_img, mask, o_sum, o_sumsq));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

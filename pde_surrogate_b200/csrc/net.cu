@@ -52,6 +52,9 @@ struct Layer {
   bool first_k;      // dedicated CUDA-core kernels of the first convolution (first_conv.cu)
   bool dense_fwd;    // fused BatchNorm+ReLU+split+conv forward of a thin 3x3 layer (conv_dense.cu)
   size_t wdn;        // float offset of its packed filter ("dx in N" layout)
+  bool bilinear;     // the x2 upsampling in front of this convolution is bilinear (align_corners), not nearest
+  bool drop;         // an nn.Dropout2d follows this convolution when the network has drop_rate > 0
+  int drop_cprefix;  // channels of the dropout sites before this one (mask block offset = B * drop_cprefix)
   bool dense_bwd;    // fused dY-correction+split+dgrad of a thin 3x3 layer (conv_dense_bwd.cu)
   size_t wdb;        // float offset of its packed filter ("dx in K" layout)
   bool wg_taps_n;    // weight gradient as ONE 1x1 GEMM over an expanded dY (few output channels, DyIm2colArgs)
@@ -80,6 +83,7 @@ struct pdes_net {
   int64_t param_floats = 0, running_floats = 0;
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
   size_t xin = 0;
+  size_t up_scratch = 0;   // float offset: fp32 NHWC scratch of the bilinear-upsampling layers (a_up / dA_up)
   int in_hw = 0, out_hw = 0;  // spatial size of the network input / output (DenseED: both imsize)
   size_t gmax_off = 0;  // double offset: running |G| maxima (unsigned float bits), one per buffer + one for dout
   size_t dyinv = 0;     // float offset: per-layer inverse of the dynamic dY scale (written by the dY split)
@@ -105,6 +109,7 @@ struct pdes_net {
   int tc_mask = 7;  // bit 0: forward, bit 1: dgrad, bit 2: wgrad on tcgen05
   int dense_on = 1; // PDES_DENSE_FWD=0: thin layers go through operand split + conv_tc2 (round-1 path)
   int dense_bwd_on = 1;  // PDES_DENSE_BWD=0: thin-layer dgrad through dY split + conv_tc2
+  const float* drop_masks = nullptr;  // masks of the current training pass (pdes_densenet_set_dropout)
   int lowp = 0;     // PDES_CONV_DTYPE = fp32 (default: two fp16 pieces, three products) | fp16 | bf16 (one piece)
   // bound
   float* p = nullptr;
@@ -207,6 +212,9 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.wdn = 0;
   L.dense_bwd = false;
   L.wdb = 0;
+  L.drop = false;
+  L.drop_cprefix = 0;
+  L.bilinear = false;
   L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
@@ -276,6 +284,19 @@ int build(pdes_net* n) {
                    c.imsize, 2 * H);
     }
   }
+  // nn.Dropout2d sites (only live when cfg.dropout): behind every dense-layer convolution (codec.py:70-71),
+  // behind conv1 / conv2 of the transitions (110-149) and behind conv1 of the last decoding (171-172)
+  {
+    int prefix = 0;
+    for (auto& L : n->layers) {
+      const bool last2 = L.conv_name == "features.LastTransUp.conv2" || L.conv_name == "features.LastTransUp.conv3";
+      L.drop = c.dropout != 0 && L.kind != 0 && !last2;
+      L.drop_cprefix = prefix;
+      if (L.drop) prefix += L.Cout;
+    }
+  }
+  PDES_REQUIRE(c.upsample == 0 || c.upsample == 1, PDES_ERR_UNSUPPORTED, "upsample mode %d (0 nearest, 1 bilinear)", c.upsample);
+  for (auto& L : n->layers) L.bilinear = L.up && c.upsample == 1;
   // last consumer of every buffer (first dgrad to run in reverse order stores, the rest accumulate)
   for (size_t b = 0; b < n->bufs.size(); ++b) {
     int lastL = -1;
@@ -427,6 +448,17 @@ int build(pdes_net* n) {
       }
     }
   }
+  {
+    size_t mx = 0;
+    for (const auto& L : n->layers)
+      if (L.bilinear) {
+        const Buf& ib = n->bufs[L.in_buf];
+        const size_t sz = (size_t)B * 4 * ib.H * ib.W * rup(L.Cin, 4);
+        if (sz > mx) mx = sz;
+      }
+    n->up_scratch = f;
+    f += pad4((int64_t)mx);
+  }
   n->dyinv = f;
   f += pad4((int64_t)n->layers.size());
   n->xin = f;
@@ -510,6 +542,7 @@ extern "C" int pdes_densenet_create(const pdes_densenet_config* cfg, pdes_net_t*
     n->dense_on = (e && e[0] == '0') ? 0 : 1;
     const char* e2 = getenv("PDES_DENSE_BWD");
     n->dense_bwd_on = (e2 && e2[0] == '0') ? 0 : 1;
+    if (cfg->dropout) n->dense_bwd_on = 0;  // the fused dgrad folds the dY correction; dropout needs it standalone
     const char* e3 = getenv("PDES_CONV_DTYPE");
     n->lowp = (e3 && !strcmp(e3, "bf16")) ? LOWP_BF16 : ((e3 && !strcmp(e3, "fp16")) ? LOWP_FP16 : LOWP_NONE);
   }
@@ -620,6 +653,25 @@ extern "C" int pdes_densenet_bn_info(const pdes_net_t* n, int idx, char* name, s
 }
 
 extern "C" int pdes_densenet_output_size(const pdes_net_t* n) { return n ? n->out_hw : 0; }
+
+extern "C" int pdes_densenet_dropout_sites(const pdes_net_t* n, int32_t* channels, int cap) {
+  if (!n) return 0;
+  int k = 0;
+  for (const auto& L : n->layers) {
+    if (!L.drop) continue;
+    if (channels && k < cap) channels[k] = L.Cout;
+    ++k;
+  }
+  return k;
+}
+
+extern "C" int pdes_densenet_set_dropout(pdes_net_t* n, const float* masks) {
+  PDES_REQUIRE(n, PDES_ERR_INVALID, "pdes_densenet_set_dropout: null net");
+  PDES_REQUIRE(masks == nullptr || n->cfg.dropout, PDES_ERR_STATE,
+               "pdes_densenet_set_dropout: the network was created without dropout");
+  n->drop_masks = masks;
+  return PDES_OK;
+}
 
 extern "C" size_t pdes_densenet_workspace_bytes(const pdes_net_t* n) { return n ? n->ws_bytes : 0; }
 
@@ -927,6 +979,36 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
         a.o_sumsq = wsd(n, ob.stat) + ob.C + L.coff;
       }
     }
+    if (L.bilinear) {
+      // a_up = bilinear(relu(bn(x))) once, fp32 NHWC; the convolution below then sees a plain direct input
+      const Buf& ib = n->bufs[L.in_buf];
+      BilinearArgs ba;
+      memset(&ba, 0, sizeof(ba));
+      ba.x = a.x;
+      ba.ldx = a.ldx;
+      ba.C = L.Cin;
+      ba.H = ib.H;
+      ba.W = ib.W;
+      ba.B = B;
+      ba.pro = a.pro;
+      ba.bn = a.bn;
+      ba.up = wsf(n, n->up_scratch);
+      ba.ldu = rup(L.Cin, 4);
+      rc = launch_bilinear_up(ba, st);
+      if (rc) return rc;
+      n->launches++;
+      mark(n, st, "bilinear.f " + L.conv_name);
+      a.x = ba.up;
+      a.ldx = ba.ldu;
+      a.Hs = 2 * ib.H;
+      a.Ws = 2 * ib.W;
+      a.pro = 0;
+      a.in_mode = IN_DIRECT;
+    }
+    const bool dropping = tr && n->drop_masks != nullptr && L.drop && L.out_buf >= 0;
+    double* drop_sum = a.o_sum;
+    double* drop_sumsq = a.o_sumsq;
+    if (dropping) a.o_sum = a.o_sumsq = nullptr;   // the statistics are those of the MASKED output (below)
     const bool use_dense = n->conv_impl == 0 && L.dense_fwd && (n->tc_mask & 1);
     const bool want_planes = n->conv_impl == 0 && (L.tc2_fwd || (tr && L.tc_wg)) && !use_dense;
     const int Hs_l = L.in_buf >= 0 ? n->bufs[L.in_buf].H : L.Hs, Ws_l = L.in_buf >= 0 ? n->bufs[L.in_buf].W : L.Ws;
@@ -939,10 +1021,10 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       sa.ldx = a.ldx;
       sa.nchw = a.in_nchw;
       sa.C = L.Cin;
-      sa.Hs = Hs_l;
-      sa.Ws = Ws_l;
+      sa.Hs = L.bilinear ? 2 * Hs_l : Hs_l;   // (bilinear: a.x is the already upsampled activation)
+      sa.Ws = L.bilinear ? 2 * Ws_l : Ws_l;
       sa.B = B;
-      sa.up = L.up;
+      sa.up = L.bilinear ? 0 : L.up;
       sa.pro = a.pro;
       sa.bn = a.bn;
       sa.out = reinterpret_cast<op16*>(wsf(n, L.planes));
@@ -1066,6 +1148,14 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     if (rc) return rc;
     n->launches++;
     mark(n, st, "conv.f " + L.conv_name, 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B);
+    if (dropping) {
+      const Buf& ob = n->bufs[L.out_buf];
+      rc = launch_dropout_fwd(wsf(n, ob.act) + L.coff, ob.ld, L.Cout, (int64_t)B * ob.H * ob.W, (int64_t)ob.H * ob.W,
+                              n->drop_masks + (size_t)B * L.drop_cprefix, drop_sum, drop_sumsq, st);
+      if (rc) return rc;
+      n->launches++;
+      mark(n, st, "dropout.f " + L.conv_name);
+    }
   }
   if (tr) {
     rc = launch_bn_running_update(bn_table(n), n->n_bn, n->maxC, 0.1f, B, st);
@@ -1133,7 +1223,12 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         f.cons_C[f.n_cons] = M.Cin;
         f.n_cons++;
       }
-      const bool fuse_fix = n->conv_impl == 0 && (use_dense_bwd || (L.tc_wg && (n->tc_mask & 4)) ||
+      const bool dropping = n->drop_masks != nullptr && L.drop;
+      if (dropping) {
+        f.drop_mask = n->drop_masks + (size_t)B * L.drop_cprefix;
+        f.pix_per_img = (int64_t)ob.H * ob.W;
+      }
+      const bool fuse_fix = !dropping && n->conv_impl == 0 && (use_dense_bwd || (L.tc_wg && (n->tc_mask & 4)) ||
                                                   (L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2)));
       if (!fuse_fix) {
         rc = launch_fix_dy(f, st);
@@ -1181,6 +1276,32 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
         w.Ws = L.Ws;
       }
       const bool use_wg = n->conv_impl == 0 && L.tc_wg && (n->tc_mask & 4);
+      if (L.bilinear && !use_wg) {
+        // CUDA-core weight gradient of a bilinear layer: its operand is the upsampled activation, recomputed
+        // into the scratch (the tensor-core path re-reads the operand planes the forward pass kept)
+        const Buf& ib = n->bufs[L.in_buf];
+        BilinearArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        ba.x = w.x;
+        ba.ldx = w.ldx;
+        ba.C = L.Cin;
+        ba.H = ib.H;
+        ba.W = ib.W;
+        ba.B = B;
+        ba.pro = 1;
+        ba.bn = w.bn;
+        ba.up = wsf(n, n->up_scratch);
+        ba.ldu = rup(L.Cin, 4);
+        rc = launch_bilinear_up(ba, st);
+        if (rc) return rc;
+        n->launches++;
+        w.x = ba.up;
+        w.ldx = ba.ldu;
+        w.Hs = 2 * ib.H;
+        w.Ws = 2 * ib.W;
+        w.pro = 0;
+        w.in_mode = IN_DIRECT;
+      }
       // (a layer with the fused dgrad has no conv_tc2 dgrad filter packed: without both backward bits it
       // falls back to the CUDA-core kernels)
       const bool use_dg = n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2) && L.in_buf >= 0;
@@ -1333,6 +1454,15 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       a.epi = EPI_BNBWD;
       a.pool = L.up;
       a.fx = wsf(n, ib.act);
+      if (L.bilinear) {
+        // the data gradient w.r.t. the UPSAMPLED activation goes to the scratch as it is; bilinear_bwd gathers
+        // it through the transposed interpolation and does the BatchNorm-backward bookkeeping
+        a.epi = EPI_NHWC;
+        a.pool = 0;
+        a.y = wsf(n, n->up_scratch);
+        a.ldy = rup(L.Cin, 4);
+        a.coff = 0;
+      }
       a.ldfx = ib.ld;
       a.Hf = ib.H;
       a.Wf = ib.W;
@@ -1397,6 +1527,28 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
       if (rc) return rc;
       n->launches++;
       mark(n, st, "dgrad " + L.conv_name, 2.0 * L.Cin * L.Cout * L.KS * L.KS * (double)L.Ho * L.Wo * B);
+      if (L.bilinear) {
+        BilinearArgs ba;
+        memset(&ba, 0, sizeof(ba));
+        ba.x = wsf(n, ib.act);
+        ba.ldx = ib.ld;
+        ba.C = L.Cin;
+        ba.H = ib.H;
+        ba.W = ib.W;
+        ba.B = B;
+        ba.bn = bn_src(n, L, B, true);
+        ba.up = wsf(n, n->up_scratch);
+        ba.ldu = rup(L.Cin, 4);
+        ba.G = wsf(n, ib.grad);
+        ba.ldG = ib.ld;
+        ba.g_accum = L.last_consumer ? 0 : 1;
+        ba.bsum = wsd(n, L.bsum);
+        ba.gmax = gmax_slot(n, L.in_buf);
+        rc = launch_bilinear_bwd(ba, st);
+        if (rc) return rc;
+        n->launches++;
+        mark(n, st, "bilinear.b " + L.conv_name);
+      }
       return PDES_OK;
     };
     // the fused dgrad produces the dY planes its layer's weight gradient reads: it goes first

@@ -18,6 +18,9 @@ class TrainStep(object):
         self.flat, self.gflat = model.flat_parameters()
         if not self.flat.is_cuda:
             raise RuntimeError("TrainStep needs the model on a CUDA device")
+        if model._cfg.get("drop_rate", 0.0) > 0:
+            raise NotImplementedError("TrainStep (CUDA-graph engine) does not redraw dropout masks inside the graph; "
+                                      "train a drop_rate > 0 network through the module API")
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         self.gw = torch.tensor([1.0, 1.0, weight_bound, weight_bound], device=self.flat.device)

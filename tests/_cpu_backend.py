@@ -15,7 +15,10 @@ class OracleExecutor(object):
 
     def _plan_state(self, requires_grad):
         m = self.m
-        plan = orc.densenet_plan(**m._cfg)
+        cfg = dict(m._cfg)
+        self.drop_rate = float(cfg.pop("drop_rate", 0.0))
+        self.upsample = cfg.pop("upsample", "nearest")
+        plan = orc.densenet_plan(**cfg)
         sd = {}
         for k, v in m.state_dict().items():
             sd[k] = v.detach().clone() if k.endswith("num_batches_tracked") else v.detach()
@@ -30,7 +33,7 @@ class OracleExecutor(object):
         need = bool(training)  # autograd.Function.forward runs with grad mode off: always keep a graph
         plan, sd, leaves = self._plan_state(need)
         with torch.enable_grad() if need else torch.no_grad():
-            out = orc.densenet_forward(plan, sd, x, training=training)
+            out = orc.densenet_forward(plan, sd, x, training=training, drop_rate=self.drop_rate, upsample=self.upsample)
         self.ctx = (out, leaves) if need else None
         return out.detach()
 

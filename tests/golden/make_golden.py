@@ -48,12 +48,12 @@ def main():
 
     DenseED, darcy, SobelFilter = import_reference()
 
-    def ref_step(cfg, B, seed, dtype, kind="lognormal"):
+    def ref_step(cfg, B, seed, dtype, kind="lognormal", upsample="nearest"):
         plan = orc.densenet_plan(**cfg)
         sd = orc.to_dtype(orc.make_state(plan, seed), dtype)
         K = orc.make_input(B, cfg["imsize"], seed, kind=kind).to(dtype)
         model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
-                        growth_rate=cfg["growth_rate"], init_features=cfg["init_features"])
+                        growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], upsample=upsample)
         model = model.to(dtype)
         missing = model.load_state_dict(sd, strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
@@ -84,9 +84,9 @@ def main():
                     l_d_notb=l_d_notb.detach(), names=[n for n, _ in model.named_parameters()],
                     model_size=model.model_size)
 
-    def save_case(fname, cfg, B, seed, full_grads, kind="lognormal", compact=False):
-        r32 = ref_step(cfg, B, seed, torch.float32, kind)
-        r64 = ref_step(cfg, B, seed, torch.float64, kind)
+    def save_case(fname, cfg, B, seed, full_grads, kind="lognormal", compact=False, upsample="nearest"):
+        r32 = ref_step(cfg, B, seed, torch.float32, kind, upsample)
+        r64 = ref_step(cfg, B, seed, torch.float64, kind, upsample)
         d = dict(input_kind=kind, cfg_in_channels=cfg["in_channels"], cfg_out_channels=cfg["out_channels"],
                  cfg_imsize=cfg["imsize"], cfg_blocks=np.array(cfg["blocks"]),
                  cfg_growth_rate=cfg["growth_rate"], cfg_init_features=cfg["init_features"], B=B,
@@ -240,8 +240,55 @@ def main():
             print("decoder", tag, "loss lin/nl", float(d[f"{tag}_lin_loss_64"]), float(d[f"{tag}_nl_loss_64"]))
         np.savez_compressed(os.path.join(HERE, "decoder_solver.npz"), **d)
 
+    def bilinear_cases():
+        # --upsample bilinear (train_codec_mixed_residual.py:47; models/codec.py:33-40, 143-146, 177-178)
+        small5 = dict(in_channels=1, out_channels=3, imsize=16, blocks=[2, 1, 2, 1, 2], growth_rate=8, init_features=16)
+        save_case("densenet_bilinear16.npz", small5, B=2, seed=41, full_grads=True, upsample="bilinear")
+        save_case("densenet_bilinear32.npz", dict(full, imsize=32), B=3, seed=43, full_grads=False, upsample="bilinear")
+
+    def dropout_case():
+        # DenseED(drop_rate=0.2) (train_codec_mixed_residual.py --drop-rate; nn.Dropout2d behind the convolutions,
+        # models/codec.py:70-71, 110-149, 171-172): one fp32 training step of the reference with the CPU
+        # generator seeded right before the forward pass - the masks are then a function of the seed alone.
+        cfg = dict(in_channels=1, out_channels=3, imsize=16, blocks=[2, 1, 2, 1, 2], growth_rate=8, init_features=16)
+        B, seed, p_drop, mask_seed = 4, 31, 0.2, 77
+        plan = orc.densenet_plan(**cfg)
+        sd = orc.make_state(plan, seed)
+        K = orc.make_input(B, cfg["imsize"], seed)
+        model = DenseED(1, 3, cfg["imsize"], cfg["blocks"], growth_rate=8, init_features=16, drop_rate=p_drop)
+        model.load_state_dict(sd, strict=True)
+        sob = SobelFilter(cfg["imsize"], correct=True, device="cpu")
+        model.train()
+        model.zero_grad()
+        torch.manual_seed(mask_seed)
+        out = model(K)
+        out.retain_grad()
+        l_c = darcy.conv_constitutive_constraint(K, out, sob)
+        l_d = darcy.conv_continuity_constraint(out, sob)
+        l_dir, l_neu = darcy.conv_boundary_condition(out)
+        loss = (l_c + l_d) + (l_dir + l_neu) * 10.0
+        loss.backward()
+        model.eval()
+        with torch.no_grad():
+            out_eval = model(K)
+        names = [n for n, _ in model.named_parameters()]
+        d = dict(cfg_imsize=16, cfg_blocks=np.array(cfg["blocks"]), cfg_growth_rate=8, cfg_init_features=16, B=B,
+                 seed=seed, drop_rate=p_drop, mask_seed=mask_seed, out=out.detach().numpy(),
+                 out_eval=out_eval.numpy(), l4=torch.stack([l_c, l_d, l_dir, l_neu]).detach().numpy(),
+                 loss=loss.detach().numpy(), dout=out.grad.numpy(), param_names=np.array(names),
+                 grads=np.concatenate([p.grad.numpy().ravel() for _, p in model.named_parameters()]),
+                 n_dropout_modules=sum(1 for m_ in model.modules() if isinstance(m_, torch.nn.Dropout2d)))
+        np.savez_compressed(os.path.join(HERE, "densenet_dropout16.npz"), **d)
+        print("dropout case: loss", float(loss), "dropout modules", d["n_dropout_modules"])
+
     if "--only-channel" in sys.argv:
         channel_case()
+        return
+    if "--only-dropout" in sys.argv:
+        dropout_case()
+        return
+    if "--only-bilinear" in sys.argv:
+        bilinear_cases()
         return
     if "--only-decoder" in sys.argv:
         decoder_cases()
@@ -265,6 +312,8 @@ def main():
     timed_shape_cases()
     trajectory_case()
     decoder_cases()
+    dropout_case()
+    bilinear_cases()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----
     rs = np.random.RandomState(42)

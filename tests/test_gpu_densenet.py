@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64", "densenet_full64_channel",
          # batch 32 = the shape bench.py times: 256-1024 pixel tiles per layer, so every persistent CTA of the
          # tensor-core kernels walks several tiles (accumulator-stage ring, operand ring wrap, multi-tile split-K)
-         "densenet_full32_b32", "densenet_full64_b32"]
+         "densenet_full32_b32", "densenet_full64_b32",
+         # DenseED(upsample='bilinear') (train_codec_mixed_residual.py --upsample bilinear)
+         "densenet_bilinear16", "densenet_bilinear32"]
 
 
 def rel(a, b):
@@ -30,13 +32,13 @@ def _cfg(g):
                 growth_rate=int(g["cfg_growth_rate"]), init_features=int(g["cfg_init_features"]))
 
 
-def _model(g):
+def _model(g, upsample="nearest"):
     from models.codec import DenseED
     cfg = _cfg(g)
     plan = orc.densenet_plan(**cfg)
     sd = orc.make_state(plan, int(g["seed"]))
     model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
-                    growth_rate=cfg["growth_rate"], init_features=cfg["init_features"])
+                    growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], upsample=upsample)
     assert list(model.state_dict().keys()) == list(sd.keys())
     model.load_state_dict(sd)
     model = model.to("cuda")
@@ -50,7 +52,7 @@ def test_train_step_matches_reference(golden_dir, name, impl):
     from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
     from utils.image_gradient import SobelFilter
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    model, K, cfg = _model(g)
+    model, K, cfg = _model(g, "bilinear" if "bilinear" in name else "nearest")
     model.conv_impl = impl  # 0: tcgen05 (two-piece fp16 operands) where supported, 1: CUDA-core fp32 everywhere
     assert tuple(model.model_size) == tuple(int(v) for v in g["model_size"])
     sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
@@ -180,7 +182,9 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         DenseED(1, 3, 64, [6, 8])
     with pytest.raises(NotImplementedError):
-        DenseED(1, 3, 64, [6, 8, 6], drop_rate=0.1)
+        DenseED(1, 3, 64, [6, 8, 6], bottleneck=True)
+    with pytest.raises(ValueError):
+        DenseED(1, 3, 64, [6, 8, 6], drop_rate=1.5)
     m = DenseED(1, 3, 16, [1, 1, 1], growth_rate=4, init_features=8)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 16, 16))  # CPU: no fallback
@@ -525,3 +529,54 @@ def test_decoder_solver_step_matches_reference(golden_dir, tag):
     for _ in range(3):
         opt.step(closure)
     assert np.all(np.isfinite(hist)) and hist[-1] < 0.5 * hist[0], hist
+
+
+def test_dropout_step_matches_reference(golden_dir):
+    """DenseED(drop_rate=0.2) (train_codec_mixed_residual.py --drop-rate): nn.Dropout2d behind the convolutions
+    (models/codec.py:70-71, 110-149, 171-172) as a per-(sample, channel) mask applied by the executor.  The masks
+    are drawn like torch.feature_dropout draws them; drawn on the CPU generator with the fixture's seed they are
+    the reference's masks, and the whole training step must match the reference's fp32 run."""
+    from models.codec import DenseED
+    from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
+    from utils.image_gradient import SobelFilter
+    g = np.load(os.path.join(golden_dir, "densenet_dropout16.npz"))
+    cfg = dict(in_channels=1, out_channels=3, imsize=int(g["cfg_imsize"]), blocks=[int(b) for b in g["cfg_blocks"]],
+               growth_rate=int(g["cfg_growth_rate"]), init_features=int(g["cfg_init_features"]))
+    plan = orc.densenet_plan(**cfg)
+    for impl in (0, 1):
+        model = DenseED(1, 3, cfg["imsize"], cfg["blocks"], growth_rate=cfg["growth_rate"],
+                        init_features=cfg["init_features"], drop_rate=float(g["drop_rate"]))
+        model.load_state_dict(orc.make_state(plan, int(g["seed"])))
+        model = model.cuda()
+        model.conv_impl = impl
+        model._mask_device = "cpu"       # draw the masks on the CPU generator, like the CPU reference did
+        K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"])).cuda()
+        sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
+        model.train()
+        model.zero_grad()
+        torch.manual_seed(int(g["mask_seed"]))
+        out = model(K)
+        out.retain_grad()
+        l_c = conv_constitutive_constraint(K, out, sob)
+        l_d = conv_continuity_constraint(out, sob)
+        l_dir, l_neu = conv_boundary_condition(out)
+        loss = (l_c + l_d) + (l_dir + l_neu) * 10.0
+        loss.backward()
+        torch.cuda.synchronize()
+        assert rel(out.detach().cpu().numpy(), g["out"]) < 1e-4, (impl, rel(out.detach().cpu().numpy(), g["out"]))
+        l4 = torch.stack([l_c, l_d, l_dir, l_neu]).detach().cpu().numpy()
+        assert np.all(np.abs(l4 - g["l4"]) <= 1e-4 * np.abs(g["l4"]))
+        assert rel(out.grad.cpu().numpy(), g["dout"]) < 1e-4
+        names = [str(s) for s in g["param_names"]]
+        params = dict(model.named_parameters())
+        flat = np.concatenate([params[n].grad.detach().cpu().numpy().ravel() for n in names])
+        assert rel(flat, g["grads"]) < 5e-3, (impl, rel(flat, g["grads"]))
+        model.eval()
+        with torch.no_grad():
+            ev = model(K)
+        assert rel(ev.cpu().numpy(), g["out_eval"]) < 1e-4
+        # device-drawn masks (the default): whole channels are dropped and the survivors scaled by 1/(1-p)
+        model._mask_device = None
+        model.train()
+        o2 = model(K)
+        assert bool(torch.isfinite(o2).all()) and rel(o2.detach().cpu().numpy(), g["out"]) > 1e-3

@@ -37,7 +37,9 @@ def test_state_dict_matches_reference_layout(golden_dir):
     with pytest.raises(ValueError):
         DenseED(1, 3, 64, [6, 8])
     with pytest.raises(NotImplementedError):
-        DenseED(1, 3, 64, [6, 8, 6], upsample='bilinear')
+        DenseED(1, 3, 64, [6, 8, 6], upsample=None)      # ConvTranspose2d transitions: not built
+    mb = DenseED(1, 3, 64, [6, 8, 6], upsample='bilinear', drop_rate=0.1)   # script-reachable options
+    assert len(mb.state_dict()) == 163
 
 
 def test_no_cpu_fallback_in_product():
@@ -225,3 +227,21 @@ def test_unmodified_solver_script_runs(tmp_path):
     vals = np.loadtxt(str(losses[0]))
     assert vals.shape == (2,) and np.all(np.isfinite(vals)) and vals[1] < vals[0]
     assert list((tmp_path / "exp").rglob("model_epoch2.pth"))
+
+
+def test_dropout_option_host_logic():
+    """DenseED(drop_rate > 0) builds, trains and evaluates through the module API (oracle-backed executor)."""
+    from models.codec import DenseED
+    from models.darcy import conv_boundary_condition
+    with cpu_backend():
+        model = DenseED(1, 3, 16, [1, 2, 1], growth_rate=4, init_features=8, drop_rate=0.3)
+        K = orc.make_input(3, 16, 3)
+        model.train()
+        out = model(K)
+        d, n = conv_boundary_condition(out)
+        (d + n).backward()
+        assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for p in model.parameters())
+        model.eval()
+        with torch.no_grad():
+            e1, e2 = model(K), model(K)
+        assert torch.equal(e1, e2)          # no dropout in evaluation mode

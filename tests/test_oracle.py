@@ -9,7 +9,12 @@ import torch
 from oracle import pdes_oracle as orc
 
 CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64", "densenet_full64_channel",
-         "densenet_full32_b32", "densenet_full64_b32"]   # *_b32: the batch bench.py times (fields stored as fp32)
+         "densenet_full32_b32", "densenet_full64_b32",   # *_b32: the batch bench.py times (fields stored as fp32)
+         "densenet_bilinear16", "densenet_bilinear32"]   # DenseED(upsample='bilinear')
+
+
+def _ups(name):
+    return "bilinear" if "bilinear" in name else "nearest"
 
 
 def _load(golden_dir, name):
@@ -48,10 +53,10 @@ def test_train_step_fp64_matches_reference(golden_dir, name):
     K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]), kind=str(g["input_kind"]) if "input_kind" in g.files else "lognormal").double()
     sd_eval = orc.to_dtype(sd, torch.float64)
     with torch.no_grad():
-        out_eval = orc.densenet_forward(plan, sd_eval, K, training=False)
+        out_eval = orc.densenet_forward(plan, sd_eval, K, training=False, upsample=_ups(name))
     ftol = 1e-7 if "compact" in g.files else 1.0   # compact fixtures hold the fp64 fields rounded to fp32
     assert rel(out_eval.numpy(), g["out_eval64"]) < (ftol if ftol < 1.0 else 1e-12)
-    out, l4, loss, dout, grads = orc.train_step(plan, sd, K)
+    out, l4, loss, dout, grads = orc.train_step(plan, sd, K, upsample=_ups(name))
     assert rel(out.numpy(), g["out64"]) < (ftol if ftol < 1.0 else 1e-11)
     assert rel(l4.numpy(), g["l4_64"]) < 1e-11
     assert abs(float(loss) - float(g["loss64"])) / float(g["loss64"]) < 1e-11
@@ -181,3 +186,32 @@ def test_decoder_and_nonlinear_law_match_reference(golden_dir, tag):
         assert np.allclose(norms, g[f"{tag}_{law}_grad_norm64"], rtol=1e-8, atol=1e-300)
         head = np.concatenate([sd[n].grad.numpy().ravel()[:16] for n in names])
         assert rel(head, g[f"{tag}_{law}_grads64_head"]) < 1e-8
+
+
+def test_dropout_step_matches_reference(golden_dir):
+    """DenseED(drop_rate=0.2): nn.Dropout2d behind the convolutions (models/codec.py:70-71, 110-149, 171-172).
+    With the CPU generator seeded right before the forward pass the oracle draws the reference's masks."""
+    torch.set_num_threads(1)
+    g = _load(golden_dir, "densenet_dropout16")
+    cfg = dict(in_channels=1, out_channels=3, imsize=int(g["cfg_imsize"]), blocks=[int(b) for b in g["cfg_blocks"]],
+               growth_rate=int(g["cfg_growth_rate"]), init_features=int(g["cfg_init_features"]))
+    plan = orc.densenet_plan(**cfg)
+    assert sum(1 for s in plan if orc._drop_site(s)) == int(g["n_dropout_modules"])
+    sd = orc.make_state(plan, int(g["seed"]))
+    names = orc.param_names(plan)
+    for n in names:
+        sd[n].requires_grad_(True)
+    K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]))
+    torch.manual_seed(int(g["mask_seed"]))
+    out = orc.densenet_forward(plan, sd, K, training=True, drop_rate=float(g["drop_rate"]))
+    out.retain_grad()
+    loss, l4 = orc.total_loss(K, out)
+    loss.backward()
+    assert rel(out.detach().numpy(), g["out"]) < 1e-5
+    assert rel(l4.detach().numpy(), g["l4"]) < 1e-5
+    assert rel(out.grad.numpy(), g["dout"]) < 1e-5
+    flat = np.concatenate([sd[n].grad.numpy().ravel() for n in names])
+    assert rel(flat, g["grads"]) < 1e-3
+    with torch.no_grad():
+        ev = orc.densenet_forward(plan, sd, K, training=False, drop_rate=float(g["drop_rate"]))
+    assert rel(ev.numpy(), g["out_eval"]) < 1e-5
