@@ -245,3 +245,20 @@ def test_dropout_option_host_logic():
         with torch.no_grad():
             e1, e2 = model(K), model(K)
         assert torch.equal(e1, e2)          # no dropout in evaluation mode
+
+
+def test_resident_loader_semantics():
+    """utils.load.ResidentLoader = DataLoader(shuffle=True, drop_last=True) over device-resident tensors
+    (CPU device here): every sample at most once per epoch, ragged tail dropped, fresh order every epoch."""
+    from utils.load import ResidentLoader
+    x = torch.arange(50, dtype=torch.float32).view(50, 1, 1, 1)
+    y = -x.clone()
+    ld = ResidentLoader([x, y], 8, "cpu")
+    assert len(ld) == 6 and ld.dataset[3][1].numel() == 1
+    torch.manual_seed(0)
+    e1 = [b for b in ld]
+    e2 = [b for b in ld]
+    seen = torch.cat([b[0].flatten() for b in e1])
+    assert seen.numel() == 48 and seen.unique().numel() == 48
+    assert all(torch.equal(b[0], -b[1]) and b[0].shape == (8, 1, 1, 1) for b in e1)
+    assert not torch.equal(seen, torch.cat([b[0].flatten() for b in e2]))
