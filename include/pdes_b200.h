@@ -102,7 +102,10 @@ typedef struct pdes_densenet_config {
   int32_t growth_rate;   /* default 16                         */
   int32_t init_features; /* default 48                         */
   int32_t max_batch;     /* capacity the workspace is sized for */
-  int32_t arch;          /* 0: DenseED (models/codec.py:210-318).  1: Decoder (models/codec.py:321-370): a plain 3x3
+  int32_t arch;          /* 2: cGlow coupling network _DenseCoupling (models/glow_msc.py:276-294): blocks[0] dense
+                          * layers on a planar (B, in_channels, imsize, imsize) input, then BatchNorm -> ReLU ->
+                          * Conv2dZeros (3x3 with bias and the exp(3*scale) gain, glow_msc.py:240-255) to out_channels.
+                          * 0: DenseED (models/codec.py:210-318).  1: Decoder (models/codec.py:321-370): a plain 3x3
                           * conv0 on a planar (B, in_channels, imsize, imsize) latent, then decoding blocks only;
                           * the output is imsize * 2^n_blocks wide.  (ABI version 2) */
   int32_t dropout;       /* 1: the network was built with drop_rate > 0 (nn.Dropout2d behind its convolutions,
@@ -156,6 +159,9 @@ int pdes_densenet_forward(pdes_net_t* net, const float* x, float* out, int B, in
  * (the caller zeroes it: model.zero_grad()).  Must follow a training forward of the
  * same B. */
 int pdes_densenet_backward(pdes_net_t* net, const float* dout, void* stream);
+/* The same for a coupling network (arch 2), also returning the gradient w.r.t. the network input:
+ * dx is a planar (B, in_channels, H, W) fp32 buffer (overwritten) or NULL. */
+int pdes_densenet_backward_dx(pdes_net_t* net, const float* dout, float* dx, void* stream);
 /* Useful (2*MAC) FLOPs of one forward / one forward+backward at batch B. */
 double pdes_densenet_flops(const pdes_net_t* net, int B, int training);
 /* Number of kernel launches issued by the last forward / backward call. */

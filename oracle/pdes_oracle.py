@@ -61,6 +61,19 @@ def decoder_plan(dim_latent, out_channels, blocks, growth_rate=16, init_features
     return st
 
 
+def coupling_plan(in_features, out_features, num_layers=3, growth_rate=16):
+    """Stage list of the cGlow coupling network `_DenseCoupling` (models/glow_msc.py:276-294): `num_layers` dense
+    layers on the input (281-284), then reduce = BatchNorm -> ReLU -> Conv2dZeros (287-293; Conv2dZeros 240-255:
+    3x3 convolution WITH bias, times exp(3 * scale))."""
+    st = []
+    for j in range(num_layers):
+        st.append(dict(kind="dense", name=f"denselayer{j + 1}", cin=in_features + j * growth_rate, cout=growth_rate,
+                       k=3, stride=1, pad=1, up=False))
+    st.append(dict(kind="zeros", name="reduce", bn="norm1", conv="conv_zero.conv", cin=in_features + num_layers * growth_rate,
+                   cout=out_features, k=3, stride=1, pad=1, up=False))
+    return st
+
+
 def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), growth_rate=16,
                   init_features=48, arch=0):
     """Ordered list of stages describing DenseED with the defaults the training script uses
@@ -74,6 +87,8 @@ def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), gr
     """
     if arch == 1:
         return decoder_plan(in_channels, out_channels, blocks, growth_rate, init_features)
+    if arch == 2:
+        return coupling_plan(in_channels, out_channels, list(blocks)[0], growth_rate)
     blocks = list(blocks)
     if len(blocks) > 1 and len(blocks) % 2 == 0:
         raise ValueError("length of blocks must be odd")  # codec.py:231-233
@@ -118,13 +133,13 @@ def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), gr
 
 
 def _bn_name(s):
-    return s["name"] + "." + (s["bn"] if s["kind"] == "bnconv" else "norm1")
+    return s["name"] + "." + (s["bn"] if s["kind"] in ("bnconv", "zeros") else "norm1")
 
 
 def _conv_name(s):
     if s["kind"] == "conv":
         return s["name"]
-    return s["name"] + "." + (s["conv"] if s["kind"] == "bnconv" else "conv1")
+    return s["name"] + "." + (s["conv"] if s["kind"] in ("bnconv", "zeros") else "conv1")
 
 
 def state_layout(plan):
@@ -137,7 +152,11 @@ def state_layout(plan):
             c = s["cin"]
             out += [(b + ".weight", (c,)), (b + ".bias", (c,)), (b + ".running_mean", (c,)),
                     (b + ".running_var", (c,)), (b + ".num_batches_tracked", ())]
+        if s["kind"] == "zeros":   # Conv2dZeros: the module's own `scale` comes before its child convolution
+            out.append((s["name"] + ".conv_zero.scale", (1, s["cout"], 1, 1)))
         out.append((_conv_name(s) + ".weight", (s["cout"], s["cin"], s["k"], s["k"])))
+        if s["kind"] == "zeros":
+            out.append((_conv_name(s) + ".bias", (s["cout"],)))
     return out
 
 
@@ -158,6 +177,8 @@ def make_state(plan, seed=0, dtype=torch.float32):
             sd[name] = torch.tensor(0.1 * rs.standard_normal(shape), dtype=dtype)
         elif name.endswith("running_var"):
             sd[name] = torch.tensor(rs.uniform(0.5, 1.5, shape), dtype=dtype)
+        elif name.endswith(".scale"):
+            sd[name] = torch.tensor(rs.uniform(-0.2, 0.2, shape), dtype=dtype)
         elif len(shape) == 4:
             bound = 1.0 / math.sqrt(shape[1] * shape[2] * shape[3])
             sd[name] = torch.tensor(rs.uniform(-bound, bound, shape), dtype=dtype)
@@ -239,6 +260,10 @@ def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_
         w = sd[_conv_name(s) + ".weight"]
         if operand_round is not None:
             a, w = round_operand(a, operand_round, 4), round_operand(w, operand_round, 8)
+        if s["kind"] == "zeros":   # Conv2dZeros.forward (glow_msc.py:253-255)
+            y = F.conv2d(a, w, sd[_conv_name(s) + ".bias"], s["stride"], s["pad"])
+            h = y * torch.exp(sd[s["name"] + ".conv_zero.scale"] * 3)
+            continue
         y = F.conv2d(a, w, None, s["stride"], s["pad"])
         if drop_rate > 0 and _drop_site(s):
             y = F.dropout2d(y, drop_rate, training)   # nn.Dropout2d: whole channels, scaled by 1/(1-p)
@@ -305,6 +330,17 @@ def constitutive_nonlinear(K, out, beta1, beta2):
     sigma = out[:, 1:3]
     rhs = sigma + beta1 * torch.sqrt(K) * sigma ** 2 + beta2 * K * sigma ** 3
     return ((ku_h - rhs[:, 0:1]) ** 2 + (ku_v - rhs[:, 1:2]) ** 2).mean()
+
+
+def affine_coupling(plan, sd, x, cond, reverse=False, training=True):
+    """AffineCouplingLayer.forward / .reverse (models/glow_msc.py:326-344) around a coupling_plan network."""
+    x1, x2 = x.chunk(2, 1)
+    h = densenet_forward(plan, sd, torch.cat((x1, cond), 1), training=training)
+    shift = h[:, 0::2]
+    scale = torch.sigmoid(h[:, 1::2] + 2.0)
+    x2 = (x2 / scale - shift) if reverse else ((x2 + shift) * scale)
+    logdet = scale.log().view(x.shape[0], -1).sum(1)
+    return torch.cat((x1, x2), 1), logdet
 
 
 def continuity(out, use_tb=True):

@@ -56,6 +56,7 @@ SIGNATURES = {
     "pdes_densenet_bind": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t]),
     "pdes_densenet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "pdes_densenet_backward": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pdes_densenet_backward_dx": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "pdes_densenet_flops": (c_double, [c_void_p, c_int, c_int]),
     "pdes_densenet_last_launches": (c_int, [c_void_p]),
     "pdes_densenet_set_conv_impl": (c_int, [c_void_p, c_int]),

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libpdes_b200.so")
-SOURCES = ["api.cu", "stencil.cu", "conv_simt.cu", "first_conv.cu", "conv_tc2.cu", "conv_dense.cu", "conv_dense_bwd.cu", "wgrad_tc.cu", "bilinear.cu", "conv_api.cu", "net.cu"]
+SOURCES = ["api.cu", "stencil.cu", "conv_simt.cu", "first_conv.cu", "conv_tc2.cu", "conv_dense.cu", "conv_dense_bwd.cu", "wgrad_tc.cu", "bilinear.cu", "coupling.cu", "conv_api.cu", "net.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -157,10 +157,10 @@ class CudaExecutor(object):
         if m._flat.device != x.device:
             raise RuntimeError("DenseED parameters are on %s but the input is on %s" % (m._flat.device, x.device))
         c = m._cfg
-        if c.get("arch", 0) == 1:
-            # Decoder: the latent's spatial size is free (models/codec.py:321-370 upstream has no imsize argument)
+        if c.get("arch", 0) >= 1:
+            # Decoder / coupling network: the input's spatial size is free (no imsize argument upstream)
             if x.dim() != 4 or x.shape[1] != c["in_channels"] or x.shape[2] != x.shape[3]:
-                raise ValueError("Decoder expects a square latent (B, %d, h, h), got %s" % (c["in_channels"], tuple(x.shape)))
+                raise ValueError("expected a square input (B, %d, h, h), got %s" % (c["in_channels"], tuple(x.shape)))
             imsize = int(x.shape[2])
         else:
             if x.dim() != 4 or tuple(x.shape[1:]) != (c["in_channels"], c["imsize"], c["imsize"]):
@@ -224,11 +224,19 @@ class CudaExecutor(object):
         _lib.check(rc, "pdes_densenet_forward")
         return out
 
-    def backward(self, dout):
+    def backward(self, dout, want_dx=False):
         dout = dout.contiguous()
+        dx = None
         with torch.cuda.device(dout.device):
-            rc = _lib.lib().pdes_densenet_backward(self.handle.h, _lib.ptr(dout), _lib.stream_ptr())
+            if want_dx:
+                c = self.m._cfg
+                dx = torch.empty(dout.shape[0], c["in_channels"], self.handle.imsize, self.handle.imsize,
+                                 dtype=torch.float32, device=dout.device)
+                rc = _lib.lib().pdes_densenet_backward_dx(self.handle.h, _lib.ptr(dout), _lib.ptr(dx), _lib.stream_ptr())
+            else:
+                rc = _lib.lib().pdes_densenet_backward(self.handle.h, _lib.ptr(dout), _lib.stream_ptr())
         _lib.check(rc, "pdes_densenet_backward")
+        return dx
 
     def flops(self, B, training):
         if self.handle is None:
@@ -255,7 +263,8 @@ class _DenseEDTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         m = ctx.module
-        if ctx.needs_input_grad[0]:
+        want_dx = bool(ctx.needs_input_grad[0])
+        if want_dx and m._cfg.get("arch", 0) != 2:
             raise NotImplementedError("pde_surrogate_b200.DenseED: gradient w.r.t. the network input is "
                                       "not implemented (the training path never needs it)")
         if ctx.fwd_gen != getattr(m._ex, "fwd_gen", None):
@@ -263,8 +272,8 @@ class _DenseEDTrainFn(torch.autograd.Function):
                                "between this output's forward and its backward; the executor keeps the saved "
                                "activations of the LAST forward only - call backward() before the next forward")
         m._prepare_grads()
-        m._ex.backward(dout)
-        return None, None, None
+        dx = m._ex.backward(dout, want_dx) if want_dx else m._ex.backward(dout)
+        return dx, None, None
 
 
 class _EvalGuardFn(torch.autograd.Function):
@@ -304,18 +313,30 @@ class _ExecutorNet(nn.Module):
         del layout
         # module tree with the reference's names; creation order == reference order so that the
         # default initialisation consumes the torch RNG identically
-        self.features = _Group()
         leaves = OrderedDict()
         for name, _off, shape, kind in self._param_table:
             path = name.split(".")[:-1]
             key = ".".join(path)
-            if key in leaves:
-                continue
             parent = self
             for part in path[:-1]:
                 if part not in parent._modules:
                     parent.add_module(part, _Group())
                 parent = parent._modules[part]
+            if kind == 4:
+                # Conv2dZeros.scale (glow_msc.py:252): a parameter of the GROUP `path[-1]`, not of a leaf
+                if path[-1] not in parent._modules:
+                    parent.add_module(path[-1], _Group())
+                parent._modules[path[-1]].register_parameter("scale", nn.Parameter(torch.zeros(shape)))
+                continue
+            if kind == 3:
+                # Conv2dZeros.conv.bias (glow_msc.py:247-251): zero-initialised, like the weight
+                torch.empty(shape).uniform_(-1.0, 1.0)   # nn.Conv2d draws its bias before Conv2dZeros zeroes it
+                leaves[key].register_parameter("bias", nn.Parameter(torch.zeros(shape)))
+                with torch.no_grad():
+                    leaves[key].weight.zero_()
+                continue
+            if key in leaves:
+                continue
             if kind == 0:
                 leaf = _ConvParams(shape[0], shape[1], shape[2])
             else:

@@ -106,6 +106,15 @@ struct BilinearArgs {
 int launch_bilinear_up(const BilinearArgs& a, cudaStream_t st);
 int launch_bilinear_bwd(const BilinearArgs& a, cudaStream_t st);
 
+// cGlow coupling network helpers (coupling.cu)
+int launch_nchw_to_block(const float* x, float* act, int ld, int C, int B, int HW, double* o_sum, double* o_sumsq,
+                         cudaStream_t st);
+int launch_block_to_nchw(const float* g, int ld, int C, int B, int HW, float* dx, cudaStream_t st);
+int launch_zeros_fwd(float* out, const float* bias, const float* scale, int B, int C, int HW, float* keep,
+                     cudaStream_t st);
+int launch_zeros_bwd(const float* dout, const float* out, const float* scale, int B, int C, int HW, float* dyg,
+                     float* dbias, float* dscale, cudaStream_t st);
+
 int launch_conv_simt(const ConvArgs& a, cudaStream_t st);
 int launch_wgrad_simt(const WgradArgs& a, cudaStream_t st);
 int launch_fix_dy(const FixDyArgs& a, cudaStream_t st);

@@ -83,6 +83,9 @@ struct pdes_net {
   int64_t param_floats = 0, running_floats = 0;
   size_t ws_floats = 0, ws_doubles = 0, ws_bytes = 0, off_doubles = 0, off_tables = 0;
   size_t xin = 0;
+  bool coupling = false;    // arch 2: cGlow _DenseCoupling (no In_conv: the input IS the block's first channels)
+  int64_t zb_off = -1, zs_off = -1;   // Conv2dZeros bias / scale in the flat parameter buffer
+  size_t out_keep = 0, dyg = 0;       // float offsets: forward output copy / dout * gain (arch 2)
   size_t up_scratch = 0;   // float offset: fp32 NHWC scratch of the bilinear-upsampling layers (a_up / dA_up)
   int in_hw = 0, out_hw = 0;  // spatial size of the network input / output (DenseED: both imsize)
   size_t gmax_off = 0;  // double offset: running |G| maxima (unsigned float bits), one per buffer + one for dout
@@ -225,65 +228,85 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
 // uses: dense layers without bottleneck, bottleneck transitions, nearest upsampling.
 int build(pdes_net* n) {
   const pdes_densenet_config& c = n->cfg;
-  PDES_REQUIRE(c.arch == 0 || c.arch == 1, PDES_ERR_INVALID, "pdes_densenet_create: arch %d (0 DenseED, 1 Decoder)", c.arch);
-  PDES_REQUIRE(c.n_blocks >= 1 && c.n_blocks <= 15 && (c.arch == 1 || c.n_blocks == 1 || c.n_blocks % 2 == 1),
+  PDES_REQUIRE(c.arch >= 0 && c.arch <= 2, PDES_ERR_INVALID,
+               "pdes_densenet_create: arch %d (0 DenseED, 1 Decoder, 2 coupling network)", c.arch);
+  PDES_REQUIRE(c.n_blocks >= 1 && c.n_blocks <= 15 && (c.arch >= 1 || c.n_blocks == 1 || c.n_blocks % 2 == 1),
                PDES_ERR_INVALID, "length of blocks must be an odd number, but got %d", c.n_blocks);
-  PDES_REQUIRE(c.in_channels >= 1 && c.out_channels >= 1 && c.imsize >= (c.arch == 1 ? 2 : 8) && c.growth_rate >= 1 &&
+  PDES_REQUIRE(c.in_channels >= 1 && c.out_channels >= 1 && c.imsize >= (c.arch >= 1 ? 2 : 8) && c.growth_rate >= 1 &&
                    c.init_features >= 1 && c.max_batch >= 1,
                PDES_ERR_INVALID, "pdes_densenet_create: invalid configuration");
   for (int i = 0; i < c.n_blocks; ++i)
     PDES_REQUIRE(c.blocks[i] >= 1 && c.blocks[i] < kMaxConsumers - 1, PDES_ERR_UNSUPPORTED,
                  "dense block of %d layers (supported: 1..%d)", c.blocks[i], kMaxConsumers - 2);
+  if (c.arch == 2) {
+    // _DenseCoupling (models/glow_msc.py:276-294): `blocks[0]` dense layers on the input, then
+    // reduce = BatchNorm -> ReLU -> Conv2dZeros(num_features, out_channels)
+    PDES_REQUIRE(c.n_blocks == 1 && c.in_channels <= 256, PDES_ERR_INVALID,
+                 "coupling network: one dense block, at most 256 input channels");
+    n->coupling = true;
+    n->in_hw = n->out_hw = c.imsize;
+    const int H = c.imsize, C0 = c.in_channels, nl = c.blocks[0];
+    const int cur = add_buf(n, H, H, C0 + nl * c.growth_rate);
+    char nm[128];
+    for (int j = 0; j < nl; ++j) {
+      snprintf(nm, sizeof(nm), "denselayer%d", j + 1);
+      add_layer(n, 1, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, cur, C0 + j * c.growth_rate,
+                C0 + j * c.growth_rate, c.growth_rate, 3, 1, 1, 0, H, H);
+    }
+    add_layer(n, 2, "reduce.conv_zero.conv", "reduce.norm1", cur, -1, 0, C0 + nl * c.growth_rate, c.out_channels, 3, 1,
+              1, 0, H, H);
+  } else {
   const bool decoder = c.arch == 1;
-  const int n_enc = decoder ? 0 : c.n_blocks / 2;
-  const int pad0 = (c.imsize % 2 == 0) ? 3 : 2;  // codec.py:238
-  int H = decoder ? c.imsize : conv_out(c.imsize, 7, 2, pad0);
-  int C = c.init_features;
-  n->in_hw = c.imsize;
-  // every dense block (or single-consumer tensor) is one buffer
-  auto block_channels = [&](int C0, int nl) { return C0 + nl * c.growth_rate; };
-  int cur = add_buf(n, H, H, block_channels(C, c.blocks[0]));
-  if (decoder)  // Decoder.conv0: Conv2d(dim_latent, init_features, 3, 1, 1, bias=False)  (codec.py:331)
-    add_layer(n, 0, "features.conv0", "", -1, cur, 0, c.in_channels, C, 3, 1, 1, 0, c.imsize, c.imsize);
-  else
-    add_layer(n, 0, "features.In_conv", "", -1, cur, 0, c.in_channels, C, 7, 2, pad0, 0, c.imsize, c.imsize);
-  char nm[128];
-  for (int bi = 0; bi < c.n_blocks; ++bi) {
-    const bool enc = bi < n_enc;
-    const int idx = enc ? bi + 1 : bi - n_enc + 1;
-    for (int j = 0; j < c.blocks[bi]; ++j) {
-      snprintf(nm, sizeof(nm), "features.%sBlock%d.denselayer%d", enc ? "Enc" : "Dec", idx, j + 1);
-      add_layer(n, 1, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, cur,
-                C + j * c.growth_rate, C + j * c.growth_rate, c.growth_rate, 3, 1, 1, 0, H, H);
+    const int n_enc = decoder ? 0 : c.n_blocks / 2;
+    const int pad0 = (c.imsize % 2 == 0) ? 3 : 2;  // codec.py:238
+    int H = decoder ? c.imsize : conv_out(c.imsize, 7, 2, pad0);
+    int C = c.init_features;
+    n->in_hw = c.imsize;
+    // every dense block (or single-consumer tensor) is one buffer
+    auto block_channels = [&](int C0, int nl) { return C0 + nl * c.growth_rate; };
+    int cur = add_buf(n, H, H, block_channels(C, c.blocks[0]));
+    if (decoder)  // Decoder.conv0: Conv2d(dim_latent, init_features, 3, 1, 1, bias=False)  (codec.py:331)
+      add_layer(n, 0, "features.conv0", "", -1, cur, 0, c.in_channels, C, 3, 1, 1, 0, c.imsize, c.imsize);
+    else
+      add_layer(n, 0, "features.In_conv", "", -1, cur, 0, c.in_channels, C, 7, 2, pad0, 0, c.imsize, c.imsize);
+    char nm[128];
+    for (int bi = 0; bi < c.n_blocks; ++bi) {
+      const bool enc = bi < n_enc;
+      const int idx = enc ? bi + 1 : bi - n_enc + 1;
+      for (int j = 0; j < c.blocks[bi]; ++j) {
+        snprintf(nm, sizeof(nm), "features.%sBlock%d.denselayer%d", enc ? "Enc" : "Dec", idx, j + 1);
+        add_layer(n, 1, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, cur,
+                  C + j * c.growth_rate, C + j * c.growth_rate, c.growth_rate, 3, 1, 1, 0, H, H);
+      }
+      C += c.blocks[bi] * c.growth_rate;
+      const bool last = (bi == c.n_blocks - 1);
+      if (!last) {
+        snprintf(nm, sizeof(nm), "features.Trans%s%d", enc ? "Down" : "Up", idx);
+        const int mid = add_buf(n, H, H, C / 2);
+        add_layer(n, 2, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, mid, 0, C, C / 2, 1,
+                  1, 0, 0, H, H);
+        const int Hn = enc ? conv_out(H, 3, 2, 1) : 2 * H;
+        const int nxt = add_buf(n, Hn, Hn, block_channels(C / 2, c.blocks[bi + 1]));
+        add_layer(n, 2, std::string(nm) + ".conv2", std::string(nm) + ".norm2", mid, nxt, 0, C / 2, C / 2,
+                  3, enc ? 2 : 1, 1, enc ? 0 : 1, H, H);
+        C /= 2;
+        H = Hn;
+        cur = nxt;
+      } else {
+        const std::string t = "features.LastTransUp";
+        const int b1 = add_buf(n, H, H, C / 2);
+        add_layer(n, 2, t + ".conv1", t + ".norm1", cur, b1, 0, C, C / 2, 3, 1, 1, 0, H, H);
+        const int b2 = add_buf(n, 2 * H, 2 * H, C / 4);
+        add_layer(n, 2, t + ".conv2", t + ".norm2", b1, b2, 0, C / 2, C / 4, 3, 1, 1, 1, H, H);
+        add_layer(n, 2, t + ".conv3", t + ".norm3", b2, -1, 0, C / 4, c.out_channels, 5, 1, 2, 0, 2 * H,
+                  2 * H);
+        n->out_hw = 2 * H;
+        PDES_REQUIRE(decoder || 2 * H == c.imsize, PDES_ERR_UNSUPPORTED,
+                     "imsize %d does not map back to itself through the encoder-decoder (got %d)",
+                     c.imsize, 2 * H);
+      }
     }
-    C += c.blocks[bi] * c.growth_rate;
-    const bool last = (bi == c.n_blocks - 1);
-    if (!last) {
-      snprintf(nm, sizeof(nm), "features.Trans%s%d", enc ? "Down" : "Up", idx);
-      const int mid = add_buf(n, H, H, C / 2);
-      add_layer(n, 2, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, mid, 0, C, C / 2, 1,
-                1, 0, 0, H, H);
-      const int Hn = enc ? conv_out(H, 3, 2, 1) : 2 * H;
-      const int nxt = add_buf(n, Hn, Hn, block_channels(C / 2, c.blocks[bi + 1]));
-      add_layer(n, 2, std::string(nm) + ".conv2", std::string(nm) + ".norm2", mid, nxt, 0, C / 2, C / 2,
-                3, enc ? 2 : 1, 1, enc ? 0 : 1, H, H);
-      C /= 2;
-      H = Hn;
-      cur = nxt;
-    } else {
-      const std::string t = "features.LastTransUp";
-      const int b1 = add_buf(n, H, H, C / 2);
-      add_layer(n, 2, t + ".conv1", t + ".norm1", cur, b1, 0, C, C / 2, 3, 1, 1, 0, H, H);
-      const int b2 = add_buf(n, 2 * H, 2 * H, C / 4);
-      add_layer(n, 2, t + ".conv2", t + ".norm2", b1, b2, 0, C / 2, C / 4, 3, 1, 1, 1, H, H);
-      add_layer(n, 2, t + ".conv3", t + ".norm3", b2, -1, 0, C / 4, c.out_channels, 5, 1, 2, 0, 2 * H,
-                2 * H);
-      n->out_hw = 2 * H;
-      PDES_REQUIRE(decoder || 2 * H == c.imsize, PDES_ERR_UNSUPPORTED,
-                   "imsize %d does not map back to itself through the encoder-decoder (got %d)",
-                   c.imsize, 2 * H);
-    }
-  }
+}
   // nn.Dropout2d sites (only live when cfg.dropout): behind every dense-layer convolution (codec.py:70-71),
   // behind conv1 / conv2 of the transitions (110-149) and behind conv1 of the last decoding (171-172)
   {
@@ -332,6 +355,22 @@ int build(pdes_net* n) {
       n->n_bn++;
       if (L.Cin > n->maxC) n->maxC = L.Cin;
     }
+    const bool zeros_head = n->coupling && L.out_buf < 0;
+    if (zeros_head) {
+      // Conv2dZeros (glow_msc.py:240-255): named_parameters() yields the module's own `scale` (1, C, 1, 1)
+      // before its child convolution's weight and bias
+      ParamInfo psz;
+      psz.name = "reduce.conv_zero.scale";
+      psz.offset = off;
+      psz.ndim = 4;
+      psz.shape[0] = 1;
+      psz.shape[1] = L.Cout;
+      psz.shape[2] = psz.shape[3] = 1;
+      psz.kind = 4;
+      n->zs_off = off;
+      off += pad4(L.Cout);
+      n->params.push_back(psz);
+    }
     ParamInfo pc;
     pc.name = L.conv_name + ".weight";
     pc.offset = off;
@@ -343,6 +382,18 @@ int build(pdes_net* n) {
     L.w_off = off;
     off += pad4((int64_t)L.Cout * L.Cin * L.KS * L.KS);
     n->params.push_back(pc);
+    if (zeros_head) {
+      ParamInfo pbz;
+      pbz.name = L.conv_name + ".bias";
+      pbz.offset = off;
+      pbz.ndim = 1;
+      pbz.shape[0] = L.Cout;
+      pbz.shape[1] = pbz.shape[2] = pbz.shape[3] = 1;
+      pbz.kind = 3;
+      n->zb_off = off;
+      off += pad4(L.Cout);
+      n->params.push_back(pbz);
+    }
   }
   n->param_floats = off;
   n->running_floats = roff;
@@ -458,6 +509,12 @@ int build(pdes_net* n) {
       }
     n->up_scratch = f;
     f += pad4((int64_t)mx);
+  }
+  if (n->coupling) {
+    n->out_keep = f;
+    f += pad4((int64_t)B * c.out_channels * n->out_hw * n->out_hw);
+    n->dyg = f;
+    f += pad4((int64_t)B * c.out_channels * n->out_hw * n->out_hw);
   }
   n->dyinv = f;
   f += pad4((int64_t)n->layers.size());
@@ -928,7 +985,14 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     n->launches++;
     mark(n, st, "pack_tc2");
   }
-  if (tr) {
+  if (n->coupling) {
+    const Buf& b0 = n->bufs[0];
+    rc = launch_nchw_to_block(x, wsf(n, b0.act), b0.ld, n->cfg.in_channels, B, b0.H * b0.W,
+                              tr ? wsd(n, b0.stat) : nullptr, tr ? wsd(n, b0.stat) + b0.C : nullptr, st);
+    if (rc) return rc;
+    n->launches++;
+    mark(n, st, "input->block");
+  } else if (tr) {
     PDES_CUDA(cudaMemcpyAsync(wsf(n, n->xin), x,
                               sizeof(float) * (size_t)B * n->cfg.in_channels * n->in_hw * n->in_hw,
                               cudaMemcpyDeviceToDevice, st));
@@ -1157,6 +1221,13 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       mark(n, st, "dropout.f " + L.conv_name);
     }
   }
+  if (n->coupling) {
+    rc = launch_zeros_fwd(out, n->p + n->zb_off, n->p + n->zs_off, B, n->cfg.out_channels, n->out_hw * n->out_hw,
+                          tr ? wsf(n, n->out_keep) : nullptr, st);
+    if (rc) return rc;
+    n->launches++;
+    mark(n, st, "conv2dzeros gain");
+  }
   if (tr) {
     rc = launch_bn_running_update(bn_table(n), n->n_bn, n->maxC, 0.1f, B, st);
     if (rc) return rc;
@@ -1170,7 +1241,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
   return PDES_OK;
 }
 
-static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
+static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* dx = nullptr) {
   PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_backward: bind() first");
   PDES_REQUIRE(n->fwd_train_done, PDES_ERR_STATE,
                "pdes_densenet_backward: needs a preceding training-mode forward");
@@ -1183,6 +1254,16 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
   bool used_wg = false;
   int wg_rr = 0, side_used = 0;
   mark(n, st, "@backward");
+  if (n->coupling) {
+    // Conv2dZeros backward of the gain: d(conv) = dout * exp(3 scale), d bias, d scale; the rest of the pass
+    // then sees dout * gain as the gradient of the last convolution's (planar) output
+    rc = launch_zeros_bwd(dout, wsf(n, n->out_keep), n->p + n->zs_off, B, n->cfg.out_channels, n->out_hw * n->out_hw,
+                          wsf(n, n->dyg), n->g + n->zb_off, n->g + n->zs_off, st);
+    if (rc) return rc;
+    n->launches++;
+    mark(n, st, "conv2dzeros bwd");
+    dout = wsf(n, n->dyg);
+  }
   if (n->conv_impl == 0) {
     // dynamic fp16 scale of the last layer's dY pieces: |dout| maximum (the other layers' slices take
     // the running maximum their gradient buffer collected from the dgrad epilogues)
@@ -1579,6 +1660,36 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream) {
   if (rc) return rc;
   n->launches++;
   mark(n, st, "bn_param_grad");
+  if (n->coupling && dx != nullptr) {
+    // gradient w.r.t. the network input = the first channels of the block's gradient buffer, after the lazy
+    // BatchNorm-backward corrections of every layer that normalises those channels
+    const Buf& b0 = n->bufs[0];
+    FixDyArgs f;
+    memset(&f, 0, sizeof(f));
+    f.G = wsf(n, b0.grad);
+    f.X = wsf(n, b0.act);
+    f.ldG = f.ldX = b0.ld;
+    f.C = n->cfg.in_channels;
+    f.npix = (int64_t)B * b0.H * b0.W;
+    f.sum = wsd(n, b0.stat);
+    f.sumsq = wsd(n, b0.stat) + b0.C;
+    f.inv_count = 1.0 / ((double)B * b0.H * b0.W);
+    f.eps = 1e-5f;
+    for (const auto& M : n->layers) {
+      if (M.in_buf != 0) continue;
+      PDES_REQUIRE(f.n_cons < kMaxConsumers, PDES_ERR_UNSUPPORTED, "too many consumers of one tensor");
+      f.cons_gamma[f.n_cons] = n->p + M.g_off;
+      f.cons_bsum[f.n_cons] = wsd(n, M.bsum);
+      f.cons_C[f.n_cons] = M.Cin;
+      f.n_cons++;
+    }
+    rc = launch_fix_dy(f, st);
+    if (rc) return rc;
+    rc = launch_block_to_nchw(f.G, b0.ld, f.C, B, b0.H * b0.W, dx, st);
+    if (rc) return rc;
+    n->launches += 2;
+    mark(n, st, "input gradient");
+  }
   n->fwd_train_done = false;
   return PDES_OK;
 }
@@ -1666,6 +1777,15 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   n->fwd_train_done = tr != 0;
   if (tr) n->last_B = B;
   return PDES_OK;
+}
+
+// Backward of a coupling network (arch 2) that also returns the gradient w.r.t. the network input
+// (dx: planar (B, in_channels, H, W), overwritten; may be NULL).  Direct launches (no executor graph).
+extern "C" int pdes_densenet_backward_dx(pdes_net_t* n, const float* dout, float* dx, void* stream) {
+  PDES_REQUIRE(n && n->ws, PDES_ERR_STATE, "pdes_densenet_backward_dx: bind() first");
+  PDES_REQUIRE(dx == nullptr || n->coupling, PDES_ERR_UNSUPPORTED,
+               "pdes_densenet_backward_dx: the input gradient is implemented for coupling networks (arch 2) only");
+  return backward_impl(n, dout, stream, dx);
 }
 
 extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* stream) {

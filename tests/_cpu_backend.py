@@ -32,17 +32,20 @@ class OracleExecutor(object):
     def forward(self, x, training):
         need = bool(training)  # autograd.Function.forward runs with grad mode off: always keep a graph
         plan, sd, leaves = self._plan_state(need)
+        xin = x.detach().clone().requires_grad_(need)
         with torch.enable_grad() if need else torch.no_grad():
-            out = orc.densenet_forward(plan, sd, x, training=training, drop_rate=self.drop_rate, upsample=self.upsample)
-        self.ctx = (out, leaves) if need else None
+            out = orc.densenet_forward(plan, sd, xin, training=training, drop_rate=self.drop_rate, upsample=self.upsample)
+        self.ctx = (out, leaves, xin) if need else None
+        self.fwd_gen = getattr(self, "fwd_gen", 0) + 1
         return out.detach()
 
-    def backward(self, dout):
-        out, leaves = self.ctx
+    def backward(self, dout, want_dx=False):
+        out, leaves, xin = self.ctx
         out.backward(dout)
         for (name, p), v in zip(self.m.named_parameters(), self.m._grad_views):
             v.add_(leaves[name].grad)
         self.ctx = None
+        return xin.grad if want_dx else None
 
     def flops(self, B, training):
         return 0.0

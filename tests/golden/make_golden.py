@@ -36,6 +36,7 @@ def import_reference():
     from models import darcy
     from utils.image_gradient import SobelFilter
     import models.codec as _codec
+    import models.glow_msc  # noqa: F401  (cGlow coupling layers; needs scipy)
     sys.path.remove(REF)
     import_reference.Decoder = _codec.Decoder
     return DenseED, darcy, SobelFilter
@@ -246,6 +247,59 @@ def main():
         save_case("densenet_bilinear16.npz", small5, B=2, seed=41, full_grads=True, upsample="bilinear")
         save_case("densenet_bilinear32.npz", dict(full, imsize=32), B=3, seed=43, full_grads=False, upsample="bilinear")
 
+    def coupling_cases():
+        # SURVEY.md section 8(f) row 1 / BASELINE config 5: the cGlow coupling network `_DenseCoupling`
+        # (models/glow_msc.py:276-294, Conv2dZeros 240-255) and `AffineCouplingLayer` forward / reverse (297-344),
+        # imported from the untouched reference (these classes do not touch the in-place clamp of line 438),
+        # with gradients w.r.t. parameters AND inputs, in fp64 and fp32.
+        from models import glow_msc as ref_glow   # resolved from /root/reference (sys.modules entry of the import above)
+        d = {}
+        # (tag, in_features, cond_features, H, B, seed): Appendix B shapes 82->16..130->2 @32^2 and 158->12 @16^2
+        for tag, (fin, fcond, H, B, seed) in dict(a=(3, 80, 32, 2, 51), b=(12, 104, 16, 3, 53), c=(6, 9, 8, 2, 55)).items():
+            for dtype, sfx in ((torch.float64, "64"), (torch.float32, "32")):
+                layer = ref_glow.AffineCouplingLayer(fin, fcond, coupling_net="dense").to(dtype)
+                net = layer.coupling_nn
+                cin = (fin // 2 + (fin % 2)) + fcond
+                cout = fin if fin % 2 == 0 else fin - 1
+                plan = orc.coupling_plan(cin, cout)
+                sd = orc.to_dtype(orc.make_state(plan, seed), dtype)
+                res = net.load_state_dict(sd, strict=True)
+                assert not res.missing_keys and not res.unexpected_keys
+                assert list(net.state_dict().keys()) == list(sd.keys()), "coupling state_dict order"
+                rs = np.random.RandomState(900 + seed)
+                x = torch.tensor(rs.standard_normal((B, fin, H, H)), dtype=dtype, requires_grad=True)
+                cond = torch.tensor(rs.standard_normal((B, fcond, H, H)), dtype=dtype, requires_grad=True)
+                wy = torch.tensor(rs.standard_normal((B, fin, H, H)), dtype=dtype)
+                layer.train()
+                for mode in ("fwd", "rev"):
+                    for m_ in layer.modules():
+                        if isinstance(m_, torch.nn.BatchNorm2d):
+                            m_.reset_running_stats()
+                    layer.zero_grad()
+                    x.grad = cond.grad = None
+                    y, logdet = (layer.forward if mode == "fwd" else layer.reverse)(x, cond)
+                    obj = (y * wy).sum() + 0.3 * logdet.sum()
+                    obj.backward()
+                    names = [n for n, _ in net.named_parameters()]
+                    if sfx == "64":
+                        d[f"{tag}_{mode}_y"], d[f"{tag}_{mode}_logdet"] = y.detach().numpy(), logdet.detach().numpy()
+                        d[f"{tag}_{mode}_dx"], d[f"{tag}_{mode}_dcond"] = x.grad.numpy().copy(), cond.grad.numpy().copy()
+                        d[f"{tag}_{mode}_grads"] = np.concatenate([p.grad.numpy().ravel() for _, p in net.named_parameters()])
+                        d[f"{tag}_{mode}_grad_norm"] = np.array([float(p.grad.norm()) for _, p in net.named_parameters()])
+                    else:
+                        g64 = d[f"{tag}_{mode}_grads"]
+                        g32 = np.concatenate([p.grad.double().numpy().ravel() for _, p in net.named_parameters()])
+                        d[f"{tag}_{mode}_grad_err32"] = float(np.linalg.norm(g32 - g64) / np.linalg.norm(g64))
+                        d[f"{tag}_{mode}_y_err32"] = float((y.detach().double() - torch.tensor(d[f"{tag}_{mode}_y"])).norm() /
+                                                          torch.tensor(d[f"{tag}_{mode}_y"]).norm())
+                d[f"{tag}_param_names"] = np.array(names)
+            d[f"{tag}_cfg"] = np.array([fin, fcond, H, B, seed, cin, cout])
+            print("coupling", tag, "cin", cin, "cout", cout, "grad_err32", d[f"{tag}_fwd_grad_err32"], d[f"{tag}_rev_grad_err32"])
+        for k in list(d):   # fields rounded to fp32 for storage (6e-8 relative, far below the 1e-4 bars)
+            if k.endswith(("_y", "_dx", "_dcond")):
+                d[k] = d[k].astype(np.float32)
+        np.savez_compressed(os.path.join(HERE, "cglow_coupling.npz"), **d)
+
     def dropout_case():
         # DenseED(drop_rate=0.2) (train_codec_mixed_residual.py --drop-rate; nn.Dropout2d behind the convolutions,
         # models/codec.py:70-71, 110-149, 171-172): one fp32 training step of the reference with the CPU
@@ -287,6 +341,9 @@ def main():
     if "--only-dropout" in sys.argv:
         dropout_case()
         return
+    if "--only-coupling" in sys.argv:
+        coupling_cases()
+        return
     if "--only-bilinear" in sys.argv:
         bilinear_cases()
         return
@@ -314,6 +371,7 @@ def main():
     decoder_cases()
     dropout_case()
     bilinear_cases()
+    coupling_cases()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----
     rs = np.random.RandomState(42)

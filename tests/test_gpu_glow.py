@@ -1,0 +1,62 @@
+"""cGlow coupling networks (BASELINE config 5) on the executor: `_DenseCoupling`
+(models/glow_msc.py:276-294 incl. Conv2dZeros 240-255) and `AffineCouplingLayer.forward / .reverse` (326-344)
+against the reference's own fp64 outputs and gradients w.r.t. parameters, flow variable and conditioning."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pdes_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_affine_coupling_layer_matches_reference(golden_dir, tag, impl):
+    from models.glow_msc import AffineCouplingLayer
+    g = np.load(os.path.join(golden_dir, "cglow_coupling.npz"))
+    fin, fcond, H, B, seed, cin, cout = [int(v) for v in g[f"{tag}_cfg"]]
+    plan = orc.coupling_plan(cin, cout)
+    names = orc.param_names(plan)
+    rs = np.random.RandomState(900 + seed)
+    x0 = rs.standard_normal((B, fin, H, H))
+    c0 = rs.standard_normal((B, fcond, H, H))
+    wy = torch.tensor(rs.standard_normal((B, fin, H, H))).float().cuda()
+    for mode in ("fwd", "rev"):
+        layer = AffineCouplingLayer(fin, fcond, coupling_net="dense")
+        assert list(layer.coupling_nn.state_dict().keys()) == [n for n, _ in orc.state_layout(plan)]
+        layer.coupling_nn.load_state_dict(orc.make_state(plan, seed))
+        layer = layer.cuda()
+        layer.coupling_nn.conv_impl = impl
+        layer.train()
+        x = torch.tensor(x0).float().cuda().requires_grad_(True)
+        cond = torch.tensor(c0).float().cuda().requires_grad_(True)
+        y, logdet = (layer.forward if mode == "fwd" else layer.reverse)(x, cond)
+        ((y * wy).sum() + 0.3 * logdet.sum()).backward()
+        torch.cuda.synchronize()
+        assert rel(y.detach().cpu().numpy(), g[f"{tag}_{mode}_y"]) < 1e-4
+        assert rel(logdet.detach().cpu().numpy(), g[f"{tag}_{mode}_logdet"]) < 1e-4
+        assert rel(x.grad.cpu().numpy(), g[f"{tag}_{mode}_dx"]) < 2e-4, rel(x.grad.cpu().numpy(), g[f"{tag}_{mode}_dx"])
+        assert rel(cond.grad.cpu().numpy(), g[f"{tag}_{mode}_dcond"]) < 2e-4, rel(cond.grad.cpu().numpy(), g[f"{tag}_{mode}_dcond"])
+        params = dict(layer.coupling_nn.named_parameters())
+        flat = np.concatenate([params[n].grad.detach().double().cpu().numpy().ravel() for n in names])
+        bar = max(1e-3, 10.0 * float(g[f"{tag}_{mode}_grad_err32"]))   # the reference's own fp32 noise (ReLU flips)
+        assert rel(flat, g[f"{tag}_{mode}_grads"]) < bar, (rel(flat, g[f"{tag}_{mode}_grads"]), bar)
+        # evaluation mode (running statistics) and the zero-initialised head of a fresh layer
+        layer.eval()
+        with torch.no_grad():
+            ye, _ = layer.reverse(x.detach(), cond.detach())
+        assert bool(torch.isfinite(ye).all())
+    fresh = AffineCouplingLayer(fin, fcond).cuda()
+    with torch.no_grad():
+        y0, ld0 = fresh(torch.tensor(x0).float().cuda(), torch.tensor(c0).float().cuda())
+    # Conv2dZeros starts at zero: shift = 0, scale = sigmoid(2)
+    x1, x2 = torch.tensor(x0).float().chunk(2, 1)
+    assert rel(y0.cpu().numpy(), torch.cat((x1, x2 * torch.sigmoid(torch.tensor(2.0))), 1).numpy()) < 1e-6

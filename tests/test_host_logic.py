@@ -262,3 +262,28 @@ def test_resident_loader_semantics():
     assert seen.numel() == 48 and seen.unique().numel() == 48
     assert all(torch.equal(b[0], -b[1]) and b[0].shape == (8, 1, 1, 1) for b in e1)
     assert not torch.equal(seen, torch.cat([b[0].flatten() for b in e2]))
+
+
+def test_coupling_layer_host_logic():
+    """`AffineCouplingLayer` / `_DenseCoupling` module surface (models/glow_msc.py:276-344 upstream) with the
+    oracle-backed executor: reference state_dict layout, gradients w.r.t. the flow variable and the conditioning."""
+    from models.glow_msc import AffineCouplingLayer
+    with cpu_backend():
+        layer = AffineCouplingLayer(6, 9)
+        plan = orc.coupling_plan(12, 6)
+        assert list(layer.coupling_nn.state_dict().keys()) == [n for n, _ in orc.state_layout(plan)]
+        layer.coupling_nn.load_state_dict(orc.make_state(plan, 55))
+        layer.train()
+        x = torch.randn(2, 6, 8, 8, requires_grad=True)
+        cond = torch.randn(2, 9, 8, 8, requires_grad=True)
+        y, logdet = layer.reverse(x, cond)
+        (y.sum() + logdet.sum()).backward()
+        assert x.grad is not None and cond.grad is not None and float(cond.grad.abs().sum()) > 0
+        sd64 = orc.to_dtype(orc.make_state(plan, 55), torch.float64)
+        x64, c64 = x.detach().double().requires_grad_(True), cond.detach().double().requires_grad_(True)
+        y64, ld64 = orc.affine_coupling(plan, sd64, x64, c64, reverse=True)
+        (y64.sum() + ld64.sum()).backward()
+        assert rel(y.detach().numpy(), y64.detach().numpy()) < 1e-5
+        assert rel(cond.grad.numpy(), c64.grad.numpy()) < 1e-4
+    with pytest.raises(ImportError):
+        from models.glow_msc import MultiScaleCondGlow  # noqa: F401

@@ -215,3 +215,34 @@ def test_dropout_step_matches_reference(golden_dir):
     with torch.no_grad():
         ev = orc.densenet_forward(plan, sd, K, training=False, drop_rate=float(g["drop_rate"]))
     assert rel(ev.numpy(), g["out_eval"]) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_cglow_coupling_matches_reference(golden_dir, tag):
+    """the oracle's `_DenseCoupling` / Conv2dZeros / AffineCouplingLayer restatement
+    (models/glow_msc.py:240-255, 276-294, 326-344) against the reference's own fp64 outputs and gradients
+    (w.r.t. parameters, the flow variable and the conditioning)."""
+    torch.set_num_threads(4)
+    g = _load(golden_dir, "cglow_coupling")
+    fin, fcond, H, B, seed, cin, cout = [int(v) for v in g[f"{tag}_cfg"]]
+    plan = orc.coupling_plan(cin, cout)
+    names = orc.param_names(plan)
+    assert names == [str(s) for s in g[f"{tag}_param_names"]]
+    rs = np.random.RandomState(900 + seed)
+    x0 = rs.standard_normal((B, fin, H, H))
+    c0 = rs.standard_normal((B, fcond, H, H))
+    wy = torch.tensor(rs.standard_normal((B, fin, H, H)))
+    for mode in ("fwd", "rev"):
+        sd = orc.to_dtype(orc.make_state(plan, seed), torch.float64)
+        for n in names:
+            sd[n].requires_grad_(True)
+        x = torch.tensor(x0, requires_grad=True)
+        cond = torch.tensor(c0, requires_grad=True)
+        y, logdet = orc.affine_coupling(plan, sd, x, cond, reverse=(mode == "rev"))
+        ((y * wy).sum() + 0.3 * logdet.sum()).backward()
+        assert rel(y.detach().numpy(), g[f"{tag}_{mode}_y"]) < 1e-6        # (stored as fp32)
+        assert rel(logdet.detach().numpy(), g[f"{tag}_{mode}_logdet"]) < 1e-11
+        assert rel(x.grad.numpy(), g[f"{tag}_{mode}_dx"]) < 1e-6
+        assert rel(cond.grad.numpy(), g[f"{tag}_{mode}_dcond"]) < 1e-6
+        flat = np.concatenate([sd[n].grad.numpy().ravel() for n in names])
+        assert rel(flat, g[f"{tag}_{mode}_grads"]) < 1e-9
