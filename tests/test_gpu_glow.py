@@ -43,8 +43,11 @@ def test_affine_coupling_layer_matches_reference(golden_dir, tag, impl):
         torch.cuda.synchronize()
         assert rel(y.detach().cpu().numpy(), g[f"{tag}_{mode}_y"]) < 1e-4
         assert rel(logdet.detach().cpu().numpy(), g[f"{tag}_{mode}_logdet"]) < 1e-4
-        assert rel(x.grad.cpu().numpy(), g[f"{tag}_{mode}_dx"]) < 2e-4, rel(x.grad.cpu().numpy(), g[f"{tag}_{mode}_dx"])
-        assert rel(cond.grad.cpu().numpy(), g[f"{tag}_{mode}_dcond"]) < 2e-4, rel(cond.grad.cpu().numpy(), g[f"{tag}_{mode}_dcond"])
+        # input gradients pass the same ReLU masks as the parameter gradients: where the reference's own fp32 run
+        # leaves its fp64 run by grad_err32 (mask flips; case a: 3e-4), any fp32 implementation does
+        gbar = max(2e-4, 3.0 * float(g[f"{tag}_{mode}_grad_err32"]))
+        assert rel(x.grad.cpu().numpy(), g[f"{tag}_{mode}_dx"]) < gbar, rel(x.grad.cpu().numpy(), g[f"{tag}_{mode}_dx"])
+        assert rel(cond.grad.cpu().numpy(), g[f"{tag}_{mode}_dcond"]) < gbar, rel(cond.grad.cpu().numpy(), g[f"{tag}_{mode}_dcond"])
         params = dict(layer.coupling_nn.named_parameters())
         flat = np.concatenate([params[n].grad.detach().double().cpu().numpy().ravel() for n in names])
         bar = max(1e-3, 10.0 * float(g[f"{tag}_{mode}_grad_err32"]))   # the reference's own fp32 noise (ReLU flips)
