@@ -7,8 +7,15 @@
  * SobelFilter).  This header is the boundary a binding for that namespace talks to:
  * extern "C", plain pointers and sizes, no torch / C++ types.  All pointers are DEVICE
  * pointers unless a parameter is documented as host.  `stream` is a cudaStream_t passed
- * as void* (NULL = legacy default stream).  Nothing here allocates or frees device
- * memory, and nothing synchronises the host: the caller owns every buffer.
+ * as void* (NULL = legacy default stream).  The caller owns every buffer; the training-path
+ * entry points (pdes_darcy_loss_*, pdes_densenet_forward/backward, pdes_adam_*) never allocate,
+ * free or synchronise the host.  Exceptions, all outside the training loop:
+ *   - pdes_densenet_bind synchronises the device once (the caller's workspace fill may be in flight
+ *     on another stream) and creates the executor's internal low-priority stream + two events;
+ *   - the unit-test entry points pdes_conv2d_fwd/dgrad/wgrad take scratch for the packed operands from
+ *     the stream-ordered allocator (cudaMallocAsync / cudaFreeAsync) and synchronise the stream once
+ *     while uploading their descriptor table;
+ *   - pdes_densenet_timing_report / _read synchronise the device (diagnostics).
  *
  * Every function returns PDES_OK (0) or a non-zero code; pdes_last_error() then holds a
  * human-readable message (thread-local).
