@@ -13,7 +13,10 @@
 //   * the packed filter ([jy][k-octet][piece][n = ci][8], <= 120 KB) is loaded once per CTA and stays resident.
 //   * the BatchNorm-backward epilogue (ReLU mask, sum dZ, sum dZ*xhat, gradient accumulation into the block's
 //     gradient buffer) no longer waits on global loads: the fp32 activations of the tile arrive through a
-//     TMA ring (32-channel boxes, 128-byte swizzle) issued far ahead of the MMAs.
+//     TMA ring (32-channel boxes, 128-byte swizzle) issued far ahead of the MMAs;
+//   * and the gradient accumulation  G[pixel, ci] += scale * dZ  no longer goes through L2 atomics (measured:
+//     ~2.5k clk per 32-channel stage, the kernel's limiter): the matching G box rides in the same ring stage,
+//     is updated in shared memory and goes back with one TMA store per stage.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
@@ -85,6 +88,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
       "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tm), "r"(c0),
+               "r"(c1), "r"(c2), "r"(smem_u32(smem_src))
+               : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
@@ -102,7 +110,8 @@ __host__ __device__ inline size_t bwd_hdr_bytes(int N) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
-conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, int XST, int AST, int ngroups) {
+conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmG,
+                      DenseBwdArgs a, int XST, int AST, int ngroups) {
   const int W = a.W, H = a.H, N = a.N;
   const int TR = 128 / W;
   const int HP = (TR + 2) * W;
@@ -112,7 +121,8 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
   const uint32_t a_piece_bytes = (uint32_t)kKO * HP * 16u;
   const uint32_t a_stage_bytes = 2u * a_piece_bytes;
   const uint32_t b_jy_bytes = (uint32_t)kKO * 2u * N * 16u;     // [k-octet][piece][n][16 B]
-  const uint32_t x_stage_bytes = 128u * 128u;                  // [pixel][32 fp32]
+  const uint32_t x_plane_bytes = 128u * 128u;                  // [pixel][32 fp32]
+  const uint32_t x_stage_bytes = 2u * x_plane_bytes;           // the activations and, behind them, the G box
   const int n_xst = (N + 31) >> 5;                             // 32-channel activation stages per tile
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -135,6 +145,8 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
   unsigned char* B_s = A_s + (size_t)AST * a_stage_bytes;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#define DBG(slot) do { if (a.dbg != nullptr && blockIdx.x < 4 && (slot) < 64) a.dbg[(size_t)blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+  if (threadIdx.x == 0) DBG(0);
   const uint32_t ts_cols = (uint32_t)(ngroups * N);
   uint32_t tmem_cols = 32;
   while (tmem_cols < ts_cols * kTS) tmem_cols <<= 1;
@@ -155,6 +167,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
     }
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmG) : "memory");
     // The packed filter was written by the pack kernel at the head of the step, several launches ago.  Under
     // programmatic dependent launch this kernel starts once the PREVIOUS kernel has passed its own
     // griddepcontrol.wait, i.e. once everything before the previous kernel has completed: the resident
@@ -173,6 +186,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
     tmem_relinquish();
   }
   griddep_wait();
+  if (threadIdx.x == 0) DBG(1);
   // dynamic power-of-two scale of the gradient pieces (same rule as act_split_kernel)
   int dyn_e = 0;
   if (a.dyn_max != nullptr) {
@@ -226,6 +240,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) DBG(2);
 
   if (warp >= kProdWarp0) {
     // ===== dY producers: G, X slices -> corrected, scaled, split -> three shifted copies in A_s =====
@@ -250,33 +265,53 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
       const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
       const int s = t_it % AST;
-      if (lane == 0) mbar_wait(&a_empty[s], (uint32_t)(((t_it / AST) & 1) ^ 1));
-      __syncwarp();
       unsigned char* st = A_s + (size_t)s * a_stage_bytes;
-      for (int sp = pt >> 1; sp < HP; sp += (kProdWarps * 32) >> 1) {
+      // HP <= 192 source pixels over 64 thread pairs: at most kIt = 3 per thread.  All global loads of the
+      // tile are issued before the first conversion (one memory latency per tile instead of three).
+      constexpr int kIt = 3, kSpStep = (kProdWarps * 32) >> 1;
+      float vv[kIt][8], xx[kIt][8];
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int sp = (pt >> 1) + it * kSpStep;
         const int prow = sp >> wsh, col = sp & (W - 1);
         const int row = r0 - 1 + prow;
-        uint4 h1 = make_uint4(0u, 0u, 0u, 0u), h2 = h1;
-        if (row >= 0 && row < H && oct * 8 < a.Cout) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) vv[it][k] = xx[it][k] = 0.f;
+        if (sp < HP && row >= 0 && row < H && oct * 8 < a.Cout) {
           const size_t pix = ((size_t)b * H + row) * W + col;
           const float* gp = f.G + pix * f.ldG + oct * 8;
           const float* xp = f.X + pix * f.ldX + oct * 8;
-          float v[8], xv[8];
           if (vec) {
             const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
-            v[0] = g0.x; v[1] = g0.y; v[2] = g0.z; v[3] = g0.w; v[4] = g1.x; v[5] = g1.y; v[6] = g1.z; v[7] = g1.w;
+            vv[it][0] = g0.x; vv[it][1] = g0.y; vv[it][2] = g0.z; vv[it][3] = g0.w;
+            vv[it][4] = g1.x; vv[it][5] = g1.y; vv[it][6] = g1.z; vv[it][7] = g1.w;
             if (fix) {
               const float4 x0 = __ldg(reinterpret_cast<const float4*>(xp)), x1 = __ldg(reinterpret_cast<const float4*>(xp + 4));
-              xv[0] = x0.x; xv[1] = x0.y; xv[2] = x0.z; xv[3] = x0.w; xv[4] = x1.x; xv[5] = x1.y; xv[6] = x1.z; xv[7] = x1.w;
+              xx[it][0] = x0.x; xx[it][1] = x0.y; xx[it][2] = x0.z; xx[it][3] = x0.w;
+              xx[it][4] = x1.x; xx[it][5] = x1.y; xx[it][6] = x1.z; xx[it][7] = x1.w;
             }
           } else {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
               const bool in = oct * 8 + k < a.Cout;
-              v[k] = in ? gp[k] : 0.f;
-              xv[k] = (in && fix) ? xp[k] : 0.f;
+              vv[it][k] = in ? gp[k] : 0.f;
+              xx[it][k] = (in && fix) ? xp[k] : 0.f;
             }
           }
+        }
+      }
+      if (lane == 0) mbar_wait(&a_empty[s], (uint32_t)(((t_it / AST) & 1) ^ 1));   // loads above are in flight
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int sp = (pt >> 1) + it * kSpStep;
+        if (sp >= HP) break;
+        const int prow = sp >> wsh, col = sp & (W - 1);
+        const int row = r0 - 1 + prow;
+        uint4 h1 = make_uint4(0u, 0u, 0u, 0u), h2 = h1;
+        if (row >= 0 && row < H && oct * 8 < a.Cout) {
+          float* v = vv[it];
+          const float* xv = xx[it];
           if (fix) {
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
@@ -326,20 +361,47 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[s]);
+      if (threadIdx.x == kProdWarp0 * 32) DBG(3 + t_it);      // A operand of tile t_it published
     }
   } else if (warp == kTmaWarp) {
     // ===== activation tiles of the BatchNorm-backward epilogue: (32 channels, 128 pixels) boxes =====
     if (lane == 0) {
+      // ring stage = [X box | G box].  Before a stage is refilled, the G box the epilogue warps updated in it
+      // (iteration q - XST) is written back with one TMA store (out-of-range channels / pixels are clipped).
       int q_it = 0;
+      int pend_c[kMaxX], pend_p[kMaxX], pend_b[kMaxX];
+      for (int i = 0; i < kMaxX; ++i) pend_c[i] = -1;
+      auto write_back = [&](int s) {
+        if (pend_c[s] >= 0) {
+          tma_store_3d(&tmG, pend_c[s], pend_p[s], pend_b[s], X_s + (size_t)s * x_stage_bytes + x_plane_bytes);
+          tma_store_commit();
+          tma_store_wait_read<0>();   // the store has read the stage: it may be refilled
+          pend_c[s] = -1;
+        }
+      };
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
         for (int j = 0; j < n_xst; ++j, ++q_it) {
           const int s = q_it % XST;
           mbar_wait(&x_empty[s], (uint32_t)(((q_it / XST) & 1) ^ 1));
-          mbar_arrive_expect_tx(&x_full[s], x_stage_bytes);
-          tma_load_3d(X_s + (size_t)s * x_stage_bytes, &tmX, j * 32, r0 * W, b, &x_full[s]);
+          write_back(s);
+          unsigned char* st = X_s + (size_t)s * x_stage_bytes;
+          mbar_arrive_expect_tx(&x_full[s], a.g_accum ? x_stage_bytes : x_plane_bytes);
+          tma_load_3d(st, &tmX, j * 32, r0 * W, b, &x_full[s]);
+          if (a.g_accum) tma_load_3d(st + x_plane_bytes, &tmG, j * 32, r0 * W, b, &x_full[s]);
+          pend_c[s] = j * 32;
+          pend_p[s] = r0 * W;
+          pend_b[s] = b;
         }
       }
+      // drain: the last XST stages
+      for (int k = 0; k < XST; ++k, ++q_it) {
+        const int s = q_it % XST;
+        if (pend_c[s] < 0) continue;
+        mbar_wait(&x_empty[s], (uint32_t)(((q_it / XST) & 1) ^ 1));
+        write_back(s);
+      }
+      tma_store_wait_all<0>();
     }
   } else if (warp == kMmaWarp) {
     if (!a.b_early && lane == 0 && (int)blockIdx.x < n_tiles) {
@@ -365,6 +427,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
       if (t_it == 0)
         for (int jy = 0; jy < 3; ++jy) mbar_wait(&b_full[jy], 0);
       tc_fence_after();
+      if (lane == 0) DBG(8 + t_it);                           // MMA issue of tile t_it starts
       const uint32_t d0 = tmem_base + (uint32_t)ts * ts_cols;
       const uint64_t ad0 = make_desc(smem_u32(A_s + (size_t)sa * a_stage_bytes), lbo_a, sbo_a);
       const uint64_t bd0 = make_desc(smem_u32(B_s), lbo_b, sbo_b);
@@ -414,13 +477,14 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
       const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
       const int row = r0 + prow;
       const bool valid = row < H;
-      const size_t pix = ((size_t)b * H + row) * W + px;
       mbar_wait(&acc_full[ts], (uint32_t)((t_it / kTS) & 1));
       tc_fence_after();
+      if (threadIdx.x == 0) DBG(12 + 2 * t_it);               // accumulator of tile t_it complete
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)ts * ts_cols;
       for (int j = 0; j < n_xst; ++j, ++q_it) {
         const int xs = q_it % XST;
         mbar_wait(&x_full[xs], (uint32_t)((q_it / XST) & 1));
+        if (threadIdx.x == 0) DBG(20 + q_it);                 // X stage q_it available to the epilogue
         const int n0 = j * 32 + half * 16;
         if (n0 < N) {
           // activations of this pixel: 16 channels = 4 swizzled 16-byte chunks of row m
@@ -453,18 +517,18 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
             o[i] = c.x * dz;
             gmx = fmaxf(gmx, fabsf(o[i]));
           }
-          if (valid) {
-            float* gp = a.G + pix * a.ldG + n0;
+          {
+            // G box of this stage: row m, the four 16-byte chunks of this warp half (same swizzle as X)
+            unsigned char* grow = X_s + (size_t)xs * x_stage_bytes + x_plane_bytes + (size_t)m * 128;
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              if (n0 + i + 3 < a.Cin) {
-                if (a.g_accum) red_add_v4(gp + i, o[i], o[i + 1], o[i + 2], o[i + 3]);
-                else *reinterpret_cast<float4*>(gp + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
-              } else {
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (n0 + i + k < a.Cin) gp[i + k] = a.g_accum ? gp[i + k] + o[i + k] : o[i + k];
+            for (int c4 = 0; c4 < 4; ++c4) {
+              float4* gp = reinterpret_cast<float4*>(grow + (((half * 4 + c4) ^ (m & 7)) << 4));
+              float4 t = make_float4(o[4 * c4], o[4 * c4 + 1], o[4 * c4 + 2], o[4 * c4 + 3]);
+              if (a.g_accum) {
+                const float4 g = *gp;
+                t.x += g.x; t.y += g.y; t.z += g.z; t.w += g.w;
               }
+              *gp = t;
             }
           }
           const float u = colsum16(s1, lane), w = colsum16(s2, lane);
@@ -474,12 +538,14 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
             r[1] += w;
           }
         }
+        fence_proxy_async_smem();   // the updated G box -> visible to the TMA store
         __syncwarp();
         if (lane == 0) mbar_arrive(&x_empty[xs]);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[ts]);
+      if (threadIdx.x == 0) DBG(13 + 2 * t_it);               // epilogue of tile t_it done
     }
     if (a.gmax != nullptr) {
       const unsigned mm = __reduce_max_sync(0xffffffffu, __float_as_uint(gmx));
@@ -500,6 +566,8 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseBwdArgs a, i
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) DBG(40);
+#undef DBG
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -513,7 +581,7 @@ bool bwd_plan(int W, int N, BwdPlan* p) {
   p->hdr = bwd_hdr_bytes(N);
   for (int ast = 2; ast >= 1; --ast)
     for (int xst = kMaxX; xst >= 2; --xst) {
-      const size_t s = 1024 + p->hdr + (size_t)xst * 128 * 128 + ast * a_stage + b_bytes;
+      const size_t s = 1024 + p->hdr + (size_t)xst * 2 * 128 * 128 + ast * a_stage + b_bytes;
       if (s <= 227 * 1024) {
         p->XST = xst;
         p->AST = ast;
@@ -579,7 +647,18 @@ int launch_conv_dense_bwd(const DenseBwdArgs& a, cudaStream_t st) {
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled (conv_dense_bwd) failed with code %d", (int)r);
   }
-  PDES_CUDA(launch_pdl(conv_dense_bwd_kernel, dim3(grid), dim3(kThreads), p.smem, st, tm, a, p.XST, p.AST, p.ngroups));
+  CUtensorMap tg;
+  {
+    const cuuint64_t gdim[3] = {(cuuint64_t)a.Cin, (cuuint64_t)a.H * a.W, (cuuint64_t)a.B};
+    const cuuint64_t gstr[2] = {(cuuint64_t)a.ldG * 4, (cuuint64_t)a.H * a.W * a.ldG * 4};
+    const cuuint32_t box[3] = {32, 128, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&tg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, a.G, gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PDES_REQUIRE(r == CUDA_SUCCESS, PDES_ERR_CUDA, "cuTensorMapEncodeTiled (conv_dense_bwd, G) failed with code %d", (int)r);
+  }
+  PDES_CUDA(launch_pdl(conv_dense_bwd_kernel, dim3(grid), dim3(kThreads), p.smem, st, tm, tg, a, p.XST, p.AST, p.ngroups));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

@@ -169,6 +169,7 @@ struct DenseBwdArgs {
   float out_scale;
   int b_early;               // 1: the filter may be fetched before griddepcontrol.wait (packed >= 2 launches ago)
   int lowp;                  // LOWP_*
+  long long* dbg;            // optional phase timestamps (clock64), 64 slots per CTA for the first 4 CTAs
 };
 bool dense_bwd_supported(int KS, int stride, int pad, int up, int Cin, int Cout, int H, int W);
 size_t dense_bwd_pack_elems(int N);

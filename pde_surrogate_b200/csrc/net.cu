@@ -1580,7 +1580,32 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
         db.out_scale = pow2f(-kWScaleLog2);
         db.lowp = n->lowp;
         db.b_early = 1;  // packed during the forward pass
-        rc = launch_conv_dense_bwd(db, st);
+        {
+          // PDES_DENSE_DBG_BWD=<layer index>: phase timestamps of that layer's fused dgrad
+          static int dbg_layer = -2;
+          static long long* dbg_buf = nullptr;
+          if (dbg_layer == -2) {
+            const char* e = getenv("PDES_DENSE_DBG_BWD");
+            dbg_layer = e ? atoi(e) : -1;
+            if (dbg_layer >= 0 && cudaMalloc((void**)&dbg_buf, sizeof(long long) * 256) != cudaSuccess) dbg_layer = -1;
+          }
+          if (dbg_layer == li && dbg_buf != nullptr && !stream_capturing(st)) {
+            cudaMemsetAsync(dbg_buf, 0, sizeof(long long) * 256, st);
+            db.dbg = dbg_buf;
+            rc = launch_conv_dense_bwd(db, st);
+            long long h[256];
+            cudaMemcpyAsync(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            for (int c = 0; c < 2; ++c) {
+              fprintf(stderr, "[dense bwd dbg] %s CTA %d:", L.conv_name.c_str(), c);
+              for (int i = 1; i < 64; ++i)
+                if (h[c * 64 + i]) fprintf(stderr, " s%d=+%lld", i, h[c * 64 + i] - h[c * 64]);
+              fprintf(stderr, "\n");
+            }
+          } else {
+            rc = launch_conv_dense_bwd(db, st);
+          }
+        }
       } else if (n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2)) {
         Tc2Args t;
         memset(&t, 0, sizeof(t));
