@@ -184,7 +184,9 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
+    fixd[lane] = 0.0;
   }
+  __syncthreads();   // barriers and the zeroed fix accumulators are visible before anybody uses them
   griddep_wait();
   if (threadIdx.x == 0) DBG(1);
   // dynamic power-of-two scale of the gradient pieces (same rule as act_split_kernel)
@@ -199,6 +201,51 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   }
   const float dmul = __uint_as_float((uint32_t)(dyn_e + 127) << 23);
   const float dinv = __uint_as_float((uint32_t)(127 - dyn_e) << 23);
+  // ===== dY producers: loads of one tile (issued for the first tile before the prologue's constants exist) =====
+  constexpr int kIt = 3, kSpStep = (kProdWarps * 32) >> 1;
+  float vv[kIt][8], xx[kIt][8];
+  const int pt = (int)threadIdx.x - kProdWarp0 * 32;   // 0..127 in the producer warps
+  const int oct = pt & 1;                              // channel octet of the 16-channel slice
+  const bool fix = a.fx.n_cons > 0;
+  const bool vec = (a.fx.ldG & 3) == 0 && (a.fx.ldX & 3) == 0 && (reinterpret_cast<uintptr_t>(a.fx.G) & 15u) == 0 &&
+                   (reinterpret_cast<uintptr_t>(a.fx.X) & 15u) == 0 && oct * 8 + 7 < a.Cout;
+  auto load_dy = [&](int tile) {
+    const FixDyArgs& f = a.fx;
+    const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
+      // HP <= 192 source pixels over 64 thread pairs: at most kIt = 3 per thread.  All global loads of the
+      // tile are issued before the first conversion (one memory latency per tile instead of three).
+#pragma unroll
+      for (int it = 0; it < kIt; ++it) {
+        const int sp = (pt >> 1) + it * kSpStep;
+        const int prow = sp >> wsh, col = sp & (W - 1);
+        const int row = r0 - 1 + prow;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) vv[it][k] = xx[it][k] = 0.f;
+        if (sp < HP && row >= 0 && row < H && oct * 8 < a.Cout) {
+          const size_t pix = ((size_t)b * H + row) * W + col;
+          const float* gp = f.G + pix * f.ldG + oct * 8;
+          const float* xp = f.X + pix * f.ldX + oct * 8;
+          if (vec) {
+            const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
+            vv[it][0] = g0.x; vv[it][1] = g0.y; vv[it][2] = g0.z; vv[it][3] = g0.w;
+            vv[it][4] = g1.x; vv[it][5] = g1.y; vv[it][6] = g1.z; vv[it][7] = g1.w;
+            if (fix) {
+              const float4 x0 = __ldg(reinterpret_cast<const float4*>(xp)), x1 = __ldg(reinterpret_cast<const float4*>(xp + 4));
+              xx[it][0] = x0.x; xx[it][1] = x0.y; xx[it][2] = x0.z; xx[it][3] = x0.w;
+              xx[it][4] = x1.x; xx[it][5] = x1.y; xx[it][6] = x1.z; xx[it][7] = x1.w;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const bool in = oct * 8 + k < a.Cout;
+              vv[it][k] = in ? gp[k] : 0.f;
+              xx[it][k] = (in && fix) ? xp[k] : 0.f;
+            }
+          }
+        }
+      }
+  };
+  if (warp >= kProdWarp0 && (int)blockIdx.x < n_tiles) load_dy((int)blockIdx.x);
   if (warp < kEpiWarps) {
     const int tt = threadIdx.x;
     for (int n = tt; n < N; n += kEpiWarps * 32) {
@@ -207,11 +254,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       *reinterpret_cast<float4*>(ep_s + 4 * n) = make_float4(s, h, is, -m * is);
     }
     for (int i = tt; i < 8 * N; i += kEpiWarps * 32) red_s[i] = 0.f;
-  } else if (warp == kMmaWarp) {
-    fixd[lane] = 0.0;
-  }
-  __syncthreads();
-  if (warp >= kMmaWarp) {
+  } else {
     // lazy BatchNorm-backward corrections of the dY channels: c1 = sum_l scale_l * sum dZ_l / count,
     // c2 = sum_l scale_l * sum dZ_l xhat / count over the consumers l.  One thread per (consumer, channel):
     // every global load of the prologue is in flight at once (one memory latency instead of n_cons)
@@ -244,10 +287,7 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 
   if (warp >= kProdWarp0) {
     // ===== dY producers: G, X slices -> corrected, scaled, split -> three shifted copies in A_s =====
-    const int pt = threadIdx.x - kProdWarp0 * 32;      // 0..127
-    const int oct = pt & 1;                            // channel octet of the 16-channel slice
     const FixDyArgs& f = a.fx;
-    const bool fix = f.n_cons > 0;
     const int CpB = (a.Cout + 7) & ~7, octB = CpB >> 3;
     const size_t planeB_elems = (size_t)a.B * H * W * CpB;
     float c1[8], c2[8], mn[8], isd[8];  // (filled below)
@@ -259,47 +299,12 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       mn[k] = on ? fix_s[32 + oct * 8 + k] : 0.f;
       isd[k] = on ? fix_s[48 + oct * 8 + k] : 0.f;
     }
-    const bool vec = (f.ldG & 3) == 0 && (f.ldX & 3) == 0 && (reinterpret_cast<uintptr_t>(f.G) & 15u) == 0 &&
-                     (reinterpret_cast<uintptr_t>(f.X) & 15u) == 0 && oct * 8 + 7 < a.Cout;
     int t_it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t_it) {
       const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
       const int s = t_it % AST;
       unsigned char* st = A_s + (size_t)s * a_stage_bytes;
-      // HP <= 192 source pixels over 64 thread pairs: at most kIt = 3 per thread.  All global loads of the
-      // tile are issued before the first conversion (one memory latency per tile instead of three).
-      constexpr int kIt = 3, kSpStep = (kProdWarps * 32) >> 1;
-      float vv[kIt][8], xx[kIt][8];
-#pragma unroll
-      for (int it = 0; it < kIt; ++it) {
-        const int sp = (pt >> 1) + it * kSpStep;
-        const int prow = sp >> wsh, col = sp & (W - 1);
-        const int row = r0 - 1 + prow;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) vv[it][k] = xx[it][k] = 0.f;
-        if (sp < HP && row >= 0 && row < H && oct * 8 < a.Cout) {
-          const size_t pix = ((size_t)b * H + row) * W + col;
-          const float* gp = f.G + pix * f.ldG + oct * 8;
-          const float* xp = f.X + pix * f.ldX + oct * 8;
-          if (vec) {
-            const float4 g0 = *reinterpret_cast<const float4*>(gp), g1 = *reinterpret_cast<const float4*>(gp + 4);
-            vv[it][0] = g0.x; vv[it][1] = g0.y; vv[it][2] = g0.z; vv[it][3] = g0.w;
-            vv[it][4] = g1.x; vv[it][5] = g1.y; vv[it][6] = g1.z; vv[it][7] = g1.w;
-            if (fix) {
-              const float4 x0 = __ldg(reinterpret_cast<const float4*>(xp)), x1 = __ldg(reinterpret_cast<const float4*>(xp + 4));
-              xx[it][0] = x0.x; xx[it][1] = x0.y; xx[it][2] = x0.z; xx[it][3] = x0.w;
-              xx[it][4] = x1.x; xx[it][5] = x1.y; xx[it][6] = x1.z; xx[it][7] = x1.w;
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const bool in = oct * 8 + k < a.Cout;
-              vv[it][k] = in ? gp[k] : 0.f;
-              xx[it][k] = (in && fix) ? xp[k] : 0.f;
-            }
-          }
-        }
-      }
+      if (t_it > 0) load_dy(tile);
       if (lane == 0) mbar_wait(&a_empty[s], (uint32_t)(((t_it / AST) & 1) ^ 1));   // loads above are in flight
       __syncwarp();
 #pragma unroll

@@ -150,7 +150,264 @@ __device__ __forceinline__ void bn_consts_w(const BnSrc& s, int c, float& scale,
 // shared-memory tile [piece][octet][x][16 B] (rows padded by 16 B against bank conflicts); phase 2
 // streams every (piece, octet) row of the tile to global memory as x-contiguous 16-byte stores.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int xs) {
+//
+// Two kernels.  act_split_generic_kernel: any layout (planar input, unaligned rows), one work item per loop
+// trip with direct global loads.  act_split_staged_kernel (the one the network uses): persistent CTAs; the
+// NHWC rows of the NEXT work item are fetched with cp.async (zero-filled beyond C) into a double-buffered
+// staging area while the current item is converted and stored, per-thread constants live in registers and
+// the conversions are the packed f16x2 forms (the first version issued ~390 instructions per channel octet
+// and ran issue-bound at ~30 % of the HBM roofline).
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2s(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_bf2s(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 2) act_split_staged_kernel(ActSplitArgs a, int xs) {
+  griddep_wait();
+  griddep_launch();  // the consumer's CTAs may take their SM slots and run their prologue now
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int Cp = a.Cp;
+  float* sc_s = reinterpret_cast<float*>(sm_raw);  // fused dY correction: c1 -> sc_s, c2 -> sh_s
+  float* sh_s = sc_s + Cp;
+  float* mean_s = sh_s + Cp;
+  float* is_s = mean_s + Cp;
+  unsigned char* tile = sm_raw + 16 * (size_t)Cp;
+  if (a.fix) {
+    const FixDyArgs& f = a.fx;
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+      float c1 = 0.f, c2 = 0.f, mean = 0.f, is = 0.f;
+      if (c < a.C) {
+        const double m = f.sum[c] * f.inv_count;
+        double var = f.sumsq[c] * f.inv_count - m * m;
+        if (var < 0.0) var = 0.0;
+        const double isd = 1.0 / sqrt(var + (double)f.eps);
+        double d1 = 0.0, d2 = 0.0;
+        for (int l = 0; l < f.n_cons; ++l) {
+          const double sc = (double)f.cons_gamma[l][c] * (double)(float)isd;
+          d1 += sc * f.cons_bsum[l][c];
+          d2 += sc * f.cons_bsum[l][f.cons_C[l] + c];
+        }
+        c1 = (float)(d1 * f.inv_count);
+        c2 = (float)(d2 * f.inv_count);
+        mean = (float)m;
+        is = (float)isd;
+      }
+      sc_s[c] = c1;
+      sh_s[c] = c2;
+      mean_s[c] = mean;
+      is_s[c] = is;
+    }
+  } else if (a.pro) {
+    for (int c = threadIdx.x; c < Cp; c += blockDim.x) {
+      float s = 0.f, h = 0.f;
+      if (c < a.C) bn_consts_w(a.bn, c, s, h);
+      sc_s[c] = s;
+      sh_s[c] = h;
+    }
+  }
+  float mul = a.scale;
+  if (a.dyn_max != nullptr) {
+    // same rule as the generic kernel: power of two that brings the running |gradient| maximum (times the
+    // number of summed consumer contributions) to 2^kDyTargetLog2
+    const unsigned m = *a.dyn_max;
+    int e = m == 0u ? 0 : kDyTargetLog2 - ((int)((m >> 23) & 0xffu) - 127);
+    if (a.fix)
+      for (int c = 1; c < a.fx.n_cons; c <<= 1) --e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    mul = __uint_as_float((uint32_t)(e + 127) << 23);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.dyn_inv = __uint_as_float((uint32_t)(127 - e) << 23);
+  }
+  const int oct = Cp >> 3;
+  const int up = a.up;
+  const int Hv = up ? 2 * a.Hs : a.Hs, Wv = up ? 2 * a.Ws : a.Ws;
+  const size_t plane = (size_t)a.B * Hv * Wv * Cp;  // elements per piece plane
+  const int XO = up ? 2 * xs : xs;                  // output pixels per segment
+  const int rstride = XO * 16 + 16;                 // bytes per (piece, octet) row of the tile
+  const int nseg = (a.Ws + xs - 1) / xs;
+  const int n_work = a.B * a.Hs * nseg;
+  // phase-1 thread grid: qp (power of two >= octets) threads along the channels of a pixel, 256/qp pixels
+  // in flight; phase-2 thread grid: xp (power of two >= output pixels) threads along x
+  int qsh = 0;
+  while ((1 << qsh) < oct) ++qsh;
+  const int tq = threadIdx.x & ((1 << qsh) - 1), tp = threadIdx.x >> qsh, pstep = 256 >> qsh;
+  const bool qon = tq < oct;
+  const int c = 8 * tq;
+  // staging: [buffer][x | fx.X][pixel][Cp] fp32 behind the tile
+  const size_t tile_bytes = (size_t)kPieces * oct * rstride;
+  const uint32_t stage_img = (uint32_t)xs * Cp * 4u;
+  const uint32_t stage_buf = stage_img * (a.fix ? 2u : 1u);
+  unsigned char* stage = tile + ((tile_bytes + 15) & ~(size_t)15);
+  // valid bytes of this thread's two 16-byte chunks (channels beyond C are zero-filled)
+  int nb0 = (a.C - c) * 4, nb1 = (a.C - c - 4) * 4;
+  nb0 = nb0 < 0 ? 0 : (nb0 > 16 ? 16 : nb0);
+  nb1 = nb1 < 0 ? 0 : (nb1 > 16 ? 16 : nb1);
+  auto issue = [&](int work, int buf) {
+    if (!qon) return;
+    const int seg = work % nseg, row = work / nseg;   // row = b * Hs + sy
+    const int x0 = seg * xs;
+    const int nx = (a.Ws - x0) < xs ? (a.Ws - x0) : xs;
+    const size_t pix = (size_t)row * a.Ws + x0 + tp;
+    const float* src = a.x + pix * a.ldx + c;
+    const float* srx = a.fix ? a.fx.X + pix * a.fx.ldX + c : nullptr;
+    unsigned char* d = stage + (size_t)buf * stage_buf + ((size_t)tp * Cp + c) * 4;
+    const size_t sstep = (size_t)pstep * a.ldx, xstep = a.fix ? (size_t)pstep * a.fx.ldX : 0;
+    const uint32_t dstep = (uint32_t)pstep * Cp * 4u;
+    for (int px = tp; px < nx; px += pstep) {
+      cp_async16_zfill(d, nb0 ? src : a.x, nb0);
+      cp_async16_zfill(d + 16, nb1 ? src + 4 : a.x, nb1);
+      if (a.fix) {
+        cp_async16_zfill(d + stage_img, nb0 ? srx : a.fx.X, nb0);
+        cp_async16_zfill(d + stage_img + 16, nb1 ? srx + 4 : a.fx.X, nb1);
+        srx += xstep;
+      }
+      src += sstep;
+      d += dstep;
+    }
+  };
+  if ((int)blockIdx.x < n_work) issue(blockIdx.x, 0);
+  cp_async_commit();
+  __syncthreads();   // constants ready
+  // per-thread constants of this thread's channel octet (zero beyond C: those lanes produce zeros).
+  //   pro: v = max(0, v*ka + kb) with the piece scale folded in (a power of two: exact)
+  //   fix: v = v - ka - ((x - kc) * kd) * kb
+  float ka[8], kb[8], kc[8], kd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const bool in = qon && c + k < a.C;
+    ka[k] = kb[k] = kc[k] = kd[k] = 0.f;
+    if (a.fix) {
+      ka[k] = in ? sc_s[c + k] : 0.f;
+      kb[k] = in ? sh_s[c + k] : 0.f;
+      kc[k] = in ? mean_s[c + k] : 0.f;
+      kd[k] = in ? is_s[c + k] : 0.f;
+    } else if (a.pro) {
+      ka[k] = in ? sc_s[c + k] * mul : 0.f;
+      kb[k] = in ? sh_s[c + k] * mul : 0.f;
+    }
+  }
+  const bool full8 = c + 7 < a.C;
+  int buf = 0;
+  for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+    const int seg = work % nseg, row = work / nseg;
+    const int sy = row % a.Hs, b = row / a.Hs;
+    const int x0 = seg * xs;
+    const int nx = (a.Ws - x0) < xs ? (a.Ws - x0) : xs;
+    if (work + (int)gridDim.x < n_work) issue(work + gridDim.x, buf ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();   // this item's rows have landed (this thread's share; the barrier publishes the rest)
+    __syncthreads();      // previous tile drained / staging visible
+    // ---- phase 1: staged rows -> transform, split -> shared tile ------------------------------
+    if (qon) {
+      const unsigned char* sp = stage + (size_t)buf * stage_buf + ((size_t)tp * Cp + c) * 4;
+      const uint32_t sstep = (uint32_t)pstep * Cp * 4u;
+      float* gp = const_cast<float*>(a.x) + ((size_t)row * a.Ws + x0 + tp) * a.ldx + c;
+      const size_t gstep = (size_t)pstep * a.ldx;
+      unsigned char* t0 = tile + (size_t)tq * rstride + (size_t)(up ? 2 * tp : tp) * 16;
+      const uint32_t tstep = (uint32_t)(up ? 2 * pstep : pstep) * 16u;
+      const uint32_t poff = (uint32_t)oct * rstride;
+      for (int px = tp; px < nx; px += pstep) {
+        const float4 f0 = *reinterpret_cast<const float4*>(sp);
+        const float4 f1 = *reinterpret_cast<const float4*>(sp + 16);
+        float v[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+        if (a.fix) {
+          // dY = G - c1 - xhat*c2 (lazy BatchNorm-backward mean corrections of every consumer), written
+          // back in fp32 for the non-tensor-core consumers of the slice
+          const float4 x0q = *reinterpret_cast<const float4*>(sp + stage_img);
+          const float4 x1q = *reinterpret_cast<const float4*>(sp + stage_img + 16);
+          const float xv[8] = {x0q.x, x0q.y, x0q.z, x0q.w, x1q.x, x1q.y, x1q.z, x1q.w};
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float xh = (xv[k] - kc[k]) * kd[k];
+            v[k] = v[k] - ka[k] - xh * kb[k];
+          }
+          if (full8) {
+            *reinterpret_cast<float4*>(gp) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(gp + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (c + k < a.C) gp[k] = v[k];
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] *= mul;
+        } else if (a.pro) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = fmaxf(0.f, fmaf(v[k], ka[k], kb[k]));
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] *= mul;
+        }
+        uint32_t p1[4], p2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (a.lowp == LOWP_BF16) {
+            p1[k] = pack_bf2s(v[2 * k], v[2 * k + 1]);
+            p2[k] = 0u;
+          } else {
+            p1[k] = pack_h2s(v[2 * k], v[2 * k + 1]);
+            const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&p1[k]));
+            p2[k] = a.lowp ? 0u : pack_h2s(v[2 * k] - fl.x, v[2 * k + 1] - fl.y);
+          }
+        }
+        const uint4 w0 = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+        const uint4 w1 = make_uint4(p2[0], p2[1], p2[2], p2[3]);
+        unsigned char* t1 = t0 + poff;
+        *reinterpret_cast<uint4*>(t0) = w0;
+        *reinterpret_cast<uint4*>(t1) = w1;
+        if (up == 1) {  // nearest x2: the same value at 2x and 2x+1
+          *reinterpret_cast<uint4*>(t0 + 16) = w0;
+          *reinterpret_cast<uint4*>(t1 + 16) = w1;
+        } else if (up == 2) {  // zero insertion: odd positions are zero
+          *reinterpret_cast<uint4*>(t0 + 16) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(t1 + 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        sp += sstep;
+        gp += gstep;
+        t0 += tstep;
+      }
+    }
+    buf ^= 1;
+    __syncthreads();
+    // ---- phase 2: tile rows -> global, x-contiguous 16-byte stores ---------------------------
+    const int nxo = up ? 2 * nx : nx, xo0 = up ? 2 * x0 : x0;
+    int xsh = 0;
+    while ((1 << xsh) < nxo) ++xsh;
+    const int ox = threadIdx.x & ((1 << xsh) - 1);
+    if (ox < nxo) {
+      const int nrows = (a.lowp ? 1 : kPieces) * oct, rstep = 256 >> xsh;
+      op16* dst0 = a.out + ((((size_t)b * Hv + (up ? 2 * sy : sy)) * oct) * Wv + xo0 + ox) * 8;
+      const size_t qstride = (size_t)Wv * 8, rowo = (size_t)oct * Wv * 8;
+      const unsigned char* tp2 = tile + (size_t)ox * 16;
+      for (int r = threadIdx.x >> xsh; r < nrows; r += rstep) {  // r = piece * oct + q
+        const int piece = r >= oct ? 1 : 0, q = r - piece * oct;
+        const uint4 val = *reinterpret_cast<const uint4*>(tp2 + (size_t)r * rstride);
+        op16* dst = dst0 + (piece ? plane : 0) + (size_t)q * qstride;
+        *reinterpret_cast<uint4*>(dst) = val;
+        if (up) {  // second output row: a copy (nearest) or zeros (zero insertion)
+          *reinterpret_cast<uint4*>(dst + rowo) = up == 1 ? val : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    }
+  }
+}
+
+
+__global__ void __launch_bounds__(256, 4) act_split_generic_kernel(ActSplitArgs a, int xs) {
   griddep_wait();
   griddep_launch();  // the consumer's CTAs may take their SM slots and run their prologue now
   extern __shared__ __align__(16) unsigned char sm_raw[];
@@ -320,6 +577,7 @@ __global__ void __launch_bounds__(256, 4) act_split_kernel(ActSplitArgs a, int x
     }
   }
 }
+
 
 // ---------------------------------------------------------------------------------------
 // the weight-gradient kernel
@@ -713,14 +971,26 @@ int launch_act_split(const ActSplitArgs& a, cudaStream_t st) {
   int xs = a.Ws;
   auto tile_bytes = [&](int x) { return (size_t)kPieces * (a.Cp / 8) * ((size_t)(a.up ? 2 * x : x) * 16 + 16); };
   while (xs > 1 && tile_bytes(xs) > 40 * 1024) xs = (xs + 1) / 2;
-  const size_t smem = 16 * (size_t)a.Cp + tile_bytes(xs);
-  PDES_REQUIRE(smem <= 48 * 1024, PDES_ERR_UNSUPPORTED, "act_split: %d channels need %zu bytes of shared memory", a.Cp, smem);
+  // staged (cp.async) input: needs 16-byte addressable NHWC rows, also of the activations the fused dY
+  // correction reads
+  bool staged = !a.nchw && (a.ldx & 3) == 0 && (reinterpret_cast<uintptr_t>(a.x) & 15u) == 0;
+  if (a.fix) staged = staged && (a.fx.ldX & 3) == 0 && (reinterpret_cast<uintptr_t>(a.fx.X) & 15u) == 0;
+  const size_t stage_bytes = staged ? (size_t)2 * (a.fix ? 2 : 1) * xs * a.Cp * sizeof(float) : 0;
+  const size_t smem = 16 * (size_t)a.Cp + ((tile_bytes(xs) + 15) & ~(size_t)15) + stage_bytes;
+  PDES_REQUIRE(smem <= (staged ? 200 : 48) * 1024, PDES_ERR_UNSUPPORTED, "act_split: %d channels need %zu bytes of shared memory", a.Cp, smem);
+  if (staged) PDES_ENSURE_SMEM(act_split_staged_kernel, smem);
   const int n_work = a.B * a.Hs * ((a.Ws + xs - 1) / xs);
+  // persistent CTAs: as many as fit an SM (shared memory, 2 x 256 threads), each looping over its items
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
   int blocks = n_work;
-  const int cap = sm_count() * 8;
+  const int cap = sm_count() * (staged ? per_sm : 8);
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  PDES_CUDA(launch_pdl(act_split_kernel, dim3(blocks), dim3(256), smem, st, a, xs));
+  if (staged)
+    PDES_CUDA(launch_pdl(act_split_staged_kernel, dim3(blocks), dim3(256), smem, st, a, xs));
+  else
+    PDES_CUDA(launch_pdl(act_split_generic_kernel, dim3(blocks), dim3(256), smem, st, a, xs));
   return PDES_OK;
 }
 
