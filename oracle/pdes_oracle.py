@@ -31,7 +31,16 @@ import torch.nn.functional as F
 # ---------------------------------------------------------------------------------------
 
 
-def decoder_plan(dim_latent, out_channels, blocks, growth_rate=16, init_features=48):
+def _up_stage(t, c, upsample):
+    """conv2 of a decoding transition (codec.py:136-150): Conv2d behind a x2 upsampling, or - upsample=None - the
+    transposed convolution convT2 = ConvTranspose2d(c, c, 3, stride 2, padding 1, output_padding 1) (139-142)."""
+    if upsample is None:
+        return dict(kind="bnconv", name=t, bn="norm2", conv="convT2", cin=c, cout=c, k=3, stride=1, pad=1, up=False,
+                    convT=True)
+    return dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c, cout=c, k=3, stride=1, pad=1, up=True)
+
+
+def decoder_plan(dim_latent, out_channels, blocks, growth_rate=16, init_features=48, upsample="nearest"):
     """Stage list of `Decoder` (models/codec.py:321-370): conv0 = Conv2d(dim_latent, init_features, 3, 1, 1)
     (line 331), dense decoding blocks (333-338), nearest-upsampling transitions between them (341-348),
     last decoding (351-353).  Same stage kinds as densenet_plan."""
@@ -48,14 +57,14 @@ def decoder_plan(dim_latent, out_channels, blocks, growth_rate=16, init_features
             t = f"features.TransUp{i + 1}"
             st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=1,
                            stride=1, pad=0, up=False))
-            st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 2,
-                           k=3, stride=1, pad=1, up=True))
+            st.append(_up_stage(t, c // 2, upsample))
             c //= 2
     t = "features.LastTransUp"
     st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=3, stride=1,
                    pad=1, up=False))
+    # last_decoding adds an upsampling module only for 'nearest' / 'bilinear' (codec.py:176-179)
     st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 4, k=3,
-                   stride=1, pad=1, up=True))
+                   stride=1, pad=1, up=upsample is not None))
     st.append(dict(kind="bnconv", name=t, bn="norm3", conv="conv3", cin=c // 4, cout=out_channels, k=5,
                    stride=1, pad=2, up=False))
     return st
@@ -75,7 +84,7 @@ def coupling_plan(in_features, out_features, num_layers=3, growth_rate=16):
 
 
 def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), growth_rate=16,
-                  init_features=48, arch=0):
+                  init_features=48, arch=0, upsample="nearest"):
     """Ordered list of stages describing DenseED with the defaults the training script uses
     (bottleneck=False in dense layers, bottleneck=True transitions, upsample='nearest',
     drop_rate=0, out_activation=None).
@@ -86,7 +95,7 @@ def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), gr
       'bnconv' : BN -> ReLU -> [nearest x2] -> conv                  codec.py:103-150, 163-188
     """
     if arch == 1:
-        return decoder_plan(in_channels, out_channels, blocks, growth_rate, init_features)
+        return decoder_plan(in_channels, out_channels, blocks, growth_rate, init_features, upsample)
     if arch == 2:
         return coupling_plan(in_channels, out_channels, list(blocks)[0], growth_rate)
     blocks = list(blocks)
@@ -119,14 +128,14 @@ def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), gr
             t = f"features.TransUp{i + 1}"
             st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=1,
                            stride=1, pad=0, up=False))
-            st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 2,
-                           k=3, stride=1, pad=1, up=True))
+            st.append(_up_stage(t, c // 2, upsample))
             c //= 2
     t = "features.LastTransUp"  # codec.py:163-188
     st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=3, stride=1,
                    pad=1, up=False))
+    # last_decoding adds an upsampling module only for 'nearest' / 'bilinear' (codec.py:176-179)
     st.append(dict(kind="bnconv", name=t, bn="norm2", conv="conv2", cin=c // 2, cout=c // 4, k=3,
-                   stride=1, pad=1, up=True))
+                   stride=1, pad=1, up=upsample is not None))
     st.append(dict(kind="bnconv", name=t, bn="norm3", conv="conv3", cin=c // 4, cout=out_channels, k=5,
                    stride=1, pad=2, up=False))
     return st
@@ -264,7 +273,10 @@ def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_
             y = F.conv2d(a, w, sd[_conv_name(s) + ".bias"], s["stride"], s["pad"])
             h = y * torch.exp(sd[s["name"] + ".conv_zero.scale"] * 3)
             continue
-        y = F.conv2d(a, w, None, s["stride"], s["pad"])
+        if s.get("convT"):   # nn.ConvTranspose2d(k3, s2, p1, op1), weight (cin, cout, 3, 3)  (codec.py:139-142)
+            y = F.conv_transpose2d(a, w, None, stride=2, padding=1, output_padding=1)
+        else:
+            y = F.conv2d(a, w, None, s["stride"], s["pad"])
         if drop_rate > 0 and _drop_site(s):
             y = F.dropout2d(y, drop_rate, training)   # nn.Dropout2d: whole channels, scaled by 1/(1-p)
         h = torch.cat([h, y], 1) if s["kind"] == "dense" else y  # codec.py:73-75
@@ -378,6 +390,10 @@ def train_step(plan, sd, K, weight_bound=10.0, upsample="nearest"):
         sd[n].grad = None
     out = densenet_forward(plan, sd, K, training=True, upsample=upsample)
     out.retain_grad()
+    if out.shape[-1] * 2 == K.shape[-1]:
+        # upsample=None: the output is imsize/2 wide (codec.py:176-179); the golden fixtures of that option take the
+        # residual loss on the 2x subsampled permeability (tests/golden/make_golden.py ref_step)
+        K = K[:, :, ::2, ::2]
     loss, l4 = total_loss(K, out, weight_bound)
     loss.backward()
     grads = OrderedDict((n, sd[n].grad.detach().clone()) for n in names)

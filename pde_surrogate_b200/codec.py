@@ -89,7 +89,7 @@ class _NetHandle(object):
         c.in_channels, c.out_channels, c.imsize = cfg["in_channels"], cfg["out_channels"], self.imsize
         c.arch = int(cfg.get("arch", 0))
         c.dropout = 1 if cfg.get("drop_rate", 0.0) > 0 else 0
-        c.upsample = {"nearest": 0, "bilinear": 1}[cfg.get("upsample", "nearest")]
+        c.upsample = {"nearest": 0, "bilinear": 1, None: 2}[cfg.get("upsample", "nearest")]
         c.n_blocks = len(cfg["blocks"])
         for i, b in enumerate(cfg["blocks"]):
             c.blocks[i] = int(b)
@@ -287,16 +287,30 @@ class _EvalGuardFn(torch.autograd.Function):
                                   "implemented; call model.train() or use torch.no_grad()")
 
 
+def activation(name):
+    """models/codec.py:190-204."""
+    if name in ['tanh', 'Tanh']:
+        return nn.Tanh()
+    elif name in ['relu', 'ReLU']:
+        return nn.ReLU(inplace=True)
+    elif name in ['lrelu', 'LReLU']:
+        return nn.LeakyReLU(inplace=True)
+    elif name in ['sigmoid', 'Sigmoid']:
+        return nn.Sigmoid()
+    elif name in ['softplus', 'Softplus']:
+        return nn.Softplus(beta=4)
+    else:
+        raise ValueError('Unknown activation function')
+
+
 def _reject_options(cls, drop_rate=0, bottleneck=False, upsample='nearest', out_activation=None):
     unsupported = []
     if drop_rate and not (0.0 <= drop_rate < 1.0):
         raise ValueError("dropout probability has to be between 0 and 1, but got {}".format(drop_rate))
     if bottleneck:
         unsupported.append("bottleneck=True")
-    if upsample not in ('nearest', 'bilinear'):
+    if upsample not in ('nearest', 'bilinear', None):
         unsupported.append("upsample=%r" % (upsample,))
-    if out_activation is not None:
-        unsupported.append("out_activation=%r" % (out_activation,))
     if unsupported:
         raise NotImplementedError("pde_surrogate_b200.%s does not implement: %s" % (cls, ", ".join(unsupported)))
 
@@ -307,6 +321,7 @@ class _ExecutorNet(nn.Module):
 
     def _build(self, cfg):
         self._cfg = cfg
+        self._out_act = None
         layout = _NetHandle(self._cfg, 1)
         self._param_table, self._n_flat = layout.params()
         self._bn_table, self._n_running = layout.bns()
@@ -430,6 +445,12 @@ class _ExecutorNet(nn.Module):
                     p.grad.zero_()
 
     def forward(self, x):
+        out = self._features(x)
+        # out_activation (models/codec.py:190-204, 288-289): an elementwise module behind the last convolution;
+        # not on the training path of any script (all use None) - applied with the stock torch op
+        return out if self._out_act is None else self._out_act(out)
+
+    def _features(self, x):
         anchor = self._params[0]
         grad_on = torch.is_grad_enabled() and anchor.requires_grad
         if self.training:
@@ -455,6 +476,12 @@ class _ExecutorNet(nn.Module):
                 if verbose:
                     print("Reset parameters in {}".format(module))
 
+    def _set_out_activation(self, name):
+        if name is not None:
+            act = activation(name)
+            self.features.add_module(name, act)   # same place in the tree as the reference (codec.py:288-289)
+            self._out_act = act
+
     def flat_parameters(self):
         """(params, grads) flat fp32 buffers; every parameter / .grad is a view into them."""
         return self._flat, self._flat_grad
@@ -467,9 +494,9 @@ class _ExecutorNet(nn.Module):
 class DenseED(_ExecutorNet):
     """Dense convolutional encoder-decoder (reference models/codec.py:210-318).
 
-    Args as in the reference.  Options the training script never uses raise a clear error
-    instead of silently differing: drop_rate > 0, bottleneck dense layers, upsample other than
-    'nearest', out_activation.
+    Args as in the reference: drop_rate, upsample in ('nearest', 'bilinear', None = transposed convolutions,
+    whose last decoding does not upsample: the output is imsize/2 wide, as in the reference) and
+    out_activation are implemented; bottleneck dense layers raise a clear error instead of silently differing.
     """
 
     def __init__(self, in_channels, out_channels, imsize, blocks, growth_rate=16, init_features=48,
@@ -482,6 +509,7 @@ class DenseED(_ExecutorNet):
         self._build(dict(in_channels=int(in_channels), out_channels=int(out_channels), imsize=int(imsize),
                          blocks=blocks, growth_rate=int(growth_rate), init_features=int(init_features), arch=0,
                          drop_rate=float(drop_rate or 0.0), upsample=upsample))
+        self._set_out_activation(out_activation)
         print('# params {}, # conv layers {}'.format(*self.model_size))
 
 
@@ -499,3 +527,4 @@ class Decoder(_ExecutorNet):
         self._build(dict(in_channels=int(dim_latent), out_channels=int(out_channels), imsize=16, blocks=blocks,
                          growth_rate=int(growth_rate), init_features=int(init_features), arch=1,
                          drop_rate=float(drop_rate or 0.0), upsample=upsample))
+        self._set_out_activation(out_activation)

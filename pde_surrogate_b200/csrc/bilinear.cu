@@ -7,6 +7,10 @@
 // transposed interpolation, followed by the same ReLU-mask / BatchNorm-backward bookkeeping the dgrad
 // epilogues do (sum dZ, sum dZ*xhat, scale*dZ accumulated into the block's gradient buffer, running |G| max).
 // Index arithmetic follows ATen's upsample_bilinear2d (float scale = (in-1)/(out-1), src = scale*dst).
+//
+// The same two kernels serve `upsample=None` (models/codec.py:139-142, nn.ConvTranspose2d(k3, s2, p1, op1)):
+// with zero_insert the "interpolation" is the zero insertion of the transposed convolution, which then is a
+// plain 3x3 / pad 1 convolution with the flipped, channel-transposed filter (convt_weight_kernel).
 #include "conv.cuh"
 #include "tc_common.cuh"
 
@@ -50,12 +54,16 @@ __global__ void __launch_bounds__(256) bilinear_up_kernel(BilinearArgs a) {
     const int ox = (int)(p % Wo);
     p /= Wo;
     const int oy = (int)(p % Ho), b = (int)(p / Ho);
-    const Lerp ly = lerp_of(oy, rh, a.H), lx = lerp_of(ox, rw, a.W);
     const float* base = a.x + (size_t)b * a.H * a.W * a.ldx + c;
     auto act = [&](int y, int x) {
       const float v = base[((size_t)y * a.W + x) * a.ldx];
       return a.pro ? fmaxf(0.f, fmaf(v, sc[c], sh[c])) : v;
     };
+    if (a.zero_insert) {
+      a.up[(((size_t)b * Ho + oy) * Wo + ox) * a.ldu + c] = ((oy | ox) & 1) ? 0.f : act(oy >> 1, ox >> 1);
+      continue;
+    }
+    const Lerp ly = lerp_of(oy, rh, a.H), lx = lerp_of(ox, rw, a.W);
     const float v = ly.w0 * (lx.w0 * act(ly.i0, lx.i0) + lx.w1 * act(ly.i0, lx.i1)) +
                     ly.w1 * (lx.w0 * act(ly.i1, lx.i0) + lx.w1 * act(ly.i1, lx.i1));
     a.up[(((size_t)b * Ho + oy) * Wo + ox) * a.ldu + c] = v;
@@ -96,7 +104,8 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(BilinearArgs a) {
     const int oy_lo = max(0, 2 * y - 3), oy_hi = min(Ho - 1, 2 * y + 3);
     const int ox_lo = max(0, 2 * x - 3), ox_hi = min(Wo - 1, 2 * x + 3);
     float acc = 0.f;
-    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+    if (a.zero_insert) acc = a.up[(((size_t)b * Ho + 2 * y) * Wo + 2 * x) * a.ldu + c];
+    for (int oy = oy_lo; oy <= oy_hi && !a.zero_insert; ++oy) {
       const Lerp ly = lerp_of(oy, rh, a.H);
       const float wy = (ly.i0 == y ? ly.w0 : 0.f) + (ly.i1 == y ? ly.w1 : 0.f);
       if (wy == 0.f) continue;
@@ -135,6 +144,26 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(BilinearArgs a) {
   }
 }
 
+__global__ void __launch_bounds__(256) convt_weight_kernel(const float* wt, float* wc, int Cin, int Cout, int KS) {
+  griddep_wait();
+  const int T = KS * KS, total = Cin * Cout * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % T, r = i / T;
+    const int ci = r % Cin, co = r / Cin;                       // i indexes wc[co][ci][tap]
+    wc[i] = wt[((size_t)ci * Cout + co) * T + (T - 1 - tap)];   // flipping both axes = reversing the tap index
+  }
+}
+__global__ void __launch_bounds__(256) convt_weight_grad_kernel(float* gc, float* gt, int Cin, int Cout, int KS) {
+  griddep_wait();
+  const int T = KS * KS, total = Cin * Cout * T;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % T, r = i / T;
+    const int ci = r % Cin, co = r / Cin;
+    gt[((size_t)ci * Cout + co) * T + (T - 1 - tap)] += gc[i];
+    gc[i] = 0.f;
+  }
+}
+
 int grid_for(int64_t total) {
   int blocks = (int)((total + 255) / 256);
   const int cap = sm_count() * 8;
@@ -156,6 +185,22 @@ int launch_bilinear_bwd(const BilinearArgs& a, cudaStream_t st) {
   PDES_REQUIRE(a.x && a.up && a.G && a.bsum && a.C >= 1 && a.C <= 1024, PDES_ERR_INVALID, "bilinear_bwd: invalid arguments");
   const int64_t total = (int64_t)a.B * a.H * a.W * a.C;
   PDES_CUDA(launch_pdl(bilinear_bwd_kernel, dim3(grid_for(total)), dim3(256), sizeof(float) * 6 * a.C, st, a));
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+int launch_convt_weight(const float* wt, float* wc, int Cin, int Cout, int KS, cudaStream_t st) {
+  PDES_REQUIRE(wt && wc && Cin >= 1 && Cout >= 1 && KS >= 1, PDES_ERR_INVALID, "convt_weight: invalid arguments");
+  PDES_CUDA(launch_pdl(convt_weight_kernel, dim3(grid_for((int64_t)Cin * Cout * KS * KS)), dim3(256), 0, st, wt, wc, Cin,
+                       Cout, KS));
+  PDES_LAUNCH_CHECK();
+  return PDES_OK;
+}
+
+int launch_convt_weight_grad(float* gc, float* gt, int Cin, int Cout, int KS, cudaStream_t st) {
+  PDES_REQUIRE(gc && gt && Cin >= 1 && Cout >= 1 && KS >= 1, PDES_ERR_INVALID, "convt_weight_grad: invalid arguments");
+  PDES_CUDA(launch_pdl(convt_weight_grad_kernel, dim3(grid_for((int64_t)Cin * Cout * KS * KS)), dim3(256), 0, st, gc, gt,
+                       Cin, Cout, KS));
   PDES_LAUNCH_CHECK();
   return PDES_OK;
 }

@@ -102,9 +102,16 @@ struct BilinearArgs {
   int ldG, g_accum;
   double* bsum;     // [0,C): sum dZ ; [C,2C): sum dZ*xhat
   unsigned* gmax;
+  int zero_insert;  // 1: the "upsampling" is the zero insertion of a stride-2 transposed convolution
+                    // (up[2y][2x] = a[y][x], zero elsewhere) instead of the bilinear interpolation
 };
 int launch_bilinear_up(const BilinearArgs& a, cudaStream_t st);
 int launch_bilinear_bwd(const BilinearArgs& a, cudaStream_t st);
+// nn.ConvTranspose2d(k, stride 2) <-> the equivalent Conv2d over the zero-inserted input (bilinear.cu):
+//   fwd:  wc[co][ci][ky][kx] = wt[ci][co][K-1-ky][K-1-kx]
+//   bwd:  gt[ci][co][K-1-ky][K-1-kx] += gc[co][ci][ky][kx];  gc = 0   (gc is a self-cleaning staging buffer)
+int launch_convt_weight(const float* wt, float* wc, int Cin, int Cout, int KS, cudaStream_t st);
+int launch_convt_weight_grad(float* gc, float* gt, int Cin, int Cout, int KS, cudaStream_t st);
 
 // cGlow coupling network helpers (coupling.cu)
 int launch_nchw_to_block(const float* x, float* act, int ld, int C, int B, int HW, double* o_sum, double* o_sumsq,

@@ -52,7 +52,10 @@ struct Layer {
   bool first_k;      // dedicated CUDA-core kernels of the first convolution (first_conv.cu)
   bool dense_fwd;    // fused BatchNorm+ReLU+split+conv forward of a thin 3x3 layer (conv_dense.cu)
   size_t wdn;        // float offset of its packed filter ("dx in N" layout)
-  bool bilinear;     // the x2 upsampling in front of this convolution is bilinear (align_corners), not nearest
+  bool bilinear;     // the x2 upsampling in front of this convolution is materialised by bilinear.cu (align_corners
+                     // interpolation, or zero insertion for the transposed convolution) instead of nearest
+  bool convT;        // nn.ConvTranspose2d(k3, s2, p1, op1): zero-insert x2 + 3x3 conv with the flipped, transposed filter
+  size_t wt = 0, gt = 0;   // float offsets (convT): equivalent Conv2d filter / its gradient
   bool drop;         // an nn.Dropout2d follows this convolution when the network has drop_rate > 0
   int drop_cprefix;  // channels of the dropout sites before this one (mask block offset = B * drop_cprefix)
   bool dense_bwd;    // fused dY-correction+split+dgrad of a thin 3x3 layer (conv_dense_bwd.cu)
@@ -218,6 +221,7 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.drop = false;
   L.drop_cprefix = 0;
   L.bilinear = false;
+  L.convT = false;
   L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
@@ -287,8 +291,11 @@ int build(pdes_net* n) {
                   1, 0, 0, H, H);
         const int Hn = enc ? conv_out(H, 3, 2, 1) : 2 * H;
         const int nxt = add_buf(n, Hn, Hn, block_channels(C / 2, c.blocks[bi + 1]));
-        add_layer(n, 2, std::string(nm) + ".conv2", std::string(nm) + ".norm2", mid, nxt, 0, C / 2, C / 2,
-                  3, enc ? 2 : 1, 1, enc ? 0 : 1, H, H);
+        // upsample=None: nn.ConvTranspose2d named convT2 (codec.py:139-142)
+        const bool convT = !enc && c.upsample == 2;
+        add_layer(n, 2, std::string(nm) + (convT ? ".convT2" : ".conv2"), std::string(nm) + ".norm2", mid, nxt, 0,
+                  C / 2, C / 2, 3, enc ? 2 : 1, 1, enc ? 0 : 1, H, H);
+        n->layers.back().convT = convT;
         C /= 2;
         H = Hn;
         cur = nxt;
@@ -296,12 +303,13 @@ int build(pdes_net* n) {
         const std::string t = "features.LastTransUp";
         const int b1 = add_buf(n, H, H, C / 2);
         add_layer(n, 2, t + ".conv1", t + ".norm1", cur, b1, 0, C, C / 2, 3, 1, 1, 0, H, H);
-        const int b2 = add_buf(n, 2 * H, 2 * H, C / 4);
-        add_layer(n, 2, t + ".conv2", t + ".norm2", b1, b2, 0, C / 2, C / 4, 3, 1, 1, 1, H, H);
-        add_layer(n, 2, t + ".conv3", t + ".norm3", b2, -1, 0, C / 4, c.out_channels, 5, 1, 2, 0, 2 * H,
-                  2 * H);
-        n->out_hw = 2 * H;
-        PDES_REQUIRE(decoder || 2 * H == c.imsize, PDES_ERR_UNSUPPORTED,
+        // upsample=None: last_decoding adds NO upsampling module (codec.py:176-179): the output stays at H
+        const int upl = c.upsample == 2 ? 0 : 1, Ho = upl ? 2 * H : H;
+        const int b2 = add_buf(n, Ho, Ho, C / 4);
+        add_layer(n, 2, t + ".conv2", t + ".norm2", b1, b2, 0, C / 2, C / 4, 3, 1, 1, upl, H, H);
+        add_layer(n, 2, t + ".conv3", t + ".norm3", b2, -1, 0, C / 4, c.out_channels, 5, 1, 2, 0, Ho, Ho);
+        n->out_hw = Ho;
+        PDES_REQUIRE(decoder || c.upsample == 2 || 2 * H == c.imsize, PDES_ERR_UNSUPPORTED,
                      "imsize %d does not map back to itself through the encoder-decoder (got %d)",
                      c.imsize, 2 * H);
       }
@@ -318,8 +326,9 @@ int build(pdes_net* n) {
       if (L.drop) prefix += L.Cout;
     }
   }
-  PDES_REQUIRE(c.upsample == 0 || c.upsample == 1, PDES_ERR_UNSUPPORTED, "upsample mode %d (0 nearest, 1 bilinear)", c.upsample);
-  for (auto& L : n->layers) L.bilinear = L.up && c.upsample == 1;
+  PDES_REQUIRE(c.upsample >= 0 && c.upsample <= 2, PDES_ERR_UNSUPPORTED,
+               "upsample mode %d (0 nearest, 1 bilinear, 2 none = transposed convolutions)", c.upsample);
+  for (auto& L : n->layers) L.bilinear = L.up && (c.upsample == 1 || L.convT);
   // last consumer of every buffer (first dgrad to run in reverse order stores, the rest accumulate)
   for (size_t b = 0; b < n->bufs.size(); ++b) {
     int lastL = -1;
@@ -509,6 +518,13 @@ int build(pdes_net* n) {
       }
     n->up_scratch = f;
     f += pad4((int64_t)mx);
+    for (auto& L : n->layers)
+      if (L.convT) {
+        L.wt = f;
+        f += pad4((int64_t)L.Cout * L.Cin * L.KS * L.KS);
+        L.gt = f;
+        f += pad4((int64_t)L.Cout * L.Cin * L.KS * L.KS);
+      }
   }
   if (n->coupling) {
     n->out_keep = f;
@@ -732,6 +748,13 @@ extern "C" int pdes_densenet_set_dropout(pdes_net_t* n, const float* masks) {
 
 extern "C" size_t pdes_densenet_workspace_bytes(const pdes_net_t* n) { return n ? n->ws_bytes : 0; }
 
+// filter / filter-gradient pointers the convolution kernels see: the parameter itself, or (transposed
+// convolution) the equivalent Conv2d filter in the workspace and its self-cleaning gradient staging buffer
+static inline const float* conv_w(const pdes_net_t* n, const Layer& L) {
+  return L.convT ? wsf(const_cast<pdes_net_t*>(n), L.wt) : n->p + L.w_off;
+}
+static inline float* conv_dw(pdes_net_t* n, const Layer& L) { return L.convT ? wsf(n, L.gt) : n->g + L.w_off; }
+
 extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, float* running,
                                   void* workspace, size_t workspace_bytes) {
   PDES_REQUIRE(n && params && running && workspace, PDES_ERR_INVALID, "pdes_densenet_bind: null pointer");
@@ -766,7 +789,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
   for (size_t i = 0; i < n->layers.size(); ++i) {
     const Layer& L = n->layers[i];
     PackDesc& d = pt[i];
-    d.w = n->p + L.w_off;
+    d.w = conv_w(n, L);
     d.wf = wsf(n, L.wf);
     d.wb = L.in_buf >= 0 ? wsf(n, L.wb) : nullptr;
     d.Cout = L.Cout;
@@ -798,7 +821,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       if (dir == 0 && L.dense_fwd) continue;
       if (dir == 1 && L.dense_bwd) continue;
       Tc2PackDesc d;
-      d.w = n->p + L.w_off;
+      d.w = conv_w(n, L);
       d.dst = reinterpret_cast<op16*>(wsf(n, dir == 0 ? L.w2f : L.w2b));
       d.Cout = L.Cout;
       d.Cin = L.Cin;
@@ -814,7 +837,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
     }
     if (L.dense_fwd) {
       Tc2PackDesc d;
-      d.w = n->p + L.w_off;
+      d.w = conv_w(n, L);
       d.dst = reinterpret_cast<op16*>(wsf(n, L.wdn));
       d.Cout = L.Cout;
       d.Cin = L.Cin;
@@ -830,7 +853,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
     }
     if (L.dense_bwd) {
       Tc2PackDesc d;
-      d.w = n->p + L.w_off;
+      d.w = conv_w(n, L);
       d.dst = reinterpret_cast<op16*>(wsf(n, L.wdb));
       d.Cout = L.Cout;
       d.Cin = L.Cin;
@@ -852,7 +875,7 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
     if (!L.tc_wg || !n->g) continue;
     TcWgradUnpack u;
     memset(&u, 0, sizeof(u));
-    u.dw = n->g + L.w_off;
+    u.dw = conv_dw(n, L);
     u.dwp = wsf(n, L.dwp);
     u.Cout = L.Cout;
     u.Cin = L.Cin;
@@ -970,6 +993,13 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     mark(n, st, "memset stats");
   }
   int rc = PDES_OK;
+  for (const auto& L : n->layers)
+    if (L.convT) {
+      rc = launch_convt_weight(n->p + L.w_off, wsf(n, L.wt), L.Cin, L.Cout, L.KS, st);
+      if (rc) return rc;
+      n->launches++;
+      mark(n, st, "convT_weight " + L.conv_name);
+    }
   bool need_simt_pack = n->conv_impl != 0 || n->tc_mask != 7;
   for (const auto& L : n->layers)
     if (!(L.tc2_fwd || L.first_k) || (L.in_buf >= 0 && !L.tc2_bwd)) need_simt_pack = true;
@@ -1048,6 +1078,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       const Buf& ib = n->bufs[L.in_buf];
       BilinearArgs ba;
       memset(&ba, 0, sizeof(ba));
+        ba.zero_insert = L.convT ? 1 : 0;
       ba.x = a.x;
       ba.ldx = a.ldx;
       ba.C = L.Cin;
@@ -1104,7 +1135,7 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       FirstConvArgs fa;
       memset(&fa, 0, sizeof(fa));
       fa.x = a.x;
-      fa.w = n->p + L.w_off;
+      fa.w = conv_w(n, L);
       fa.y = a.y;
       fa.ldy = a.ldy;
       fa.coff = a.coff;
@@ -1349,7 +1380,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
       w.stride = L.stride;
       w.Ho = L.Ho;
       w.Wo = L.Wo;
-      w.dw = n->g + L.w_off;
+      w.dw = conv_dw(n, L);
       if (L.in_buf < 0) {
         w.x = wsf(n, n->xin);  // NCHW copy made by the training forward
         w.in_nchw = 1;
@@ -1363,6 +1394,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
         const Buf& ib = n->bufs[L.in_buf];
         BilinearArgs ba;
         memset(&ba, 0, sizeof(ba));
+        ba.zero_insert = L.convT ? 1 : 0;
         ba.x = w.x;
         ba.ldx = w.ldx;
         ba.C = L.Cin;
@@ -1636,6 +1668,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
       if (L.bilinear) {
         BilinearArgs ba;
         memset(&ba, 0, sizeof(ba));
+        ba.zero_insert = L.convT ? 1 : 0;
         ba.x = wsf(n, ib.act);
         ba.ldx = ib.ld;
         ba.C = L.Cin;
@@ -1681,6 +1714,13 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
     n->launches++;
     mark(n, st, "wgrad_unpack");
   }
+  for (const auto& L : n->layers)
+    if (L.convT) {
+      rc = launch_convt_weight_grad(wsf(n, L.gt), n->g + L.w_off, L.Cin, L.Cout, L.KS, st);
+      if (rc) return rc;
+      n->launches++;
+      mark(n, st, "convT_weight_grad " + L.conv_name);
+    }
   rc = launch_bn_param_grad(bn_table(n), n->n_bn, n->maxC, st);
   if (rc) return rc;
   n->launches++;

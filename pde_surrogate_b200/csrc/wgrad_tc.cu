@@ -41,6 +41,7 @@ constexpr int kThreads = 192;
 constexpr int kTH = 16, kTW = 8;
 constexpr int kMC = 128;  // input channels per CTA (GEMM M)
 constexpr int kPasses = kPieces;
+constexpr int kIm2colMaxN = 256;  // dy_im2col: padded column count (taps * Cout rounded up to 8)
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
@@ -752,6 +753,20 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // dY expansion for the taps-in-N weight gradient (DyIm2colArgs): one thread per (pixel, n-octet),
 // x-contiguous gathers and 16-byte stores.
 __global__ void __launch_bounds__(256) dy_im2col_kernel(DyIm2colArgs a) {
+  // column n = tap * Cout + co reads dy[b][co][y - ty + pad][x - tx + pad]: the per-column offsets are the
+  // same for every pixel, so they are tabulated once per CTA (the first version divided per element and ran
+  // issue-bound)
+  __shared__ int4 tab[kIm2colMaxN];   // {offset co*H*W + dy*W + dx, dy, dx, valid}
+  const int nreal = a.KS * a.KS * a.Cout;
+  for (int n = threadIdx.x; n < a.Np; n += blockDim.x) {
+    int4 t = make_int4(0, 0, 0, 0);
+    if (n < nreal) {
+      const int tap = n / a.Cout, co = n - tap * a.Cout;
+      const int dy = a.pad - tap / a.KS, dx = a.pad - tap % a.KS;
+      t = make_int4((co * a.H + dy) * a.W + dx, dy, dx, 1);
+    }
+    tab[n] = t;
+  }
   griddep_wait();
   float mul = 1.f;
   if (a.dyn_max != nullptr) {
@@ -761,32 +776,40 @@ __global__ void __launch_bounds__(256) dy_im2col_kernel(DyIm2colArgs a) {
     mul = __uint_as_float((uint32_t)(e + 127) << 23);
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.dyn_inv = __uint_as_float((uint32_t)(127 - e) << 23);
   }
-  const int oct = a.Np >> 3, nreal = a.KS * a.KS * a.Cout;
+  __syncthreads();
+  const int oct = a.Np >> 3;
   const size_t plane = (size_t)a.B * a.H * a.W * a.Np;
   const size_t total = (size_t)a.B * a.H * oct * a.W;
+  const size_t img = (size_t)a.Cout * a.H * a.W;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % a.W);
     size_t r = i / a.W;
     const int q = (int)(r % oct);
     r /= oct;
     const int y = (int)(r % a.H), b = (int)(r / a.H);
-    uint32_t h0[8], h1[8];
+    const float* base = a.dy + (size_t)b * img + (size_t)y * a.W + x;
+    float v[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int n = 8 * q + k;
-      float v = 0.f;
-      if (n < nreal) {
-        const int tap = n / a.Cout, co = n - tap * a.Cout;
-        const int sy = y - tap / a.KS + a.pad, sx = x - tap % a.KS + a.pad;
-        if (sy >= 0 && sy < a.H && sx >= 0 && sx < a.W) v = __ldg(a.dy + (((size_t)b * a.Cout + co) * a.H + sy) * a.W + sx);
+      const int4 t = tab[8 * q + k];
+      const bool in = t.w && (unsigned)(y + t.y) < (unsigned)a.H && (unsigned)(x + t.z) < (unsigned)a.W;
+      v[k] = in ? __ldg(base + t.x) * mul : 0.f;
+    }
+    uint32_t p1[4], p2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (a.lowp == LOWP_BF16) {
+        p1[k] = pack_bf2s(v[2 * k], v[2 * k + 1]);
+        p2[k] = 0u;
+      } else {
+        p1[k] = pack_h2s(v[2 * k], v[2 * k + 1]);
+        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&p1[k]));
+        p2[k] = a.lowp ? 0u : pack_h2s(v[2 * k] - fl.x, v[2 * k + 1] - fl.y);
       }
-      split_mode(v * mul, a.lowp, h0[k], h1[k]);
     }
     op16* dst = a.out + i * 8;  // (((b*H + y)*oct + q)*W + x)*8
-    *reinterpret_cast<uint4*>(dst) =
-        make_uint4(h0[0] | (h0[1] << 16), h0[2] | (h0[3] << 16), h0[4] | (h0[5] << 16), h0[6] | (h0[7] << 16));
-    *reinterpret_cast<uint4*>(dst + plane) =
-        make_uint4(h1[0] | (h1[1] << 16), h1[2] | (h1[3] << 16), h1[4] | (h1[5] << 16), h1[6] | (h1[7] << 16));
+    *reinterpret_cast<uint4*>(dst) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    *reinterpret_cast<uint4*>(dst + plane) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
   }
 }
 
@@ -944,7 +967,7 @@ size_t act_planes_bytes(int B, int H, int W, int C) {
 }
 
 int launch_dy_im2col(const DyIm2colArgs& a, cudaStream_t st) {
-  PDES_REQUIRE(a.dy && a.out && a.Np % 8 == 0 && a.Np >= a.KS * a.KS * a.Cout, PDES_ERR_INVALID,
+  PDES_REQUIRE(a.dy && a.out && a.Np % 8 == 0 && a.Np >= a.KS * a.KS * a.Cout && a.Np <= kIm2colMaxN, PDES_ERR_INVALID,
                "dy_im2col: invalid arguments");
   const size_t total = (size_t)a.B * a.H * (a.Np / 8) * a.W;
   int blocks = (int)((total + 255) / 256);

@@ -18,7 +18,7 @@ class OracleExecutor(object):
         cfg = dict(m._cfg)
         self.drop_rate = float(cfg.pop("drop_rate", 0.0))
         self.upsample = cfg.pop("upsample", "nearest")
-        plan = orc.densenet_plan(**cfg)
+        plan = orc.densenet_plan(**cfg, upsample=self.upsample)
         sd = {}
         for k, v in m.state_dict().items():
             sd[k] = v.detach().clone() if k.endswith("num_batches_tracked") else v.detach()

@@ -50,7 +50,7 @@ def main():
     DenseED, darcy, SobelFilter = import_reference()
 
     def ref_step(cfg, B, seed, dtype, kind="lognormal", upsample="nearest"):
-        plan = orc.densenet_plan(**cfg)
+        plan = orc.densenet_plan(**cfg, upsample=upsample)
         sd = orc.to_dtype(orc.make_state(plan, seed), dtype)
         K = orc.make_input(B, cfg["imsize"], seed, kind=kind).to(dtype)
         model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
@@ -59,7 +59,11 @@ def main():
         missing = model.load_state_dict(sd, strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
         assert [k for k in model.state_dict().keys()] == list(sd.keys()), "state_dict key order"
-        sob = SobelFilter(cfg["imsize"], correct=True, device="cpu")
+        # upsample=None: the reference's last decoding does not upsample (codec.py:176-179), the output is
+        # imsize/2 wide; the residual loss of these fixtures is taken on the 2x subsampled permeability
+        osz = cfg["imsize"] if upsample is not None else cfg["imsize"] // 2
+        Kl = K if upsample is not None else K[:, :, ::2, ::2].contiguous()
+        sob = SobelFilter(osz, correct=True, device="cpu")
         if dtype == torch.float64:
             for a in ("HSOBEL_WEIGHTS_3x3", "VSOBEL_WEIGHTS_3x3", "modifier"):
                 setattr(sob, a, getattr(sob, a).double())
@@ -71,8 +75,9 @@ def main():
         model.train()
         model.zero_grad()
         out = model(K)
+        assert out.shape[-1] == osz
         out.retain_grad()
-        l_c = darcy.conv_constitutive_constraint(K, out, sob)
+        l_c = darcy.conv_constitutive_constraint(Kl, out, sob)
         l_d = darcy.conv_continuity_constraint(out, sob)
         l_dir, l_neu = darcy.conv_boundary_condition(out)
         loss = (l_c + l_d) + (l_dir + l_neu) * 10.0
@@ -247,6 +252,13 @@ def main():
         save_case("densenet_bilinear16.npz", small5, B=2, seed=41, full_grads=True, upsample="bilinear")
         save_case("densenet_bilinear32.npz", dict(full, imsize=32), B=3, seed=43, full_grads=False, upsample="bilinear")
 
+    def convt_cases():
+        # upsample=None: nn.ConvTranspose2d transitions (models/codec.py:139-142), no upsampling in last_decoding
+        small5 = dict(in_channels=1, out_channels=3, imsize=16, blocks=[2, 1, 2, 1, 2], growth_rate=8, init_features=16)
+        save_case("densenet_convt16.npz", small5, B=2, seed=47, full_grads=True, upsample=None)
+        save_case("densenet_convt32.npz", dict(full, imsize=32, blocks=[3, 4, 3, 4, 3]), B=3, seed=53, full_grads=False,
+                  upsample=None)
+
     def coupling_cases():
         # SURVEY.md section 8(f) row 1 / BASELINE config 5: the cGlow coupling network `_DenseCoupling`
         # (models/glow_msc.py:276-294, Conv2dZeros 240-255) and `AffineCouplingLayer` forward / reverse (297-344),
@@ -344,6 +356,9 @@ def main():
     if "--only-coupling" in sys.argv:
         coupling_cases()
         return
+    if "--only-convt" in sys.argv:
+        convt_cases()
+        return
     if "--only-bilinear" in sys.argv:
         bilinear_cases()
         return
@@ -371,6 +386,7 @@ def main():
     decoder_cases()
     dropout_case()
     bilinear_cases()
+    convt_cases()
     coupling_cases()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----

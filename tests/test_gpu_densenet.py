@@ -18,7 +18,13 @@ CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_
          # tensor-core kernels walks several tiles (accumulator-stage ring, operand ring wrap, multi-tile split-K)
          "densenet_full32_b32", "densenet_full64_b32",
          # DenseED(upsample='bilinear') (train_codec_mixed_residual.py --upsample bilinear)
-         "densenet_bilinear16", "densenet_bilinear32"]
+         "densenet_bilinear16", "densenet_bilinear32",
+         # DenseED(upsample=None): nn.ConvTranspose2d transitions, output imsize/2 wide (models/codec.py:139-142, 176-179)
+         "densenet_convt16", "densenet_convt32"]
+
+
+def _ups(name):
+    return "bilinear" if "bilinear" in name else (None if "convt" in name else "nearest")
 
 
 def rel(a, b):
@@ -35,7 +41,7 @@ def _cfg(g):
 def _model(g, upsample="nearest"):
     from models.codec import DenseED
     cfg = _cfg(g)
-    plan = orc.densenet_plan(**cfg)
+    plan = orc.densenet_plan(**cfg, upsample=upsample)
     sd = orc.make_state(plan, int(g["seed"]))
     model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
                     growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], upsample=upsample)
@@ -52,10 +58,12 @@ def test_train_step_matches_reference(golden_dir, name, impl):
     from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
     from utils.image_gradient import SobelFilter
     g = np.load(os.path.join(golden_dir, name + ".npz"))
-    model, K, cfg = _model(g, "bilinear" if "bilinear" in name else "nearest")
+    model, K, cfg = _model(g, _ups(name))
     model.conv_impl = impl  # 0: tcgen05 (two-piece fp16 operands) where supported, 1: CUDA-core fp32 everywhere
     assert tuple(model.model_size) == tuple(int(v) for v in g["model_size"])
-    sob = SobelFilter(cfg["imsize"], correct=True, device="cuda")
+    osz = cfg["imsize"] // 2 if _ups(name) is None else cfg["imsize"]
+    Kl = K[:, :, ::2, ::2].contiguous() if _ups(name) is None else K   # (as the fixture generator does)
+    sob = SobelFilter(osz, correct=True, device="cuda")
     # eval forward with the given running statistics
     model.eval()
     with torch.no_grad():
@@ -65,8 +73,9 @@ def test_train_step_matches_reference(golden_dir, name, impl):
     model.train()
     model.zero_grad()
     out = model(K)
+    assert out.shape[-1] == osz
     out.retain_grad()
-    l_c = conv_constitutive_constraint(K, out, sob)
+    l_c = conv_constitutive_constraint(Kl, out, sob)
     l_d = conv_continuity_constraint(out, sob)
     l_dir, l_neu = conv_boundary_condition(out)
     loss = (l_c + l_d) + (l_dir + l_neu) * 10.0
@@ -580,3 +589,31 @@ def test_dropout_step_matches_reference(golden_dir):
         model.train()
         o2 = model(K)
         assert bool(torch.isfinite(o2).all()) and rel(o2.detach().cpu().numpy(), g["out"]) > 1e-3
+
+
+@pytest.mark.parametrize("act", ["tanh", "softplus", "sigmoid", "lrelu"])
+def test_out_activation(golden_dir, act):
+    """out_activation (models/codec.py:190-204, 288-289): the named module sits behind the last convolution in
+    `features`; forward and the parameter gradients equal the chain rule through the plain network."""
+    from models.codec import DenseED
+    g = np.load(os.path.join(golden_dir, "densenet_small16.npz"))
+    base, K, cfg = _model(g)
+    model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"], growth_rate=cfg["growth_rate"],
+                    init_features=cfg["init_features"], out_activation=act).to("cuda")
+    model.load_state_dict(base.state_dict())
+    assert list(model.features._modules)[-1] == act
+    ref_act = {"tanh": torch.tanh, "sigmoid": torch.sigmoid, "lrelu": torch.nn.functional.leaky_relu,
+               "softplus": lambda t: torch.nn.functional.softplus(t, beta=4)}[act]
+    base.train(), model.train()
+    base.zero_grad(), model.zero_grad()
+    z = base(K)
+    zl = z.detach().clone().requires_grad_(True)
+    w = torch.linspace(-1.0, 1.0, z.numel(), device="cuda").view_as(z)
+    (ref_act(zl) * w).sum().backward()
+    z.backward(zl.grad)
+    out = model(K)
+    assert torch.allclose(out, ref_act(z.detach()), rtol=1e-6, atol=1e-7)
+    (out * w).sum().backward()
+    for (n, p), (_, q) in zip(model.named_parameters(), base.named_parameters()):
+        # (two executions of the same backward: equal up to the order of the atomic accumulations)
+        assert rel(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < 1e-4, n

@@ -37,7 +37,14 @@ def test_state_dict_matches_reference_layout(golden_dir):
     with pytest.raises(ValueError):
         DenseED(1, 3, 64, [6, 8])
     with pytest.raises(NotImplementedError):
-        DenseED(1, 3, 64, [6, 8, 6], upsample=None)      # ConvTranspose2d transitions: not built
+        DenseED(1, 3, 64, [6, 8, 6], bottleneck=True)     # bottleneck dense layers: not built, loud
+    with pytest.raises(NotImplementedError):
+        DenseED(1, 3, 64, [6, 8, 6], upsample='bicubic')
+    # upsample=None: ConvTranspose2d transitions named convT2, same state_dict layout as the reference
+    mt = DenseED(1, 3, 64, [6, 8, 6], upsample=None, out_activation='softplus')
+    plan_t = orc.densenet_plan(1, 3, 64, [6, 8, 6], upsample=None)
+    assert [(k, tuple(v.shape)) for k, v in mt.state_dict().items()] == [(k, tuple(s)) for k, s in orc.state_layout(plan_t)]
+    assert "features.TransUp1.convT2.weight" in mt.state_dict() and isinstance(mt.features.softplus, torch.nn.Softplus)
     mb = DenseED(1, 3, 64, [6, 8, 6], upsample='bilinear', drop_rate=0.1)   # script-reachable options
     assert len(mb.state_dict()) == 163
 
