@@ -118,7 +118,9 @@ typedef struct pdes_densenet_config {
   int32_t dropout;       /* 1: the network was built with drop_rate > 0 (nn.Dropout2d behind its convolutions,
                           * models/codec.py:70-71, 110-149, 171-172): pdes_densenet_set_dropout may be used */
   int32_t upsample;      /* x2 upsampling of the decoding transitions (models/codec.py:139-150, 175-178):
-                          * 0 'nearest' (default), 1 'bilinear' (align_corners=True) */
+                          * 0 'nearest' (default), 1 'bilinear' (align_corners=True), 2 None: the transitions use
+                          * nn.ConvTranspose2d(k3, s2, p1, op1) named convT2 (weight (Cin, Cout, 3, 3), codec.py:139-142)
+                          * and the last decoding does not upsample (codec.py:176-179): the output is half as wide */
 } pdes_densenet_config;
 
 /* Host-side object (no device memory). */
