@@ -599,44 +599,54 @@ __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
   griddep_wait();
   const Tc2PackDesc d = tab[blockIdx.y];
   const int T = d.dxn ? d.KS : d.KS * d.KS;   // dxn: one "tap" per filter ROW, the columns live in n (1) / in k (2)
-  const int koct = d.KC >> 3;
+  const int koct = d.KC >> 3, KK = d.KS * d.KS;
   const size_t per_tap = (size_t)koct * d.N * 8;  // elements of ONE piece of one (chunk, tap)
-  const size_t total = (size_t)d.nchunks * T * per_tap;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const size_t step = i / per_tap;
-    size_t r = i - step * per_tap;
-    const int ko = (int)(r / ((size_t)d.N * 8));
-    r -= (size_t)ko * d.N * 8;
-    const int n = (int)(r >> 3), k8 = (int)(r & 7);
-    const int chunk = (int)(step / T), tap = (int)(step % T);
-    const int k = chunk * d.KC + ko * 8 + k8;
-    float v = 0.f;
-    if (d.dxn == 2) {
-      // data gradient: k = (jx, co), n = ci, tap = jy; flipped filter W[co, ci, 2-jy, 2-jx]
-      const int jx = k >> 4, co = k & 15;
-      if (n < d.Cin && co < d.Cout)
-        v = d.w[((size_t)co * d.Cin + n) * (d.KS * d.KS) + (d.KS - 1 - tap) * d.KS + (d.KS - 1 - jx)];
-    } else if (d.dxn) {
-      const int kx = n / d.CoP, co = n - kx * d.CoP;
-      if (co < d.Cout && k < d.Cin) v = d.w[((size_t)co * d.Cin + k) * (d.KS * d.KS) + tap * d.KS + kx];
-    } else if (!d.transpose) {
-      if (n < d.Cout && k < d.Cin) v = d.w[((size_t)n * d.Cin + k) * T + tap];
-    } else {
-      if (n < d.Cin && k < d.Cout) v = d.w[((size_t)k * d.Cin + n) * T + (T - 1 - tap)];
-    }
-    uint32_t p[kPieces];
-    v *= (float)(1 << kWScaleLog2);
-    if (d.lowp == LOWP_BF16) {
-      p[0] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
-      p[1] = 0u;
-    } else {
-      p[0] = f2h_sat(v);
-      p[1] = d.lowp ? 0u : f2h_sat(v - __half2float(__ushort_as_half((unsigned short)p[0])));
-    }
-    op16* base = d.dst + step * per_tap * kPieces + (size_t)ko * kPieces * d.N * 8 + (size_t)n * 8 + k8;
+  const int rows = d.nchunks * T * koct * d.N;    // 16-byte rows: 8 consecutive k of one (chunk, tap, k octet, n)
+  const float wscale = (float)(1 << kWScaleLog2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+    const int n = i % d.N;
+    int r = i / d.N;
+    const int ko = r % koct;
+    r /= koct;                                  // = step
+    const int chunk = r / T, tap = r - chunk * T;
+    const int k0 = chunk * d.KC + ko * 8;
+    float v[8];
 #pragma unroll
-    for (int pc = 0; pc < kPieces; ++pc) base[(size_t)pc * d.N * 8] = __ushort_as_half((unsigned short)p[pc]);
+    for (int k8 = 0; k8 < 8; ++k8) {
+      const int k = k0 + k8;
+      float x = 0.f;
+      if (d.dxn == 2) {
+        // data gradient: k = (jx, co), n = ci, tap = jy; flipped filter W[co, ci, 2-jy, 2-jx]
+        const int jx = k >> 4, co = k & 15;
+        if (n < d.Cin && co < d.Cout && jx < d.KS)
+          x = d.w[((size_t)co * d.Cin + n) * KK + (d.KS - 1 - tap) * d.KS + (d.KS - 1 - jx)];
+      } else if (d.dxn) {
+        const int kx = n / d.CoP, co = n - kx * d.CoP;
+        if (co < d.Cout && k < d.Cin) x = d.w[((size_t)co * d.Cin + k) * KK + tap * d.KS + kx];
+      } else if (!d.transpose) {
+        if (n < d.Cout && k < d.Cin) x = d.w[((size_t)n * d.Cin + k) * T + tap];
+      } else {
+        if (n < d.Cin && k < d.Cout) x = d.w[((size_t)k * d.Cin + n) * T + (T - 1 - tap)];
+      }
+      v[k8] = x * wscale;
+    }
+    uint32_t p1[4], p2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (d.lowp == LOWP_BF16) {
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+        p2[j] = 0u;
+      } else {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(p1[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+        const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&p1[j]));
+        p2[j] = 0u;
+        if (!d.lowp)
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(p2[j]) : "f"(v[2 * j + 1] - fl.y), "f"(v[2 * j] - fl.x));
+      }
+    }
+    op16* base = d.dst + (size_t)r * per_tap * kPieces + (size_t)ko * kPieces * d.N * 8 + (size_t)n * 8;
+    *reinterpret_cast<uint4*>(base) = make_uint4(p1[0], p1[1], p1[2], p1[3]);
+    *reinterpret_cast<uint4*>(base + (size_t)d.N * 8) = make_uint4(p2[0], p2[1], p2[2], p2[3]);
   }
 }
 
@@ -773,8 +783,8 @@ int launch_conv_tc2(const Tc2Args& t, const op16* planes, int Hv, int Wv, int Ci
 
 int launch_pack_tc2(const Tc2PackDesc* dev_table, int n, size_t max_elems, cudaStream_t st) {
   if (n == 0) return PDES_OK;
-  int bx = (int)((max_elems / kPieces + 255) / 256);
-  if (bx > 128) bx = 128;
+  int bx = (int)((max_elems / kPieces / 8 + 255) / 256);   // one thread per 16-byte row
+  if (bx > 32) bx = 32;
   if (bx < 1) bx = 1;
   PDES_CUDA(launch_pdl(pack_tc2_kernel, dim3(bx, n), dim3(256), 0, st, dev_table));
   PDES_LAUNCH_CHECK();

@@ -1009,11 +1009,22 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
     n->launches++;
     mark(n, st, "pack_weights");
   }
+  // The filter packing is independent of the first convolution (dedicated CUDA-core kernel on the raw
+  // filter): it runs beside it on a side stream and joins before the first tensor-core layer.
+  bool pack_forked = false;
   if (n->conv_impl == 0 && n->n_tc2 > 0) {
-    rc = launch_pack_tc2(tc2_table(n), n->n_tc2, n->max_tc2_pack, st);
+    cudaStream_t pst = st;
+    if (n->n_side > 0 && n->side[0] && !n->timing && !n->layers.empty() && n->layers[0].first_k && !n->coupling) {
+      PDES_CUDA(cudaEventRecord(n->ev_fork[0], st));
+      PDES_CUDA(cudaStreamWaitEvent(n->side[0], n->ev_fork[0], 0));
+      pst = n->side[0];
+      pack_forked = true;
+    }
+    rc = launch_pack_tc2(tc2_table(n), n->n_tc2, n->max_tc2_pack, pst);
     if (rc) return rc;
     n->launches++;
     mark(n, st, "pack_tc2");
+    if (pack_forked) PDES_CUDA(cudaEventRecord(n->ev_join[0], n->side[0]));
   }
   if (n->coupling) {
     const Buf& b0 = n->bufs[0];
@@ -1152,6 +1163,10 @@ static int forward_impl(pdes_net_t* n, const float* x, float* out, int B, int tr
       fa.Ho = L.Ho;
       fa.Wo = L.Wo;
       rc = launch_first_conv_fwd(fa, st);
+      if (pack_forked) {   // join: every later layer reads the packed filters
+        PDES_CUDA(cudaStreamWaitEvent(st, n->ev_join[0], 0));
+        pack_forked = false;
+      }
     } else if (use_dense) {
       // thin layer: BatchNorm + ReLU + fp16 split happen inside the convolution kernel, which also emits
       // the operand planes of the weight gradient (training)
@@ -1284,6 +1299,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
   int rc;
   bool used_wg = false;
   int wg_rr = 0, side_used = 0;
+  bool prejoined = false, tail_side = false;
   mark(n, st, "@backward");
   if (n->coupling) {
     // Conv2dZeros backward of the gain: d(conv) = dout * exp(3 scale), d bias, d scale; the rest of the pass
@@ -1531,7 +1547,20 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
         fa.pad = L.pad;
         fa.Ho = L.Ho;
         fa.Wo = L.Wo;
-        rc = launch_first_conv_wgrad(fa, st);
+        if (n->n_side > 0 && n->side[0] && !n->timing) {
+          // The last weight gradient of the pass.  Every tensor-core weight gradient issued so far is joined
+          // first (pre-join events), so that the unpack of their staging buffers runs on the main stream
+          // BESIDE this kernel instead of behind it.
+          for (int k = 0; k < 2; ++k)
+            if (side_used & (1 << k)) PDES_CUDA(cudaEventRecord(n->ev_join[k], n->side[k]));
+          prejoined = true;
+          PDES_CUDA(cudaEventRecord(n->ev_fork[0], st));
+          PDES_CUDA(cudaStreamWaitEvent(n->side[0], n->ev_fork[0], 0));
+          rc = launch_first_conv_wgrad(fa, n->side[0]);
+          tail_side = true;
+        } else {
+          rc = launch_first_conv_wgrad(fa, st);
+        }
       } else {
         rc = launch_wgrad_simt(w, st);
       }
@@ -1705,7 +1734,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
   }
   for (int k = 0; k < 2; ++k) {
     if (!(side_used & (1 << k))) continue;  // join: the unpack reads every staging gradient
-    PDES_CUDA(cudaEventRecord(n->ev_join[k], n->side[k]));
+    if (!prejoined) PDES_CUDA(cudaEventRecord(n->ev_join[k], n->side[k]));
     PDES_CUDA(cudaStreamWaitEvent(st, n->ev_join[k], 0));
   }
   if (used_wg) {
@@ -1713,6 +1742,10 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
     if (rc) return rc;
     n->launches++;
     mark(n, st, "wgrad_unpack");
+  }
+  if (tail_side) {   // the first convolution's weight gradient (side stream 0) joins here
+    PDES_CUDA(cudaEventRecord(n->ev_join[0], n->side[0]));
+    PDES_CUDA(cudaStreamWaitEvent(st, n->ev_join[0], 0));
   }
   for (const auto& L : n->layers)
     if (L.convT) {
