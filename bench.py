@@ -468,6 +468,10 @@ def main():
 
     # ---- e2e: the unmodified script's loop body through the reference-facing modules ---------
     model2 = make_model()
+    # the optimizer the unmodified script gets under run_reference_script.py: `optim.Adam` resolves to the fused
+    # subclass of torch.optim.Adam (pde_surrogate_b200/optim.py)
+    from pde_surrogate_b200 import optim as pdes_optim
+    pdes_optim.install()
     opt = torch.optim.Adam(model2.parameters(), lr=1e-3, weight_decay=0.0)
     sob = SobelFilter(IMSIZE, correct=True, device=dev)
     if world > 1:
@@ -490,6 +494,12 @@ def main():
 
     ms_e = timed(e2e_step, args.steps, max(args.warmup, 3))
     e2e_val = world * BATCH * args.steps / (ms_e * 1e-3)
+    fused_adam_steps = int(getattr(opt, "fused_steps", 0))
+    # the same loop with torch's own Adam step (PDES_FUSED_ADAM=0), reported beside the headline
+    os.environ["PDES_FUSED_ADAM"] = "0"
+    ms_e_stock = timed(e2e_step, args.steps, 3)
+    os.environ.pop("PDES_FUSED_ADAM")
+    e2e_stock_val = world * BATCH * args.steps / (ms_e_stock * 1e-3)
 
     cpu = None
     lib_base = None
@@ -512,7 +522,11 @@ def main():
                                             if not lowp else "one %s piece per operand, 1 tensor-core product" % args.dtype)),
                     e2e=dict(value=round(e2e_val, 1), unit="samples/s", h2d_bytes_per_step=BATCH * IMSIZE * IMSIZE * 4,
                              d2h_bytes_per_step=4, ms_per_step=round(ms_e / args.steps, 4),
-                             api="models.codec.DenseED + models.darcy.conv_* + torch.optim.Adam, loss.item() per step"),
+                             api="models.codec.DenseED + models.darcy.conv_* + optim.Adam as run_reference_script.py "
+                                 "installs it (fused subclass of torch.optim.Adam), loss.item() per step",
+                             fused_adam_steps=fused_adam_steps,
+                             stock_adam=dict(value=round(e2e_stock_val, 1), ms_per_step=round(ms_e_stock / args.steps, 4),
+                                             note="same loop, torch's own foreach Adam step (PDES_FUSED_ADAM=0)")),
                     gpu_launches=launches, launches_per_step=ts.kernel_launches, clocks=clocks,
                     roofline=roofline, roofline_step=roofline_step, roofline_families=families,
                     roofline_stencil=roofline_stencil, cpu_baseline=cpu, gpu_library_baseline=lib_base,

@@ -13,6 +13,7 @@ that data-parallel training all-reduces, and a fused Adam can walk one array.
 """
 import math
 import os
+import weakref
 from collections import OrderedDict
 from ctypes import byref, c_int32, c_int64, c_void_p, create_string_buffer
 
@@ -20,6 +21,20 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+
+
+_OWNERS = weakref.WeakValueDictionary()   # id(parameter) -> the executor network whose flat buffer holds it
+
+
+def owner_of(param):
+    """The executor network (DenseED / Decoder / coupling network) `param` belongs to, or None."""
+    m = _OWNERS.get(id(param))
+    if m is None:
+        return None
+    for q in m._params:
+        if q is param:
+            return m
+    return None
 
 
 def module_size(module):
@@ -387,6 +402,7 @@ class _ExecutorNet(nn.Module):
                     p.grad = gv
                 self._params.append(p)
                 self._grad_views.append(gv)
+                _OWNERS[id(p)] = self
             mods = dict(self.named_modules())
             run = torch.zeros(self._n_running, dtype=ref.dtype, device=ref.device)
             nbt = torch.zeros(len(self._bn_table), dtype=torch.long, device=ref.device)

@@ -8,7 +8,8 @@ this repo's backend:
 The repo root is put FIRST on sys.path so that `models.codec`, `models.darcy`,
 `utils.image_gradient`, `utils.load`, ... resolve to this repo (the script's own directory would
 otherwise shadow them), stand-ins for matplotlib / h5py are added only if the real packages are
-missing, and the script is executed with runpy as __main__.
+missing, `torch.optim.Adam` is pointed at the fused subclass (pde_surrogate_b200/optim.py), and the script is
+executed with runpy as __main__.
 """
 import importlib.util
 import os
@@ -46,6 +47,10 @@ def main(argv):
     import utils.image_gradient, utils.load, utils.misc, utils.plot, utils.practices  # noqa: F401,E401
     if code_dir in sys.path:
         sys.path.remove(code_dir)
+    # optim.Adam(model.parameters(), ...) in the script resolves to the fused subclass (one launch per step when the
+    # parameters are an executor network's; the stock torch step otherwise; PDES_FUSED_ADAM=0 keeps torch's class)
+    from pde_surrogate_b200 import optim as _optim
+    _optim.install()
     runpy.run_path(script, run_name="__main__")
 
 

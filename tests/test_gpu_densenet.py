@@ -617,3 +617,50 @@ def test_out_activation(golden_dir, act):
     for (n, p), (_, q) in zip(model.named_parameters(), base.named_parameters()):
         # (two executions of the same backward: equal up to the order of the atomic accumulations)
         assert rel(p.grad.cpu().numpy(), q.grad.cpu().numpy()) < 1e-4, n
+
+
+def test_fused_adam_optimizer_matches_torch(golden_dir):
+    """pde_surrogate_b200.optim.Adam (what run_reference_script.py installs as torch.optim.Adam): eight training
+    steps with OneCycle-style lr / beta changes and weight decay give the parameters torch's own Adam gives; the
+    optimizer state keeps torch's layout, survives state_dict round trips and a switch to the stock step."""
+    from models.darcy import conv_boundary_condition
+    from pde_surrogate_b200 import optim as pdes_optim
+    g = np.load(os.path.join(golden_dir, "densenet_small16.npz"))
+    ma, K, cfg = _model(g)
+    mb, _, _ = _model(g)
+    stock = pdes_optim._StockAdam
+    assert not getattr(stock, "_pdes_fused", False)
+    oa = pdes_optim.Adam(ma.parameters(), lr=1e-3, weight_decay=1e-3)
+    ob = stock(mb.parameters(), lr=1e-3, weight_decay=1e-3)
+
+    def one(model, opt, i):
+        for grp in opt.param_groups:
+            grp["lr"] = 1e-3 * (1.0 + 0.3 * i)
+            grp["betas"] = (0.95 - 0.01 * i, 0.999)
+        model.train()
+        model.zero_grad()
+        out = model(K)
+        d, n = conv_boundary_condition(out)
+        ((out ** 2).mean() + d + n).backward()
+        opt.step()
+
+    for i in range(4):
+        one(ma, oa, i), one(mb, ob, i)
+    assert oa.fused_steps == 4
+    sd = oa.state_dict()
+    assert len(sd["state"]) == len(list(ma.parameters())) and float(sd["state"][0]["step"]) == 4.0
+    oa.load_state_dict(sd)   # fresh state tensors: re-bound (and copied into the flat moments) at the next step
+    for i in range(4, 6):
+        one(ma, oa, i), one(mb, ob, i)
+    assert oa.fused_steps == 6
+    os.environ["PDES_FUSED_ADAM"] = "0"   # the stock step takes over mid-run on the same state
+    try:
+        for i in range(6, 8):
+            one(ma, oa, i), one(mb, ob, i)
+    finally:
+        os.environ.pop("PDES_FUSED_ADAM")
+    assert oa.fused_steps == 6
+    for (n, p), (_, q) in zip(ma.named_parameters(), mb.named_parameters()):
+        assert rel(p.detach().cpu().numpy(), q.detach().cpu().numpy()) < 2e-5, n
+    st = oa.state[next(iter(ma.parameters()))]
+    assert float(st["step"]) == 8.0

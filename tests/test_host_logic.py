@@ -294,3 +294,27 @@ def test_coupling_layer_host_logic():
         assert rel(cond.grad.numpy(), c64.grad.numpy()) < 1e-4
     with pytest.raises(ImportError):
         from models.glow_msc import MultiScaleCondGlow  # noqa: F401
+
+
+def test_fused_adam_class_falls_back_to_stock_step():
+    """pde_surrogate_b200.optim.Adam on parameters that are not an executor network's (here: a CPU nn.Linear) is
+    torch.optim.Adam, bit for bit; install() / uninstall() swap the name the scripts resolve."""
+    from pde_surrogate_b200 import optim as pdes_optim
+    stock = pdes_optim._StockAdam
+    torch.manual_seed(0)
+    a, b = torch.nn.Linear(5, 3), torch.nn.Linear(5, 3)
+    b.load_state_dict(a.state_dict())
+    oa, ob = pdes_optim.Adam(a.parameters(), lr=1e-2, weight_decay=1e-2), stock(b.parameters(), lr=1e-2, weight_decay=1e-2)
+    x = torch.randn(7, 5)
+    for _ in range(3):
+        for m, o in ((a, oa), (b, ob)):
+            o.zero_grad()
+            m(x).pow(2).sum().backward()
+            o.step()
+    assert oa.fused_steps == 0
+    assert all(torch.equal(p, q) for p, q in zip(a.parameters(), b.parameters()))
+    try:
+        assert pdes_optim.install() and torch.optim.Adam is pdes_optim.Adam and issubclass(torch.optim.Adam, stock)
+    finally:
+        pdes_optim.uninstall()
+    assert torch.optim.Adam is stock
