@@ -110,6 +110,7 @@ struct pdes_net {
   };
   GraphSlot gfwd[4], gbwd[2];
   int use_graph = 0;
+  cudaStream_t cap_stream = nullptr;   // private stream the executor graphs are captured on
   size_t xs = 0, outs = 0, douts = 0;  // float offsets of the static x / out / dout buffers
   int n_wg_bound = 0;
   int tc_mask = 7;  // bit 0: forward, bit 1: dgrad, bit 2: wgrad on tcgen05
@@ -673,12 +674,23 @@ void ensure_side_streams(pdes_net* n) {
 }
 }  // namespace
 
+// The executor graphs bake in the launch structure: anything that changes it (implementation switches,
+// timing marks, re-binding) drops them; the next calls capture again.
+static void drop_exec_graphs(pdes_net_t* n) {
+  for (auto& gs : n->gfwd) {
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+    gs = pdes_net::GraphSlot();
+  }
+  for (auto& gs : n->gbwd) {
+    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+    gs = pdes_net::GraphSlot();
+  }
+}
+
 extern "C" void pdes_densenet_destroy(pdes_net_t* net) {
   if (!net) return;
-  for (auto& gs : net->gfwd)
-    if (gs.exec) cudaGraphExecDestroy(gs.exec);
-  for (auto& gs : net->gbwd)
-    if (gs.exec) cudaGraphExecDestroy(gs.exec);
+  drop_exec_graphs(net);
+  if (net->cap_stream) cudaStreamDestroy(net->cap_stream);
   drop_side_streams(net);
   delete net;
 }
@@ -766,18 +778,21 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
   // synchronous table uploads below do not order against): wait for everything first.
   PDES_CUDA(cudaDeviceSynchronize());
   ensure_side_streams(n);
-  for (auto& gs : n->gfwd) {
-    if (gs.exec) cudaGraphExecDestroy(gs.exec);
-    gs = pdes_net::GraphSlot();
-  }
-  for (auto& gs : n->gbwd) {
-    if (gs.exec) cudaGraphExecDestroy(gs.exec);
-    gs = pdes_net::GraphSlot();
-  }
+  drop_exec_graphs(n);
   {
-    // opt-in (PDES_EXEC_GRAPH=1): measured no gain for the per-step-synchronising script loop
+    // Executor graphs (the module API: forward / backward called from a Python loop): from the second call with
+    // the same batch size on, the launches of a pass are replayed as ONE CUDA graph captured on a private
+    // stream (the caller's stream may be the legacy default stream, which cannot be captured) and launched into
+    // the caller's stream.  PDES_EXEC_GRAPH=0 keeps direct launches.  (Round 1 tried to capture on the caller's
+    // stream, which silently failed on torch's default stream: "no gain" was the fallback path.)
     const char* e = getenv("PDES_EXEC_GRAPH");
-    n->use_graph = (e && e[0] == '1') ? 1 : 0;
+    n->use_graph = (e && e[0] == '0') ? 0 : 1;
+    if (n->use_graph && !n->cap_stream &&
+        cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      n->cap_stream = nullptr;
+      n->use_graph = 0;
+    }
   }
   n->p = params;
   n->g = grads;
@@ -905,6 +920,7 @@ extern "C" int pdes_densenet_set_conv_impl(pdes_net_t* n, int impl) {
   // the exact-fp32 baseline whose forward is bitwise the forward of 4 and 5
   // 7 = exact-fp32 forward of 6 with BOTH backward kernels on tcgen05 (the fused thin-layer dgrad needs both)
   PDES_REQUIRE(n && impl >= 0 && impl <= 7, PDES_ERR_INVALID, "pdes_densenet_set_conv_impl: impl in 0..7");
+  drop_exec_graphs(n);
   n->conv_impl = impl == 1 ? 1 : 0;
   n->tc_mask = impl == 3 ? 1 : (impl == 4 ? 2 : (impl == 5 ? 4 : (impl == 6 ? 0 : (impl == 7 ? 6 : 7))));
   return PDES_OK;
@@ -915,6 +931,7 @@ extern "C" int pdes_densenet_set_timing(pdes_net_t* n, int on) {
   for (auto& m : n->marks) cudaEventDestroy(m.second);
   n->marks.clear();
   n->timing = on != 0;
+  drop_exec_graphs(n);
   return PDES_OK;
 }
 
@@ -1806,13 +1823,21 @@ bool stream_is_capturing(cudaStream_t st) {
   }
   return cs != cudaStreamCaptureStatusNone;
 }
+// direct launches when: graphs are off, the caller is capturing already (the training engine), per-launch timing
+// is on, the network draws dropout masks (a new mask tensor per call) or a kernel debug knob is set
+bool exec_graph_ok(const pdes_net* n, cudaStream_t st) {
+  static int dbg = -1;
+  if (dbg < 0) dbg = (getenv("PDES_DENSE_DBG") || getenv("PDES_DENSE_DBG_BWD")) ? 1 : 0;
+  return n->use_graph && !dbg && !n->timing && !n->cfg.dropout && !stream_is_capturing(st);
+}
 template <class F>
-int capture_into(pdes_net::GraphSlot& gs, pdes_net* n, cudaStream_t st, F&& body) {
-  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+int capture_into(pdes_net::GraphSlot& gs, pdes_net* n, F&& body) {
+  cudaStream_t st = n->cap_stream;
+  if (st == nullptr || cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     return -1;
   }
-  const int rc = body();
+  const int rc = body((void*)st);
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(st, &g);
   if (rc != PDES_OK || e != cudaSuccess || g == nullptr) {
@@ -1840,7 +1865,7 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   PDES_REQUIRE(B >= 1 && B <= n->cfg.max_batch, PDES_ERR_INVALID,
                "pdes_densenet_forward: batch %d outside 1..%d", B, n->cfg.max_batch);
   cudaStream_t st = (cudaStream_t)stream;
-  if (!n->use_graph || stream_is_capturing(st)) return forward_impl(n, x, out, B, training, stream);
+  if (!exec_graph_ok(n, st)) return forward_impl(n, x, out, B, training, stream);
   const int tr = training != 0;
   pdes_net::GraphSlot* gs = nullptr;
   for (auto& s : n->gfwd)
@@ -1860,8 +1885,8 @@ extern "C" int pdes_densenet_forward(pdes_net_t* n, const float* x, float* out, 
   const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->out_hw * n->out_hw;
   if (!gs->exec) {
     pdes_net* nn = n;
-    const int rc = capture_into(*gs, n, st, [&]() {
-      return forward_impl(nn, wsf(nn, nn->xs), wsf(nn, nn->outs), B, training, stream);
+    const int rc = capture_into(*gs, n, [&](void* cs) {
+      return forward_impl(nn, wsf(nn, nn->xs), wsf(nn, nn->outs), B, training, cs);
     });
     if (rc != 0) {  // capture unavailable: stay on direct launches
       n->use_graph = 0;
@@ -1893,7 +1918,7 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
   PDES_REQUIRE(n->g != nullptr, PDES_ERR_STATE, "pdes_densenet_backward: no gradient buffer bound");
   PDES_REQUIRE(dout != nullptr, PDES_ERR_INVALID, "pdes_densenet_backward: null dout");
   cudaStream_t st = (cudaStream_t)stream;
-  if (!n->use_graph || stream_is_capturing(st)) return backward_impl(n, dout, stream);
+  if (!exec_graph_ok(n, st)) return backward_impl(n, dout, stream);
   const int B = n->last_B;
   pdes_net::GraphSlot* gs = nullptr;
   for (auto& s : n->gbwd)
@@ -1911,7 +1936,7 @@ extern "C" int pdes_densenet_backward(pdes_net_t* n, const float* dout, void* st
   const size_t obytes = sizeof(float) * (size_t)B * n->cfg.out_channels * n->out_hw * n->out_hw;
   if (!gs->exec) {
     pdes_net* nn = n;
-    const int rc = capture_into(*gs, n, st, [&]() { return backward_impl(nn, wsf(nn, nn->douts), stream); });
+    const int rc = capture_into(*gs, n, [&](void* cs) { return backward_impl(nn, wsf(nn, nn->douts), cs); });
     n->fwd_train_done = true;  // the captured body cleared it on the host
     if (rc != 0) {
       n->use_graph = 0;

@@ -15,6 +15,8 @@ from utils.image_gradient import SobelFilter  # noqa: E402
 dev = torch.device("cuda:0")
 torch.manual_seed(1)
 model = DenseED(1, 3, 64, [6, 8, 6]).to(dev)
+from pde_surrogate_b200 import optim as pdes_optim  # noqa: E402
+pdes_optim.install()   # what run_reference_script.py does (PDES_FUSED_ADAM=0: torch's own step)
 opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 sob = SobelFilter(64, correct=True, device=dev)
 host = torch.exp(0.5 * torch.randn(4096, 1, 64, 64)).pin_memory()
