@@ -750,6 +750,164 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Thin 3x3 layers (16 output channels, stride 1, pad 1): all nine taps in ONE GEMM-N.
+//
+//   dW[tap][ci][co] = sum_q act[q][ci] * dY[q - s_tap][co]          (q over the image, dY zero outside)
+//
+// wgrad_tc_kernel<3, 1> keeps dY fixed and shifts the activation tile per tap: 72 MMAs of N = 32 / 16 per
+// 128-pixel tile, each paced by the shared-memory fetch of its M = 128 activation operand (~45 clk for
+// 1-2 KB of B).  Here the dY tile is loaded NINE times at the shifted origins (TMA zero-fills outside the image;
+// dY is the small operand: 4 KB per piece and tap) into consecutive N-chunks, so that one K = 16 step is
+// a1 x [taps 0-7] (N = 256) + a1 x [tap 8] (N = 32), or a2 x [all taps of d1] (N = 144): 16 / 8 MMAs per tile and the
+// activation tile needs no halo.  The accumulator columns are those of wgrad_tc_kernel<3, 1> (tap * NW +
+// piece * 16 + co): same epilogue, same staging gradient.
+// ---------------------------------------------------------------------------------------
+constexpr int kTnStages = 2;
+constexpr uint32_t kTnABytes = (kMC / 8) * 128u * 16u;   // 16 channel octets x 128 pixels x 16 B
+constexpr uint32_t kTnBOct = 128u * 16u;                 // one (tap, piece, co-octet) chunk
+constexpr uint32_t kTnStage = kTnABytes + 9u * kPieces * 2u * kTnBOct;
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcWgradArgs t) {
+  constexpr int KS = 3, T = 9, kNC = 16;
+  const int passes = t.lowp ? 1 : kPasses;
+  const int pass = blockIdx.z % passes;             // which fp16 piece of `a` this CTA streams
+  const int NP = t.lowp ? 1 : kPasses - pass;       // dY pieces multiplied: 2, 1
+  const int NW = NP * kNC;                          // accumulator columns per tap
+
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // [kTnStages]
+  uint64_t* empty = full + kTnStages;                        // [kTnStages]
+  uint64_t* acc_full = full + 2 * kTnStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 2 * kTnStages + 1);
+  unsigned char* stage0 = smem + 128;
+
+  const int c0 = blockIdx.y * kMC;
+  const int tiles_x = (t.Wo + kTW - 1) / kTW, tiles_y = (t.Ho + kTH - 1) / kTH;
+  const int n_tiles = tiles_x * tiles_y * t.B;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < (uint32_t)(T * NW)) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTnStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_wait();  // operand planes / staging gradient come from earlier kernels of the step
+
+  int my_tiles = 0;
+  for (int pt = blockIdx.x; pt < n_tiles; pt += gridDim.x) ++my_tiles;
+
+  if (warp == 0) {
+    // ===== TMA producer: the activation tile and the nine shifted dY tiles =====
+    if (lane == 0) {
+      int it = 0;
+      for (int pt = blockIdx.x; pt < n_tiles; pt += gridDim.x, ++it) {
+        const int s = it % kTnStages;
+        int rem = pt;
+        const int tx = rem % tiles_x;
+        rem /= tiles_x;
+        const int ty = rem % tiles_y;
+        const int b = rem / tiles_y;
+        const int y0 = ty * kTH, x0 = tx * kTW;
+        mbar_wait(&empty[s], (uint32_t)(((it / kTnStages) & 1) ^ 1));
+        unsigned char* st = stage0 + (size_t)s * kTnStage;
+        mbar_arrive_expect_tx(&full[s], kTnABytes + (uint32_t)(T * NP) * 2u * kTnBOct);
+        tma_load_4d(st, &tmA, x0 * 8, y0, c0 >> 3, pass * t.B + b, &full[s]);
+        unsigned char* bs = st + kTnABytes;
+        for (int tap = 0; tap < T; ++tap)
+          for (int piece = 0; piece < NP; ++piece)
+            tma_load_4d(bs + (size_t)(tap * NP + piece) * 2u * kTnBOct, &tmB, (x0 + t.pad - tap % KS) * 8,
+                        y0 + t.pad - tap / KS, 0, piece * t.B + b, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (my_tiles > 0) {
+      // MN-major canonical layout: SBO strides along the channels (next octet), LBO along the pixels
+      const uint32_t sbo = kTnBOct, lbo = 128u;
+      const uint32_t ncols = (uint32_t)(T * NW);                 // 288 (a1 x [d1|d2]) or 144 (a2 x d1)
+      const uint32_t n_hi = ncols > 256u ? 256u : ncols, n_lo = ncols - n_hi;
+      const uint32_t idesc_hi = make_idesc_f16_mn(128, (int)n_hi) | idesc_fmt_bits(t.lowp);
+      const uint32_t idesc_lo = n_lo ? (make_idesc_f16_mn(128, (int)n_lo) | idesc_fmt_bits(t.lowp)) : 0u;
+      int s = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(stage0 + (size_t)s * kTnStage);
+        const uint64_t ad0 = make_desc(a_base, lbo, sbo);
+        const uint64_t bd0 = make_desc(a_base + kTnABytes, lbo, sbo);
+        const uint32_t a_lo0 = (uint32_t)ad0, a_hi = (uint32_t)(ad0 >> 32);
+        const uint32_t b_lo0 = (uint32_t)bd0, b_hi = (uint32_t)(bd0 >> 32);
+        if (elect_one_w()) {
+#pragma unroll 1
+          for (int r = 0; r < kTH; r += 2) {                      // K = 16 pixels = two 8-pixel tile rows
+            const uint32_t off = (uint32_t)(r * 8);              // r * 128 B in 16-byte units
+            const uint32_t acc = (it | r) != 0 ? 1u : 0u;
+            umma_f16_w(tmem_base, a_lo0 + off, a_hi, b_lo0 + off, b_hi, idesc_hi, acc);
+            if (n_lo)   // chunks 32.. (= tap 8): 32 chunks x 2 KB further on
+              umma_f16_w(tmem_base + n_hi, a_lo0 + off, a_hi, b_lo0 + off + ((32u * kTnBOct) >> 4), b_hi, idesc_lo, acc);
+          }
+          umma_commit(&empty[s]);
+          if (it == my_tiles - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+        if (++s == kTnStages) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+    griddep_launch();
+  } else if (my_tiles > 0) {
+    // ===== epilogue: TMEM -> coalesced vector reductions into dWp[tap][ci][co] =====
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int quarter = warp & 3;
+    const int ci = c0 + quarter * 32 + lane;
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float osc = t.out_scale * (t.dyn_scale != nullptr ? *t.dyn_scale : 1.f);
+    for (int tap = 0; tap < T; ++tap) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)(tap * NW + (NP - 1) * kNC), v);  // smallest terms first
+      for (int piece = NP - 2; piece >= 0; --piece) {
+        float x[16];
+        tmem_ld16(taddr + (uint32_t)(tap * NW + piece * kNC), x);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += x[i];
+      }
+      if (ci < t.Cin) {
+        float* dst = t.dwp + ((size_t)tap * t.ci_pad + ci) * t.co_pad;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          red_add_v4(dst + i, v[i] * osc, v[i + 1] * osc, v[i + 2] * osc, v[i + 3] * osc);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // dY expansion for the taps-in-N weight gradient (DyIm2colArgs): one thread per (pixel, n-octet),
 // x-contiguous gathers and 16-byte stores.
 __global__ void __launch_bounds__(256) dy_im2col_kernel(DyIm2colArgs a) {
@@ -945,6 +1103,16 @@ int wg_waves() {
   return w;
 }
 
+// thin 3x3 layers through wgrad_tn_kernel (PDES_WGRAD_TAPSN=0: wgrad_tc_kernel<3, 1>)
+bool wg_taps_n_on() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("PDES_WGRAD_TAPSN");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 template <int KS, int CT>
 size_t wg_smem() {
   constexpr int HP = (kTH + KS - 1) * (kTW + KS - 1);
@@ -1029,6 +1197,20 @@ int launch_wgrad_tc(const TcWgradArgs& t, cudaStream_t st) {
   rc = make_plane_map(&tmB, t.planesB, t.B, t.Ho, t.Wo, CpB, kTW, kTH, 2 * CT);
   if (rc) return rc;
   const int tiles = ((t.Wo + kTW - 1) / kTW) * ((t.Ho + kTH - 1) / kTH) * t.B;
+  if (wg_taps_n_on() && t.KS == 3 && t.pad == 1 && n_co == 1 && t.Hv == t.Ho && t.Wv == t.Wo) {
+    // thin 3x3 layer: all taps in one GEMM-N (wgrad_tn_kernel); the activation tile has no halo
+    rc = make_plane_map(&tmA, t.planesA, t.B, t.Hv, t.Wv, CpA, kTW, kTH, kMC / 8);
+    if (rc) return rc;
+    const int passes = t.lowp ? 1 : kPasses;
+    int P = (wg_waves() * sm_count()) / (n_ci * passes);
+    if (P < 1) P = 1;
+    if (P > tiles) P = tiles;
+    const size_t smem = 128 + (size_t)kTnStages * kTnStage;
+    PDES_ENSURE_SMEM(wgrad_tn_kernel, smem);
+    PDES_CUDA(launch_pdl(wgrad_tn_kernel, dim3(P, n_ci, passes), dim3(kThreads), smem, st, tmA, tmB, t));
+    PDES_LAUNCH_CHECK();
+    return PDES_OK;
+  }
   const int n_cog = (n_co + CT - 1) / CT;
   const int T = t.KS * t.KS;
   const int TG = CT == 1 ? (T <= 9 ? T : 10) : (T < 3 ? T : 3);
