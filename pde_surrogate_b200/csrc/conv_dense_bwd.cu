@@ -186,7 +186,10 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     tmem_relinquish();
     fixd[lane] = 0.0;
   }
-  __syncthreads();   // barriers and the zeroed fix accumulators are visible before anybody uses them
+  tc_fence_before();
+  __syncthreads();   // barriers, the TMEM base and the zeroed fix accumulators are visible before anybody uses them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
   griddep_wait();
   if (threadIdx.x == 0) DBG(1);
   // dynamic power-of-two scale of the gradient pieces (same rule as act_split_kernel)
@@ -279,11 +282,14 @@ conv_dense_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) DBG(2);
+  // Two independent prologues: the epilogue warps only need their own BatchNorm constants, the producers (and
+  // the MMA / TMA warps that helped computing them) only the dY corrections - the dY conversion of the first tile
+  // does not wait for the epilogue's constants.
+  if (warp < kEpiWarps)
+    named_bar_sync(1, kEpiWarps * 32);
+  else
+    named_bar_sync(2, kThreads - kEpiWarps * 32);
+  if (threadIdx.x == kEpiWarps * 32) DBG(2);
 
   if (warp >= kProdWarp0) {
     // ===== dY producers: G, X slices -> corrected, scaled, split -> three shifted copies in A_s =====
