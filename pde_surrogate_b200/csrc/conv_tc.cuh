@@ -121,6 +121,7 @@ struct Tc2PackDesc {
   int lowp;        // LOWP_*: only the first piece is written, in fp16 or bf16
   int dxn, CoP;    // dxn = 1: "dx in N" layout of conv_dense.cu, [chunk][ky][k-octet][piece][n = kx*CoP + co][8]
                    // dxn = 2: "dx in K" layout of conv_dense_bwd.cu, [jy][k-octet (jx, co octet)][piece][n = ci][8]
+                   // dxn = 3: data gradient over the (tap, co)-expanded dY planes: conv_tc2 1x1 layout, k = tap*Cout + co
 };
 void tc2_plan(int KS, int Cin_k, int N, Tc2Plan* p, int lowp = 0);
 bool tc2_supported(int KS, int stride, int Cin_k, int N);

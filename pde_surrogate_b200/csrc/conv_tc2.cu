@@ -598,7 +598,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, Tc2Args t) {
 __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
   griddep_wait();
   const Tc2PackDesc d = tab[blockIdx.y];
-  const int T = d.dxn ? d.KS : d.KS * d.KS;   // dxn: one "tap" per filter ROW, the columns live in n (1) / in k (2)
+  // dxn: one "tap" per filter ROW, the columns live in n (1) / in k (2); 3: every tap lives in k (one 1x1 GEMM)
+  const int T = d.dxn == 3 ? 1 : (d.dxn ? d.KS : d.KS * d.KS);
   const int koct = d.KC >> 3, KK = d.KS * d.KS;
   const size_t per_tap = (size_t)koct * d.N * 8;  // elements of ONE piece of one (chunk, tap)
   const int rows = d.nchunks * T * koct * d.N;    // 16-byte rows: 8 consecutive k of one (chunk, tap, k octet, n)
@@ -615,7 +616,12 @@ __global__ void __launch_bounds__(256) pack_tc2_kernel(const Tc2PackDesc* tab) {
     for (int k8 = 0; k8 < 8; ++k8) {
       const int k = k0 + k8;
       float x = 0.f;
-      if (d.dxn == 2) {
+      if (d.dxn == 3) {
+        // data gradient over the (tap, co)-expanded dY: k = tap * Cout + co, n = ci; W[co, ci, tap] (no flip: the
+        // expansion already reads dY at q - tap + pad)
+        const int tp = k / d.Cout, co = k - tp * d.Cout;
+        if (n < d.Cin && tp < KK) x = d.w[((size_t)co * d.Cin + n) * KK + tp];
+      } else if (d.dxn == 2) {
         // data gradient: k = (jx, co), n = ci, tap = jy; flipped filter W[co, ci, 2-jy, 2-jx]
         const int jx = k >> 4, co = k & 15;
         if (n < d.Cin && co < d.Cout && jx < d.KS)

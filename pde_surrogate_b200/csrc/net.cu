@@ -54,6 +54,9 @@ struct Layer {
   size_t wdn;        // float offset of its packed filter ("dx in N" layout)
   bool bilinear;     // the x2 upsampling in front of this convolution is materialised by bilinear.cu (align_corners
                      // interpolation, or zero insertion for the transposed convolution) instead of nearest
+  bool dg_im2col;    // data gradient = ONE 1x1 GEMM over the (tap, co)-expanded dY planes the weight gradient builds
+  Tc2Plan p2i;       // its conv_tc2 plan (KS = 1, GEMM-K = padded taps * Cout)
+  size_t w2i = 0;    // float offset of its packed filter [(tap, co)][ci]
   bool convT;        // nn.ConvTranspose2d(k3, s2, p1, op1): zero-insert x2 + 3x3 conv with the flipped, transposed filter
   size_t wt = 0, gt = 0;   // float offsets (convT): equivalent Conv2d filter / its gradient
   bool drop;         // an nn.Dropout2d follows this convolution when the network has drop_rate > 0
@@ -223,6 +226,8 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.drop_cprefix = 0;
   L.bilinear = false;
   L.convT = false;
+  L.dg_im2col = false;
+  memset(&L.p2i, 0, sizeof(L.p2i));
   L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
   L.dwp = 0;
@@ -502,6 +507,17 @@ int build(pdes_net* n) {
         const int Np = (L.KS * L.KS * L.Cout + 7) & ~7;
         L.planesI = f;
         f += pad4((int64_t)((act_planes_bytes(B, L.Ho, L.Wo, Np) + 3) / 4)) + 64;
+        // The same expanded planes are the GEMM-K operand of the layer's data gradient:
+        //   dX[q][ci] = sum_(tap, co) I[q][(tap, co)] * W[co][ci][tap]   - one 1x1 GEMM (K = Np) instead of KS^2 taps
+        // of K = 16 with 3 useful channels each.  Replaces the conv_tc2 dgrad filter entry of the pack table.
+        static const bool on = []() { const char* e = getenv("PDES_DGRAD_IM2COL"); return !(e && e[0] == '0'); }();
+        if (on && L.in_buf >= 0 && L.tc2_bwd && !L.dense_bwd && tc2_supported(1, 1, Np, L.Nb)) {
+          L.dg_im2col = true;
+          tc2_plan(1, Np, L.Nb, &L.p2i, n->lowp);
+          L.w2i = f;
+          f += pad4((int64_t)((L.p2i.pack_elems + 1) / 2));
+          if (L.p2i.pack_elems > n->max_tc2_pack) n->max_tc2_pack = L.p2i.pack_elems;
+        }
       }
       if (L.in_buf >= 0 && (L.tc_wg || L.tc2_bwd)) {
         L.planesB = f;
@@ -835,6 +851,23 @@ extern "C" int pdes_densenet_bind(pdes_net_t* n, float* params, float* grads, fl
       if (!(dir == 0 ? L.tc2_fwd : L.tc2_bwd)) continue;
       if (dir == 0 && L.dense_fwd) continue;
       if (dir == 1 && L.dense_bwd) continue;
+      if (dir == 1 && L.dg_im2col) {
+        Tc2PackDesc d;
+        d.w = conv_w(n, L);
+        d.dst = reinterpret_cast<op16*>(wsf(n, L.w2i));
+        d.Cout = L.Cout;
+        d.Cin = L.Cin;
+        d.KS = L.KS;
+        d.N = L.Nb;
+        d.KC = L.p2i.KC;
+        d.nchunks = L.p2i.nchunks;
+        d.transpose = 0;
+        d.dxn = 3;
+        d.CoP = 0;
+        d.lowp = n->lowp;
+        t2.push_back(d);
+        continue;
+      }
       Tc2PackDesc d;
       d.w = conv_w(n, L);
       d.dst = reinterpret_cast<op16*>(wsf(n, dir == 0 ? L.w2f : L.w2b));
@@ -1451,7 +1484,9 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
       // (a layer with the fused dgrad has no conv_tc2 dgrad filter packed: without both backward bits it
       // falls back to the CUDA-core kernels)
       const bool use_dg = n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2) && L.in_buf >= 0;
-      if ((use_wg || use_dg) && !use_dense_bwd) {
+      // data gradient as one 1x1 GEMM over the expanded dY planes (needs the weight gradient's expansion)
+      const bool dg_i2c = use_dg && use_wg && L.dg_im2col && L.wg_taps_n && !have_fix;
+      if ((use_wg || use_dg) && !use_dense_bwd && !(dg_i2c && L.wg_taps_n)) {
         // fp16 pieces of the corrected dY slice: GEMM-K operand of dgrad, GEMM-N operand of wgrad
         ActSplitArgs sb;
         memset(&sb, 0, sizeof(sb));
@@ -1494,7 +1529,7 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
         ia.dyn_inv = wsf(n, n->dyinv) + li;  // the same value the dY split publishes
         ia.lowp = n->lowp;
         cudaStream_t ist = st;
-        if (n->n_side > 0 && n->side[0]) {
+        if (n->n_side > 0 && n->side[0] && !dg_i2c) {
           // off the critical path: the expansion and the GEMM that reads it both run on the side stream
           // (wg_rr is advanced by the wgrad launch below, which therefore picks the same stream)
           const int k = wg_rr % n->n_side;
@@ -1684,7 +1719,32 @@ static int backward_impl(pdes_net_t* n, const float* dout, void* stream, float* 
             rc = launch_conv_dense_bwd(db, st);
           }
         }
-      } else if (n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && (n->tc_mask & 2)) {
+      } else if (n->conv_impl == 0 && L.dg_im2col && L.wg_taps_n && L.tc_wg && (n->tc_mask & 2) && (n->tc_mask & 4) &&
+                 !have_fix) {
+        // (the expanded planes were written by dy_im2col_kernel in run_wgrad, on this stream)
+        const int Np = (L.KS * L.KS * L.Cout + 7) & ~7;
+        Tc2Args t;
+        memset(&t, 0, sizeof(t));
+        t.c = a;
+        t.c.Cin = Np;
+        t.c.KS = 1;
+        t.c.pad = 0;
+        t.c.in_mode = IN_DIRECT;
+        t.wpk = reinterpret_cast<const op16*>(wsf(n, L.w2i));
+        t.lowp = n->lowp;
+        t.out_scale = pow2f(-kWScaleLog2);
+        t.dyn_scale = wsf(n, n->dyinv) + li;
+        t.N = L.Nb;
+        t.KC = L.p2i.KC;
+        t.nchunks = L.p2i.nchunks;
+        t.ngroups = L.p2i.ngroups;
+        t.S = L.p2i.S;
+        t.TS = L.p2i.TS;
+        t.AST = L.p2i.AST;
+        t.NB = L.p2i.NB;
+        t.TPB = L.p2i.TPB;
+        rc = launch_conv_tc2(t, reinterpret_cast<const op16*>(wsf(n, L.planesI)), L.Ho, L.Wo, Np, st);
+      } else if (n->conv_impl == 0 && L.tc2_bwd && !L.dense_bwd && !L.dg_im2col && (n->tc_mask & 2)) {
         Tc2Args t;
         memset(&t, 0, sizeof(t));
         t.c = a;
