@@ -148,7 +148,8 @@ int pdes_densenet_bn_info(const pdes_net_t* net, int idx, char* name, size_t nam
 int pdes_densenet_dropout_sites(const pdes_net_t* net, int32_t* channels, int cap);
 int pdes_densenet_set_dropout(pdes_net_t* net, const float* masks);
 
-/* Spatial size (H = W) of the network output: imsize for DenseED, imsize * 2^n_blocks for Decoder. */
+/* Spatial size (H = W) of the network output: imsize for DenseED (imsize / 2 with upsample = 2), imsize * 2^n_blocks
+ * for Decoder (imsize * 2^(n_blocks-1) with upsample = 2). */
 int pdes_densenet_output_size(const pdes_net_t* net);
 
 size_t pdes_densenet_workspace_bytes(const pdes_net_t* net);
@@ -161,7 +162,11 @@ int pdes_densenet_bind(pdes_net_t* net, float* params, float* grads, float* runn
 /* x: (B,in_channels,imsize,imsize) NCHW fp32; out: (B,out_channels,imsize,imsize) NCHW.
  * training != 0: batch statistics, running-stat update (momentum 0.1, unbiased var,
  * torch.nn.BatchNorm2d semantics) and activations kept for backward.
- * training == 0: running statistics (model.eval()). */
+ * training == 0: running statistics (model.eval()).
+ * From the second call with the same (B, training) on, the launches of the pass are replayed as ONE CUDA graph
+ * (captured once on a private stream, launched into `stream`; x / out are staged through the workspace); the same
+ * holds for pdes_densenet_backward.  Not while `stream` itself is being captured (then the launches are recorded
+ * into the caller's graph), not for dropout networks, not with PDES_EXEC_GRAPH=0 in the environment. */
 int pdes_densenet_forward(pdes_net_t* net, const float* x, float* out, int B, int training,
                           void* stream);
 /* dout: dL/d(out), (B,out_channels,imsize,imsize).  ADDS dL/d(param) into `grads`
