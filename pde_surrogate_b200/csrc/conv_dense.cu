@@ -175,8 +175,25 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
     tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
-  griddep_wait();  // x, the batch statistics and the packed filter come from earlier kernels of the step
+  __syncthreads();  // barrier initialisation visible: the first raw loads go out before the constants below
+  griddep_wait();   // x, the batch statistics and the packed filter come from earlier kernels of the step
   if (threadIdx.x == 0) DBG(1);
+  // the first RST raw chunks need no free-slot wait: issued now, they are in flight while the BatchNorm
+  // constants are computed (saves one load latency per launch)
+  int pre_issued = 0;
+  if (warp == kTmaWarp && lane == 0 && !(a.exp & 4) && (int)blockIdx.x < n_tiles) {
+    int tile = blockIdx.x, ch = 0;
+    while (pre_issued < RST && tile < n_tiles) {
+      const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
+      mbar_arrive_expect_tx(&raw_full[pre_issued], raw_stage_bytes);
+      tma_load_3d(R_s + (size_t)pre_issued * raw_stage_bytes, &tmX, ch * kKC, (r0 - 1) * W, b, &raw_full[pre_issued]);
+      ++pre_issued;
+      if (++ch == nchunks) {
+        ch = 0;
+        tile += gridDim.x;
+      }
+    }
+  }
   if (warp >= kProdWarp0) {
     // BatchNorm constants of this layer, the activation scale folded in: relu(s*x+h)*2^k = relu(2^k s x + 2^k h)
     const float mul = (float)(1 << kActScaleLog2);
@@ -210,6 +227,7 @@ conv_dense_fwd_kernel(const __grid_constant__ CUtensorMap tmX, DenseFwdArgs a, i
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int b = tile / tiles_per_img, r0 = (tile - b * tiles_per_img) * TR;
         for (int ch = 0; ch < nchunks; ++ch, ++q_it) {
+          if (q_it < pre_issued) continue;   // issued before the prologue (stage q_it, first pass of the ring)
           const int s = q_it % RST;
           mbar_wait(&raw_empty[s], (uint32_t)(((q_it / RST) & 1) ^ 1));
           if (a.exp & 4) {

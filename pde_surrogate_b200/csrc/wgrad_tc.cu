@@ -259,7 +259,11 @@ __global__ void __launch_bounds__(256, 2) act_split_staged_kernel(ActSplitArgs a
   nb1 = nb1 < 0 ? 0 : (nb1 > 16 ? 16 : nb1);
   auto issue = [&](int work, int buf) {
     if (!qon) return;
-    const int seg = work % nseg, row = work / nseg;   // row = b * Hs + sy
+    int seg = 0, row = work;   // row = b * Hs + sy
+    if (nseg > 1) {
+      seg = work % nseg;
+      row = work / nseg;
+    }
     const int x0 = seg * xs;
     const int nx = (a.Ws - x0) < xs ? (a.Ws - x0) : xs;
     const size_t pix = (size_t)row * a.Ws + x0 + tp;
@@ -302,10 +306,21 @@ __global__ void __launch_bounds__(256, 2) act_split_staged_kernel(ActSplitArgs a
     }
   }
   const bool full8 = c + 7 < a.C;
+  const bool hs_pow2 = (a.Hs & (a.Hs - 1)) == 0;
+  int hs_sh = 0;
+  while ((1 << hs_sh) < a.Hs) ++hs_sh;
+  // phase-2 lane grid of a full-width segment (recomputed only for a shorter last segment)
+  int xsh_full = 0;
+  while ((1 << xsh_full) < (up ? 2 * xs : xs)) ++xsh_full;
   int buf = 0;
   for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
-    const int seg = work % nseg, row = work / nseg;
-    const int sy = row % a.Hs, b = row / a.Hs;
+    int seg = 0, row = work;
+    if (nseg > 1) {
+      seg = work % nseg;
+      row = work / nseg;
+    }
+    // (image sizes are powers of two in every configuration of the scripts: shift / mask instead of a division)
+    const int b = hs_pow2 ? (row >> hs_sh) : row / a.Hs, sy = row - b * a.Hs;
     const int x0 = seg * xs;
     const int nx = (a.Ws - x0) < xs ? (a.Ws - x0) : xs;
     if (work + (int)gridDim.x < n_work) issue(work + gridDim.x, buf ^ 1);
@@ -386,8 +401,11 @@ __global__ void __launch_bounds__(256, 2) act_split_staged_kernel(ActSplitArgs a
     __syncthreads();
     // ---- phase 2: tile rows -> global, x-contiguous 16-byte stores ---------------------------
     const int nxo = up ? 2 * nx : nx, xo0 = up ? 2 * x0 : x0;
-    int xsh = 0;
-    while ((1 << xsh) < nxo) ++xsh;
+    int xsh = xsh_full;
+    if (nx != xs) {
+      xsh = 0;
+      while ((1 << xsh) < nxo) ++xsh;
+    }
     const int ox = threadIdx.x & ((1 << xsh) - 1);
     if (ox < nxo) {
       const int nrows = (a.lowp ? 1 : kPieces) * oct, rstep = 256 >> xsh;
