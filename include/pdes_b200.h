@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PDES_ABI_VERSION 2
+#define PDES_ABI_VERSION 3
 
 #define PDES_OK 0
 #define PDES_ERR_INVALID 1     /* bad argument (shape, null pointer, alignment)        */
@@ -121,6 +121,10 @@ typedef struct pdes_densenet_config {
                           * 0 'nearest' (default), 1 'bilinear' (align_corners=True), 2 None: the transitions use
                           * nn.ConvTranspose2d(k3, s2, p1, op1) named convT2 (weight (Cin, Cout, 3, 3), codec.py:139-142)
                           * and the last decoding does not upsample (codec.py:176-179): the output is half as wide */
+  int32_t bottleneck;    /* bottleneck * growth_rate = the width above which a dense layer takes the bottleneck form
+                          * norm1 -> relu -> conv1 (1x1, in -> bottleneck * growth) -> norm2 -> relu -> conv2 (3x3 -> growth)
+                          * (models/codec.py:56-64: DenseED(bottleneck=True, bn_size=...)); 0 = plain dense layers.
+                          * (ABI version 3) */
 } pdes_densenet_config;
 
 /* Host-side object (no device memory). */

@@ -31,6 +31,20 @@ import torch.nn.functional as F
 # ---------------------------------------------------------------------------------------
 
 
+def _dense_stages(name, cin, growth, bottleneck):
+    """One _DenseLayer (codec.py:43-75).  `bottleneck` = bn_size when DenseED(bottleneck=True), else 0: a layer whose
+    input is wider than bn_size * growth takes the bottleneck form norm1-relu-conv1 (1x1, cin -> bn_size * growth)
+    - norm2-relu-conv2 (3x3 -> growth) (lines 56-64), expressed here as two 'bnconv' stages: the first keeps the
+    layer input aside, the second concatenates it with its output (line 75)."""
+    if bottleneck and cin > bottleneck * growth:
+        mid = bottleneck * growth
+        return [dict(kind="bnconv", name=name, bn="norm1", conv="conv1", cin=cin, cout=mid, k=1, stride=1, pad=0,
+                     up=False, keep=True),
+                dict(kind="bnconv", name=name, bn="norm2", conv="conv2", cin=mid, cout=growth, k=3, stride=1, pad=1,
+                     up=False, cat=True)]
+    return [dict(kind="dense", name=name, cin=cin, cout=growth, k=3, stride=1, pad=1, up=False)]
+
+
 def _up_stage(t, c, upsample):
     """conv2 of a decoding transition (codec.py:136-150): Conv2d behind a x2 upsampling, or - upsample=None - the
     transposed convolution convT2 = ConvTranspose2d(c, c, 3, stride 2, padding 1, output_padding 1) (139-142)."""
@@ -84,7 +98,7 @@ def coupling_plan(in_features, out_features, num_layers=3, growth_rate=16):
 
 
 def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), growth_rate=16,
-                  init_features=48, arch=0, upsample="nearest"):
+                  init_features=48, arch=0, upsample="nearest", bottleneck=0):
     """Ordered list of stages describing DenseED with the defaults the training script uses
     (bottleneck=False in dense layers, bottleneck=True transitions, upsample='nearest',
     drop_rate=0, out_activation=None).
@@ -110,8 +124,7 @@ def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), gr
     c = init_features
     for i, n in enumerate(enc):  # codec.py:247-262
         for j in range(n):
-            st.append(dict(kind="dense", name=f"features.EncBlock{i + 1}.denselayer{j + 1}",
-                           cin=c + j * growth_rate, cout=growth_rate, k=3, stride=1, pad=1, up=False))
+            st += _dense_stages(f"features.EncBlock{i + 1}.denselayer{j + 1}", c + j * growth_rate, growth_rate, bottleneck)
         c += n * growth_rate
         t = f"features.TransDown{i + 1}"
         st.append(dict(kind="bnconv", name=t, bn="norm1", conv="conv1", cin=c, cout=c // 2, k=1,
@@ -121,8 +134,7 @@ def densenet_plan(in_channels=1, out_channels=3, imsize=64, blocks=(6, 8, 6), gr
         c //= 2
     for i, n in enumerate(dec):  # codec.py:265-282
         for j in range(n):
-            st.append(dict(kind="dense", name=f"features.DecBlock{i + 1}.denselayer{j + 1}",
-                           cin=c + j * growth_rate, cout=growth_rate, k=3, stride=1, pad=1, up=False))
+            st += _dense_stages(f"features.DecBlock{i + 1}.denselayer{j + 1}", c + j * growth_rate, growth_rate, bottleneck)
         c += n * growth_rate
         if i < len(dec) - 1:
             t = f"features.TransUp{i + 1}"
@@ -232,7 +244,8 @@ def round_operand(t, mode, scale_log2=0):
 def _drop_site(s):
     """nn.Dropout2d follows every convolution but In_conv / conv0 and the last two of the last decoding
     (codec.py:70-71, 110-149, 171-172)."""
-    return s["kind"] != "conv" and not (s["name"] == "features.LastTransUp" and s.get("conv") in ("conv2", "conv3"))
+    return (s["kind"] != "conv" and not s.get("keep") and
+            not (s["name"] == "features.LastTransUp" and s.get("conv") in ("conv2", "conv3")))
 
 
 def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_running=True, operand_round=None,
@@ -247,7 +260,10 @@ def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_
     exactly as nn.BatchNorm2d does.
     """
     h = x
+    kept = None
     for s in plan:
+        if s.get("keep"):
+            kept = h   # input of a bottleneck dense layer (concatenated with the layer's output below)
         if s["kind"] == "conv":
             h = F.conv2d(h, sd[_conv_name(s) + ".weight"], None, s["stride"], s["pad"])
             continue
@@ -279,7 +295,10 @@ def densenet_forward(plan, sd, x, training=True, momentum=0.1, eps=1e-5, update_
             y = F.conv2d(a, w, None, s["stride"], s["pad"])
         if drop_rate > 0 and _drop_site(s):
             y = F.dropout2d(y, drop_rate, training)   # nn.Dropout2d: whole channels, scaled by 1/(1-p)
-        h = torch.cat([h, y], 1) if s["kind"] == "dense" else y  # codec.py:73-75
+        if s.get("cat"):
+            h = torch.cat([kept, y], 1)
+        else:
+            h = torch.cat([h, y], 1) if s["kind"] == "dense" else y  # codec.py:73-75
     return h
 
 

@@ -16,7 +16,7 @@ _lib = None
 class DensenetConfig(Structure):
     _fields_ = [("in_channels", c_int32), ("out_channels", c_int32), ("imsize", c_int32),
                 ("n_blocks", c_int32), ("blocks", c_int32 * 15), ("growth_rate", c_int32),
-                ("init_features", c_int32), ("max_batch", c_int32), ("arch", c_int32), ("dropout", c_int32), ("upsample", c_int32)]
+                ("init_features", c_int32), ("max_batch", c_int32), ("arch", c_int32), ("dropout", c_int32), ("upsample", c_int32), ("bottleneck", c_int32)]
 
 
 class ConvDesc(Structure):

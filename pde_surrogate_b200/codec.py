@@ -105,6 +105,7 @@ class _NetHandle(object):
         c.arch = int(cfg.get("arch", 0))
         c.dropout = 1 if cfg.get("drop_rate", 0.0) > 0 else 0
         c.upsample = {"nearest": 0, "bilinear": 1, None: 2}[cfg.get("upsample", "nearest")]
+        c.bottleneck = int(cfg.get("bottleneck", 0))
         c.n_blocks = len(cfg["blocks"])
         for i, b in enumerate(cfg["blocks"]):
             c.blocks[i] = int(b)
@@ -322,8 +323,6 @@ def _reject_options(cls, drop_rate=0, bottleneck=False, upsample='nearest', out_
     unsupported = []
     if drop_rate and not (0.0 <= drop_rate < 1.0):
         raise ValueError("dropout probability has to be between 0 and 1, but got {}".format(drop_rate))
-    if bottleneck:
-        unsupported.append("bottleneck=True")
     if upsample not in ('nearest', 'bilinear', None):
         unsupported.append("upsample=%r" % (upsample,))
     if unsupported:
@@ -512,7 +511,7 @@ class DenseED(_ExecutorNet):
 
     Args as in the reference: drop_rate, upsample in ('nearest', 'bilinear', None = transposed convolutions,
     whose last decoding does not upsample: the output is imsize/2 wide, as in the reference) and
-    out_activation are implemented; bottleneck dense layers raise a clear error instead of silently differing.
+    out_activation and bottleneck dense layers (bottleneck=True, bn_size) are implemented.
     """
 
     def __init__(self, in_channels, out_channels, imsize, blocks, growth_rate=16, init_features=48,
@@ -524,7 +523,8 @@ class DenseED(_ExecutorNet):
         _reject_options("DenseED", drop_rate, bottleneck, upsample, out_activation)
         self._build(dict(in_channels=int(in_channels), out_channels=int(out_channels), imsize=int(imsize),
                          blocks=blocks, growth_rate=int(growth_rate), init_features=int(init_features), arch=0,
-                         drop_rate=float(drop_rate or 0.0), upsample=upsample))
+                         drop_rate=float(drop_rate or 0.0), upsample=upsample,
+                         bottleneck=int(bn_size) if bottleneck else 0))
         self._set_out_activation(out_activation)
         print('# params {}, # conv layers {}'.format(*self.model_size))
 

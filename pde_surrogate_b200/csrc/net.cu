@@ -54,6 +54,7 @@ struct Layer {
   size_t wdn;        // float offset of its packed filter ("dx in N" layout)
   bool bilinear;     // the x2 upsampling in front of this convolution is materialised by bilinear.cu (align_corners
                      // interpolation, or zero insertion for the transposed convolution) instead of nearest
+  bool no_drop;      // no nn.Dropout2d behind this convolution (conv1 of a bottleneck dense layer)
   bool dg_im2col;    // data gradient = ONE 1x1 GEMM over the (tap, co)-expanded dY planes the weight gradient builds
   Tc2Plan p2i;       // its conv_tc2 plan (KS = 1, GEMM-K = padded taps * Cout)
   size_t w2i = 0;    // float offset of its packed filter [(tap, co)][ci]
@@ -227,6 +228,7 @@ void add_layer(pdes_net* n, int kind, const std::string& conv_name, const std::s
   L.bilinear = false;
   L.convT = false;
   L.dg_im2col = false;
+  L.no_drop = false;
   memset(&L.p2i, 0, sizeof(L.p2i));
   L.planesI = 0;
   L.ci_pad = L.co_pad = 0;
@@ -285,6 +287,17 @@ int build(pdes_net* n) {
       const int idx = enc ? bi + 1 : bi - n_enc + 1;
       for (int j = 0; j < c.blocks[bi]; ++j) {
         snprintf(nm, sizeof(nm), "features.%sBlock%d.denselayer%d", enc ? "Enc" : "Dec", idx, j + 1);
+        const int cin_j = C + j * c.growth_rate, mid_c = c.bottleneck * c.growth_rate;
+        if (c.bottleneck > 0 && cin_j > mid_c) {
+          // bottleneck form (codec.py:56-64): 1x1 to bn_size * growth channels in a buffer of its own, then the 3x3
+          // convolution writes the layer's slice of the block buffer; nn.Dropout2d follows conv2 only (codec.py:70-71)
+          const int tmp = add_buf(n, H, H, mid_c);
+          add_layer(n, 2, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, tmp, 0, cin_j, mid_c, 1, 1, 0, 0, H, H);
+          n->layers.back().no_drop = true;
+          add_layer(n, 2, std::string(nm) + ".conv2", std::string(nm) + ".norm2", tmp, cur, cin_j, mid_c, c.growth_rate, 3, 1,
+                    1, 0, H, H);
+          continue;
+        }
         add_layer(n, 1, std::string(nm) + ".conv1", std::string(nm) + ".norm1", cur, cur,
                   C + j * c.growth_rate, C + j * c.growth_rate, c.growth_rate, 3, 1, 1, 0, H, H);
       }
@@ -327,7 +340,7 @@ int build(pdes_net* n) {
     int prefix = 0;
     for (auto& L : n->layers) {
       const bool last2 = L.conv_name == "features.LastTransUp.conv2" || L.conv_name == "features.LastTransUp.conv3";
-      L.drop = c.dropout != 0 && L.kind != 0 && !last2;
+      L.drop = c.dropout != 0 && L.kind != 0 && !last2 && !L.no_drop;
       L.drop_cprefix = prefix;
       if (L.drop) prefix += L.Cout;
     }

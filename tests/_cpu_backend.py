@@ -18,7 +18,7 @@ class OracleExecutor(object):
         cfg = dict(m._cfg)
         self.drop_rate = float(cfg.pop("drop_rate", 0.0))
         self.upsample = cfg.pop("upsample", "nearest")
-        plan = orc.densenet_plan(**cfg, upsample=self.upsample)
+        plan = orc.densenet_plan(**cfg, upsample=self.upsample)   # (cfg carries `bottleneck` = bn_size or 0)
         sd = {}
         for k, v in m.state_dict().items():
             sd[k] = v.detach().clone() if k.endswith("num_batches_tracked") else v.detach()

@@ -49,12 +49,14 @@ def main():
 
     DenseED, darcy, SobelFilter = import_reference()
 
-    def ref_step(cfg, B, seed, dtype, kind="lognormal", upsample="nearest"):
-        plan = orc.densenet_plan(**cfg, upsample=upsample)
+    def ref_step(cfg, B, seed, dtype, kind="lognormal", upsample="nearest", bn_size=0):
+        # bn_size > 0: DenseED(bottleneck=True, bn_size=bn_size) (models/codec.py:56-64)
+        plan = orc.densenet_plan(**cfg, upsample=upsample, bottleneck=bn_size)
         sd = orc.to_dtype(orc.make_state(plan, seed), dtype)
         K = orc.make_input(B, cfg["imsize"], seed, kind=kind).to(dtype)
         model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
-                        growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], upsample=upsample)
+                        growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], upsample=upsample,
+                        **(dict(bottleneck=True, bn_size=bn_size) if bn_size else {}))
         model = model.to(dtype)
         missing = model.load_state_dict(sd, strict=True)
         assert not missing.missing_keys and not missing.unexpected_keys
@@ -90,13 +92,13 @@ def main():
                     l_d_notb=l_d_notb.detach(), names=[n for n, _ in model.named_parameters()],
                     model_size=model.model_size)
 
-    def save_case(fname, cfg, B, seed, full_grads, kind="lognormal", compact=False, upsample="nearest"):
-        r32 = ref_step(cfg, B, seed, torch.float32, kind, upsample)
-        r64 = ref_step(cfg, B, seed, torch.float64, kind, upsample)
+    def save_case(fname, cfg, B, seed, full_grads, kind="lognormal", compact=False, upsample="nearest", bn_size=0):
+        r32 = ref_step(cfg, B, seed, torch.float32, kind, upsample, bn_size)
+        r64 = ref_step(cfg, B, seed, torch.float64, kind, upsample, bn_size)
         d = dict(input_kind=kind, cfg_in_channels=cfg["in_channels"], cfg_out_channels=cfg["out_channels"],
                  cfg_imsize=cfg["imsize"], cfg_blocks=np.array(cfg["blocks"]),
                  cfg_growth_rate=cfg["growth_rate"], cfg_init_features=cfg["init_features"], B=B,
-                 seed=seed, model_size=np.array(r32["model_size"]),
+                 seed=seed, bn_size=bn_size, model_size=np.array(r32["model_size"]),
                  out=r32["out"].numpy(), out_eval=r32["out_eval"].numpy(), l4=r32["l4"].numpy(),
                  loss=r32["loss"].numpy(), dout=r32["dout"].numpy(), l_d_notb=r32["l_d_notb"].numpy(),
                  out64=r64["out"].numpy().astype(np.float64), l4_64=r64["l4"].numpy(),
@@ -259,6 +261,12 @@ def main():
         save_case("densenet_convt32.npz", dict(full, imsize=32, blocks=[3, 4, 3, 4, 3]), B=3, seed=53, full_grads=False,
                   upsample=None)
 
+    def bottleneck_cases():
+        # DenseED(bottleneck=True): dense layers wider than bn_size * growth take the 1x1 -> 3x3 form (codec.py:56-64)
+        small = dict(in_channels=1, out_channels=3, imsize=16, blocks=[2, 3, 2], growth_rate=4, init_features=8)
+        save_case("densenet_bottleneck16.npz", small, B=3, seed=59, full_grads=True, bn_size=2)
+        save_case("densenet_bottleneck32.npz", dict(full, imsize=32), B=3, seed=61, full_grads=False, bn_size=4)
+
     def coupling_cases():
         # SURVEY.md section 8(f) row 1 / BASELINE config 5: the cGlow coupling network `_DenseCoupling`
         # (models/glow_msc.py:276-294, Conv2dZeros 240-255) and `AffineCouplingLayer` forward / reverse (297-344),
@@ -356,6 +364,9 @@ def main():
     if "--only-coupling" in sys.argv:
         coupling_cases()
         return
+    if "--only-bottleneck" in sys.argv:
+        bottleneck_cases()
+        return
     if "--only-convt" in sys.argv:
         convt_cases()
         return
@@ -387,6 +398,7 @@ def main():
     dropout_case()
     bilinear_cases()
     convt_cases()
+    bottleneck_cases()
     coupling_cases()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----

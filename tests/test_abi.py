@@ -29,7 +29,7 @@ def test_header_symbols_exported(built_lib):
 def test_host_only_calls(built_lib):
     from ctypes import byref, c_void_p
     from pde_surrogate_b200 import _lib
-    assert built_lib.pdes_abi_version() == 2
+    assert built_lib.pdes_abi_version() == 3
     cfg = _lib.DensenetConfig()
     cfg.in_channels, cfg.out_channels, cfg.imsize, cfg.n_blocks = 1, 3, 64, 3
     for i, b in enumerate([6, 8, 6]):

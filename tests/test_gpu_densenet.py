@@ -20,7 +20,9 @@ CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_
          # DenseED(upsample='bilinear') (train_codec_mixed_residual.py --upsample bilinear)
          "densenet_bilinear16", "densenet_bilinear32",
          # DenseED(upsample=None): nn.ConvTranspose2d transitions, output imsize/2 wide (models/codec.py:139-142, 176-179)
-         "densenet_convt16", "densenet_convt32"]
+         "densenet_convt16", "densenet_convt32",
+         # DenseED(bottleneck=True, bn_size=...): 1x1 -> 3x3 dense layers above bn_size * growth channels (codec.py:56-64)
+         "densenet_bottleneck16", "densenet_bottleneck32"]
 
 
 def _ups(name):
@@ -41,10 +43,12 @@ def _cfg(g):
 def _model(g, upsample="nearest"):
     from models.codec import DenseED
     cfg = _cfg(g)
-    plan = orc.densenet_plan(**cfg, upsample=upsample)
+    bn_size = int(g["bn_size"]) if "bn_size" in g.files else 0
+    plan = orc.densenet_plan(**cfg, upsample=upsample, bottleneck=bn_size)
     sd = orc.make_state(plan, int(g["seed"]))
     model = DenseED(cfg["in_channels"], cfg["out_channels"], cfg["imsize"], cfg["blocks"],
-                    growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], upsample=upsample)
+                    growth_rate=cfg["growth_rate"], init_features=cfg["init_features"], upsample=upsample,
+                    **(dict(bottleneck=True, bn_size=bn_size) if bn_size else {}))
     assert list(model.state_dict().keys()) == list(sd.keys())
     model.load_state_dict(sd)
     model = model.to("cuda")

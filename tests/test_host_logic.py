@@ -36,8 +36,13 @@ def test_state_dict_matches_reference_layout(golden_dir):
     assert m2._flat.dtype == torch.float64 and len(m2.state_dict()) == 163
     with pytest.raises(ValueError):
         DenseED(1, 3, 64, [6, 8])
-    with pytest.raises(NotImplementedError):
-        DenseED(1, 3, 64, [6, 8, 6], bottleneck=True)     # bottleneck dense layers: not built, loud
+    # bottleneck dense layers (codec.py:56-64): conv1 (1x1) / conv2 (3x3) above bn_size * growth input channels
+    mk = DenseED(1, 3, 64, [6, 8, 6], bottleneck=True, bn_size=4)
+    plan_k = orc.densenet_plan(1, 3, 64, [6, 8, 6], bottleneck=4)
+    assert [(k, tuple(v.shape)) for k, v in mk.state_dict().items()] == [(k, tuple(s)) for k, s in orc.state_layout(plan_k)]
+    assert tuple(mk.state_dict()["features.EncBlock1.denselayer2.conv1.weight"].shape) == (16, 64, 3, 3)   # 64 <= 4 * 16
+    assert tuple(mk.state_dict()["features.EncBlock1.denselayer3.conv1.weight"].shape) == (64, 80, 1, 1)
+    assert tuple(mk.state_dict()["features.EncBlock1.denselayer3.conv2.weight"].shape) == (16, 64, 3, 3)
     with pytest.raises(NotImplementedError):
         DenseED(1, 3, 64, [6, 8, 6], upsample='bicubic')
     # upsample=None: ConvTranspose2d transitions named convT2, same state_dict layout as the reference

@@ -11,11 +11,16 @@ from oracle import pdes_oracle as orc
 CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_full64", "densenet_full64_channel",
          "densenet_full32_b32", "densenet_full64_b32",   # *_b32: the batch bench.py times (fields stored as fp32)
          "densenet_bilinear16", "densenet_bilinear32",   # DenseED(upsample='bilinear')
-         "densenet_convt16", "densenet_convt32"]         # DenseED(upsample=None): nn.ConvTranspose2d transitions
+         "densenet_convt16", "densenet_convt32",         # DenseED(upsample=None): nn.ConvTranspose2d transitions
+         "densenet_bottleneck16", "densenet_bottleneck32"]   # DenseED(bottleneck=True, bn_size=...)
 
 
 def _ups(name):
     return "bilinear" if "bilinear" in name else (None if "convt" in name else "nearest")
+
+
+def _bn(g):
+    return int(g["bn_size"]) if "bn_size" in g.files else 0
 
 
 def _load(golden_dir, name):
@@ -36,7 +41,7 @@ def rel(a, b):
 @pytest.mark.parametrize("name", CASES)
 def test_structure_matches_reference(golden_dir, name):
     g = _load(golden_dir, name)
-    plan = orc.densenet_plan(**_cfg(g), upsample=_ups(name))
+    plan = orc.densenet_plan(**_cfg(g), upsample=_ups(name), bottleneck=_bn(g))
     assert orc.param_names(plan) == [str(s) for s in g["param_names"]]
     n_params = sum(int(np.prod(s)) for n, s in orc.state_layout(plan)
                    if n in set(orc.param_names(plan)))
@@ -49,7 +54,7 @@ def test_train_step_fp64_matches_reference(golden_dir, name):
     torch.set_num_threads(4)
     g = _load(golden_dir, name)
     cfg = _cfg(g)
-    plan = orc.densenet_plan(**cfg, upsample=_ups(name))
+    plan = orc.densenet_plan(**cfg, upsample=_ups(name), bottleneck=_bn(g))
     sd = orc.to_dtype(orc.make_state(plan, int(g["seed"])), torch.float64)
     K = orc.make_input(int(g["B"]), cfg["imsize"], int(g["seed"]), kind=str(g["input_kind"]) if "input_kind" in g.files else "lognormal").double()
     sd_eval = orc.to_dtype(sd, torch.float64)
