@@ -266,6 +266,8 @@ def main():
         small = dict(in_channels=1, out_channels=3, imsize=16, blocks=[2, 3, 2], growth_rate=4, init_features=8)
         save_case("densenet_bottleneck16.npz", small, B=3, seed=59, full_grads=True, bn_size=2)
         save_case("densenet_bottleneck32.npz", dict(full, imsize=32), B=3, seed=61, full_grads=False, bn_size=4)
+        save_case("densenet_bottleneck32b.npz", dict(full, imsize=32, blocks=[3, 4, 3]), B=2, seed=67, full_grads=False,
+                  bn_size=4)
 
     def coupling_cases():
         # SURVEY.md section 8(f) row 1 / BASELINE config 5: the cGlow coupling network `_DenseCoupling`

@@ -22,7 +22,10 @@ CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_
          # DenseED(upsample=None): nn.ConvTranspose2d transitions, output imsize/2 wide (models/codec.py:139-142, 176-179)
          "densenet_convt16", "densenet_convt32",
          # DenseED(bottleneck=True, bn_size=...): 1x1 -> 3x3 dense layers above bn_size * growth channels (codec.py:56-64)
-         "densenet_bottleneck16", "densenet_bottleneck32"]
+         # (the deeper `densenet_bottleneck32` fixture - 46 convolutions - stays a CPU oracle pin: on the GPU it is a
+         # ReLU-mask-flip lottery; tools/diag_fixture.py shows the CUDA-core path flipping in
+         # DecBlock2.denselayer3 and the tensor-core path not at all)
+         "densenet_bottleneck16", "densenet_bottleneck32b"]
 
 
 def _ups(name):
@@ -195,7 +198,7 @@ def test_errors_are_loud():
     with pytest.raises(ValueError):
         DenseED(1, 3, 64, [6, 8])
     with pytest.raises(NotImplementedError):
-        DenseED(1, 3, 64, [6, 8, 6], bottleneck=True)
+        DenseED(1, 3, 64, [6, 8, 6], upsample='bicubic')
     with pytest.raises(ValueError):
         DenseED(1, 3, 64, [6, 8, 6], drop_rate=1.5)
     m = DenseED(1, 3, 16, [1, 1, 1], growth_rate=4, init_features=8)

@@ -12,7 +12,7 @@ CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_
          "densenet_full32_b32", "densenet_full64_b32",   # *_b32: the batch bench.py times (fields stored as fp32)
          "densenet_bilinear16", "densenet_bilinear32",   # DenseED(upsample='bilinear')
          "densenet_convt16", "densenet_convt32",         # DenseED(upsample=None): nn.ConvTranspose2d transitions
-         "densenet_bottleneck16", "densenet_bottleneck32"]   # DenseED(bottleneck=True, bn_size=...)
+         "densenet_bottleneck16", "densenet_bottleneck32", "densenet_bottleneck32b"]   # DenseED(bottleneck=True, bn_size=...)
 
 
 def _ups(name):
