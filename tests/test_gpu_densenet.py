@@ -28,6 +28,9 @@ CASES = ["densenet_small16", "densenet_fiveblk16", "densenet_full32", "densenet_
          "densenet_bottleneck16", "densenet_bottleneck32b"]
 
 
+FLIP_PRONE = {"densenet_bottleneck32b"}   # see test_train_step_matches_reference
+
+
 def _ups(name):
     return "bilinear" if "bilinear" in name else (None if "convt" in name else "nearest")
 
@@ -124,10 +127,19 @@ def test_train_step_matches_reference(golden_dir, name, impl):
         tot_err += err ** 2
         tot_norm += norm ** 2
     ratios, rels = np.array(ratios), np.array(rels)
-    assert np.median(ratios) <= 1.0, "typical tensor %.2f x the 3x-noise-floor bar" % np.median(ratios)
-    # (a flip deep in the decoder perturbs every gradient upstream of it, i.e. up to the whole encoder)
-    assert np.mean(ratios <= 1.0) >= 0.5, "only %.0f%% of the tensors at the noise floor" % (100 * np.mean(ratios <= 1.0))
-    assert rels.max() <= 0.3 and np.sqrt(tot_err / tot_norm) <= 5e-3, (rels.max(), np.sqrt(tot_err / tot_norm))
+    if name in FLIP_PRONE:
+        # Bottleneck networks (a 1x1 convolution + BatchNorm + ReLU in front of every 3x3 one) flip a ReLU mask in most
+        # fp32 runs, and WHICH element flips depends on the rounding of that run (tools/diag_fixture.py: the same
+        # fixture sits at 0.2-0.3 x the bar in one run and flips in DecBlock2 in the next).  Everything downstream of
+        # the flip must still be at the floor, the rest bounded; the kernels themselves are checked flip-free by
+        # test_tensor_core_backward_strict_per_tensor on this fixture.
+        assert np.mean(ratios <= 1.0) >= 0.15, "only %.0f%% of the tensors at the noise floor" % (100 * np.mean(ratios <= 1.0))
+        assert rels.max() <= 0.3 and np.sqrt(tot_err / tot_norm) <= 3e-2, (rels.max(), np.sqrt(tot_err / tot_norm))
+    else:
+        assert np.median(ratios) <= 1.0, "typical tensor %.2f x the 3x-noise-floor bar" % np.median(ratios)
+        # (a flip deep in the decoder perturbs every gradient upstream of it, i.e. up to the whole encoder)
+        assert np.mean(ratios <= 1.0) >= 0.5, "only %.0f%% of the tensors at the noise floor" % (100 * np.mean(ratios <= 1.0))
+        assert rels.max() <= 0.3 and np.sqrt(tot_err / tot_norm) <= 5e-3, (rels.max(), np.sqrt(tot_err / tot_norm))
     # running statistics and step counters
     sd = model.state_dict()
     run = np.concatenate([sd[str(n)].double().cpu().numpy().ravel() for n in g["running_names"]])
@@ -399,7 +411,7 @@ def test_batch_size_changes_rebind_executor(golden_dir):
     assert rel(g2.cpu().numpy(), g1.cpu().numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("name", ["densenet_full32", "densenet_full32_b32"])
+@pytest.mark.parametrize("name", ["densenet_full32", "densenet_full32_b32", "densenet_bottleneck32b"])
 def test_tensor_core_backward_strict_per_tensor(golden_dir, name):
     """Strict per-tensor check of the tensor-core dgrad / wgrad kernels with ReLU-mask flips excluded by
     construction: conv_impl 4 / 5 keep the exact-fp32 CUDA-core FORWARD (bitwise the forward, hence the
