@@ -23,6 +23,10 @@ for impl in impls:
     model.load_state_dict(sd); model = model.cuda(); model.conv_impl = impl
     K = orc.make_input(int(g['B']), cfg["imsize"], int(g['seed'])).cuda()
     sob = SobelFilter(cfg["imsize"], device='cuda')
+    if os.environ.get("DIAG_EVAL_FIRST"):   # the parity test's order: an eval-mode forward before the training step
+        model.eval()
+        with torch.no_grad():
+            model(K)
     model.train(); model.zero_grad()
     out = model(K); out.retain_grad()
     loss = conv_constitutive_constraint(K, out, sob) + conv_continuity_constraint(out, sob)
