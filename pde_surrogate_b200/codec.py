@@ -480,6 +480,41 @@ class _ExecutorNet(nn.Module):
             out = _EvalGuardFn.apply(out, anchor)
         return out
 
+    def forward_test(self, x):
+        """The reference's shape trace (models/codec.py:298-304, 365-370): prints the tensor size behind every
+        top-level module of `features`, then returns the output.  The executor does not materialise per-module
+        tensors on the host, so the sizes are derived from the layer table (they are what the reference prints)."""
+        print('input: {}'.format(x.data.size()))
+        out = self.forward(x)
+        c = self._cfg
+        B, h = int(x.shape[0]), int(x.shape[-1])
+        arch, blocks, g = c.get("arch", 0), list(c["blocks"]), c["growth_rate"]
+        ch = c["init_features"]
+        lines = []
+        if arch == 0:
+            pad = 3 if h % 2 == 0 else 2
+            h = (h + 2 * pad - 7) // 2 + 1
+            lines.append(("In_conv", ch, h))
+            n_enc = len(blocks) // 2
+        else:
+            lines.append(("conv0", ch, h))
+            n_enc = 0
+        for i, nl in enumerate(blocks):
+            enc = i < n_enc
+            ch += nl * g
+            lines.append(("%sBlock%d" % ("Enc" if enc else "Dec", i + 1 if enc else i - n_enc + 1), ch, h))
+            if i < len(blocks) - 1:
+                ch //= 2
+                h = (h + 2 - 3) // 2 + 1 if enc else 2 * h
+                lines.append(("Trans%s%d" % ("Down" if enc else "Up", i + 1 if enc else i - n_enc + 1), ch, h))
+        lines.append(("LastTransUp", c["out_channels"], int(out.shape[-1])))
+        for name, cc, hh in lines:
+            print('{}: {}'.format(name, torch.Size([B, cc, hh, hh])))
+        for name, module in self.features._modules.items():
+            if module is self._out_act:
+                print('{}: {}'.format(name, out.data.size()))
+        return out
+
     @property
     def model_size(self):
         return module_size(self)

@@ -323,3 +323,47 @@ def test_fused_adam_class_falls_back_to_stock_step():
     finally:
         pdes_optim.uninstall()
     assert torch.optim.Adam is stock
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout (build container only)")
+@pytest.mark.parametrize("kw", [dict(), dict(upsample=None), dict(bottleneck=True, bn_size=2, out_activation="tanh")])
+def test_forward_test_prints_the_reference_trace(kw, capsys):
+    """DenseED.forward_test / Decoder.forward_test (models/codec.py:298-304, 365-370): the printed shape trace is the
+    reference's own, line for line (the reference is imported from /root/reference for this comparison only)."""
+    import importlib.util
+    import sys
+    shim = os.path.join(ROOT, "pde_surrogate_b200", "_shims")
+    added = importlib.util.find_spec("matplotlib") is None
+    if added:
+        sys.path.insert(0, shim)
+    saved = {k: sys.modules.pop(k) for k in [m for m in sys.modules if m.split(".")[0] in ("models", "utils")]}
+    sys.path.insert(0, "/root/reference")
+    try:
+        ref_codec = importlib.import_module("models.codec")
+        assert ref_codec.__file__.startswith("/root/reference")
+        ref = ref_codec.DenseED(1, 3, 32, [2, 3, 2], growth_rate=4, init_features=8, **kw)
+        ref_dec = ref_codec.Decoder(2, 3, [2, 2], growth_rate=4, init_features=8)
+        capsys.readouterr()
+        ref.eval(), ref_dec.eval()
+        with torch.no_grad():
+            ref.forward_test(torch.zeros(2, 1, 32, 32))
+            ref_dec.forward_test(torch.zeros(2, 2, 8, 8))
+        want = capsys.readouterr().out
+    finally:
+        sys.path.remove("/root/reference")
+        if added:
+            sys.path.remove(shim)
+        for k in [m for m in sys.modules if m.split(".")[0] in ("models", "utils")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    from pde_surrogate_b200.codec import DenseED, Decoder
+    with cpu_backend():
+        mine = DenseED(1, 3, 32, [2, 3, 2], growth_rate=4, init_features=8, **kw)
+        mine_dec = Decoder(2, 3, [2, 2], growth_rate=4, init_features=8)
+        capsys.readouterr()
+        mine.eval(), mine_dec.eval()
+        with torch.no_grad():
+            mine.forward_test(torch.zeros(2, 1, 32, 32))
+            mine_dec.forward_test(torch.zeros(2, 2, 8, 8))
+        got = capsys.readouterr().out
+    assert got == want
