@@ -353,6 +353,18 @@ def constitutive(K, out):
     return (r1 ** 2 + r2 ** 2).mean()
 
 
+def constitutive_nonlinear_exp(K, out):
+    """conv_constitutive_constraint_nonlinear_exp (darcy.py:193-207): sigma = -exp(K u) grad(u)."""
+    u = out[:, 0:1]
+    ke = torch.exp(K * u)
+    return ((out[:, 1:2] + ke * sobel_grad_h(u)) ** 2 + (out[:, 2:3] + ke * sobel_grad_v(u)) ** 2).mean()
+
+
+def energy_functional_exp(K, u):
+    """energy_functional_exp (darcy.py:151-159): mean[0.5 exp(K u) |grad u|^2]."""
+    return (0.5 * torch.exp(K * u) * (sobel_grad_h(u) ** 2 + sobel_grad_v(u) ** 2)).mean()
+
+
 def constitutive_nonlinear(K, out, beta1, beta2):
     """conv_constitutive_constraint_nonlinear (darcy.py:179-191):
     -K grad(u) = sigma + beta1 sqrt(K) sigma^2 + beta2 K sigma^3, squared residual mean."""

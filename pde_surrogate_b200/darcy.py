@@ -149,6 +149,22 @@ def conv_constitutive_constraint_nonlinear(input, output, sobel_filter, beta1, b
     return _fused_parts(input, output, betas=(float(beta1), float(beta2)))[0]
 
 
+def conv_constitutive_constraint_nonlinear_exp(input, output, sobel_filter):
+    """Exponential nonlinear law sigma = -exp(K u) grad(u) (darcy.py:193-207; no script uses it): residual of the two
+    flux channels, on the Sobel kernels (`SobelFilter.grad_h / grad_v` are differentiable) and elementwise torch ops."""
+    u = output[:, [0]]
+    k_eff = torch.exp(input * u)
+    r_h = output[:, [1]] + k_eff * sobel_filter.grad_h(u)
+    r_v = output[:, [2]] + k_eff * sobel_filter.grad_v(u)
+    return (r_h ** 2 + r_v ** 2).mean()
+
+
+def energy_functional_exp(input, output, sobel_filter):
+    """V(u, K) = mean[ 0.5 exp(K u) |grad u|^2 ] (darcy.py:151-159; no script uses it), on the Sobel kernels."""
+    g2 = sobel_filter.grad_h(output) ** 2 + sobel_filter.grad_v(output) ** 2
+    return (0.5 * torch.exp(input * output) * g2).mean()
+
+
 def conv_continuity_constraint(output, sobel_filter, use_tb=True):
     """div(sigma) = 0: mean[(d sigma1/dx + d sigma2/dy)^2]  (darcy.py:210-224)."""
     if _needs_composite(sobel_filter):

@@ -76,9 +76,10 @@ def cpu_backend():
 
     def sobel_call(image, direction, correct, adjoint):
         if adjoint:
-            x = torch.zeros_like(image, requires_grad=True)
-            y = orc.sobel_grad_h(x, correct) if direction == 0 else orc.sobel_grad_v(x, correct)
-            g, = torch.autograd.grad(y, x, image)
+            with torch.enable_grad():   # (called from an autograd.Function.backward: grad mode is off there)
+                x = torch.zeros_like(image, requires_grad=True)
+                y = orc.sobel_grad_h(x, correct) if direction == 0 else orc.sobel_grad_v(x, correct)
+                g, = torch.autograd.grad(y, x, image)
             return g
         with torch.no_grad():
             return orc.sobel_grad_h(image, correct) if direction == 0 else orc.sobel_grad_v(image, correct)

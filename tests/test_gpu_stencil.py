@@ -117,3 +117,26 @@ def test_errors_are_loud():
         sob.grad_h(torch.zeros(1, 1, 16, 16, device="cuda"), filter_size=5)
     with pytest.raises(TypeError):
         darcy.conv_boundary_condition(torch.zeros(1, 3, 16, 16, device="cuda", dtype=torch.float64))
+
+
+def test_exponential_law_losses_vs_oracle():
+    """conv_constitutive_constraint_nonlinear_exp / energy_functional_exp (models/darcy.py:151-159, 193-207) on the GPU
+    Sobel kernels vs the fp64 oracle: values and gradients."""
+    from oracle import pdes_oracle as orc
+    from models.darcy import conv_constitutive_constraint_nonlinear_exp, energy_functional_exp
+    from utils.image_gradient import SobelFilter
+    torch.manual_seed(5)
+    K = torch.exp(0.3 * torch.randn(3, 1, 32, 32))
+    out = 0.3 * torch.randn(3, 3, 32, 32)
+    u = 0.3 * torch.randn(3, 1, 32, 32)
+    sob = SobelFilter(32, correct=True, device="cuda")
+    for fn, ofn, arg in ((conv_constitutive_constraint_nonlinear_exp, orc.constitutive_nonlinear_exp, out),
+                         (energy_functional_exp, orc.energy_functional_exp, u)):
+        a = arg.cuda().requires_grad_(True)
+        v = fn(K.cuda(), a, sob)
+        g, = torch.autograd.grad(v, a)
+        a64 = arg.double().requires_grad_(True)
+        v64 = ofn(K.double(), a64)
+        g64, = torch.autograd.grad(v64, a64)
+        assert abs(float(v) - float(v64)) <= 1e-5 * abs(float(v64))
+        assert float((g.cpu().double() - g64).norm() / g64.norm()) < 1e-5

@@ -367,3 +367,46 @@ def test_forward_test_prints_the_reference_trace(kw, capsys):
             mine_dec.forward_test(torch.zeros(2, 2, 8, 8))
         got = capsys.readouterr().out
     assert got == want
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout (build container only)")
+def test_exponential_law_losses_match_reference():
+    """conv_constitutive_constraint_nonlinear_exp / energy_functional_exp (models/darcy.py:151-159, 193-207; unused by
+    the scripts): values and gradients equal the reference's functions evaluated with the reference's SobelFilter."""
+    import importlib.util
+    import sys
+    shim = os.path.join(ROOT, "pde_surrogate_b200", "_shims")
+    added = importlib.util.find_spec("matplotlib") is None
+    if added:
+        sys.path.insert(0, shim)
+    saved = {k: sys.modules.pop(k) for k in [m for m in sys.modules if m.split(".")[0] in ("models", "utils")]}
+    sys.path.insert(0, "/root/reference")
+    torch.manual_seed(3)
+    K = torch.exp(0.3 * torch.randn(2, 1, 16, 16))
+    out = (0.3 * torch.randn(2, 3, 16, 16)).requires_grad_(True)
+    u = (0.3 * torch.randn(2, 1, 16, 16)).requires_grad_(True)
+    try:
+        ref_darcy = importlib.import_module("models.darcy")
+        ref_sob = importlib.import_module("utils.image_gradient").SobelFilter(16, correct=True, device="cpu")
+        assert ref_darcy.__file__.startswith("/root/reference")
+        want = []
+        for fn, arg in ((ref_darcy.conv_constitutive_constraint_nonlinear_exp, out), (ref_darcy.energy_functional_exp, u)):
+            v = fn(K, arg, ref_sob)
+            g, = torch.autograd.grad(v, arg)
+            want.append((v.detach(), g))
+    finally:
+        sys.path.remove("/root/reference")
+        if added:
+            sys.path.remove(shim)
+        for k in [m for m in sys.modules if m.split(".")[0] in ("models", "utils")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    from pde_surrogate_b200 import darcy as my_darcy
+    from pde_surrogate_b200.image_gradient import SobelFilter
+    with cpu_backend():
+        sob = SobelFilter(16, correct=True, device="cpu")
+        for (fn, arg), (v_ref, g_ref) in zip(((my_darcy.conv_constitutive_constraint_nonlinear_exp, out),
+                                              (my_darcy.energy_functional_exp, u)), want):
+            v = fn(K, arg, sob)
+            g, = torch.autograd.grad(v, arg)
+            assert torch.allclose(v, v_ref, rtol=1e-5, atol=1e-7) and torch.allclose(g, g_ref, rtol=1e-4, atol=1e-7)
