@@ -24,6 +24,9 @@ names = ["h2d", "zero_grad", "forward", "losses", "backward", "adam", "item"]
 H = {n: [] for n in names}
 G = {n: [] for n in names}
 tot_h, tot_g = [], []
+_side = torch.cuda.Stream() if os.environ.get("E2E_STREAM") else None   # E2E_STREAM=1: the loop on a non-default stream
+if _side is not None:
+    torch.cuda.set_stream(_side)
 for it in range(60):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
     t = [time.perf_counter()]
