@@ -64,6 +64,11 @@ TC_CASES = [
     (32, 64, 49, 3, 5, 1, 2, 0, 1),    # LastTransUp.conv3
     (32, 32, 144, 72, 1, 1, 0, 0, 1),  # TransDown1.conv1
     (5, 24, 36, 16, 3, 1, 1, 0, 1),    # ragged: 5 x 2 x 3 = 30 partial tiles
+    # wide rows with many channels: the operand-split kernel cuts a row into segments (its tile would not fit):
+    # two equal segments, two segments under the x2 upsampling, and a shorter last segment (73 = 37 + 36)
+    (1, 64, 200, 16, 1, 1, 0, 0, 1),
+    (2, 64, 104, 16, 3, 1, 1, 1, 1),
+    (1, 73, 200, 16, 1, 1, 0, 0, 1),
 ]
 
 
