@@ -120,6 +120,9 @@ def write_script_datasets(data_dir, imsize, ntrain, ntest, kind="grf_kle512", se
     if kind == "grf_kle512":
         x = grf_kle(ntrain + ntest, imsize, 512, 0.1, seed=seed, device=device).numpy()
         names = ("kle512_lhs10000_train.hdf5", "kle512_lhs1000_val.hdf5")
+    elif kind == "grf_kle100":   # train_cglow_reverse_kl.py:113-121 (--kle 100, 32x32)
+        x = grf_kle(ntrain + ntest, imsize, 100, 0.1, seed=seed, device=device).numpy()
+        names = ("kle100_lhs10000_train.hdf5", "kle100_lhs1000_val.hdf5")
     elif kind == "channelized":
         x = channelized(ntrain + ntest, imsize, seed=seed).numpy()
         names = ("channel_ng64_n4096_train.hdf5", "channel_ng64_n512_test.hdf5")

@@ -410,3 +410,36 @@ def test_exponential_law_losses_match_reference():
             v = fn(K, arg, sob)
             g, = torch.autograd.grad(v, arg)
             assert torch.allclose(v, v_ref, rtol=1e-5, atol=1e-7) and torch.allclose(g, g_ref, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "train_cglow_reverse_kl.py")),
+                    reason="reference checkout not present (only in the build container)")
+def test_unmodified_cglow_reverse_kl_script_runs(tmp_path):
+    """SURVEY section 8(f) row 1 / BASELINE config 5: train_cglow_reverse_kl.py, byte for byte, on this repo's
+    models.glow_msc (coupling networks on the executor - here its oracle-backed stand-in - flow plumbing in PyTorch),
+    the fused Darcy losses and the harness modules: two epochs of reverse-KL training, the test pass with
+    `model.predict` / `model.sample`, checkpoint and statistics."""
+    from pde_surrogate_b200 import data
+    d = tmp_path / "datasets" / "32x32"
+    d.mkdir(parents=True)
+    rs = np.random.RandomState(2)
+    x = data.grf_kle(16, 32, 64, 0.2, seed=3, device="cpu").numpy()
+    data.write_hdf5(str(d / "kle100_lhs10000_train.hdf5"), x[:8])
+    data.write_hdf5(str(d / "kle100_lhs1000_val.hdf5"), x[8:], rs.standard_normal((8, 3, 32, 32)))
+    import run_reference_script
+    argv = ["--script", os.path.join(REF, "train_cglow_reverse_kl.py"), "--", "--data-dir", str(tmp_path / "datasets"),
+            "--exp-dir", str(tmp_path / "exp"), "--imsize", "32", "--ntrain", "8", "--ntest", "8", "--batch-size", "4",
+            "--test-batch-size", "8", "--epochs", "2", "--cuda", "0", "--plot-freq", "1000", "--ckpt-freq", "2"]
+    # (two epochs: the script divides by (epochs - 1) * steps_per_epoch, train_cglow_reverse_kl.py:233, 268; a test
+    # batch of >= 6: its last epoch plots six members of the first test batch, 198-202)
+    old_argv, old_path = list(sys.argv), list(sys.path)
+    try:
+        with cpu_backend():
+            run_reference_script.main(argv)
+    finally:
+        sys.argv, sys.path[:] = old_argv, old_path
+    run = list((tmp_path / "exp").rglob("args.txt"))[0].parent
+    ck = torch.load(str(run / "checkpoints" / "model_epoch2.pth"), weights_only=False)
+    assert "flow.revblock3.revlayers.revlayer6.coupling.coupling_nn.reduce.conv_zero.conv.weight" in ck["model_state_dict"]
+    assert (run / "training" / "loss_train.txt").exists() and (run / "training" / "entropy_test.txt").exists()
+    assert np.isfinite(np.loadtxt(str(run / "training" / "loss_train.txt"))).all()

@@ -51,6 +51,49 @@ def plot_prediction_det_animate2(save_dir, target, prediction, epoch, index, i_p
     plot_prediction_det(save_dir, target, prediction, epoch, index, plot_fn=plot_fn, cmap=cmap, same_scale=same_scale)
 
 
+def plot_prediction_bayes2(save_dir, target, pred_mean, pred_var, epoch, index, plot_fn='imshow', cmap='jet',
+                           same_scale=False):
+    """Predictive mean / variance writer of train_cglow_reverse_kl.py:207-209 (utils/plot.py:181 upstream): the
+    numeric arrays are always saved, a 4-row figure (target, mean, error, variance) when matplotlib exists."""
+    target, pred_mean, pred_var = to_numpy(target), to_numpy(pred_mean), to_numpy(pred_var)
+    np.save(save_dir + '/pred_bayes_epoch{}_{}.npy'.format(epoch, index), np.stack([target, pred_mean, pred_var]))
+    plt = _pyplot()
+    if plt is None:
+        return
+    rows = [target, pred_mean, target - pred_mean, pred_var]
+    fig, axes = plt.subplots(4, target.shape[0], figsize=(3.5 * target.shape[0], 12))
+    axes = np.atleast_2d(axes)
+    for r, fields in enumerate(rows):
+        for c in range(target.shape[0]):
+            ax = axes[r, c]
+            im = (ax.contourf(fields[c], 50, cmap=cmap) if plot_fn == 'contourf' else
+                  ax.imshow(fields[c], cmap=cmap, origin='lower', interpolation='bilinear'))
+            ax.set_axis_off()
+            fig.colorbar(im, ax=ax, fraction=0.046, pad=0.04)
+    fig.savefig(save_dir + '/pred_bayes_epoch{}_{}.png'.format(epoch, index), bbox_inches='tight')
+    plt.close(fig)
+
+
+def save_samples(save_dir, images, epoch, index, name, nrow=4, heatmap=True, cmap='jet', title=False):
+    """Sample-grid writer of train_cglow_reverse_kl.py:215-216 (utils/plot.py:644 upstream): (N, C, H, W) samples,
+    one grid per channel; the array is always saved."""
+    images = to_numpy(images)
+    np.save(save_dir + '/{}_epoch{}_{}.npy'.format(name, epoch, index), images)
+    plt = _pyplot()
+    if plt is None:
+        return
+    n, ch = images.shape[0], images.shape[1]
+    ncol = (n + nrow - 1) // nrow
+    for c in range(ch):
+        fig, axes = plt.subplots(nrow, ncol, figsize=(2.5 * ncol, 2.5 * nrow))
+        for k, ax in enumerate(np.atleast_1d(axes).ravel()):
+            ax.set_axis_off()
+            if k < n:
+                ax.imshow(images[k, c], cmap=cmap if heatmap else 'gray', origin='lower', interpolation='bilinear')
+        fig.savefig(save_dir + '/{}_epoch{}_{}_c{}.png'.format(name, epoch, index, c), bbox_inches='tight')
+        plt.close(fig)
+
+
 def save_stats(save_dir, logger, *metrics):
     plt = _pyplot()
     for metric in metrics:
