@@ -322,6 +322,71 @@ def main():
                 d[k] = d[k].astype(np.float32)
         np.savez_compressed(os.path.join(HERE, "cglow_coupling.npz"), **d)
 
+    def cglow_model_case():
+        # The whole MultiScaleCondGlow (models/glow_msc.py:672-828) through ONE reverse-KL step body
+        # (train_cglow_reverse_kl.py:250-262): generate -> Darcy residuals -> entropy term -> backward, in fp64 and fp32.
+        # The reference runs with ONE patch: GaussianDiag's in-place clamp (glow_msc.py:438), which current PyTorch
+        # refuses to differentiate, is made out of place (same values and gradients).
+        import math
+        from models import glow_msc as ref_glow
+        from models import darcy as ref_darcy
+
+        def patched_init(self, mean, log_stddev):
+            self.mean = mean
+            self.log_stddev = log_stddev.clamp(min=-10., max=math.log(5.))
+        ref_glow.GaussianDiag.__init__ = patched_init
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_glow_flow import randomise
+        cfg = dict(img_size=16, x_channels=1, y_channels=3, enc_blocks=[2, 2, 2], flow_blocks=[2, 3, 2], LUdecompose=True)
+        np.random.seed(21)
+        torch.manual_seed(21)
+        base = ref_glow.MultiScaleCondGlow(**cfg)
+        sd = randomise(base, 23)
+        B = 4
+        x = torch.exp(0.3 * torch.randn(B, 1, 16, 16))
+        eps = [0.7 * torch.randn(B, *s_) for s_ in base._z_shapes()]
+        d = dict(x=x.numpy(), B=B)
+        for i, e in enumerate(eps):
+            d["eps%d" % i] = e.numpy()
+        names = list(sd.keys())
+        d["state_names"] = np.array(names)
+        for i, k in enumerate(names):
+            d["state%d" % i] = sd[k].numpy()
+        for dtype, sfx in ((torch.float64, "64"), (torch.float32, "32")):
+            np.random.seed(21)
+            torch.manual_seed(21)
+            model = ref_glow.MultiScaleCondGlow(**cfg)
+            model.load_state_dict(sd)
+            model = model.to(dtype)
+            sob = SobelFilter(16, correct=True, device="cpu")
+            if dtype == torch.float64:
+                for a in ("HSOBEL_WEIGHTS_3x3", "VSOBEL_WEIGHTS_3x3", "modifier"):
+                    setattr(sob, a, getattr(sob, a).double())
+            model.train()
+            model.zero_grad()
+            xi = x.to(dtype)
+            y, logp = model.generate(xi, eps_list=[e.to(dtype) for e in eps])
+            res = ref_darcy.conv_constitutive_constraint(xi, y, sob) + ref_darcy.conv_continuity_constraint(y, sob)
+            l_dir, l_neu = ref_darcy.conv_boundary_condition(y)
+            neg_entropy = logp.mean() / math.log(2.) / (3 * 16 * 16)
+            loss = (res + (l_dir + l_neu) * 50.0) * 150.0 + neg_entropy
+            loss.backward()
+            pn = [n for n, p in model.named_parameters() if p.grad is not None]
+            g = np.concatenate([p.grad.double().numpy().ravel() for n, p in model.named_parameters() if p.grad is not None])
+            if sfx == "64":
+                d["y64"], d["logp64"], d["loss64"] = y.detach().numpy().astype(np.float32), logp.detach().numpy(), float(loss)
+                d["grads64"] = g.astype(np.float32)
+                d["grad_names"] = np.array(pn)
+                d["grad_sizes"] = np.array([p.grad.numel() for n, p in model.named_parameters() if p.grad is not None])
+                g64 = g
+            else:
+                d["y_err32"] = float((y.detach().double().numpy() - d["y64"]).ravel().__abs__().max())
+                d["grad_err32"] = float(np.linalg.norm(g - g64) / np.linalg.norm(g64))
+                d["loss32"] = float(loss)
+        d["cfg_enc"], d["cfg_flow"] = np.array(cfg["enc_blocks"]), np.array(cfg["flow_blocks"])
+        np.savez_compressed(os.path.join(HERE, "cglow_model.npz"), **d)
+        print("cglow model: loss64", d["loss64"], "loss32", d["loss32"], "grad_err32", d["grad_err32"], "n state", len(names))
+
     def dropout_case():
         # DenseED(drop_rate=0.2) (train_codec_mixed_residual.py --drop-rate; nn.Dropout2d behind the convolutions,
         # models/codec.py:70-71, 110-149, 171-172): one fp32 training step of the reference with the CPU
@@ -363,6 +428,9 @@ def main():
     if "--only-dropout" in sys.argv:
         dropout_case()
         return
+    if "--only-cglow-model" in sys.argv:
+        cglow_model_case()
+        return
     if "--only-coupling" in sys.argv:
         coupling_cases()
         return
@@ -402,6 +470,7 @@ def main():
     convt_cases()
     bottleneck_cases()
     coupling_cases()
+    cglow_model_case()
 
     # ---- Sobel operators and loss terms on their own, incl. odd size and autograd adjoint ----
     rs = np.random.RandomState(42)

@@ -147,3 +147,54 @@ def test_default_initialisation_is_the_reference_stream():
     assert list(a) == list(b)
     for k in a:
         assert torch.allclose(a[k].float(), b[k].float(), rtol=1e-6, atol=1e-7), k
+
+
+def load_cglow_fixture(golden_dir, device="cpu"):
+    """(model, x, eps, fixture) of tests/golden/cglow_model.npz (reference-generated: make_golden.py cglow_model_case)."""
+    from models.glow_msc import MultiScaleCondGlow
+    g = np.load(os.path.join(golden_dir, "cglow_model.npz"))
+    np.random.seed(0)
+    model = MultiScaleCondGlow(16, 1, 3, [int(v) for v in g["cfg_enc"]], [int(v) for v in g["cfg_flow"]], LUdecompose=True)
+    sd = {str(k): torch.tensor(g["state%d" % i]) for i, k in enumerate(g["state_names"])}
+    model.load_state_dict(sd)
+    model = model.to(device)
+    x = torch.tensor(g["x"]).to(device)
+    eps = [torch.tensor(g["eps%d" % i]).to(device) for i in range(len(model.flow_blocks) - 1)]
+    return model, x, eps, g
+
+
+def reverse_kl_step(model, x, eps, sobel):
+    """The step body of train_cglow_reverse_kl.py:250-262 (beta 150, weight_bound 50) with given noise."""
+    from models.darcy import conv_boundary_condition, conv_constitutive_constraint, conv_continuity_constraint
+    model.train()
+    model.zero_grad()
+    y, logp = model.generate(x, eps_list=eps)
+    res = conv_constitutive_constraint(x, y, sobel) + conv_continuity_constraint(y, sobel)
+    l_dir, l_neu = conv_boundary_condition(y)
+    neg_entropy = logp.mean() / math.log(2.) / (3 * 16 * 16)
+    loss = (res + (l_dir + l_neu) * 50.0) * 150.0 + neg_entropy
+    loss.backward()
+    return y, logp, loss
+
+
+def check_against_fixture(model, g, y, logp, loss, grad_bar):
+    assert rel(y.cpu(), torch.tensor(g["y64"])) < 1e-4
+    assert rel(logp.cpu(), torch.tensor(g["logp64"])) < 1e-4
+    assert abs(float(loss) - float(g["loss64"])) <= 1e-4 * abs(float(g["loss64"]))
+    params = dict(model.named_parameters())
+    got = np.concatenate([params[str(n)].grad.detach().double().cpu().numpy().ravel() for n in g["grad_names"]])
+    ref = g["grads64"].astype(np.float64)
+    assert got.shape == ref.shape
+    err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    assert err < grad_bar, err
+    return err
+
+
+def test_cglow_fixture_replays_on_the_cpu_stand_in(golden_dir):
+    """The reference-generated reverse-KL step fixture, replayed without the reference (this is what the GPU test
+    does on the B200): model from the stored state, same noise, same loss; fp32 CPU stand-in of the executor."""
+    with cpu_backend():
+        from utils.image_gradient import SobelFilter
+        model, x, eps, g = load_cglow_fixture(golden_dir)
+        y, logp, loss = reverse_kl_step(model, x, eps, SobelFilter(16, correct=True, device="cpu"))
+        check_against_fixture(model, g, y.detach(), logp.detach(), loss.detach(), 1e-4)
