@@ -28,6 +28,17 @@ from .glow import AffineCouplingLayer
 _LOG_STD_MIN, _LOG_STD_MAX = -10.0, math.log(5.0)
 
 
+def _exact_torch_convolutions():
+    """The PyTorch parts of the flow (input encoder, 1x1 convolutions, prior heads) run cuDNN convolutions, which
+    PyTorch lets use TF32 by default: measured on the B200, that alone puts 6e-4 on the conditioning features and 7e-4
+    on the generated fields (tools/diag_cglow.py) - seven times the 1e-4 parity bar, with the executor's own
+    convolutions exact.  The model therefore switches cuDNN TF32 off for the process (forward AND the autograd
+    backward, which runs outside any scoped flag); PDES_ALLOW_TF32=1 leaves PyTorch's default."""
+    import os
+    if os.environ.get("PDES_ALLOW_TF32", "0") != "1":
+        torch.backends.cudnn.allow_tf32 = False
+
+
 # ------------------------------------------------------------------------------------------------
 # elementwise / 1x1 flow steps
 # ------------------------------------------------------------------------------------------------
@@ -462,6 +473,7 @@ class MultiScaleCondGlow(nn.Module):
     def __init__(self, img_size, x_channels, y_channels, enc_blocks, flow_blocks, flow_coupling='dense', squeeze_factor=2,
                  LUdecompose=False, train_sampling=True, data_init=False):
         super(MultiScaleCondGlow, self).__init__()
+        _exact_torch_convolutions()
         if isinstance(img_size, int):
             self.img_size = [img_size, img_size]
         else:
