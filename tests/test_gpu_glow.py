@@ -69,15 +69,15 @@ def test_cglow_reverse_kl_step_matches_reference(golden_dir):
     """BASELINE config 5 / SURVEY 8(f) row 1: one reverse-KL step of the WHOLE MultiScaleCondGlow (generate -> Darcy
     residuals -> entropy -> backward) against the reference-generated fixture: the coupling networks on the sm_100a
     executor (tcgen05 two-piece fp16 convolutions, input gradients), the losses on the fused stencil kernels, the
-    flow plumbing in PyTorch.  Fields / log-likelihood / loss within 1e-4; parameter gradients within 2e-2 aggregate
-    (the coupling networks are BatchNorm-ReLU stacks: a flipped ReLU mask moves everything upstream of it, DESIGN
-    section 2) - measured value printed."""
+    flow plumbing in PyTorch.  Fields / log-likelihood / loss within 1e-4; parameter gradients within 5e-3 aggregate
+    (measured 2.1e-6 against the reference's own fp32-vs-fp64 8.2e-7; the bar leaves room for a flipped ReLU mask in
+    the BatchNorm-ReLU stacks of the coupling networks) - measured value printed."""
     from tests.test_glow_flow import check_against_fixture, load_cglow_fixture, reverse_kl_step
     from utils.image_gradient import SobelFilter
     model, x, eps, g = load_cglow_fixture(golden_dir, device="cuda")
     y, logp, loss = reverse_kl_step(model, x, eps, SobelFilter(16, correct=True, device="cuda"))
     torch.cuda.synchronize()
-    err = check_against_fixture(model, g, y.detach(), logp.detach(), loss.detach(), 2e-2)
+    err = check_against_fixture(model, g, y.detach(), logp.detach(), loss.detach(), 5e-3)
     print("cGlow reverse-KL step: gradient rel-L2 vs the fp64 reference %.3e (reference fp32: %.1e)" % (err, float(g["grad_err32"])))
     # a second step (executor graphs of the coupling networks now replay) still runs and stays finite
     y2, logp2, loss2 = reverse_kl_step(model, x, eps, SobelFilter(16, correct=True, device="cuda"))
