@@ -198,3 +198,34 @@ def test_cglow_fixture_replays_on_the_cpu_stand_in(golden_dir):
         model, x, eps, g = load_cglow_fixture(golden_dir)
         y, logp, loss = reverse_kl_step(model, x, eps, SobelFilter(16, correct=True, device="cpu"))
         check_against_fixture(model, g, y.detach(), logp.detach(), loss.detach(), 1e-4)
+
+
+def test_propagate_matches_reference():
+    """Uncertainty propagation (glow_msc.py:939-966): same Monte-Carlo statistics as the reference under the same
+    torch RNG stream (the noise comes from create_fixed_noise)."""
+    from torch.utils.data import DataLoader, TensorDataset
+    ref_glow = reference_glow()
+    cfg = dict(img_size=16, x_channels=1, y_channels=3, enc_blocks=[2, 2, 2], flow_blocks=[2, 2, 2], LUdecompose=True)
+    np.random.seed(7)
+    torch.manual_seed(7)
+    ref = ref_glow.MultiScaleCondGlow(**cfg)
+    sd = randomise(ref, 13)
+    ref.load_state_dict(sd)
+    xs = torch.exp(0.3 * torch.randn(4, 1, 16, 16))
+    loader = DataLoader(TensorDataset(xs, torch.zeros(4, 3, 16, 16)), batch_size=2)
+    ref.eval()
+    with torch.no_grad():
+        torch.manual_seed(99)
+        want = ref.propagate(loader, n_samples=2, temperature=1.0, var_samples=2)
+    with cpu_backend():
+        from models.glow_msc import MultiScaleCondGlow
+        np.random.seed(7)
+        torch.manual_seed(7)
+        mine = MultiScaleCondGlow(**cfg)
+        mine.load_state_dict(sd)
+        mine.eval()
+        with torch.no_grad():
+            torch.manual_seed(99)
+            got = mine.propagate(loader, n_samples=2, temperature=1.0, var_samples=2)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and rel(a, b) < 1e-4
