@@ -229,3 +229,38 @@ def test_propagate_matches_reference():
             got = mine.propagate(loader, n_samples=2, temperature=1.0, var_samples=2)
     for a, b in zip(got, want):
         assert a.shape == b.shape and rel(a, b) < 1e-4
+
+
+def test_actnorm_data_initialisation_matches_reference():
+    """--data-init (train_cglow_reverse_kl.py:239-248): the first encoding pass initialises every ActNorm from its
+    input minibatch (glow_msc.py:71-84); same parameters and the same (z, log p) as the reference afterwards."""
+    ref_glow = reference_glow()
+    cfg = dict(img_size=16, x_channels=1, y_channels=3, enc_blocks=[2, 2, 2], flow_blocks=[2, 2, 2], LUdecompose=False,
+               data_init=True)
+    np.random.seed(9)
+    torch.manual_seed(9)
+    ref = ref_glow.MultiScaleCondGlow(**cfg)
+    sd = randomise(ref, 17)
+    ref.load_state_dict(sd)
+    x = torch.exp(0.3 * torch.randn(3, 1, 16, 16))
+    y = torch.randn(3, 3, 16, 16)
+    ref.train()
+    with torch.no_grad():
+        z_r, lp_r, _ = ref(y, x)
+    with cpu_backend():
+        from models.glow_msc import ActNorm, MultiScaleCondGlow
+        np.random.seed(9)
+        torch.manual_seed(9)
+        mine = MultiScaleCondGlow(**cfg)
+        mine.load_state_dict(sd)
+        mine.train()
+        with torch.no_grad():
+            z_m, lp_m, _ = mine(y, x)
+        assert all(m.data_initialized for m in mine.modules() if isinstance(m, ActNorm))
+    assert rel(z_m, z_r) < 1e-4 and rel(lp_m, lp_r) < 1e-4
+    a, b = mine.state_dict(), ref.state_dict()
+    for k in a:
+        if k.endswith(("norm.weight", "norm.bias")) and a[k].dim() == 3:
+            assert rel(a[k], b[k]) < 1e-4, k
+    mine.init_actnorm()
+    assert mine.data_initialized
