@@ -15,7 +15,6 @@ convolution output (glow_msc.py:438), which current PyTorch refuses to different
 out of place - same values, same gradient (identity inside [-10, log 5], zero outside).
 """
 import math
-from collections import OrderedDict
 
 import numpy as np
 import torch
